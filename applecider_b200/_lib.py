@@ -1,0 +1,130 @@
+"""ctypes binding of libapplecider_b200.so (the C-ABI declared in include/applecider_b200.h).
+
+There is no CPU fallback: if the library is missing or a tensor is not on a CUDA
+device, the call raises.  Signature strings: p = pointer, i = int, l = long long,
+f = float; the trailing ``stream`` pointer is appended automatically.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libapplecider_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
+RES_NONE, RES_ADD, RES_MUL = 0, 1, 2
+
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "applecider_b200.h")
+
+
+def _parse_header(path: str) -> dict:
+    """Derive ctypes signatures from the C header: p = pointer, i = int, l = long long, f = float."""
+    import re
+
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    sigs = {}
+    for m in re.finditer(r"\bint\s+(acb_\w+)\s*\(([^)]*)\)\s*;", text):
+        name, args = m.group(1), m.group(2)
+        kinds = []
+        for a in args.split(","):
+            a = a.strip()
+            if not a or a == "void":
+                continue
+            if "*" in a:
+                kinds.append("p")
+            elif "long long" in a:
+                kinds.append("l")
+            elif re.search(r"\bfloat\b", a):
+                kinds.append("f")
+            else:
+                kinds.append("i")
+        if kinds and kinds[-1] == "p" and "stream" in args.split(",")[-1]:
+            kinds = kinds[:-1]  # the stream is appended by call()
+            sigs[name] = "".join(kinds)
+    return sigs
+
+
+SIGNATURES = _parse_header(HEADER_PATH)
+
+_KIND = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"applecider_b200: CUDA library not built ({LIB_PATH} missing). "
+                "Run `python -m applecider_b200.build` (nvcc, sm_100a); there is no CPU fallback."
+            )
+        l = ctypes.CDLL(LIB_PATH)
+        l.acb_last_error.restype = ctypes.c_char_p
+        l.acb_launch_count.restype = ctypes.c_longlong
+        for name, sig in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = [_KIND[k] for k in sig] + [ctypes.c_void_p]
+        _lib = l
+    return _lib
+
+
+def dtype_tag(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"applecider_b200: unsupported dtype {t.dtype}")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        if not a.is_cuda:
+            raise RuntimeError("applecider_b200: tensors must live on a CUDA device (no CPU fallback)")
+        if not a.is_contiguous():
+            raise RuntimeError("applecider_b200: tensors must be contiguous")
+        return a.data_ptr()
+    if isinstance(a, ctypes.Array):
+        return ctypes.cast(a, ctypes.c_void_p)
+    if isinstance(a, int):
+        return a
+    raise TypeError(f"cannot pass {type(a)} as a pointer")
+
+
+def call(name: str, *args):
+    l = lib()
+    sig = SIGNATURES[name]
+    if len(args) != len(sig):
+        raise TypeError(f"{name}: expected {len(sig)} arguments, got {len(args)}")
+    conv = []
+    for k, a in zip(sig, args):
+        if k == "p":
+            conv.append(_ptr(a))
+        elif k == "f":
+            conv.append(float(a))
+        else:
+            conv.append(int(a))
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = getattr(l, name)(*conv, stream)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {l.acb_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().acb_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().acb_reset_launch_count()
+
+
+def exported_symbols():
+    return sorted(SIGNATURES) + ["acb_last_error", "acb_version", "acb_launch_count", "acb_reset_launch_count"]

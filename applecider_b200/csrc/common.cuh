@@ -1,0 +1,107 @@
+// Common device/host helpers for the applecider_b200 sm_100a kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/applecider_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (C-ABI: every entry point returns 0 or a negative code; message via acb_last_error)
+// ---------------------------------------------------------------------------------------------
+void acb_set_error(const char* fmt, ...);
+
+#define ACB_CHECK(cond, ...)            \
+  do {                                  \
+    if (!(cond)) {                      \
+      acb_set_error(__VA_ARGS__);       \
+      return ACB_ERR_INVALID;           \
+    }                                   \
+  } while (0)
+
+#define ACB_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      acb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return ACB_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define ACB_LAUNCH_CHECK() ACB_CUDA(cudaGetLastError())
+
+void acb_count_launch(int n = 1);  // product-side launch counter (bench.py "gpu_launches")
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// dtype helpers
+// ---------------------------------------------------------------------------------------------
+typedef __nv_bfloat16 bf16;
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// generic typed load/store through a runtime dtype tag (0 = f32, 1 = bf16)
+__device__ __forceinline__ float ld_any(const void* p, long long i, int dt) {
+  return dt == ACB_F32 ? ((const float*)p)[i] : __bfloat162float(((const bf16*)p)[i]);
+}
+__device__ __forceinline__ void st_any(void* p, long long i, int dt, float v) {
+  if (dt == ACB_F32) ((float*)p)[i] = v;
+  else ((bf16*)p)[i] = __float2bfloat16_rn(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// math
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACB_ACT_RELU: return fmaxf(v, 0.0f);
+    case ACB_ACT_GELU: return gelu_erf(v);
+    case ACB_ACT_TANH: return tanhf(v);
+    case ACB_ACT_SIGMOID: return sigmoidf_(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum for blockDim.x <= 1024 (result broadcast to all threads)
+__device__ __forceinline__ float block_sum(float v, float* sh /* >= 33 floats */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0f;
+  if (w == 0) {
+    r = warp_sum(r);
+    if (lane == 0) sh[32] = r;
+  }
+  __syncthreads();
+  return sh[32];
+}

@@ -1,0 +1,204 @@
+// ConvNeXt-T support kernels (channels-last): stem patchify, depthwise 7x7 + LayerNorm,
+// LayerNorm2d + 2x2 patch gather for the downsample convs, global-average-pool + LayerNorm head.
+// The dense parts (stem / MLP / downsample) are GEMMs (gemm_f32.cu / gemm_tc.cu).
+#include "common.cuh"
+
+namespace {
+
+template <typename T>
+__global__ void patchify_kernel(const float* __restrict__ img, int B, int Cin, int H, int W, int p, T* __restrict__ out) {
+  const int Ho = H / p, Wo = W / p, K = Cin * p * p;
+  const long long total = (long long)B * Ho * Wo * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    long long m = i / K;
+    const int ox = (int)(m % Wo);
+    m /= Wo;
+    const int oy = (int)(m % Ho);
+    const int b = (int)(m / Ho);
+    const int kx = k % p, ky = (k / p) % p, ci = k / (p * p);
+    out[i] = from_f<T>(__ldg(img + (((long long)b * Cin + ci) * H + (oy * p + ky)) * W + (ox * p + kx)));
+  }
+}
+
+// One CTA per (image, output row). Input rows oy-3..oy+3 are staged in shared memory (fp32, zero
+// padded), every thread produces (ox, c) outputs, then one warp per pixel applies LayerNorm over C.
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                                         const float* __restrict__ ln_b, float eps, T* __restrict__ y,
+                                                         int H, int W, int C) {
+  extern __shared__ float sm[];
+  float* in = sm;                         // [7][W][C]
+  float* cv = sm + (size_t)7 * W * C;     // [W][C]
+  const int b = blockIdx.x / H, oy = blockIdx.x % H;
+  const int WC = W * C;
+  for (int i = threadIdx.x; i < 7 * WC; i += blockDim.x) {
+    const int r = i / WC, rem = i - r * WC;
+    const int iy = oy + r - 3;
+    in[i] = (iy >= 0 && iy < H) ? to_f<T>(x[((long long)b * H + iy) * WC + rem]) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < WC; i += blockDim.x) {
+    const int ox = i / C, c = i - ox * C;
+    const float* wc = w + c * 49;
+    float acc = bias[c];
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const int ix = ox + kx - 3;
+        if (ix >= 0 && ix < W) acc = fmaf(in[(ky * W + ix) * C + c], __ldg(wc + ky * 7 + kx), acc);
+      }
+    }
+    cv[i] = acc;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int ox = wid; ox < W; ox += nw) {
+    const float* v = cv + ox * C;
+    float s = 0.0f;
+    for (int c = lane; c < C; c += 32) s += v[c];
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.0f;
+    for (int c = lane; c < C; c += 32) {
+      const float d = v[c] - mean;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    T* o = y + (((long long)b * H + oy) * W + ox) * C;
+    for (int c = lane; c < C; c += 32) o[c] = from_f<T>((v[c] - mean) * rstd * ln_w[c] + ln_b[c]);
+  }
+}
+
+// warp per INPUT pixel inside the floor(H/2) x floor(W/2) region
+template <typename T>
+__global__ void __launch_bounds__(256) ln_patch2_kernel(const T* __restrict__ x, const float* __restrict__ ln_w,
+                                                        const float* __restrict__ ln_b, float eps, T* __restrict__ out,
+                                                        int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int lane = threadIdx.x & 31;
+  const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long total = (long long)B * Ho * 2 * Wo * 2;
+  if (pix >= total) return;
+  const int ix = (int)(pix % (Wo * 2));
+  long long t = pix / (Wo * 2);
+  const int iy = (int)(t % (Ho * 2));
+  const int b = (int)(t / (Ho * 2));
+  const T* v = x + (((long long)b * H + iy) * W + ix) * C;
+  float s = 0.0f;
+  for (int c = lane; c < C; c += 32) s += to_f<T>(v[c]);
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.0f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = to_f<T>(v[c]) - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  const int oy = iy >> 1, ox = ix >> 1, ky = iy & 1, kx = ix & 1;
+  T* o = out + (((long long)b * Ho + oy) * Wo + ox) * (4LL * C) + (ky * 2 + kx) * C;
+  for (int c = lane; c < C; c += 32) o[c] = from_f<T>((to_f<T>(v[c]) - mean) * rstd * ln_w[c] + ln_b[c]);
+}
+
+// CTA per image: mean over HW per channel, then LayerNorm over C
+template <typename T>
+__global__ void __launch_bounds__(256) gap_ln_kernel(const T* __restrict__ x, const float* __restrict__ ln_w,
+                                                     const float* __restrict__ ln_b, float eps, float* __restrict__ out,
+                                                     int HW, int C) {
+  extern __shared__ float sm[];  // [C] + 33
+  float* mean_c = sm;
+  float* red = sm + C;
+  const int b = blockIdx.x;
+  const T* xb = x + (long long)b * HW * C;
+  float part = 0.0f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.0f;
+    for (int i = 0; i < HW; ++i) s += to_f<T>(xb[(long long)i * C + c]);
+    s /= (float)HW;
+    mean_c[c] = s;
+    part += s;
+  }
+  const float mean = block_sum(part, red) / (float)C;
+  float q = 0.0f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float d = mean_c[c] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / (float)C + eps);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[(long long)b * C + c] = (mean_c[c] - mean) * rstd * ln_w[c] + ln_b[c];
+}
+
+inline unsigned grid_for(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  const long long cap = 148LL * 32;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" {
+
+int acb_patchify_nchw(const float* img, int B, int Cin, int H, int W, int p, void* out, int out_dtype, void* stream) {
+  ACB_CHECK(img && out && B > 0 && Cin > 0 && p > 0 && H >= p && W >= p, "acb_patchify_nchw: bad arguments");
+  const long long n = (long long)B * (H / p) * (W / p) * Cin * p * p;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == ACB_F32)
+    patchify_kernel<float><<<grid_for(n), 256, 0, st>>>(img, B, Cin, H, W, p, (float*)out);
+  else
+    patchify_kernel<bf16><<<grid_for(n), 256, 0, st>>>(img, B, Cin, H, W, p, (bf16*)out);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+int acb_dwconv7_ln(const void* x, int dtype, const float* w, const float* b, const float* ln_w, const float* ln_b,
+                   float eps, void* y, int B, int H, int W, int C, void* stream) {
+  ACB_CHECK(x && y && w && b && ln_w && ln_b && B > 0 && H > 0 && W > 0 && C > 0, "acb_dwconv7_ln: bad arguments");
+  const size_t smem = (size_t)8 * W * C * sizeof(float);
+  ACB_CHECK(smem <= 200 * 1024, "acb_dwconv7_ln: row tile W*C=%d too large", W * C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((long long)B * H);
+  if (dtype == ACB_F32) {
+    auto k = dwconv7_ln_kernel<float>;
+    if (smem > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, st>>>((const float*)x, w, b, ln_w, ln_b, eps, (float*)y, H, W, C);
+  } else {
+    auto k = dwconv7_ln_kernel<bf16>;
+    if (smem > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, st>>>((const bf16*)x, w, b, ln_w, ln_b, eps, (bf16*)y, H, W, C);
+  }
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+int acb_ln_patch2(const void* x, int dtype, const float* ln_w, const float* ln_b, float eps, void* out, int B, int H,
+                  int W, int C, void* stream) {
+  ACB_CHECK(x && out && ln_w && ln_b && B > 0 && H >= 2 && W >= 2 && C > 0, "acb_ln_patch2: bad arguments");
+  const long long pix = (long long)B * (H / 2) * 2 * (W / 2) * 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((pix + 7) / 8);
+  if (dtype == ACB_F32)
+    ln_patch2_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ln_w, ln_b, eps, (float*)out, B, H, W, C);
+  else
+    ln_patch2_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, ln_w, ln_b, eps, (bf16*)out, B, H, W, C);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+int acb_gap_ln(const void* x, int dtype, const float* ln_w, const float* ln_b, float eps, float* out, int B, int HW,
+               int C, void* stream) {
+  ACB_CHECK(x && out && ln_w && ln_b && B > 0 && HW > 0 && C > 0, "acb_gap_ln: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)(C + 40) * sizeof(float);
+  if (dtype == ACB_F32)
+    gap_ln_kernel<float><<<B, 256, smem, st>>>((const float*)x, ln_w, ln_b, eps, out, HW, C);
+  else
+    gap_ln_kernel<bf16><<<B, 256, smem, st>>>((const bf16*)x, ln_w, ln_b, eps, out, HW, C);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+}  // extern "C"

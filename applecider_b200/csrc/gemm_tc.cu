@@ -1,0 +1,428 @@
+// bf16 tcgen05 GEMM / implicit-GEMM conv1d for sm_100a.
+//
+//   warp 0      : TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B tiles, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA M=128, N=BN, K=16, fp32 accum in TMEM)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> bias/act/residual/pool -> global)
+//
+// One CTA computes a 128 x BN output tile over a range of 64-wide K blocks.  The A operand is a 3-D
+// tensor map (channel, row, sample): a conv tap only shifts the row coordinate of the box and the TMA
+// unit zero-fills rows outside [0, L) — the im2col matrix never exists in memory.  Element strides of
+// the map may overlap (polyphase view of the 1-channel input signal for SpectraNet stage 0).
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;  // bf16 elements per K block = one 128-byte swizzle row
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_NT = 32;
+constexpr int TC_MAX_CB = 64;
+
+struct TcArgs {
+  int Lbox, Bbox, tps;  // tile geometry: rows per sample in a tile, samples per tile, tiles per sample
+  int nbatch, L;
+  int taps, pad, cpt, Cin;
+  int N, ldc, c_dtype;
+  void* C;
+  const float* bias;
+  int act;
+  const void* res;
+  int res_dtype, ldr;
+  const float* gamma;
+  int res_mode, pool4;
+  const int* m_valid_dev;
+  int has_ranges, has_coloff;
+  int kb_lo[TC_MAX_NT], kb_hi[TC_MAX_NT];
+  int col_off[TC_MAX_CB];
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// bounded wait: a protocol bug traps (-> launch failure reported to the host) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+__host__ __device__ constexpr int tmem_cols() {
+  return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB,
+                                                             const __grid_constant__ TcArgs p) {
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
+  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_holder;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x, nt = blockIdx.y;
+  const int n0 = nt * BN;
+
+  const int sample0 = (mt / p.tps) * p.Bbox;
+  const int l0 = (mt % p.tps) * p.Lbox;
+  if (p.m_valid_dev) {
+    if ((long long)sample0 * p.L + l0 >= (long long)(*p.m_valid_dev)) return;
+  }
+
+  const int kb_total = p.taps * p.cpt;
+  const int kb_lo = p.has_ranges ? p.kb_lo[nt] : 0;
+  const int kb_hi = p.has_ranges ? p.kb_hi[nt] : kb_total;
+  const int nkb = kb_hi - kb_lo;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[STAGES]);
+  const uint32_t bar_acc = smem_u32(&bars[2 * STAGES]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
+                 "r"((uint32_t)tmem_cols<BN>())
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t a_box_bytes = (uint32_t)TC_BK * 2u * (uint32_t)p.Lbox * (uint32_t)p.Bbox;
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        const int kb = kb_lo + it;
+        const int tap = kb / p.cpt, cc = kb - tap * p.cpt;
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+        mbar_expect_tx(bar_full + 8 * s, a_box_bytes + B_BYTES);
+        tma_load_3d(sa, &tmA, cc * TC_BK, l0 + tap - p.pad, sample0, bar_full + 8 * s);
+        tma_load_2d(sb, &tmB, tap * p.Cin + cc * TC_BK, n0, bar_full + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          umma_bf16(tmem_base, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), IDESC, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_empty + 8 * s);  // frees the smem stage once these MMAs retire
+      }
+      umma_commit(bar_acc);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter accessible to this warp
+    const int r = q * 32 + lane;
+    const int s_in_tile = r / p.Lbox;
+    const int l = l0 + (r - s_in_tile * p.Lbox);
+    const int sample = sample0 + s_in_tile;
+    long long m = (long long)sample * p.L + l;
+    bool valid = (s_in_tile < p.Bbox) && (sample < p.nbatch) && (l < p.L);
+    if (p.m_valid_dev) valid = valid && (m < (long long)(*p.m_valid_dev));
+    if (nkb > 0) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+    }
+    const long long out_row = p.pool4 ? (m >> 2) : m;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      const int n_first = n0 + c0;
+      if (n_first >= p.N) break;  // warp-uniform
+      uint32_t raw[32];
+      if (nkb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) raw[i] = 0u;
+      }
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+      const int out_col = (p.has_coloff ? p.col_off[n_first >> 6] : (n_first & ~63)) + (n_first & 63);
+      const int ncols = min(32, p.N - n_first);
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) v[i] += __ldg(p.bias + n_first + i);
+      }
+      if (p.act != ACB_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+      }
+      if (p.res_mode != ACB_RES_NONE && valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < ncols) {
+            const float rv = ld_any(p.res, m * p.ldr + out_col + i, p.res_dtype);
+            if (p.res_mode == ACB_RES_ADD) v[i] = rv + (p.gamma ? __ldg(p.gamma + n_first + i) : 1.0f) * v[i];
+            else v[i] = rv * v[i];
+          }
+        }
+      }
+      bool writer = valid;
+      if (p.pool4) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+          v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 2));
+        }
+        writer = valid && ((lane & 3) == 0);
+      }
+      if (!writer) continue;
+      const long long off = out_row * p.ldc + out_col;
+      if (p.c_dtype == ACB_BF16) {
+        bf16* o = (bf16*)p.C + off;
+        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 pk;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2);
+            pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(o + g * 8) = pk;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) o[i] = __float2bfloat16_rn(v[i]);
+        }
+      } else {
+        float* o = (float*)p.C + off;
+        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(o + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) o[i] = v[i];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols<BN>()) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (PFN_cuTensorMapEncodeTiled_v12000)f;
+  }
+  return fn;
+}
+
+template <int BN, int STAGES>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024;
+  auto k = gemm_tc_kernel<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  k<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, args);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+}  // namespace
+
+extern "C" int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype, int nbatch, int L, int Cin, int taps,
+                             int pad, long long a_batch_stride, long long a_row_stride, int N, int ldb, int ldc, int bn,
+                             const int* tile_kb_host, const int* colblk_off_host, const float* bias, int act,
+                             const void* res, int res_dtype, int ldr, const float* gamma, int res_mode, int pool4,
+                             const int* m_valid_dev, void* stream) {
+  ACB_CHECK(A && Bw && C, "acb_gemm_bf16: null operand");
+  ACB_CHECK(nbatch > 0 && L > 0 && Cin > 0 && taps > 0 && N > 0, "acb_gemm_bf16: bad shape");
+  ACB_CHECK(bn == 64 || bn == 128 || bn == 256, "acb_gemm_bf16: bn must be 64, 128 or 256 (got %d)", bn);
+  ACB_CHECK(((uintptr_t)A % 16 == 0) && ((uintptr_t)Bw % 16 == 0), "acb_gemm_bf16: operands must be 16-byte aligned");
+  ACB_CHECK(a_row_stride % 8 == 0 && a_batch_stride % 8 == 0 && ldb % 8 == 0, "acb_gemm_bf16: strides must be multiples of 8 elements");
+  ACB_CHECK(res_mode == ACB_RES_NONE || res != nullptr, "acb_gemm_bf16: res_mode set without res");
+  const int cpt = cdiv(Cin, TC_BK);
+  const int NT = cdiv(N, bn);
+  ACB_CHECK(NT <= TC_MAX_NT || !tile_kb_host, "acb_gemm_bf16: too many N tiles for K ranges");
+  ACB_CHECK(cdiv(N, 64) <= TC_MAX_CB || !colblk_off_host, "acb_gemm_bf16: too many column blocks");
+  if (pool4) ACB_CHECK(nbatch == 1 && L % 4 == 0 && taps == 1, "acb_gemm_bf16: pool4 needs a plain GEMM with M %% 4 == 0");
+
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
+  ACB_CHECK(enc != nullptr, "acb_gemm_bf16: cuTensorMapEncodeTiled unavailable");
+
+  TcArgs args;
+  memset(&args, 0, sizeof(args));
+  args.Lbox = L >= TC_BM ? TC_BM : L;
+  args.Bbox = L >= TC_BM ? 1 : (TC_BM / L);
+  args.tps = L >= TC_BM ? cdiv(L, TC_BM) : 1;
+  args.nbatch = nbatch; args.L = L;
+  args.taps = taps; args.pad = pad; args.cpt = cpt; args.Cin = Cin;
+  args.N = N; args.ldc = ldc; args.c_dtype = c_dtype; args.C = C;
+  args.bias = bias; args.act = act; args.res = res; args.res_dtype = res_dtype; args.ldr = ldr; args.gamma = gamma;
+  args.res_mode = res_mode; args.pool4 = pool4; args.m_valid_dev = m_valid_dev;
+  const int kb_total = taps * cpt;
+  if (tile_kb_host) {
+    args.has_ranges = 1;
+    for (int i = 0; i < NT; ++i) {
+      args.kb_lo[i] = tile_kb_host[2 * i];
+      args.kb_hi[i] = tile_kb_host[2 * i + 1];
+      ACB_CHECK(args.kb_lo[i] >= 0 && args.kb_hi[i] <= kb_total && args.kb_lo[i] <= args.kb_hi[i], "acb_gemm_bf16: bad K range for tile %d", i);
+    }
+  }
+  if (colblk_off_host) {
+    args.has_coloff = 1;
+    for (int i = 0; i < cdiv(N, 64); ++i) args.col_off[i] = colblk_off_host[i];
+  }
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)L, (cuuint64_t)nbatch};
+    cuuint64_t strides[2] = {(cuuint64_t)a_row_stride * 2, (cuuint64_t)(nbatch > 1 ? a_batch_stride : (long long)a_row_stride * L) * 2};
+    if (strides[1] == 0) strides[1] = 16;
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)args.Lbox, (cuuint32_t)args.Bbox};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(A), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACB_CHECK(r == CUDA_SUCCESS, "acb_gemm_bf16: cuTensorMapEncodeTiled(A) failed with %d (dims %d,%d,%d strides %lld,%lld)", (int)r,
+              Cin, L, nbatch, (long long)strides[0], (long long)strides[1]);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)((long long)taps * Cin), (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)ldb * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(Bw), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACB_CHECK(r == CUDA_SUCCESS, "acb_gemm_bf16: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+
+  const long long MT = (long long)cdiv(nbatch, args.Bbox) * args.tps;
+  ACB_CHECK(MT < (1LL << 31) && NT <= 65535, "acb_gemm_bf16: grid too large");
+  dim3 grid((unsigned)MT, (unsigned)NT);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (bn) {
+    case 64: return launch_tc<64, 4>(tmA, tmB, args, grid, st);
+    case 128: return launch_tc<128, 3>(tmA, tmB, args, grid, st);
+    default: return launch_tc<256, 4>(tmA, tmB, args, grid, st);
+  }
+}

@@ -1,0 +1,96 @@
+"""Late-fusion AppleCider classifier (reference: _archive/notebooks/brew_cider.py:807-862 head over the
+three src/ encoders — DECISION-1 in SURVEY.md §8b) and the fusion collate (models/Time2Vec.py:18-45)."""
+from __future__ import annotations
+
+import copy
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .astrominn import AstroMiNN
+from .photo import HyraxBaselineCLS
+from .spectra import SpectraNet
+
+
+class AppleCider(nn.Module):
+    """forward(photometry, photometry_mask, metadata, images, spectra) -> (B, num_classes) logits."""
+
+    def __init__(self, config, hidden_dim=64, fusion="avg", num_classes=5, compute_dtype=None):
+        super().__init__()
+        if fusion not in ("avg", "concat"):
+            raise NotImplementedError(fusion)
+        cfg = copy.deepcopy(config)
+        cfg["model"]["HyraxBaselineCLS"]["mode"] = "all"  # encoder returns norm(z[:,0]) (HyraxBaselineCLS.py:37,81)
+        cfg["model"]["HyraxBaselineCLS"]["use_probabilities"] = False
+        cfg["model"]["HyraxBaselineCLS"]["pretrained_weights_path_"] = False
+        cfg["model"]["AstroMiNN"]["use_probabilities"] = False
+        if compute_dtype is not None:
+            for k in ("HyraxBaselineCLS", "AstroMiNN", "SpectraNet"):
+                cfg["model"][k]["compute_dtype"] = compute_dtype
+        self.config = cfg
+        self.fusion, self.hidden_dim, self.num_classes = fusion, hidden_dim, num_classes
+        self.classification = True
+        self.photometry_encoder = HyraxBaselineCLS(cfg)
+        self.spectra_encoder = SpectraNet(cfg)
+        self.img_metadata_encoder = AstroMiNN(cfg)
+        sc = cfg["model"]["SpectraNet"]
+        spec_out = 1 if sc["redshift"] else sc["class_order"]
+        self.photometry_proj = nn.Linear(cfg["model"]["HyraxBaselineCLS"]["d_model"], hidden_dim)
+        self.spectra_proj = nn.Linear(spec_out, hidden_dim)
+        self.img_metadata_proj = nn.Linear(5, hidden_dim)
+        self.fc = nn.Linear(hidden_dim * 3 if fusion == "concat" else hidden_dim, num_classes)
+
+    def _encode(self, photometry, photometry_mask, metadata, images, spectra):
+        p = self.photometry_encoder((photometry, photometry_mask, None))
+        s = self.spectra_encoder((spectra, None, None))
+        if s.dim() == 1:
+            s = s[:, None].contiguous()
+        im = self.img_metadata_encoder((metadata, images, None))
+        return p, im, s
+
+    def _head(self, p, im, s, want_emb):
+        B = p.shape[0]
+        logits = torch.empty((B, self.num_classes), dtype=torch.float32, device=p.device)
+        emb = torch.empty((3, B, self.hidden_dim), dtype=torch.float32, device=p.device) if want_emb else None
+        ops.call(
+            "acb_fusion_head", p, p.shape[1], im, im.shape[1], s, s.shape[1], self.photometry_proj.weight, self.photometry_proj.bias,
+            self.img_metadata_proj.weight, self.img_metadata_proj.bias, self.spectra_proj.weight, self.spectra_proj.bias,
+            self.fc.weight, self.fc.bias, self.hidden_dim, int(self.fusion == "concat"), self.num_classes, logits, emb, B,
+        )
+        return logits, emb
+
+    def get_embeddings(self, photometry, photometry_mask, metadata, images, spectra):
+        p, im, s = self._encode(photometry, photometry_mask, metadata, images, spectra)
+        _, emb = self._head(p, im, s, True)
+        return emb[0], emb[1], emb[2]
+
+    def forward(self, photometry, photometry_mask, metadata, images, spectra):
+        if self.training and torch.is_grad_enabled():
+            from .train import fusion_forward_train
+
+            return fusion_forward_train(self, photometry, photometry_mask, metadata, images, spectra)
+        p, im, s = self._encode(photometry, photometry_mask, metadata, images, spectra)
+        return self._head(p, im, s, False)[0]
+
+
+def fusion_collate(batch, mean, std, device="cuda"):
+    """Fusion collate contract of models/Time2Vec.py:18-45 with the hard-coded stats path turned into
+    arguments: batch of (photo[L,7], metadata, image, spectra[1,Ls], label) ->
+    (photo[B,Lmax,7] normalised, mask[B,Lmax] bool True=pad, metadata, images, spectra, labels)."""
+    photo, meta, img, spec, labels = zip(*batch)
+    lens = [int(s.shape[0]) for s in photo]
+    Lmax = max(lens)
+    B = len(photo)
+    x = torch.zeros((B, Lmax, 7), dtype=torch.float32)
+    mask = torch.ones((B, Lmax), dtype=torch.bool)
+    for i, s in enumerate(photo):
+        x[i, : lens[i]] = torch.as_tensor(s, dtype=torch.float32)
+        mask[i, : lens[i]] = False
+    mean = torch.as_tensor(mean, dtype=torch.float32)
+    std = torch.as_tensor(std, dtype=torch.float32)
+    x[..., :4] = (x[..., :4] - mean) / (std + 1e-8)
+    to = lambda t: t.to(device, non_blocking=True)  # noqa: E731
+    return (to(x), to(mask), to(torch.stack([torch.as_tensor(m, dtype=torch.float32) for m in meta])),
+            to(torch.stack([torch.as_tensor(i, dtype=torch.float32) for i in img])),
+            to(torch.stack([torch.as_tensor(s, dtype=torch.float32) for s in spec])), to(torch.as_tensor(labels)))

@@ -1,0 +1,207 @@
+"""Thin Python wrappers over the C-ABI (allocation + argument marshalling only; no math here)."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, BF16, F32, RES_ADD, RES_MUL, RES_NONE, call, dtype_tag  # noqa: F401
+
+
+def _elt(t: torch.Tensor) -> int:
+    return t.element_size()
+
+
+def _offset_ptr(t: torch.Tensor, elems: int) -> int:
+    if not t.is_cuda or not t.is_contiguous():
+        raise RuntimeError("applecider_b200: output views need a contiguous CUDA base tensor")
+    return t.data_ptr() + elems * t.element_size()
+
+
+def _int_array(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def pick_bn(n: int) -> int:
+    if n % 256 == 0:
+        return 256
+    if n > 64:
+        return 128
+    return 64
+
+
+def gemm(a, w, bias=None, act=ACT_NONE, res=None, gamma=None, res_mode=RES_NONE, out=None, out_dtype=None,
+         out_col=0, conv=None, pool4=False, bn=None, tile_kb=None, colblk_off=None, a_view=None):
+    """C = epilogue(A @ W^T).  a: [M,K] (or [B,L,Cin] with conv=(taps,pad)); w: [N,K'] row-major.
+
+    f32 operands run the CUDA-core kernel, bf16 operands the tcgen05 kernel.
+    ``out``/``out_col`` let the result land in a column slice of a wider row-major buffer.
+    ``a_view`` = (nbatch, L, Cin, batch_stride, row_stride) overrides the A geometry (bf16 only).
+    """
+    N = w.shape[0]
+    ldb = w.shape[1]
+    if conv is not None:
+        taps, pad = conv
+        nb, L, cin = a.shape
+        M = nb * L
+    else:
+        taps, pad = 1, 0
+        if a_view is not None:
+            nb, L, cin = a_view[0], a_view[1], a_view[2]
+            M = nb * L
+        else:
+            M, cin = a.shape[0], a.shape[-1]
+            nb, L = 1, M
+    K = taps * cin
+    if out is None:
+        odt = out_dtype if out_dtype is not None else a.dtype
+        rows = M // 4 if pool4 else M
+        out = torch.empty((rows, N), dtype=odt, device=a.device)
+    ldc = out.shape[-1]
+    c_ptr = _offset_ptr(out, out_col)
+    ldr = res.shape[-1] if res is not None else 0
+    if a.dtype == torch.float32:
+        assert w.dtype == torch.float32 and out.dtype == torch.float32 and not pool4 and a_view is None
+        assert res is None or res.dtype == torch.float32
+        call("acb_gemm_f32", a, w, c_ptr, M, N, K, cin, ldb, ldc, (L if conv is not None else 0), (cin if conv is not None else 0), pad,
+             bias, act, res, ldr, gamma, res_mode)
+    elif a.dtype == torch.bfloat16:
+        assert w.dtype == torch.bfloat16
+        if a_view is not None:
+            bstride, rstride = a_view[3], a_view[4]
+        else:
+            bstride, rstride = L * cin, cin
+        if bn is None:
+            bn = pick_bn(N)
+        kb = _int_array(tile_kb) if tile_kb is not None else None
+        co = _int_array(colblk_off) if colblk_off is not None else None
+        call("acb_gemm_bf16", a, w, c_ptr, dtype_tag(out), nb, L, cin, taps, pad, bstride, rstride, N, ldb, ldc, bn, kb, co,
+             bias, act, res, (dtype_tag(res) if res is not None else 0), ldr, gamma, res_mode, int(pool4), None)
+    else:
+        raise TypeError(f"gemm: unsupported dtype {a.dtype}")
+    return out
+
+
+def layernorm(x, w, b, eps, res=None, pre_gelu=False, post_act=ACT_NONE, out_dtype=None):
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty(x.shape, dtype=(out_dtype or x.dtype), device=x.device)
+    call("acb_layernorm", x, dtype_tag(x), res, (dtype_tag(res) if res is not None else 0), w, b, y, dtype_tag(y), rows, C, eps,
+         int(pre_gelu), post_act)
+    return y
+
+
+def cast(x, dtype):
+    if x.dtype == dtype:
+        return x
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    call("acb_cast", x, dtype_tag(x), y, dtype_tag(y), x.numel())
+    return y
+
+
+def photo_compact(pad):
+    B, L = pad.shape
+    pad_u8 = pad.view(torch.uint8) if pad.dtype == torch.bool else pad
+    cu = torch.empty(B + 1, dtype=torch.int32, device=pad.device)
+    src = torch.empty(B * (L + 1), dtype=torch.int32, device=pad.device)
+    call("acb_photo_compact", pad_u8, B, L, cu, src)
+    return cu, src
+
+
+def photo_embed(x, src, total, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype):
+    out = torch.empty((total, D), dtype=dtype, device=x.device)
+    call("acb_photo_embed", x, src, None, total, D, w_in, b_in, w0, b0, w, b, cls_tok, out, dtype_tag(out))
+    return out
+
+
+def attention_varlen(qkv, cu, B, n_heads, dh, max_seqlen):
+    T = qkv.shape[0]
+    out = torch.empty((T, n_heads * dh), dtype=qkv.dtype, device=qkv.device)
+    call("acb_attention_varlen", qkv, dtype_tag(qkv), cu, B, n_heads, dh, max_seqlen, out)
+    return out
+
+
+def gather_cls(x, cu, B):
+    D = x.shape[-1]
+    out = torch.empty((B, D), dtype=torch.float32, device=x.device)
+    call("acb_gather_cls", x, dtype_tag(x), cu, B, D, out)
+    return out
+
+
+def patchify(img, p, dtype):
+    B, C, H, W = img.shape
+    out = torch.empty((B * (H // p) * (W // p), C * p * p), dtype=dtype, device=img.device)
+    call("acb_patchify_nchw", img, B, C, H, W, p, out, dtype_tag(out))
+    return out
+
+
+def dwconv7_ln(x, B, H, W, C, w, b, ln_w, ln_b, eps):
+    y = torch.empty_like(x)
+    call("acb_dwconv7_ln", x, dtype_tag(x), w, b, ln_w, ln_b, eps, y, B, H, W, C)
+    return y
+
+
+def ln_patch2(x, B, H, W, C, ln_w, ln_b, eps):
+    out = torch.empty((B * (H // 2) * (W // 2), 4 * C), dtype=x.dtype, device=x.device)
+    call("acb_ln_patch2", x, dtype_tag(x), ln_w, ln_b, eps, out, B, H, W, C)
+    return out
+
+
+def gap_ln(x, B, HW, C, ln_w, ln_b, eps):
+    out = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    call("acb_gap_ln", x, dtype_tag(x), ln_w, ln_b, eps, out, B, HW, C)
+    return out
+
+
+def maxpool4(x, B, L, C):
+    y = torch.empty((B, L // 4, C), dtype=x.dtype, device=x.device)
+    call("acb_maxpool4_cl", x, dtype_tag(x), y, B, L, C)
+    return y
+
+
+def globalmax(x, B, L, C):
+    y = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    call("acb_globalmax_cl", x, dtype_tag(x), y, B, L, C)
+    return y
+
+
+def softmax_rows(x):
+    y = torch.empty_like(x)
+    call("acb_softmax_rows", x, y, x.shape[0], x.shape[1])
+    return y
+
+
+def pack_conv_weight(w, out, row_stride, tap_off):
+    cout, cin, k = w.shape
+    call("acb_pack_conv_weight", w, out, dtype_tag(out), cout, cin, k, row_stride, tap_off)
+
+
+def pack_conv2d_weight(w, dtype):
+    cout, cin, kh, kw = w.shape
+    out = torch.empty((cout, kh * kw * cin), dtype=dtype, device=w.device)
+    call("acb_pack_conv2d_weight", w, out, dtype_tag(out), cout, cin, kh, kw)
+    return out
+
+
+class DerivedCache:
+    """Derived (re-laid-out / down-cast) copies of parameters, refreshed when a source changes.
+
+    The state_dict schema stays the reference's; these buffers are never persisted.
+    """
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key, params, builder):
+        sig = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        with torch.no_grad():
+            val = builder()
+        self._store[key] = (sig, val)
+        return val
+
+    def clear(self):
+        self._store.clear()

@@ -1,0 +1,160 @@
+/* applecider_b200 — C-ABI of the B200 (sm_100a) hot path of the AppleCiDEr multimodal classifier.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The host layer
+ * (applecider_b200/*.py, torch.nn.Modules with the reference's forward signatures and
+ * state_dict keys) binds these symbols with ctypes and passes tensor.data_ptr() values and the
+ * current CUDA stream; INTEGRATION.md shows the same stub added to the reference.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - activations are channels-last ([rows, C] row-major); weights keep PyTorch layouts
+ *     ((out, in[, k])) unless a "packed" layout is stated;
+ *   - dtype tags: ACB_F32 / ACB_BF16; bf16 tensors are raw uint16 storage of __nv_bfloat16;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the host;
+ *   - return value 0 = success, <0 = error (message: acb_last_error()); there is NO CPU
+ *     fallback anywhere behind this interface.
+ *
+ * Each entry point cites the reference code (paths relative to the reference root) it replaces.
+ */
+#ifndef APPLECIDER_B200_H
+#define APPLECIDER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACB_F32 0
+#define ACB_BF16 1
+
+#define ACB_ACT_NONE 0
+#define ACB_ACT_RELU 1
+#define ACB_ACT_GELU 2 /* exact erf GELU (torch F.gelu default) */
+#define ACB_ACT_TANH 3
+#define ACB_ACT_SIGMOID 4
+
+#define ACB_RES_NONE 0
+#define ACB_RES_ADD 1 /* C = res + gamma[n] * v   (gamma may be NULL = 1) */
+#define ACB_RES_MUL 2 /* C = res * v */
+
+#define ACB_OK 0
+#define ACB_ERR_INVALID (-1)
+#define ACB_ERR_CUDA (-2)
+#define ACB_ERR_UNSUPPORTED (-3)
+
+/* ---- library management -------------------------------------------------------------------- */
+const char* acb_last_error(void);
+int acb_version(void);
+long long acb_launch_count(void); /* kernels launched by this library since the last reset */
+void acb_reset_launch_count(void);
+
+/* ---- GEMM / implicit-GEMM conv1d ---------------------------------------------------------------
+ * v[m,n] = sum_k A(m,k) * Bw[n*ldb + k] (+ bias[n]); C = epilogue(act(v)).
+ * Plain GEMM: conv_L = 0, A is [M, lda].  Implicit conv1d ("same" zero padding): conv_L = L > 0,
+ * A is the channels-last signal [M/L, L, conv_Cin]; k = tap*conv_Cin + ci reads row l+tap-conv_pad.
+ * Replaces nn.Linear / nn.Conv1d / nn.Conv2d-as-patch-GEMM call sites:
+ *   src/applecider/models/HyraxBaselineCLS.py:60,78 ; spectranet.py:29,37 ; astrominn.py:12-41,270-295.
+ */
+
+/* fp32 CUDA-core path (parity mode, and every tiny-N head). */
+int acb_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, int K, int lda, int ldb, int ldc,
+                 int conv_L, int conv_Cin, int conv_pad, const float* bias, int act, const float* res, int ldr,
+                 const float* gamma, int res_mode, void* stream);
+
+/* bf16 tcgen05 path: TMA-fed UMMA (M=128 x BN tiles, fp32 accumulators in TMEM).
+ * A is viewed as [nbatch, L, Cin] with element strides (a_batch_stride, a_row_stride, 1) — strides may
+ * overlap (polyphase view of a 1-channel signal); K = taps*Cin with tap shifting the row by tap-pad and
+ * out-of-range rows reading zeros (TMA OOB fill).  Plain GEMM: nbatch=1, L=M, Cin=K, taps=1, pad=0.
+ * Bw is [N, ldb] bf16, K-major.  tile_kb_host (optional, host memory, [N/BN][2]) restricts every
+ * N tile to a range of 64-wide K blocks (zero weights outside are never touched).
+ * colblk_off_host (optional, host memory, [N/64]) remaps each 64-column block of the result to
+ * column offset colblk_off[j] of C (default j*64).  pool4 != 0 max-pools groups of 4 consecutive rows.
+ * m_valid_dev (optional) holds the number of valid rows on the device (tiles beyond it exit). */
+int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype, int nbatch, int L, int Cin, int taps, int pad,
+                  long long a_batch_stride, long long a_row_stride, int N, int ldb, int ldc, int bn,
+                  const int* tile_kb_host, const int* colblk_off_host, const float* bias, int act, const void* res,
+                  int res_dtype, int ldr, const float* gamma, int res_mode, int pool4, const int* m_valid_dev,
+                  void* stream);
+
+/* Weight packing (derived, non-persistent buffers; refreshed after load_state_dict / optimizer step).
+ * out[co*row_stride + (tap + tap_off)*Cin + ci] = w[co, ci, tap]     (w = PyTorch (Cout, Cin, k)) */
+int acb_pack_conv_weight(const float* w, void* out, int out_dtype, int Cout, int Cin, int k, long long row_stride,
+                         int tap_off, void* stream);
+/* polyphase packing of a 1-input-channel conv (spectranet.py stage 0): rows (r, co), columns kk:
+ * out[(row_off + r*rows_per_phase + co)*row_stride + kk] = w[co,0,kk - r + pad - halo], 0 elsewhere */
+int acb_pack_polyphase_weight(const float* w, void* out, int out_dtype, int Cout, int k, int phases, int halo,
+                              int rows_per_phase, int row_off, long long row_stride, int Kp, void* stream);
+int acb_cast(const void* in, int in_dtype, void* out, int out_dtype, long long n, void* stream);
+/* out[b*out_stride + lead + i] = in[b*L + i] (bf16/f32), buffer pre-zeroed by the caller */
+int acb_pad_signal(const float* in, void* out, int out_dtype, int nb, int L, long long out_stride, int lead,
+                   void* stream);
+
+/* ---- row-wise LayerNorm (+ fused pre-GELU / residual / post-activation) --------------------------
+ * v = x[r,:]; if pre_gelu v = gelu(v); if res v += res[r,:]; y = (v-mean)*rstd*w + b; y = act(y).
+ * nn.LayerNorm call sites: HyraxBaselineCLS.py:26-33,79 ; spectranet.py:32,145 ; astrominn.py:23-34,48-54 ;
+ * timm LayerNorm/LayerNorm2d (eps 1e-6). */
+int acb_layernorm(const void* x, int x_dtype, const void* res, int res_dtype, const float* w, const float* b,
+                  void* y, int y_dtype, long long rows, int C, float eps, int pre_gelu, int post_act, void* stream);
+
+/* ---- photometry transformer pieces --------------------------------------------------------------- */
+/* pad[B,L] (bool bytes, nonzero = padding) -> cu_seqlens[B+1] (tokens incl. CLS) and src_idx[T]
+ * (source row b*L+l of every packed token, -1-b for the CLS token of sequence b).
+ * HyraxBaselineCLS.py:71-78 (CLS prepend + key-padding mask); equals PyTorch's nested-tensor packing. */
+int acb_photo_compact(const uint8_t* pad, int B, int L, int* cu_seqlens, int* src_idx, void* stream);
+/* packed tokens h[t,:] = in_proj(x[src]) + Time2Vec(x[src,0]) or cls_tok  (HyraxBaselineCLS.py:60-72,
+ * Time2Vec.py:63-72).  D = d_model. */
+int acb_photo_embed(const float* x, const int* src_idx, const int* total_dev, int max_tokens, int D, const float* w_in,
+                    const float* b_in, const float* w0, const float* b0, const float* w, const float* b,
+                    const float* cls_tok, void* out, int out_dtype, void* stream);
+/* fused masked varlen multi-head attention over packed tokens; qkv[T,3D] rows = [q|k|v], head h uses
+ * columns h*dh..; softmax(q k^T / sqrt(dh)) v with fp32 math.  nn.MultiheadAttention inside
+ * nn.TransformerEncoderLayer (HyraxBaselineCLS.py:26-33,78). dh must be 16. */
+int acb_attention_varlen(const void* qkv, int dtype, const int* cu_seqlens, int B, int n_heads, int dh,
+                         int max_seqlen, void* out, void* stream);
+/* out[b,:] = x[cu_seqlens[b],:]  (CLS read-out z[:,0], HyraxBaselineCLS.py:79) */
+int acb_gather_cls(const void* x, int dtype, const int* cu_seqlens, int B, int D, float* out, void* stream);
+
+/* ---- ConvNeXt-T pieces (timm convnext_tiny via astrominn.py:12-17; channels-last activations) ---- */
+/* NCHW f32 image -> patch matrix [B*Ho*Wo, Cin*p*p] (k = ci*p*p + ky*p + kx), Ho = H/p (floor). */
+int acb_patchify_nchw(const float* img, int B, int Cin, int H, int W, int p, void* out, int out_dtype, void* stream);
+/* depthwise 7x7 (pad 3) + LayerNorm over C (eps) : x,y = [B,H,W,C]; w = (C,1,7,7), b = (C). */
+int acb_dwconv7_ln(const void* x, int dtype, const float* w, const float* b, const float* ln_w, const float* ln_b,
+                   float eps, void* y, int B, int H, int W, int C, void* stream);
+/* LayerNorm2d(eps) then 2x2/stride-2 patch gather: x=[B,H,W,C] -> out=[B*(H/2)*(W/2), 4*C],
+ * column (ky*2+kx)*C + c  (weights must be packed in the same (ky,kx,ci) order). */
+int acb_ln_patch2(const void* x, int dtype, const float* ln_w, const float* ln_b, float eps, void* out, int B, int H,
+                  int W, int C, void* stream);
+/* global average pool over HW then LayerNorm(C, eps): x=[B,HW,C] -> out[B,C] f32 (timm head). */
+int acb_gap_ln(const void* x, int dtype, const float* ln_w, const float* ln_b, float eps, float* out, int B, int HW,
+               int C, void* stream);
+/* out[b, (ky*2+kx)... generic weight re-layout (Cout,Cin,kh,kw) -> [Cout, kh*kw*Cin] ((ky,kx,ci) order) */
+int acb_pack_conv2d_weight(const float* w, void* out, int out_dtype, int Cout, int Cin, int kh, int kw, void* stream);
+
+/* ---- SpectraNet pooling (spectranet.py:25,38-40,163) ------------------------------------------ */
+int acb_maxpool4_cl(const void* x, int dtype, void* y, int B, int L, int C, void* stream); /* -> [B, L/4, C] */
+int acb_globalmax_cl(const void* x, int dtype, float* y, int B, int L, int C, void* stream); /* -> [B, C] f32 */
+
+/* ---- metadata towers / MoE / fusion head -------------------------------------------------------- */
+/* ResidualTowerBlock (astrominn.py:44-64), eval: s = gelu(W0 x + b0); y = (W1 ln1(s) + b1) * sigmoid(W2 ln2(s) + b2)
+ * + (Ws x + bs | x).  x = X[r, cols[i]] (cols == NULL: identity), Y[r, y_off + o].  hid <= 256, in <= 512, out <= 32 */
+int acb_tower_fwd(const float* X, int ldx, const int* cols, int in_dim, int hid, int out_dim, const float* W0,
+                  const float* b0, const float* ln1w, const float* ln1b, const float* W1, const float* b1,
+                  const float* ln2w, const float* ln2b, const float* W2, const float* b2, const float* Ws,
+                  const float* bs, float* Y, int ldy, int y_off, int rows, void* stream);
+/* top-2-of-E sigmoid-gated mixture (astrominn.py:270-295): gate[B,E], expert_out[E][B,C] (stride E*C per row:
+ * expert_out[r*E*C + e*C + c]) -> out[B,C]; also writes the selected indices (top_idx[B,2]) for parity checks. */
+int acb_moe_combine(const float* gate, const float* expert_out, float* out, int* top_idx, int B, int E, int C,
+                    void* stream);
+/* late fusion (brew_cider.py:834-860): three Linear -> L2 normalise -> avg|concat -> fc.
+ * emb_out (optional) = [3][B,H] (p, im, s). */
+int acb_fusion_head(const float* p_in, int p_dim, const float* im_in, int im_dim, const float* s_in, int s_dim,
+                    const float* Wp, const float* bp, const float* Wim, const float* bim, const float* Ws,
+                    const float* bs, const float* Wfc, const float* bfc, int H, int concat, int num_classes,
+                    float* logits, float* emb_out, int B, void* stream);
+int acb_softmax_rows(const float* x, float* y, int rows, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APPLECIDER_B200_H */

@@ -1,0 +1,218 @@
+"""GPU model parity (B200 box): drop-in modules vs the CPU oracle (live, same weights/inputs) and vs the
+committed golden outputs of the REAL reference (tests/golden/*.npz).
+
+Tolerances (SURVEY.md §7 hard part 6): fp32 path |err| <= 1e-4 * max(1, |ref|_inf); bf16 path
+|err| <= 3e-2 * max(1, |ref|_inf) with 100 % argmax agreement on rows whose top-2 margin exceeds
+the same bound."""
+import pytest
+import torch
+
+from util import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+FP32_TOL = 1e-4
+BF16_TOL = 3e-2
+
+
+def _pair(name, cfg_edit=None, dtype="fp32", **kw):
+    """(product module on GPU, oracle module on CPU) with identical deterministic weights."""
+    import applecider_b200 as ab
+    from applecider_b200 import synth
+    from oracle import models as om
+
+    cfg = ab.default_config()
+    if cfg_edit:
+        cfg_edit(cfg)
+    ocfg = om.default_config()
+    if cfg_edit:
+        cfg_edit(ocfg)
+    for k in cfg["model"]:
+        cfg["model"][k]["compute_dtype"] = dtype
+    oracle = getattr(om, name)(ocfg, **kw).eval()
+    sd = synth.det_state_dict(oracle, 0)
+    oracle.load_state_dict(sd)
+    prod = getattr(ab, name)(cfg, **kw)
+    missing = prod.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return prod.to(DEV).eval(), oracle
+
+
+def _argmax_agree(got, ref, tol):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    top2 = ref.topk(2, -1).values
+    margin = top2[:, 0] - top2[:, 1]
+    keep = margin > 2 * tol * max(1.0, ref.abs().max().item())
+    assert (got.argmax(-1)[keep] == ref.argmax(-1)[keep]).all(), "argmax disagreement on margin-filtered rows"
+
+
+# ---- photometry ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_photo_matches_golden_and_oracle(golden_dir, dtype, tol):
+    g = load_golden(golden_dir, "photo")
+    prod, oracle = _pair("HyraxBaselineCLS", dtype=dtype)
+    with torch.no_grad():
+        got = prod((g["x"].to(DEV), g["pad"].to(DEV), None))
+        ref_live = oracle((g["x"], g["pad"], None))
+    assert_close(ref_live, g["logits"], 1e-5, "oracle vs golden(real reference)")
+    assert_close(got, g["logits"], tol, f"photo {dtype} vs golden")
+    assert_close(got, g["logits_slowpath"], tol, f"photo {dtype} vs golden slow path")
+    _argmax_agree(got, g["logits"], tol)
+    Ls = int((~g["pad"]).sum(1).max())
+    with torch.no_grad():
+        got_s = prod((g["x"][:, :Ls].contiguous().to(DEV), g["pad"][:, :Ls].contiguous().to(DEV), None))
+    assert_close(got_s, g["logits_short"], tol, f"photo {dtype} short layout")
+
+
+def test_photo_arbitrary_mask_and_embedding_mode():
+    from applecider_b200 import synth
+
+    def edit(c):
+        c["model"]["HyraxBaselineCLS"]["mode"] = "all"
+
+    prod, oracle = _pair("HyraxBaselineCLS", cfg_edit=edit)
+    x, pad, _ = synth.photometry_batch(6, seed=21, L=64)
+    gen = torch.Generator().manual_seed(1)
+    pad = pad | (torch.rand(pad.shape, generator=gen) < 0.2)  # holes in the middle of sequences
+    pad[2] = True  # fully padded: only the CLS token attends to itself
+    with torch.no_grad():
+        got = prod((x.to(DEV), pad.to(DEV), None))
+        ref = oracle((x, pad, None))
+    assert got.shape == (6, 128)
+    assert_close(got, ref, FP32_TOL, "photo arbitrary mask (embedding mode)")
+
+
+def test_photo_probabilities_and_legacy_signature():
+    import applecider_b200 as ab
+    from applecider_b200 import synth
+
+    def edit(c):
+        c["model"]["HyraxBaselineCLS"]["use_probabilities"] = True
+
+    prod, oracle = _pair("HyraxBaselineCLS", cfg_edit=edit)
+    x, pad, _ = synth.photometry_batch(5, seed=22, L=40)
+    with torch.no_grad():
+        got = prod((x.to(DEV), pad.to(DEV), None))
+        ref = oracle((x, pad, None))
+    assert_close(got, ref, FP32_TOL, "photo probabilities")
+    assert_close(got.sum(1), torch.ones(5), 1e-5, "rows sum to 1")
+    # legacy BaselineCLS(x, pad_mask) = head(norm(z[:,0]))
+    legacy = ab.BaselineCLS(128, 8, 4, 5, 0.4)
+    sd = {k: v for k, v in synth.det_state_dict(oracle, 0).items() if not k.startswith("fc.")}
+    legacy.load_state_dict(sd, strict=True)
+    legacy = legacy.to(DEV).eval()
+    with torch.no_grad():
+        got = legacy(x.to(DEV), pad.to(DEV))
+        z = oracle.encode(x, pad)
+        ref = torch.nn.functional.linear(z, sd["head.weight"], sd["head.bias"])
+    assert_close(got, ref, FP32_TOL, "legacy BaselineCLS")
+
+
+# ---- spectra ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_spectra_matches_golden(golden_dir, dtype, tol):
+    g = load_golden(golden_dir, "spectra")
+    prod, oracle = _pair("SpectraNet", dtype=dtype)
+    with torch.no_grad():
+        got4096 = prod((g["s4096"].to(DEV), None, None))
+        got3481 = prod((g["s3481"].to(DEV), None, None))
+    assert_close(got4096, g["logits4096"], tol, f"spectra {dtype} L=4096 vs golden")
+    assert_close(got3481, g["logits3481"], tol, f"spectra {dtype} L=3481 vs golden")
+    if dtype == "fp32":
+        blk = prod.all_stages[0][0]
+        y, Lo = blk.forward_cl(g["s4096"].to(DEV).view(2, 4096, 1), 2, 4096, torch.float32)
+        assert Lo == 1024
+        assert_close(y[0, :, 0], g["stage0_b0_c0"], tol, "stage-0 output b0 c0")
+        assert_close(y[1, :, 63], g["stage0_b1_c63"], tol, "stage-0 output b1 c63")
+
+
+def test_spectra_tiny_config_with_committed_weights(golden_dir):
+    import applecider_b200 as ab
+
+    g = load_golden(golden_dir, "spectra_tiny")
+    cfg = ab.default_config()
+    cfg["model"]["SpectraNet"].update(
+        channels=[8, 16, 16, 32, 32], kernel_sizes_per_stage=[[3, 9, 33], [3, 7, 17], [3, 5, 9], [3, 5, 7], [3, 5, 7]], flat_dim=96, class_order=4
+    )
+    m = ab.SpectraNet(cfg)
+    m.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith("w::")}, strict=True)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        got = m((g["x"].to(DEV), None, None))
+    assert_close(got, g["logits"], FP32_TOL, "tiny SpectraNet (ragged L=777) vs real reference")
+
+
+def test_spectra_redshift_head():
+    from applecider_b200 import synth
+
+    def edit(c):
+        c["model"]["SpectraNet"]["redshift"] = True
+
+    prod, oracle = _pair("SpectraNet", cfg_edit=edit)
+    s = synth.spectra(2, seed=31, L=1024)
+    with torch.no_grad():
+        got = prod((s.to(DEV), None, None))
+        ref = oracle((s, None, None))
+    assert got.shape == (2,)
+    assert_close(got, ref, FP32_TOL, "redshift regressor")
+
+
+# ---- image + metadata ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_astrominn_matches_golden(golden_dir, dtype, tol):
+    g = load_golden(golden_dir, "astrominn")
+    prod, oracle = _pair("AstroMiNN", dtype=dtype)
+    with torch.no_grad():
+        feat = prod.image_tower.backbone.forward_features(g["image"].to(DEV), prod.compute_dtype)
+        got = prod((g["metadata"].to(DEV), g["image"].to(DEV), None))
+    assert_close(feat, g["backbone"], tol, f"ConvNeXt-T features {dtype} vs golden")
+    assert_close(got, g["logits"], tol, f"AstroMiNN logits {dtype} vs golden")
+    _argmax_agree(got, g["logits"], tol)
+
+
+def test_astrominn_router_indices_exact():
+    """top-2 expert selection is integer work: must match the oracle exactly (fp32 path)."""
+    from applecider_b200 import ops, synth
+
+    prod, oracle = _pair("AstroMiNN")
+    meta, img = synth.metadata(32, seed=41, missing_frac=0.0), synth.cutouts(32, seed=41)
+    with torch.no_grad():
+        feats = prod.features(meta.to(DEV), img.to(DEV))
+        ofeats = oracle.features(meta, img)
+        assert_close(feats, ofeats, FP32_TOL, "concatenated tower features")
+        r = prod.fusion_router
+        gate = ops.gemm(ops.gemm(feats, r[0].weight, r[0].bias, act=ops.ACT_TANH), r[3].weight, r[3].bias, act=ops.ACT_SIGMOID)
+        ogate = oracle.fusion_router(ofeats)
+    sel = torch.topk(gate.cpu(), 2, -1).indices
+    osel = torch.topk(ogate, 2, -1).indices
+    top3 = ogate.topk(3, -1).values
+    safe = (top3[:, 1] - top3[:, 2]) > 1e-5  # ignore numerically tied gates
+    assert torch.equal(sel[safe], osel[safe])
+
+
+# ---- fusion ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fusion", ["avg", "concat"])
+@pytest.mark.parametrize("dtype,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_fusion_matches_golden(golden_dir, fusion, dtype, tol):
+    g = load_golden(golden_dir, f"fusion_{fusion}")
+    import applecider_b200 as ab
+    from applecider_b200 import synth
+    from oracle import models as om
+
+    oracle = om.AppleCider(om.default_config(), hidden_dim=64, fusion=fusion).eval()
+    sd = synth.det_state_dict(oracle, 0)
+    oracle.load_state_dict(sd)
+    prod = ab.AppleCider(ab.default_config(), hidden_dim=64, fusion=fusion, compute_dtype=dtype)
+    prod.load_state_dict(sd, strict=True)
+    prod = prod.to(DEV).eval()
+    args = [g[k].to(DEV) for k in ("x", "pad", "metadata", "image", "spectra")]
+    with torch.no_grad():
+        got = prod(*args)
+        p, im, s = prod.get_embeddings(*args)
+        ref_live = oracle(*[g[k] for k in ("x", "pad", "metadata", "image", "spectra")])
+    assert_close(ref_live, g["logits"], 1e-5, "oracle fusion vs golden")
+    assert_close(got, g["logits"], tol, f"fusion {fusion} {dtype} logits vs golden")
+    if dtype == "fp32":
+        assert_close(p, g["p_emb"], tol, "photometry embedding")
+        assert_close(im, g["im_emb"], tol, "image+metadata embedding")
+        assert_close(s, g["s_emb"], tol, "spectra embedding")
