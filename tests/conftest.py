@@ -9,6 +9,11 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    import torch
+
+    # torch references used as checkers must be true fp32 (cuDNN/cuBLAS default to TF32 for convs)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
