@@ -71,6 +71,140 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const T* __restrict__ x
   }
 }
 
+// v2 (W known at compile time): thread = channel, CTA = (image, strip of R output rows).  The 49 taps live in
+// registers, one input row segment (W values) is loaded per ky and reused by all W x 7 taps (register
+// sliding window), so shared-memory traffic drops 5x against the generic kernel; out-of-range taps vanish
+// at compile time.  LayerNorm: conv row -> smem -> warp per pixel, channel pairs per lane.
+template <int W>
+constexpr int dw_max_threads() { return W >= 15 ? 256 : (W >= 7 ? 512 : 768); }
+
+template <typename T, int W>
+__global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                                           const float* __restrict__ ln_b, float eps, T* __restrict__ y,
+                                                           int H, int C, int R, int use_wsm) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int strips = (H + R - 1) / R;
+  const int b = blockIdx.x / strips, oy0 = (blockIdx.x % strips) * R;
+  const int rows = min(R, H - oy0);
+  const int WC = W * C;
+  T* in = reinterpret_cast<T*>(smraw);
+  const size_t in_bytes = (((size_t)(R + 6) * WC * sizeof(T)) + 15) & ~(size_t)15;
+  float* cv = reinterpret_cast<float*>(smraw + in_bytes);
+  float* wsm = cv + WC;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  {  // stage input rows oy0-3 .. oy0+rows+2 (16-byte copies; rows outside the image are zero)
+    const int v_per_row = (int)((size_t)WC * sizeof(T) / 16);
+    const int nvec = (rows + 6) * v_per_row;
+    const uint4* xg = reinterpret_cast<const uint4*>(x + (long long)b * H * WC);
+    uint4* ins = reinterpret_cast<uint4*>(in);
+    for (int i = tid; i < nvec; i += nthr) {
+      const int rr = i / v_per_row, rem = i - rr * v_per_row;
+      const int iy = oy0 + rr - 3;
+      ins[i] = (iy >= 0 && iy < H) ? __ldg(xg + (long long)iy * v_per_row + rem) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  if (use_wsm) {
+    for (int i = tid; i < 49 * C; i += nthr) {
+      const int cc = i / 49, j = i - cc * 49;
+      wsm[j * (C + 1) + cc] = __ldg(w + i);
+    }
+  }
+  __syncthreads();
+  const int c = tid;
+  float wr[49];
+  float bc = 0.0f;
+  if (c < C) {
+#pragma unroll
+    for (int j = 0; j < 49; ++j) wr[j] = use_wsm ? wsm[j * (C + 1) + c] : __ldg(w + c * 49 + j);
+    bc = bias[c];
+  }
+  const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+  for (int r = 0; r < rows; ++r) {
+    if (c < C) {
+      float acc[W];
+#pragma unroll
+      for (int ox = 0; ox < W; ++ox) acc[ox] = bc;
+#pragma unroll
+      for (int ky = 0; ky < 7; ++ky) {
+        float iv[W];
+        const T* rowp = in + (size_t)(r + ky) * WC + c;
+#pragma unroll
+        for (int ix = 0; ix < W; ++ix) iv[ix] = to_f<T>(rowp[ix * C]);
+#pragma unroll
+        for (int ox = 0; ox < W; ++ox) {
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx) {
+            const int ix = ox + kx - 3;
+            if (ix >= 0 && ix < W) acc[ox] = fmaf(iv[ix], wr[ky * 7 + kx], acc[ox]);
+          }
+        }
+      }
+#pragma unroll
+      for (int ox = 0; ox < W; ++ox) cv[ox * C + c] = acc[ox];
+    }
+    __syncthreads();
+    for (int ox = wid; ox < W; ox += nw) {
+      const float* v = cv + ox * C;
+      float s = 0.0f;
+      for (int cc = lane * 2; cc < C; cc += 64) {
+        const float2 t = *reinterpret_cast<const float2*>(v + cc);
+        s += t.x + t.y;
+      }
+      const float mean = warp_sum(s) / (float)C;
+      float q = 0.0f;
+      for (int cc = lane * 2; cc < C; cc += 64) {
+        const float2 t = *reinterpret_cast<const float2*>(v + cc);
+        q += (t.x - mean) * (t.x - mean) + (t.y - mean) * (t.y - mean);
+      }
+      const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+      T* o = y + (((long long)b * H + oy0 + r) * W + ox) * C;
+      for (int cc = lane * 2; cc < C; cc += 64) {
+        const float2 t = *reinterpret_cast<const float2*>(v + cc);
+        const float2 g = *reinterpret_cast<const float2*>(ln_w + cc);
+        const float2 be = *reinterpret_cast<const float2*>(ln_b + cc);
+        const float o0 = (t.x - mean) * rstd * g.x + be.x, o1 = (t.y - mean) * rstd * g.y + be.y;
+        if (sizeof(T) == 2) {
+          *reinterpret_cast<__nv_bfloat162*>(o + cc) = __floats2bfloat162_rn(o0, o1);
+        } else {
+          *reinterpret_cast<float2*>(o + cc) = make_float2(o0, o1);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int W>
+int launch_dwconv_w(const void* x, const float* w, const float* b, const float* ln_w, const float* ln_b, float eps, void* y,
+                    int B, int H, int C, cudaStream_t st) {
+  const int R = W >= 15 ? 5 : (W >= 7 ? 7 : (W >= 3 ? 3 : 1));
+  const int use_wsm = C <= 192 ? 1 : 0;
+  const size_t in_bytes = (((size_t)(R + 6) * W * C * sizeof(T)) + 15) & ~(size_t)15;
+  const size_t smem = in_bytes + (size_t)W * C * 4 + (use_wsm ? (size_t)49 * (C + 1) * 4 : 0);
+  auto k = dwconv7_ln_w_kernel<T, W>;
+  ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int threads = ((C + 31) / 32) * 32;
+  if (threads > dw_max_threads<W>() || smem > 200 * 1024) return 1;  // fall back to the generic kernel
+  const unsigned grid = (unsigned)((long long)B * ((H + R - 1) / R));
+  k<<<grid, threads, smem, st>>>((const T*)x, w, b, ln_w, ln_b, eps, (T*)y, H, C, R, use_wsm);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+template <typename T>
+int dispatch_dwconv_w(int W, const void* x, const float* w, const float* b, const float* ln_w, const float* ln_b, float eps,
+                      void* y, int B, int H, int C, cudaStream_t st) {
+  switch (W) {
+    case 15: return launch_dwconv_w<T, 15>(x, w, b, ln_w, ln_b, eps, y, B, H, C, st);
+    case 7: return launch_dwconv_w<T, 7>(x, w, b, ln_w, ln_b, eps, y, B, H, C, st);
+    case 3: return launch_dwconv_w<T, 3>(x, w, b, ln_w, ln_b, eps, y, B, H, C, st);
+    case 1: return launch_dwconv_w<T, 1>(x, w, b, ln_w, ln_b, eps, y, B, H, C, st);
+  }
+  return 1;  // not specialised
+}
+
 // warp per INPUT pixel inside the floor(H/2) x floor(W/2) region
 template <typename T>
 __global__ void __launch_bounds__(256) ln_patch2_kernel(const T* __restrict__ x, const float* __restrict__ ln_w,
@@ -154,9 +288,15 @@ int acb_patchify_nchw(const float* img, int B, int Cin, int H, int W, int p, voi
 int acb_dwconv7_ln(const void* x, int dtype, const float* w, const float* b, const float* ln_w, const float* ln_b,
                    float eps, void* y, int B, int H, int W, int C, void* stream) {
   ACB_CHECK(x && y && w && b && ln_w && ln_b && B > 0 && H > 0 && W > 0 && C > 0, "acb_dwconv7_ln: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool aligned = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)ln_w | (uintptr_t)ln_b) % 16 == 0);
+  if ((W == 15 || W == 7 || W == 3 || W == 1) && C % 8 == 0 && C <= 768 && aligned) {
+    const int rc = dtype == ACB_F32 ? dispatch_dwconv_w<float>(W, x, w, b, ln_w, ln_b, eps, y, B, H, C, st)
+                                    : dispatch_dwconv_w<bf16>(W, x, w, b, ln_w, ln_b, eps, y, B, H, C, st);
+    if (rc <= 0) return rc;
+  }
   const size_t smem = (size_t)8 * W * C * sizeof(float);
   ACB_CHECK(smem <= 200 * 1024, "acb_dwconv7_ln: row tile W*C=%d too large", W * C);
-  cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((long long)B * H);
   if (dtype == ACB_F32) {
     auto k = dwconv7_ln_kernel<float>;

@@ -132,13 +132,84 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TX* __restrict__ x
   }
 }
 
+// Register-cached variant for C <= 128*NC (every row element is read from global exactly once);
+// GELU uses the 1.5e-7-accurate rational when the result is rounded to bf16 anyway.
+template <typename TX, typename TR, typename TY, int NC>
+__global__ void __launch_bounds__(256) layernorm_cached_kernel(const TX* __restrict__ x, const TR* __restrict__ res,
+                                                               const float* __restrict__ w, const float* __restrict__ b,
+                                                               TY* __restrict__ y, long long rows, int C, float eps,
+                                                               int pre_gelu, int post_act) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const TX* xr = x + row * C;
+  const TR* rr = res ? res + row * C : nullptr;
+  TY* yr = y + row * C;
+  constexpr bool FAST = sizeof(TY) == 2;
+  float v[NC][4];
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int c = lane * 4 + k * 128;
+    if (c < C) {
+      Vec4<TX>::load(xr + c, v[k]);
+      if (pre_gelu) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[k][i] = FAST ? gelu_fast(v[k][i]) : gelu_erf(v[k][i]);
+      }
+      if (rr) {
+        float r4[4];
+        Vec4<TR>::load(rr + c, r4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[k][i] += r4[i];
+      }
+      s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    if (lane * 4 + k * 128 < C) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) q += (v[k][i] - mean) * (v[k][i] - mean);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int c = lane * 4 + k * 128;
+    if (c < C) {
+      const float4 w4 = *reinterpret_cast<const float4*>(w + c);
+      const float4 b4 = *reinterpret_cast<const float4*>(b + c);
+      float o[4];
+      o[0] = (v[k][0] - mean) * rstd * w4.x + b4.x;
+      o[1] = (v[k][1] - mean) * rstd * w4.y + b4.y;
+      o[2] = (v[k][2] - mean) * rstd * w4.z + b4.z;
+      o[3] = (v[k][3] - mean) * rstd * w4.w + b4.w;
+      if (post_act == ACB_ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = FAST ? gelu_fast(o[i]) : gelu_erf(o[i]);
+      } else if (post_act != ACB_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = apply_act(o[i], post_act);
+      }
+      Vec4<TY>::store(yr + c, o);
+    }
+  }
+}
+
 template <typename TX, typename TR, typename TY>
 int launch_ln(const void* x, const void* res, const float* w, const float* b, void* y, long long rows, int C,
               float eps, int pre_gelu, int post_act, cudaStream_t st) {
   const int wpb = 8;
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
   const bool vec = (C % 4 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)w | (uintptr_t)b) % 16 == 0);
-  if (vec)
+  if (vec && C <= 256)
+    layernorm_cached_kernel<TX, TR, TY, 2><<<grid, wpb * 32, 0, st>>>((const TX*)x, (const TR*)res, w, b, (TY*)y, rows, C, eps, pre_gelu, post_act);
+  else if (vec && C <= 768)
+    layernorm_cached_kernel<TX, TR, TY, 6><<<grid, wpb * 32, 0, st>>>((const TX*)x, (const TR*)res, w, b, (TY*)y, rows, C, eps, pre_gelu, post_act);
+  else if (vec)
     layernorm_kernel<TX, TR, TY, true><<<grid, wpb * 32, 0, st>>>((const TX*)x, (const TR*)res, w, b, (TY*)y, rows, C, eps, pre_gelu, post_act);
   else
     layernorm_kernel<TX, TR, TY, false><<<grid, wpb * 32, 0, st>>>((const TX*)x, (const TR*)res, w, b, (TY*)y, rows, C, eps, pre_gelu, post_act);

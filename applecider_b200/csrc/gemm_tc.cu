@@ -216,19 +216,27 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     }
   } else {
     // ===================== epilogue =====================
+    // TMEM -> registers (thread = output row) -> bias/act/residual/pool -> per-warp smem transpose
+    // (the pipeline stages are idle by now) -> row-contiguous 16-byte global stores.
     const int q = warp & 3;  // TMEM lane quarter accessible to this warp
     const int r = q * 32 + lane;
     const int s_in_tile = r / p.Lbox;
     const int l = l0 + (r - s_in_tile * p.Lbox);
     const int sample = sample0 + s_in_tile;
-    long long m = (long long)sample * p.L + l;
+    const long long m = (long long)sample * p.L + l;
     bool valid = (s_in_tile < p.Bbox) && (sample < p.nbatch) && (l < p.L);
     if (p.m_valid_dev) valid = valid && (m < (long long)(*p.m_valid_dev));
     if (nkb > 0) {
       mbar_wait(bar_acc, 0);
       tc_fence_after();
     }
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + (warp - 2) * (32 * 33);
     const long long out_row = p.pool4 ? (m >> 2) : m;
+    const bool writer = valid && (!p.pool4 || (lane & 3) == 0);
+    const unsigned wmask = __ballot_sync(0xffffffffu, writer);
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const int esz = p.c_dtype == ACB_BF16 ? 2 : 4;
+    const int rsz = p.res_dtype == ACB_BF16 ? 2 : 4;
     for (int c0 = 0; c0 < BN; c0 += 32) {
       const int n_first = n0 + c0;
       if (n_first >= p.N) break;  // warp-uniform
@@ -245,66 +253,123 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
       const int out_col = (p.has_coloff ? p.col_off[n_first >> 6] : (n_first & ~63)) + (n_first & 63);
       const int ncols = min(32, p.N - n_first);
       if (p.bias) {
+        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(p.bias + n_first) & 15) == 0)) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_first);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < ncols) v[i] += __ldg(p.bias + n_first + i);
-      }
-      if (p.act != ACB_ACT_NONE) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
-      }
-      if (p.res_mode != ACB_RES_NONE && valid) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < ncols) {
-            const float rv = ld_any(p.res, m * p.ldr + out_col + i, p.res_dtype);
-            if (p.res_mode == ACB_RES_ADD) v[i] = rv + (p.gamma ? __ldg(p.gamma + n_first + i) : 1.0f) * v[i];
-            else v[i] = rv * v[i];
+          for (int g = 0; g < 8; ++g) {
+            const float4 t = __ldg(b4 + g);
+            v[g * 4 + 0] += t.x; v[g * 4 + 1] += t.y; v[g * 4 + 2] += t.z; v[g * 4 + 3] += t.w;
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) v[i] += __ldg(p.bias + n_first + i);
         }
       }
-      bool writer = valid;
+      switch (p.act) {  // warp-uniform: one branch per 32-column chunk, not per element
+        case ACB_ACT_RELU:
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+          break;
+        case ACB_ACT_GELU:
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+          break;
+        case ACB_ACT_TANH:
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+          break;
+        case ACB_ACT_SIGMOID:
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = sigmoidf_(v[i]);
+          break;
+        default: break;
+      }
+      if (p.res_mode != ACB_RES_NONE) {
+        const bool rvec = ncols == 32 && ((((uintptr_t)p.res + (size_t)out_col * rsz) & 15) == 0) && ((((size_t)p.ldr * rsz) & 15) == 0);
+        float rv[32];
+        if (rvec) {
+          // coalesced: (16 / rsz) columns per lane, consecutive lanes walk along a row
+          const int cpl = 16 / rsz, lpr = 32 / cpl, rpi = 32 / lpr;  // cols/lane, lanes/row, rows/iter
+#pragma unroll 1
+          for (int it = 0; it < 32 / rpi; ++it) {
+            const int rr = it * rpi + lane / lpr, cg = (lane % lpr) * cpl;
+            const long long mr = __shfl_sync(0xffffffffu, m, rr);
+            if ((vmask >> rr) & 1u) {
+              const uint4 pk = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.res) + ((size_t)mr * p.ldr + out_col + cg) * rsz);
+              if (rsz == 4) {
+                stg[rr * 33 + cg + 0] = __uint_as_float(pk.x); stg[rr * 33 + cg + 1] = __uint_as_float(pk.y);
+                stg[rr * 33 + cg + 2] = __uint_as_float(pk.z); stg[rr * 33 + cg + 3] = __uint_as_float(pk.w);
+              } else {
+                const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  stg[rr * 33 + cg + 2 * j] = __uint_as_float(w4[j] << 16);
+                  stg[rr * 33 + cg + 2 * j + 1] = __uint_as_float(w4[j] & 0xffff0000u);
+                }
+              }
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rv[i] = stg[lane * 33 + i];
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rv[i] = (valid && i < ncols) ? ld_any(p.res, m * p.ldr + out_col + i, p.res_dtype) : 0.0f;
+        }
+        if (p.res_mode == ACB_RES_ADD) {
+          if (p.gamma) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = rv[i] + ((i < ncols) ? __ldg(p.gamma + n_first + i) : 0.0f) * v[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = rv[i] + v[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = rv[i] * v[i];
+        }
+      }
       if (p.pool4) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
           v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 2));
         }
-        writer = valid && ((lane & 3) == 0);
       }
-      if (!writer) continue;
-      const long long off = out_row * p.ldc + out_col;
-      if (p.c_dtype == ACB_BF16) {
-        bf16* o = (bf16*)p.C + off;
-        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      const bool cvec = ncols == 32 && ((((uintptr_t)p.C + (size_t)out_col * esz) & 15) == 0) && ((((size_t)p.ldc * esz) & 15) == 0);
+      if (cvec) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+        for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = v[i];
+        __syncwarp();
+        const int cpl = 16 / esz, lpr = 32 / cpl, rpi = 32 / lpr;
+#pragma unroll 1
+        for (int it = 0; it < 32 / rpi; ++it) {
+          const int rr = it * rpi + lane / lpr, cg = (lane % lpr) * cpl;
+          const long long orow = __shfl_sync(0xffffffffu, out_row, rr);
+          if ((wmask >> rr) & 1u) {
+            const float* sv = stg + rr * 33 + cg;
             uint4 pk;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&h0);
-            pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<uint32_t*>(&h2);
-            pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(o + g * 8) = pk;
+            if (esz == 4) {
+              pk.x = __float_as_uint(sv[0]); pk.y = __float_as_uint(sv[1]); pk.z = __float_as_uint(sv[2]); pk.w = __float_as_uint(sv[3]);
+            } else {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(sv[0], sv[1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(sv[2], sv[3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(sv[4], sv[5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(sv[6], sv[7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.C) + ((size_t)orow * p.ldc + out_col + cg) * esz) = pk;
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < ncols) o[i] = __float2bfloat16_rn(v[i]);
         }
-      } else {
-        float* o = (float*)p.C + off;
-        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+        __syncwarp();
+      } else if (writer) {
+        const long long off = out_row * p.ldc + out_col;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(o + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < ncols) o[i] = v[i];
-        }
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) st_any(p.C, off + i, p.c_dtype, v[i]);
       }
     }
   }
@@ -420,9 +485,16 @@ extern "C" int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype
   ACB_CHECK(MT < (1LL << 31) && NT <= 65535, "acb_gemm_bf16: grid too large");
   dim3 grid((unsigned)MT, (unsigned)NT);
   cudaStream_t st = (cudaStream_t)stream;
+  // short-K problems (<= 4 K blocks per tile) are epilogue/latency bound: shallow pipeline, more CTAs per SM
+  int max_kb = kb_total;
+  if (tile_kb_host) {
+    max_kb = 0;
+    for (int i = 0; i < NT; ++i) max_kb = args.kb_hi[i] - args.kb_lo[i] > max_kb ? args.kb_hi[i] - args.kb_lo[i] : max_kb;
+  }
+  const bool short_k = max_kb <= 4;
   switch (bn) {
-    case 64: return launch_tc<64, 4>(tmA, tmB, args, grid, st);
-    case 128: return launch_tc<128, 3>(tmA, tmB, args, grid, st);
-    default: return launch_tc<256, 4>(tmA, tmB, args, grid, st);
+    case 64: return short_k ? launch_tc<64, 2>(tmA, tmB, args, grid, st) : launch_tc<64, 4>(tmA, tmB, args, grid, st);
+    case 128: return short_k ? launch_tc<128, 2>(tmA, tmB, args, grid, st) : launch_tc<128, 3>(tmA, tmB, args, grid, st);
+    default: return short_k ? launch_tc<256, 2>(tmA, tmB, args, grid, st) : launch_tc<256, 4>(tmA, tmB, args, grid, st);
   }
 }

@@ -9,6 +9,42 @@ from . import _lib
 from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, BF16, F32, RES_ADD, RES_MUL, RES_NONE, call, dtype_tag  # noqa: F401
 
 
+# ---- optional per-region CUDA-event timing (bench.py roofline; off by default) ----------------------
+_PROF = None  # dict: tag -> list[(start_event, end_event)]
+
+
+def profile_start():
+    global _PROF
+    _PROF = {}
+
+
+def profile_stop():
+    """Returns {tag: [ms, ...]} (synchronises)."""
+    global _PROF
+    torch.cuda.synchronize()
+    out = {k: [a.elapsed_time(b) for a, b in v] for k, v in (_PROF or {}).items()}
+    _PROF = None
+    return out
+
+
+class region:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if _PROF is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROF is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _PROF.setdefault(self.tag, []).append((self.a, b))
+        return False
+
+
 def _elt(t: torch.Tensor) -> int:
     return t.element_size()
 

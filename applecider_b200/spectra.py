@@ -101,7 +101,8 @@ class SpectraNetBlock(nn.Module):
             kj = self.kernel_sizes[(nt * bn) // cout]
             t_lo, t_hi = kmax // 2 - kj // 2, kmax // 2 + kj // 2 + 1
             ranges += [t_lo * cpt, t_hi * cpt]
-        return ops.gemm(x.view(B, L, cin), w, bias, conv=(kmax, kmax // 2), bn=bn, tile_kb=ranges)
+        with ops.region(f"spectra.conv.cin{cin}"):
+            return ops.gemm(x.view(B, L, cin), w, bias, conv=(kmax, kmax // 2), bn=bn, tile_kb=ranges)
 
     def _convs_bf16_polyphase(self, x_f32, B, L):
         """x_f32: [B, L] fp32 raw signal. Returns ([B*L8, 3C] bf16, L8)."""
@@ -126,8 +127,9 @@ class SpectraNetBlock(nn.Module):
             r, co = divmod(rem, cout)
             coloff.append(r * self.k * cout + j * cout + co)
         y = torch.empty((B * L8, self.k * cout), dtype=torch.bfloat16, device=x_f32.device)
-        ops.gemm(xp, w, bias, out=y.view(B * L8 // _PHASES, _PHASES * self.k * cout), bn=bn, tile_kb=ranges, colblk_off=coloff,
-                 a_view=(B, L8 // _PHASES, kp, stride, _PHASES))
+        with ops.region("spectra.conv.cin1"):
+            ops.gemm(xp, w, bias, out=y.view(B * L8 // _PHASES, _PHASES * self.k * cout), bn=bn, tile_kb=ranges, colblk_off=coloff,
+                     a_view=(B, L8 // _PHASES, kp, stride, _PHASES))
         return y, L8
 
     def forward_cl(self, x, B, L, dtype, raw_signal=None):

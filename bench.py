@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the AppleCiDEr hot path on B200.
+
+Workload (BASELINE.json configs[1]): full multimodal fusion INFERENCE (photometry transformer +
+metadata towers/MoE + 63x63x3 cutout ConvNeXt-T + SpectraNet + late-fusion head), batch 4096
+synthetic ZTF-shaped alerts per GPU, bf16 tcgen05 path.  One "step" = one forward over one batch.
+N > 1 (torchrun): alerts are independent, every rank runs its own batch (weak scaling, no
+collective on the data path); value = all alerts of all ranks / max-over-ranks device time.
+
+  python bench.py --gpus 1 --steps 10 --warmup 3
+  python bench.py --impl reference        # CPU oracle port of the reference path, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# algorithmic forward FLOPs per alert
+FLOPS_SPECTRA_STAGE1_CONV = 2.0 * 1024 * 64 * (3 + 31 + 251) * 128  # 4.782 GFLOP
+FLOPS_FUSION_FWD = 9.20e9
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": (float(np.median(sm)) if sm else None), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(B, seed):
+    from applecider_b200 import synth
+
+    x, pad, lens = synth.photometry_batch(B, seed=seed)
+    return {
+        "x": x, "pad": pad, "tokens": int(lens.sum()) + B,
+        "meta": synth.metadata(B, seed=seed), "img": synth.cutouts(B, seed=seed), "spec": synth.spectra(B, seed=seed, L=4096),
+    }
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference modules (oracle/models.py, pinned against the real
+    reference by tests/golden) on all host cores, fp32, eval/no-grad, bounded sample per step."""
+    from applecider_b200 import synth
+    from oracle import models as om
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = args.cpu_sample
+    model = om.AppleCider(om.default_config(), hidden_dim=64, fusion="avg").eval()
+    model.load_state_dict(synth.det_state_dict(model, 0))
+    inp = make_inputs(sample, 1337)
+    call = lambda: model(inp["x"], inp["pad"], inp["meta"], inp["img"], inp["spec"])  # noqa: E731
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 1))):
+            call()
+        steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call()
+        dt = time.perf_counter() - t0
+    val = sample * steps / dt
+    out = {
+        "impl": "reference", "metric": "fusion_inference_alerts_per_sec", "value": val, "unit": "alerts/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "fusion_inference_b4096_bf16 (CPU arm: same model/inputs, bounded sample)", "batch_per_step": sample},
+        "cpu_baseline": {"value": val, "unit": "alerts/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} alerts/step x {steps} steps, torch CPU fp32, {cores} threads (oracle port of the reference modules)"},
+        "e2e": {"value": val, "unit": "alerts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample", type=int, default=32, dest="cpu_sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import applecider_b200 as ab
+    from applecider_b200 import _lib, ops, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W = max(args.warmup, 3)
+    K = args.steps
+    B = args.batch
+    peaks = load_peaks()
+
+    model = ab.AppleCider(ab.default_config(), hidden_dim=64, fusion="avg", compute_dtype=args.dtype)
+    model.load_state_dict(synth.det_state_dict(model, 0), strict=True)  # random-init-like deterministic weights
+    model = model.cuda().eval()
+
+    host = make_inputs(B, 1337 + rank)
+    pinned = {k: v.pin_memory() for k, v in host.items() if torch.is_tensor(v)}
+    dev = {k: v.cuda() for k, v in pinned.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    logits_host = torch.empty((B, 5), dtype=torch.float32).pin_memory()
+
+    def step_dev():
+        return model(dev["x"], dev["pad"], dev["meta"], dev["img"], dev["spec"])
+
+    def step_e2e():
+        d = {k: v.cuda(non_blocking=True) for k, v in pinned.items()}
+        out = model(d["x"], d["pad"], d["meta"], d["img"], d["spec"])
+        logits_host.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+        return logits_host
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(W):
+            step_dev()
+        # ---- device-resident throughput ("value") ----
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        _lib.reset_launch_count()
+        ops.profile_start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            step_dev()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count()
+        regions = ops.profile_stop()
+        clocks = sampler.stop() if rank == 0 else None
+        # ---- end to end through the public API with host buffers ("e2e") ----
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step_e2e()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        value = world * B * K / (ms / 1e3)
+        e2e = world * B * K / (e2e_ms / 1e3)
+        k_ms = float(np.mean(regions.get("spectra.conv.cin64", [float("nan")])))
+        achieved = FLOPS_SPECTRA_STAGE1_CONV * B / (k_ms / 1e3) / 1e12
+        out = {
+            "metric": "fusion_inference_alerts_per_sec", "value": value, "unit": "alerts/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {
+                "workload": f"fusion_inference_b{B}_{args.dtype}", "batch_per_gpu": B, "spectrum_len": 4096, "cutout": "3x63x63",
+                "photometry": "Hyrax (B,257,7) layout, lognormal lengths, varlen-packed on device", "tokens_per_batch": host["tokens"],
+                "l2": "inputs (293 MB/batch) and activations (>6 GB/step) exceed the 126 MB L2; no explicit flush",
+                "parallelism": f"independent alert shards x{world}, no collective",
+                "fraction_of_fusion_tensor_roofline": value / world * FLOPS_FUSION_FWD / (peaks["tf_sustained"] * 1e12),
+            },
+            "e2e": {"value": e2e, "unit": "alerts/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": B * 5 * 4},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {
+                "kernel": "gemm_tc_kernel<128,3> — SpectraNet stage-1 multi-kernel Conv1d(64->3x128, k=3/31/251) implicit GEMM (tcgen05)",
+                "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "kernel_ms": k_ms, "algorithmic_flops_per_launch": FLOPS_SPECTRA_STAGE1_CONV * B, "traffic": None,
+                "region_ms": {k: float(np.mean(v)) for k, v in regions.items()},
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import models as om  # CPU baseline leg only
+
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            cm = om.AppleCider(om.default_config(), hidden_dim=64, fusion="avg").eval()
+            cm.load_state_dict(synth.det_state_dict(cm, 0))
+            n = args.cpu_sample
+            with torch.no_grad():
+                a = [host["x"][:n], host["pad"][:n], host["meta"][:n], host["img"][:n], host["spec"][:n]]
+                cm(*a)
+                t0 = time.perf_counter()
+                reps = 2
+                for _ in range(reps):
+                    cm(*a)
+                dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": n * reps / dt, "unit": "alerts/s", "cores": cores, "kind": "port",
+                                   "sample": f"first {n} alerts of the same batch x {reps} reps, torch CPU fp32, {cores} threads (oracle port)"}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
