@@ -1,0 +1,524 @@
+// Array-level preprocessing kernels: light-curve feature/collate/normalise,
+// detection merging + event features, spectrum resampling + mean/MAD scaling, cutout crop + normalise,
+// streaming feature statistics.  HBM-bound / latency-bound integer+float work on CUDA cores; index and
+// segmentation results are bit-exact, float32 results use the same operation order as the reference.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace {
+
+// ================================ P1: light curves =================================================
+// One warp per object: horizon cut (stable compaction), log1p / one-hot features, pad|truncate to max_len,
+// mask, (x - mean) / (std + 1e-8) on channels 0..3 of every row including padding.
+__global__ void __launch_bounds__(256) prep_lightcurve_kernel(const float* __restrict__ raw, const long long* __restrict__ offsets,
+                                                              int B, float horizon, const float* __restrict__ mean,
+                                                              const float* __restrict__ stdv, int max_len,
+                                                              float* __restrict__ x, uint8_t* __restrict__ mask,
+                                                              int* __restrict__ lengths) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const long long r0 = offsets[b];
+  const int n = (int)(offsets[b + 1] - r0);
+  float mu[4], sd[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    mu[c] = mean[c];
+    sd[c] = stdv[c] + 1e-8f;
+  }
+  float* xb = x + (long long)b * max_len * 7;
+  int kept = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    float dt = 0.f, dtp = 0.f, band = 0.f, lf = 0.f, lfe = 0.f;
+    bool keep = false;
+    if (i < n) {
+      const float* r = raw + (r0 + i) * 5;
+      dt = r[0]; dtp = r[1]; band = r[2]; lf = r[3]; lfe = r[4];
+      keep = dt <= horizon;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    const int pos = kept + __popc(m & ((1u << lane) - 1u));
+    if (keep && pos < max_len) {
+      float* o = xb + (long long)pos * 7;
+      o[0] = (log1pf(dt) - mu[0]) / sd[0];
+      o[1] = (log1pf(dtp) - mu[1]) / sd[1];
+      o[2] = (lf - mu[2]) / sd[2];
+      o[3] = (lfe - mu[3]) / sd[3];
+      const int bi = (int)band;
+      o[4] = bi == 0 ? 1.f : 0.f;
+      o[5] = bi == 1 ? 1.f : 0.f;
+      o[6] = bi == 2 ? 1.f : 0.f;
+    }
+    kept += __popc(m);
+  }
+  const int len = min(kept, max_len);
+  if (lane == 0 && lengths) lengths[b] = len;
+  float pv[7];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) pv[c] = (0.0f - mu[c]) / sd[c];
+  pv[4] = pv[5] = pv[6] = 0.f;
+  for (int e = len * 7 + lane; e < max_len * 7; e += 32) xb[e] = pv[e % 7];
+  for (int l = lane; l < max_len; l += 32) mask[(long long)b * max_len + l] = l >= len ? 1 : 0;
+}
+
+// ================================ P2: merge + event features ======================================
+// One thread per object.  Per band (reference group order g, i, r) a greedy anchored window merge in
+// fp64 with un-fused multiply/add (same rounding sequence as the reference loop), then a stable 3-way
+// merge by time and the float32 feature columns.
+__global__ void __launch_bounds__(128) prep_events_kernel(const double* __restrict__ mjd, const double* __restrict__ mag,
+                                                          const double* __restrict__ magerr, const int* __restrict__ fid,
+                                                          const long long* __restrict__ offsets, int B, double dt_days,
+                                                          double* __restrict__ tmp /* [3][total] t,f,e */, signed char* __restrict__ tmp_b,
+                                                          long long total, float* __restrict__ o_dt, float* __restrict__ o_dtp,
+                                                          signed char* __restrict__ o_band, float* __restrict__ o_lf,
+                                                          float* __restrict__ o_lfe, int* __restrict__ n_events) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const long long r0 = offsets[b], r1 = offsets[b + 1];
+  double* tt = tmp + r0;
+  double* tf = tmp + total + r0;
+  double* te = tmp + 2 * total + r0;
+  signed char* tb = tmp_b + r0;
+  const double eps = 1e-8;
+  const double c_err = 2.5 / 2.302585092994046;  // 2.5 / ln(10)
+  const int order[3] = {1, 3, 2};
+  int seg_start[4];
+  int cnt = 0;
+  for (int g = 0; g < 3; ++g) {
+    seg_start[g] = cnt;
+    const int band = order[g];
+    long long i = r0;
+    while (i < r1) {
+      while (i < r1 && fid[i] != band) ++i;
+      if (i >= r1) break;
+      // window [i .. j] over detections of this band (time ordered)
+      const double t0 = mjd[i];
+      long long j = i, scan = i + 1;
+      for (; scan < r1; ++scan) {
+        if (fid[scan] != band) continue;
+        if (mjd[scan] - t0 <= dt_days) j = scan; else break;
+      }
+      double totw = 0.0;
+      for (long long k = i; k <= j; ++k) {
+        if (fid[k] != band) continue;
+        const double flux = pow(10.0, -0.4 * (mag[k] - 23.9));
+        const double err = __dmul_rn(magerr[k] / c_err, flux);
+        totw = __dadd_rn(totw, 1.0 / __dadd_rn(err, eps));
+      }
+      double tw = 0.0, fw = 0.0, ew = 0.0;
+      for (long long k = i; k <= j; ++k) {
+        if (fid[k] != band) continue;
+        const double flux = pow(10.0, -0.4 * (mag[k] - 23.9));
+        const double err = __dmul_rn(magerr[k] / c_err, flux);
+        const double w = (1.0 / __dadd_rn(err, eps)) / totw;
+        tw = __dadd_rn(tw, __dmul_rn(w, mjd[k]));
+        fw = __dadd_rn(fw, __dmul_rn(w, flux));
+        ew = __dadd_rn(ew, __dmul_rn(w, err));
+      }
+      tt[cnt] = tw; tf[cnt] = fw; te[cnt] = ew; tb[cnt] = (signed char)(band - 1);
+      ++cnt;
+      i = scan;  // first detection of this band beyond the window (or r1)
+    }
+  }
+  seg_start[3] = cnt;
+  n_events[b] = cnt;
+  // stable 3-way merge by merged time
+  int p[3] = {seg_start[0], seg_start[1], seg_start[2]};
+  double t_first = 0.0, t_prev = 0.0;
+  for (int o = 0; o < cnt; ++o) {
+    int best = -1;
+    for (int g = 0; g < 3; ++g) {
+      if (p[g] < seg_start[g + 1] && (best < 0 || tt[p[g]] < tt[p[best]])) best = g;
+    }
+    const int s = p[best]++;
+    const double t = tt[s];
+    if (o == 0) { t_first = t; t_prev = t; }
+    const float f32 = fmaxf((float)tf[s], 1e-6f);
+    o_dt[r0 + o] = (float)(t - t_first);
+    o_dtp[r0 + o] = (float)(t - t_prev);
+    o_band[r0 + o] = tb[s];
+    o_lf[r0 + o] = log10f(f32);
+    o_lfe[r0 + o] = (float)(__dmul_rn((double)(float)te[s], 0.43429448190325176) / (double)f32);
+    t_prev = t;
+  }
+}
+
+// ================================ selection helper ===================================================
+// k-th smallest (0-based) of `n` keys produced by key(i), radix select over NB-bit unsigned keys, 8 bits/pass.
+template <typename KeyT, typename KeyFn>
+__device__ KeyT block_select(int n, int k, KeyFn key, unsigned* hist /* 256 */, unsigned* sh_k /* 2 */) {
+  constexpr int NBITS = sizeof(KeyT) * 8;
+  KeyT prefix = 0, pmask = 0;
+  for (int shift = NBITS - 8; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const KeyT kk = key(i);
+      if ((kk & pmask) == prefix) atomicAdd(&hist[(unsigned)((kk >> shift) & 0xff)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned acc = 0;
+      int bin = 0;
+      for (; bin < 256; ++bin) {
+        if (acc + hist[bin] > (unsigned)k) break;
+        acc += hist[bin];
+      }
+      sh_k[0] = (unsigned)bin;
+      sh_k[1] = (unsigned)k - acc;
+    }
+    __syncthreads();
+    prefix |= (KeyT)sh_k[0] << shift;
+    pmask |= (KeyT)0xff << shift;
+    k = (int)sh_k[1];
+    __syncthreads();
+  }
+  return prefix;
+}
+
+__device__ __forceinline__ unsigned long long dkey(double v) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+  const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ unsigned fkey(float v) {
+  const unsigned u = __float_as_uint(v);
+  return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned k) {
+  const unsigned u = (k >> 31) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+__device__ double block_sum_d(double v, double* sh /* 33 */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if (lane == 0) sh[32] = r;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+// ================================ P3: spectrum resampling ============================================
+// One CTA per spectrum: finite filter (stable), sort by wavelength when needed (bitonic, smem), linear
+// interpolation with linear extrapolation at searchsorted-left intervals (un-fused fp64, scipy order of
+// operations), mean, MAD by radix selection, (y - mean) / scale -> float32.
+__global__ void __launch_bounds__(256) prep_spectrum_kernel(const double* __restrict__ wl, const double* __restrict__ fx,
+                                                            const long long* __restrict__ offsets, int cap,
+                                                            const float* __restrict__ grid, int n_grid, float* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  double* xs = reinterpret_cast<double*>(sm_raw);
+  double* ys = xs + cap;
+  double* yg = ys + cap;
+  double* red = yg + n_grid;                                  // 33 doubles
+  unsigned* hist = reinterpret_cast<unsigned*>(red + 34);     // 256
+  unsigned* shk = hist + 256;                                  // 2
+  int* shi = reinterpret_cast<int*>(shk + 2);                  // counters
+  const int b = blockIdx.x;
+  const long long r0 = offsets[b];
+  const int n_in = (int)(offsets[b + 1] - r0);
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+  float* ob = out + (long long)b * n_grid;
+
+  // ---- stable compaction of finite samples ----
+  if (tid == 0) shi[0] = 0;
+  __syncthreads();
+  for (int base = 0; base < n_in; base += nthr) {
+    const int i = base + tid;
+    double xv = 0.0, yv = 0.0;
+    bool ok = false;
+    if (i < n_in) {
+      xv = wl[r0 + i];
+      yv = fx[r0 + i];
+      ok = isfinite(xv) && isfinite(yv);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    int* wcnt = shi + 1;  // per-warp counts
+    if (lane == 0) wcnt[wid] = __popc(m);
+    __syncthreads();
+    int off = shi[0];
+    for (int w = 0; w < wid; ++w) off += wcnt[w];
+    if (ok) {
+      const int pos = off + __popc(m & ((1u << lane) - 1u));
+      xs[pos] = xv;
+      ys[pos] = yv;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < nw; ++w) t += wcnt[w];
+      shi[0] += t;
+    }
+    __syncthreads();
+  }
+  const int n = shi[0];
+  if (n < 2) {
+    for (int g = tid; g < n_grid; g += nthr) ob[g] = CUDART_NAN_F;
+    return;
+  }
+  // ---- sort by wavelength if needed ----
+  int unsorted = 0;
+  for (int i = tid; i + 1 < n; i += nthr) unsorted |= (xs[i] > xs[i + 1]);
+  unsorted = __syncthreads_or(unsorted);
+  if (unsorted) {
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = n + tid; i < np2; i += nthr) { xs[i] = CUDART_INF; ys[i] = 0.0; }
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < np2; i += nthr) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const bool up = (i & k) == 0;
+            const double a = xs[i], c = xs[ixj];
+            if ((a > c) == up) {
+              xs[i] = c; xs[ixj] = a;
+              const double t = ys[i]; ys[i] = ys[ixj]; ys[ixj] = t;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  // ---- interpolation ----
+  double s_loc = 0.0;
+  for (int g = tid; g < n_grid; g += nthr) {
+    const double xn = (double)grid[g];
+    int lo = 0, hi = n;  // first index with xs[idx] >= xn
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (xs[mid] < xn) lo = mid + 1; else hi = mid;
+    }
+    int ih = min(max(lo, 1), n - 1);
+    const int il = ih - 1;
+    const double slope = __ddiv_rn(__dsub_rn(ys[ih], ys[il]), __dsub_rn(xs[ih], xs[il]));
+    const double v = __dadd_rn(__dmul_rn(slope, __dsub_rn(xn, xs[il])), ys[il]);
+    yg[g] = v;
+    if (!isnan(v)) s_loc += v;
+  }
+  __syncthreads();
+  int nfin_loc = 0;
+  for (int g = tid; g < n_grid; g += nthr) nfin_loc += !isnan(yg[g]);
+  const int nfin = (int)(block_sum_d((double)nfin_loc, red) + 0.5);
+  const double mean = block_sum_d(s_loc, red) / (double)nfin;
+  // ---- median and MAD (NaNs sort last: select among the nfin smallest keys) ----
+  double scale = 1.0;
+  if (nfin > 0) {
+    auto key_y = [&](int i) { const double v = yg[i]; return isnan(v) ? ~0ull : dkey(v); };
+    double med = dkey_inv(block_select<unsigned long long>(n_grid, (nfin - 1) / 2, key_y, hist, shk));
+    if ((nfin & 1) == 0) med = 0.5 * (med + dkey_inv(block_select<unsigned long long>(n_grid, nfin / 2, key_y, hist, shk)));
+    auto key_d = [&](int i) { const double v = yg[i]; return isnan(v) ? ~0ull : dkey(fabs(v - med)); };
+    double mad = dkey_inv(block_select<unsigned long long>(n_grid, (nfin - 1) / 2, key_d, hist, shk));
+    if ((nfin & 1) == 0) mad = 0.5 * (mad + dkey_inv(block_select<unsigned long long>(n_grid, nfin / 2, key_d, hist, shk)));
+    if (!isfinite(mad) || mad == 0.0) {
+      double q = 0.0;
+      for (int g = tid; g < n_grid; g += nthr) {
+        const double v = yg[g];
+        if (!isnan(v)) q += (v - mean) * (v - mean);
+      }
+      const double sd = sqrt(block_sum_d(q, red) / (double)nfin);
+      scale = (isfinite(sd) && sd > 0.0) ? sd : 1.0;
+    } else {
+      scale = mad;
+    }
+  }
+  for (int g = tid; g < n_grid; g += nthr) ob[g] = (float)((yg[g] - mean) / scale);
+}
+
+// ================================ P4: cutouts =========================================================
+// mode 0: per channel  x -= lower_median; x /= (unbiased std + 1e-8)      (ImageAndMetadataDataset.get_image)
+// mode 2: per channel  x -= median; x /= population std (<= 1e-8 -> 1)     (Fusion_Dataset._normalize_image)
+// CTA per (image, channel); the plane lives in shared memory, the median comes from a radix select.
+__global__ void __launch_bounds__(256) cutout_median_kernel(const float* __restrict__ img, int C, int H, int W, int i1, int S,
+                                                            int mode, float* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  float* pl = reinterpret_cast<float*>(sm_raw);
+  double* red = reinterpret_cast<double*>(pl + ((S * S + 3) & ~3));
+  unsigned* hist = reinterpret_cast<unsigned*>(red + 34);
+  unsigned* shk = hist + 256;
+  const int bc = blockIdx.x;  // b*C + c
+  const float* src = img + (long long)bc * H * W;
+  const int n = S * S;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int yy = i / S, xx = i - yy * S;
+    pl[i] = src[(yy + i1) * W + (xx + i1)];
+  }
+  __syncthreads();
+  auto key = [&](int i) { return fkey(pl[i]); };
+  float med = fkey_inv(block_select<unsigned>(n, (n - 1) / 2, key, hist, shk));
+  if (mode == 2 && (n & 1) == 0) med = 0.5f * (med + fkey_inv(block_select<unsigned>(n, n / 2, key, hist, shk)));
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float p = pl[i] - med;
+    pl[i] = p;
+    s += (double)p;
+  }
+  const double mean = block_sum_d(s, red) / (double)n;
+  double q = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = (double)pl[i] - mean;
+    q += d * d;
+  }
+  q = block_sum_d(q, red);
+  float denom;
+  if (mode == 0) {
+    denom = (float)sqrt(q / (double)(n - 1)) + 1e-8f;
+  } else {
+    const double sd = sqrt(q / (double)n);
+    denom = (isfinite(sd) && sd > 1e-8) ? (float)sd : 1.0f;
+  }
+  float* dst = out + (long long)bc * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = pl[i] / denom;
+}
+
+// mode 1: x / ||x||_2 over all channels of the (cropped) cutout.  CTA per image.
+__global__ void __launch_bounds__(256) cutout_l2_kernel(const float* __restrict__ img, int C, int H, int W, int i1, int S,
+                                                        float* __restrict__ out) {
+  __shared__ double red[34];
+  const int b = blockIdx.x;
+  const int n = C * S * S;
+  const float* src = img + (long long)b * C * H * W;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i / (S * S), rem = i - c * S * S, yy = rem / S, xx = rem - yy * S;
+    const double v = (double)src[(c * H + yy + i1) * W + xx + i1];
+    s += v * v;
+  }
+  const float nrm = (float)sqrt(block_sum_d(s, red));
+  float* dst = out + (long long)b * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i / (S * S), rem = i - c * S * S, yy = rem / S, xx = rem - yy * S;
+    dst[i] = src[(c * H + yy + i1) * W + xx + i1] / nrm;
+  }
+}
+
+// ================================ P5: feature statistics =============================================
+__global__ void __launch_bounds__(256) feature_sums_kernel(const float* __restrict__ data, long long rows, int F, int rows_per_block,
+                                                           double* __restrict__ sums /* [2F] */) {
+  __shared__ double sh[2 * 256];
+  const int active = (256 / F) * F;
+  for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) sh[i] = 0.0;
+  __syncthreads();
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  if (threadIdx.x < active && r0 < r1) {
+    const int col = threadIdx.x % F;
+    double s = 0.0, q = 0.0;
+    const long long e1 = (r1 - r0) * F;
+    const float* base = data + r0 * F;
+    for (long long e = threadIdx.x; e < e1; e += active) {
+      const double v = (double)__ldg(base + e);
+      s += v;
+      q += v * v;
+    }
+    atomicAdd(&sh[col], s);
+    atomicAdd(&sh[F + col], q);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) atomicAdd(&sums[i], sh[i]);
+}
+
+__global__ void feature_finalize_kernel(const double* __restrict__ sums, long long rows, int F, float* __restrict__ mean,
+                                        float* __restrict__ stdv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= F) return;
+  const float tot = (float)rows;
+  const float m = (float)sums[c] / tot;
+  const float var = (float)sums[F + c] / tot - m * m;
+  mean[c] = m;
+  stdv[c] = sqrtf(fmaxf(var, 0.0f));
+}
+
+}  // namespace
+
+extern "C" {
+
+int acb_prep_lightcurve(const float* raw, const long long* offsets, int B, float horizon, const float* mean, const float* stdv,
+                        int max_len, float* x, uint8_t* mask, int* lengths, void* stream) {
+  ACB_CHECK(raw && offsets && mean && stdv && x && mask && B > 0 && max_len > 0, "acb_prep_lightcurve: bad arguments");
+  prep_lightcurve_kernel<<<cdiv(B, 8), 256, 0, (cudaStream_t)stream>>>(raw, offsets, B, horizon, mean, stdv, max_len, x, mask, lengths);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+int acb_prep_events(const double* mjd, const double* mag, const double* magerr, const int* fid, const long long* offsets, int B,
+                    long long total, double dt_days, double* tmp, signed char* tmp_b, float* dt, float* dt_prev,
+                    signed char* band_id, float* logflux, float* logflux_err, int* n_events, void* stream) {
+  ACB_CHECK(mjd && mag && magerr && fid && offsets && tmp && tmp_b && dt && dt_prev && band_id && logflux && logflux_err && n_events && B > 0,
+            "acb_prep_events: bad arguments");
+  prep_events_kernel<<<cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(mjd, mag, magerr, fid, offsets, B, dt_days, tmp, tmp_b, total, dt,
+                                                                      dt_prev, band_id, logflux, logflux_err, n_events);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+int acb_prep_spectrum_resample(const double* wl, const double* fx, const long long* offsets, int B, int max_n, const float* grid,
+                               int n_grid, float* out, void* stream) {
+  ACB_CHECK(wl && fx && offsets && grid && out && B > 0 && n_grid > 0 && max_n > 0, "acb_prep_spectrum_resample: bad arguments");
+  int cap = 64;
+  while (cap < max_n) cap <<= 1;
+  const size_t smem = (size_t)(2 * cap + n_grid + 34) * 8 + (256 + 2 + 16) * 4;
+  ACB_CHECK(smem <= 220 * 1024, "acb_prep_spectrum_resample: spectrum too long for shared memory (max_n=%d, n_grid=%d)", max_n, n_grid);
+  auto k = prep_spectrum_kernel;
+  ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<B, 256, smem, (cudaStream_t)stream>>>(wl, fx, offsets, cap, grid, n_grid, out);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+int acb_prep_cutout_norm(const float* img, int B, int C, int H, int W, int cutout_size, int mode, float* out, void* stream) {
+  ACB_CHECK(img && out && B > 0 && C > 0 && H == W && H > 0, "acb_prep_cutout_norm: bad arguments");
+  ACB_CHECK(mode >= 0 && mode <= 2, "acb_prep_cutout_norm: mode must be 0 (median/std), 1 (L2) or 2 (notebook median/std)");
+  int i1 = 0, i2 = H;
+  if (cutout_size != H) {
+    i1 = (int)((H - cutout_size) / 2.0);  // int((63 - cutout_size) / 2) in the reference (float division, truncation)
+    i2 = H - i1;
+  }
+  const int S = i2 - i1;
+  ACB_CHECK(S > 0 && i1 >= 0, "acb_prep_cutout_norm: bad crop");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 1) {
+    cutout_l2_kernel<<<B, 256, 0, st>>>(img, C, H, W, i1, S, out);
+  } else {
+    const size_t smem = (size_t)((S * S + 3) & ~3) * 4 + 34 * 8 + 258 * 4;
+    auto k = cutout_median_kernel;
+    if (smem > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<B * C, 256, smem, st>>>(img, C, H, W, i1, S, mode, out);
+  }
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+int acb_feature_stats(const float* data, long long rows, int F, double* work, float* mean, float* stdv, void* stream) {
+  ACB_CHECK(data && work && mean && stdv && rows > 0 && F > 0 && F <= 256, "acb_feature_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ACB_CUDA(cudaMemsetAsync(work, 0, sizeof(double) * 2 * F, st));
+  const int rows_per_block = 2048;
+  feature_sums_kernel<<<cdiv(rows, rows_per_block), 256, 0, st>>>(data, rows, F, rows_per_block, work);
+  ACB_LAUNCH_CHECK();
+  feature_finalize_kernel<<<cdiv(F, 64), 64, 0, st>>>(work, rows, F, mean, stdv);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch(2);
+  return ACB_OK;
+}
+
+}  // extern "C"

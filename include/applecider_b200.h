@@ -154,6 +154,38 @@ int acb_fusion_head(const float* p_in, int p_dim, const float* im_in, int im_dim
                     float* logits, float* emb_out, int B, void* stream);
 int acb_softmax_rows(const float* x, float* y, int rows, int C, void* stream);
 
+/* ---- array-level preprocessing ------------------------------------------------ */
+/* P1  datasets/photo_dataset.py:85-101,117-152 + models/HyraxBaselineCLS.py:157.
+ * raw = concatenated (L_i,5) f32 rows [dt, dt_prev, band, logflux, logflux_err]; offsets[B+1] (int64).
+ * horizon cut dt <= horizon -> log1p(dt), log1p(dt_prev), logf, logfe, one-hot band -> pad|truncate to
+ * max_len -> (x - mean)/(std + 1e-8) on channels 0..3 (padding rows too).  x[B,max_len,7] f32,
+ * mask[B,max_len] (1 = padding), lengths[B] (optional). */
+int acb_prep_lightcurve(const float* raw, const long long* offsets, int B, float horizon, const float* mean,
+                        const float* stdv, int max_len, float* x, uint8_t* mask, int* lengths, void* stream);
+/* P2  preprocessing_utils/preprocess_multimodal.py:84-111,176-180,291-336.
+ * Per object (detections time-ordered, offsets[B+1]): mag->flux, per-band greedy window merge (window
+ * dt_days from the anchor, weights 1/(err+1e-8), fp64), 3-way merge by time, event features
+ * dt, dt_prev, band_id (0 g,1 r,2 i), log10(clip(flux,1e-6)), flux_err/(ln10*flux).  Outputs use the input
+ * offsets (an object has at most as many events as detections); n_events[B] = events per object.
+ * tmp = 3*total doubles, tmp_b = total bytes of scratch. */
+int acb_prep_events(const double* mjd, const double* mag, const double* magerr, const int* fid, const long long* offsets,
+                    int B, long long total, double dt_days, double* tmp, signed char* tmp_b, float* dt, float* dt_prev,
+                    signed char* band_id, float* logflux, float* logflux_err, int* n_events, void* stream);
+/* P3  preprocess_multimodal.py:146-170 (_interp_with_extrap), :135-143 (_mad), :598-609.
+ * Ragged spectra (wavelength, flux f64; any order; non-finite samples dropped) -> linear interpolation with
+ * linear extrapolation onto grid[n_grid] (f32 wavelengths) -> subtract mean, divide by MAD (fallback std, 1)
+ * -> out[B,n_grid] f32.  max_n = longest input spectrum. */
+int acb_prep_spectrum_resample(const double* wl, const double* fx, const long long* offsets, int B, int max_n,
+                               const float* grid, int n_grid, float* out, void* stream);
+/* P4  datasets/image_and_metadata_dataset.py:78-99; Fusion_Dataset.ipynb cell 0.
+ * img[B,C,H,W] f32 -> centre crop [i1:i2] (i1 = int((H-cutout_size)/2), i2 = H-i1) -> mode 0: per-channel
+ * lower-median subtraction and division by (unbiased std + 1e-8); mode 1: division by the L2 norm over all
+ * channels; mode 2: notebook variant (true median, population std, std<=1e-8 -> 1).  out[B,C,S,S]. */
+int acb_prep_cutout_norm(const float* img, int B, int C, int H, int W, int cutout_size, int mode, float* out, void* stream);
+/* P5  preprocess_multimodal.py:863-895.  Column mean and population std (clipped at 0) of data[rows,F] f32
+ * from streamed sums / sums of squares (fp64 accumulation).  work = 2*F doubles of scratch. */
+int acb_feature_stats(const float* data, long long rows, int F, double* work, float* mean, float* stdv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
