@@ -41,6 +41,8 @@ def _parse_header(path: str) -> dict:
                 kinds.append("l")
             elif re.search(r"\bfloat\b", a):
                 kinds.append("f")
+            elif re.search(r"\bdouble\b", a):
+                kinds.append("d")
             else:
                 kinds.append("i")
         if kinds and kinds[-1] == "p" and "stream" in args.split(",")[-1]:
@@ -51,7 +53,7 @@ def _parse_header(path: str) -> dict:
 
 SIGNATURES = _parse_header(HEADER_PATH)
 
-_KIND = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float}
+_KIND = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float, "d": ctypes.c_double}
 
 _lib = None
 
@@ -108,7 +110,7 @@ def call(name: str, *args):
     for k, a in zip(sig, args):
         if k == "p":
             conv.append(_ptr(a))
-        elif k == "f":
+        elif k in ("f", "d"):
             conv.append(float(a))
         else:
             conv.append(int(a))

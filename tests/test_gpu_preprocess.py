@@ -36,7 +36,8 @@ def test_p1_lightcurve(g):
     xg = x.cpu().numpy()
     assert np.array_equal(xg[..., 4:], g["p1_x"][..., 4:]), "one-hot band must be bit-exact"
     assert np.array_equal(xg[..., 2:4], g["p1_x"][..., 2:4]), "normalised logf/logfe are pure IEEE sub/div: bit-exact"
-    _ulp_close(xg[..., :2], g["p1_x"][..., :2], 4, "log1p columns")
+    # log1p differs by <= 1 ulp between libm and the GPU; the normalisation (x - mu) / sd then divides that by sd
+    np.testing.assert_allclose(xg[..., :2], g["p1_x"][..., :2], rtol=0, atol=2e-6, err_msg="log1p columns")
 
 
 def test_p1_large_batch_properties():
@@ -51,7 +52,7 @@ def test_p1_large_batch_properties():
     xo, mo = op.collate_photometry(seqs, mean.numpy(), std.numpy())
     assert np.array_equal(mask.cpu().numpy(), mo)
     assert np.array_equal(x.cpu().numpy()[..., 2:], xo[..., 2:].astype(np.float32))
-    _ulp_close(x.cpu().numpy()[..., :2], xo[..., :2], 4, "log1p columns (3000 objects)")
+    np.testing.assert_allclose(x.cpu().numpy()[..., :2], xo[..., :2], rtol=0, atol=2e-6, err_msg="log1p columns (3000 objects)")
 
 
 def test_p2_events(g):
@@ -111,7 +112,7 @@ def test_p4_cutouts(g):
     assert m49.shape == (4, 3, 49, 49)
     _ulp_close(m49, g["p4_median49"], 2, "median/std crop 49")
     l2 = pp.normalize_cutouts(img, "L2").cpu().numpy()
-    _ulp_close(l2, g["p4_l2_63"], 2, "L2")
+    np.testing.assert_allclose(l2, g["p4_l2_63"], rtol=5e-6, atol=0, err_msg="L2")  # the reference's torch.norm sums in float32
     nb = pp.normalize_cutouts(img, "median_notebook").cpu().numpy()
     ref = np.stack([op.normalize_cutout(i, "median", 63, variant="notebook") for i in g["p4_img"]])
     _ulp_close(nb, ref, 2, "notebook median/std")
