@@ -245,7 +245,7 @@ class AstroMiNN(nn.Module):
 
     def forward(self, batch):
         metadata, image, _ = batch
-        if self.training and torch.is_grad_enabled():
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .train import astrominn_forward_train
 
             return astrominn_forward_train(self, metadata, image)

@@ -1,0 +1,821 @@
+// Backward / training kernels: generic strided fp32 GEMM with split-K (dgrad / wgrad / conv wgrad),
+// column reductions, activation / LayerNorm / attention / depthwise-conv / pooling backward, embedding and
+// MoE backward, losses, dropout.  Elementwise kernels are dtype-tagged (f32 | bf16 IO, fp32 math).
+#include "common.cuh"
+
+namespace {
+
+inline unsigned grid_for(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  const long long cap = 148LL * 32;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// ================================ generic strided GEMM (fp32 accumulate) ==============================
+// C[m,n] (+)= sum_k A(m,k) * B(n,k);  A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk] (dtype-tagged).
+// convT != 0: A is the transposed im2col of a channels-last signal X[nb, L, Cin]:
+//   m = tap*Cin + ci, k = b*L + l  ->  X[b, l + tap - pad, ci] (zero outside [0, L)).
+// grid.z splits K; with splits > 1 (or accumulate) results are atomically added into fp32 C.
+struct GemmExArgs {
+  const void* A; const void* B; float* C;
+  int a_dt, b_dt;
+  int M, N, K;
+  long long sam, sak, sbn, sbk;
+  int ldc;
+  int convT, conv_L, conv_Cin, conv_pad;
+  int k_chunk, atomic;
+};
+
+__global__ void __launch_bounds__(256) gemm_ex_kernel(const GemmExArgs p) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int k_begin = blockIdx.z * p.k_chunk;
+  const int k_end = min(p.K, k_begin + p.k_chunk);
+  float acc[4][4] = {};
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      // A tile: when sak == 1 walk k fastest, else walk m fastest (coalescing)
+      int lk, lm;
+      if (p.sak == 1 && !p.convT) { lk = e & (BK - 1); lm = e >> 4; } else { lm = e & (BM - 1); lk = e >> 6; }
+      const int m = m0 + lm, kk = k0 + lk;
+      float av = 0.0f;
+      if (m < p.M && kk < k_end) {
+        if (p.convT) {
+          const int tap = m / p.conv_Cin, ci = m - tap * p.conv_Cin;
+          const int b = kk / p.conv_L, l = kk - b * p.conv_L + tap - p.conv_pad;
+          if (l >= 0 && l < p.conv_L) av = ld_any(p.A, ((long long)b * p.conv_L + l) * p.conv_Cin + ci, p.a_dt);
+        } else {
+          av = ld_any(p.A, (long long)m * p.sam + (long long)kk * p.sak, p.a_dt);
+        }
+      }
+      As[lk][lm] = av;
+      int bk, bn_;
+      if (p.sbk == 1) { bk = e & (BK - 1); bn_ = e >> 4; } else { bn_ = e & (BN - 1); bk = e >> 6; }
+      const int n = n0 + bn_, kb = k0 + bk;
+      float bv = 0.0f;
+      if (n < p.N && kb < k_end) bv = ld_any(p.B, (long long)n * p.sbn + (long long)kb * p.sbk, p.b_dt);
+      Bs[bk][bn_] = bv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float* c = p.C + (long long)m * p.ldc + n;
+      if (p.atomic) atomicAdd(c, acc[i][j]); else *c = acc[i][j];
+    }
+  }
+}
+
+// ================================ reductions / elementwise ==========================================
+// out[n] (+)= sum_m a[m,n] * (b ? b[m,n] : 1)
+__global__ void __launch_bounds__(256) colsum_kernel(const void* a, int a_dt, const void* b, int b_dt, long long M, int N,
+                                                     long long ld, int rows_per_block, float* out) {
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;  // 8 row lanes
+  float s = 0.0f;
+  if (n < N) {
+    for (long long m = r0 + rl; m < r1; m += 8) {
+      float v = ld_any(a, m * ld + n, a_dt);
+      if (b) v *= ld_any(b, m * ld + n, b_dt);
+      s += v;
+    }
+  }
+  __shared__ float sh[8][33];
+  sh[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && n < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x & 31];
+    atomicAdd(out + n, t);
+  }
+}
+
+__global__ void act_fwd_kernel(const void* x, int x_dt, void* y, int y_dt, int act, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    st_any(y, i, y_dt, apply_act(ld_any(x, i, x_dt), act));
+}
+
+// dx = dy * act'(x)   (x = pre-activation)
+__global__ void act_bwd_kernel(const void* dy, int dy_dt, const void* x, int x_dt, void* dx, int dx_dt, int act, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = ld_any(dy, i, dy_dt), v = ld_any(x, i, x_dt);
+    float d;
+    switch (act) {
+      case ACB_ACT_RELU: d = v > 0.0f ? 1.0f : 0.0f; break;
+      case ACB_ACT_GELU: d = gelu_erf_grad(v); break;
+      case ACB_ACT_TANH: { const float t = tanhf(v); d = 1.0f - t * t; break; }
+      case ACB_ACT_SIGMOID: { const float s = sigmoidf_(v); d = s * (1.0f - s); break; }
+      default: d = 1.0f;
+    }
+    st_any(dx, i, dx_dt, g * d);
+  }
+}
+
+// op 0: y = a + b; 1: y = a * b; 2: y = a + g[col]*b; 3: y = g[col]*a; 4: y = a*s0 + b*s1 (scalars); 5: y = a * g[0]
+__global__ void ew_kernel(const void* a, int a_dt, const void* b, int b_dt, const float* g, void* y, int y_dt, int op, int C,
+                          float s0, float s1, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float av = ld_any(a, i, a_dt);
+    const float bv = b ? ld_any(b, i, b_dt) : 0.0f;
+    float r;
+    switch (op) {
+      case 0: r = av + bv; break;
+      case 1: r = av * bv; break;
+      case 2: r = av + g[i % C] * bv; break;
+      case 3: r = g[i % C] * av; break;
+      case 5: r = av * g[0]; break;
+      default: r = av * s0 + bv * s1;
+    }
+    st_any(y, i, y_dt, r);
+  }
+}
+
+__global__ void copy2d_kernel(const void* src, int s_dt, long long lds, void* dst, int d_dt, long long ldd, long long rows, int cols) {
+  const long long n = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    st_any(dst, r * ldd + c, d_dt, ld_any(src, r * lds + c, s_dt));
+  }
+}
+
+__global__ void gather_cols_kernel(const float* X, int ldx, const int* cols, int n, float* Y, long long rows) {
+  const long long tot = rows * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / n;
+    Y[i] = X[r * ldx + cols[i - r * n]];
+  }
+}
+
+// dW[co,ci,tap] = G[(tap*Cin + ci)*Cout + co]   (G = output of the convT wgrad GEMM)
+__global__ void unpack_conv_wgrad_kernel(const float* G, float* dW, int Cout, int Cin, int k) {
+  const long long tot = (long long)Cout * Cin * k;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % k);
+    const long long t = i / k;
+    const int ci = (int)(t % Cin);
+    const int co = (int)(t / Cin);
+    dW[i] = G[((long long)tap * Cin + ci) * Cout + co];
+  }
+}
+// dgrad weights: out[ci*(k*Cout) + tap*Cout + co] = w[co, ci, k-1-tap]
+__global__ void pack_conv_dgrad_kernel(const float* w, void* out, int odt, int Cout, int Cin, int k) {
+  const long long tot = (long long)Cout * Cin * k;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const long long t = i / Cout;
+    const int tap = (int)(t % k);
+    const int ci = (int)(t / k);
+    st_any(out, i, odt, w[((long long)co * Cin + ci) * k + (k - 1 - tap)]);
+  }
+}
+
+// ================================ LayerNorm backward ================================================
+// warp per row; dx = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*w; dw += dy*xhat, db += dy (atomics per block)
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* x, int x_dt, const void* dy, int dy_dt, const float* w,
+                                                            void* dx, int dx_dt, float* dw, float* db, long long rows, int C,
+                                                            float eps, int rows_per_warp) {
+  extern __shared__ float shacc[];  // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) shacc[i] = 0.0f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long row0 = ((long long)blockIdx.x * nw + wid) * rows_per_warp;
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const long long row = row0 + rr;
+    if (row >= rows) break;
+    float s = 0.0f;
+    for (int c = lane; c < C; c += 32) s += ld_any(x, row * C + c, x_dt);
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.0f;
+    for (int c = lane; c < C; c += 32) {
+      const float d = ld_any(x, row * C + c, x_dt) - mean;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    float sg = 0.0f, sgx = 0.0f;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (ld_any(x, row * C + c, x_dt) - mean) * rstd;
+      const float g = ld_any(dy, row * C + c, dy_dt) * w[c];
+      sg += g;
+      sgx += g * xh;
+    }
+    sg = warp_sum(sg) / (float)C;
+    sgx = warp_sum(sgx) / (float)C;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (ld_any(x, row * C + c, x_dt) - mean) * rstd;
+      const float dyv = ld_any(dy, row * C + c, dy_dt);
+      st_any(dx, row * C + c, dx_dt, rstd * (dyv * w[c] - sg - xh * sgx));
+      atomicAdd(&shacc[c], dyv * xh);
+      atomicAdd(&shacc[C + c], dyv);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dw + i, shacc[i]);
+    atomicAdd(db + i, shacc[C + i]);
+  }
+}
+
+// ================================ attention backward ================================================
+// CTA per (sequence, head); Q, K, V, dO in shared memory; pass A (thread per query): lse, D, dQ;
+// pass B (thread per key): dK, dV.
+__device__ __forceinline__ unsigned attn_hash(unsigned long long seed, int bh, int i, int j) {
+  unsigned long long v = seed * 0x9E3779B97F4A7C15ULL + (((unsigned long long)bh << 26) | ((unsigned long long)i << 13) | (unsigned long long)j);
+  v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
+  return (unsigned)v;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128) attention_bwd_kernel(const void* qkv, int dt, const void* dout, int do_dt, const int* cu,
+                                                            int n_heads, float drop_p, unsigned long long seed, void* dqkv, int dq_dt) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int t0 = cu[b], n = cu[b + 1] - t0;
+  const int D = n_heads * DH;
+  float* Qs = sm;
+  float* Ks = Qs + (size_t)n * DH;
+  float* Vs = Ks + (size_t)n * DH;
+  float* Os = Vs + (size_t)n * DH;   // dO
+  float* lse = Os + (size_t)n * DH;  // [n]
+  float* Dr = lse + n;               // [n]
+  const float scale = rsqrtf((float)DH);
+  const float drop_inv = 1.0f / (1.0f - drop_p);
+  const unsigned drop_thr = (unsigned)(drop_p * 4294967296.0);
+  const int bh = b * n_heads + h;
+  for (int i = threadIdx.x; i < n * DH; i += blockDim.x) {
+    const int r = i / DH, c = i - r * DH;
+    const long long row = (long long)(t0 + r) * 3 * D;
+    Qs[i] = ld_any(qkv, row + h * DH + c, dt) * scale;
+    Ks[i] = ld_any(qkv, row + D + h * DH + c, dt);
+    Vs[i] = ld_any(qkv, row + 2 * D + h * DH + c, dt);
+    Os[i] = ld_any(dout, (long long)(t0 + r) * D + h * DH + c, do_dt);
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    float q[DH], go[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) { q[c] = Qs[r * DH + c]; go[c] = Os[r * DH + c]; }
+    float m = -INFINITY;
+    for (int j = 0; j < n; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) s = fmaf(q[c], Ks[j * DH + c], s);
+      m = fmaxf(m, s);
+    }
+    float l = 0.0f, dsum = 0.0f;
+    for (int j = 0; j < n; ++j) {
+      float s = 0.0f, dp = 0.0f;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) { s = fmaf(q[c], Ks[j * DH + c], s); dp = fmaf(go[c], Vs[j * DH + c], dp); }
+      const float e = expf(s - m);
+      l += e;
+      if (drop_p > 0.0f) dp = attn_hash(seed, bh, r, j) >= drop_thr ? dp * drop_inv : 0.0f;
+      dsum += e * dp;
+    }
+    const float L = m + logf(l);
+    const float Dv = dsum / l;  // sum_j P_ij dP_ij
+    lse[r] = L;
+    Dr[r] = Dv;
+    float dq[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) dq[c] = 0.0f;
+    for (int j = 0; j < n; ++j) {
+      float s = 0.0f, dp = 0.0f;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) { s = fmaf(q[c], Ks[j * DH + c], s); dp = fmaf(go[c], Vs[j * DH + c], dp); }
+      if (drop_p > 0.0f) dp = attn_hash(seed, bh, r, j) >= drop_thr ? dp * drop_inv : 0.0f;
+      const float ds = expf(s - L) * (dp - Dv);
+#pragma unroll
+      for (int c = 0; c < DH; ++c) dq[c] = fmaf(ds, Ks[j * DH + c], dq[c]);
+    }
+    const long long row = (long long)(t0 + r) * 3 * D + h * DH;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) st_any(dqkv, row + c, dq_dt, dq[c] * scale);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    float k[DH], v[DH], dk[DH], dv[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) { k[c] = Ks[j * DH + c]; v[c] = Vs[j * DH + c]; dk[c] = 0.0f; dv[c] = 0.0f; }
+    for (int r = 0; r < n; ++r) {
+      float s = 0.0f, dp = 0.0f;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) { s = fmaf(Qs[r * DH + c], k[c], s); dp = fmaf(Os[r * DH + c], v[c], dp); }
+      const float pr = expf(s - lse[r]);
+      float pd = pr;
+      if (drop_p > 0.0f) {
+        const bool keep = attn_hash(seed, bh, r, j) >= drop_thr;
+        dp = keep ? dp * drop_inv : 0.0f;
+        pd = keep ? pr * drop_inv : 0.0f;
+      }
+      const float ds = pr * (dp - Dr[r]);
+#pragma unroll
+      for (int c = 0; c < DH; ++c) { dv[c] = fmaf(pd, Os[r * DH + c], dv[c]); dk[c] = fmaf(ds, Qs[r * DH + c], dk[c]); }
+    }
+    const long long row = (long long)(t0 + j) * 3 * D + h * DH;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) {
+      st_any(dqkv, row + D + c, dq_dt, dk[c]);  // Qs already carries the 1/sqrt(dh) factor
+      st_any(dqkv, row + 2 * D + c, dq_dt, dv[c]);
+    }
+  }
+}
+
+// ================================ photometry embedding backward =====================================
+// grads[0:7D] d in_proj.weight (D,7) | [7D:8D] d in_proj.bias | [8D] dw0 | [8D+1] db0 | [8D+2 : 9D+1] dw (D-1)
+// | [9D+1 : 10D] db (D-1) | [10D : 11D] d cls_tok
+__global__ void __launch_bounds__(128) photo_embed_bwd_kernel(const float* x, const int* src, int T, int D, const void* dh, int dh_dt,
+                                                              const float* w, const float* bb, int tok_per_block, float* grads) {
+  const int c = threadIdx.x;  // channel
+  const int t0 = blockIdx.x * tok_per_block, t1 = min(T, t0 + tok_per_block);
+  if (c >= D) return;
+  float gw[7] = {}, gb = 0.f, g0 = 0.f, g1 = 0.f, gc = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    const float g = ld_any(dh, (long long)t * D + c, dh_dt);
+    const int s = src[t];
+    if (s < 0) { gc += g; continue; }
+    const float* xr = x + (long long)s * 7;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) gw[j] = fmaf(g, xr[j], gw[j]);
+    gb += g;
+    const float tt = xr[0];
+    if (c == 0) { g0 += g * tt; g1 += g; }
+    else { const float cs = cosf(tt * w[c - 1] + bb[c - 1]); g0 += g * cs * tt; g1 += g * cs; }
+  }
+#pragma unroll
+  for (int j = 0; j < 7; ++j) atomicAdd(grads + c * 7 + j, gw[j]);
+  atomicAdd(grads + 7 * D + c, gb);
+  if (c == 0) { atomicAdd(grads + 8 * D, g0); atomicAdd(grads + 8 * D + 1, g1); }
+  else { atomicAdd(grads + 8 * D + 2 + (c - 1), g0); atomicAdd(grads + 9 * D + 1 + (c - 1), g1); }
+  atomicAdd(grads + 10 * D + c, gc);
+}
+
+__global__ void scatter_cls_kernel(const float* dcls, const int* cu, int B, int D, void* dh, int dh_dt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * D) return;
+  const int b = (int)(i / D), c = (int)(i % D);
+  st_any(dh, (long long)cu[b] * D + c, dh_dt, dcls[i]);
+}
+
+// ================================ depthwise 7x7 (no LN): fwd / bwd-data / bwd-weight ==================
+// flip = 0: y = conv(x, w) + bias ; flip = 1: y = conv(x, flipped w)  (gradient w.r.t. the input)
+__global__ void __launch_bounds__(256) dwconv7_kernel(const void* x, int x_dt, const float* w, const float* bias, int flip, void* y,
+                                                      int y_dt, int B, int H, int W, int C) {
+  const long long tot = (long long)B * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int ox = (int)(t % W);
+    t /= W;
+    const int oy = (int)(t % H);
+    const long long b = t / H;
+    float acc = bias ? bias[c] : 0.0f;
+    for (int ky = 0; ky < 7; ++ky) {
+      const int iy = oy + ky - 3;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < 7; ++kx) {
+        const int ix = ox + kx - 3;
+        if (ix < 0 || ix >= W) continue;
+        const float wv = flip ? w[c * 49 + (6 - ky) * 7 + (6 - kx)] : w[c * 49 + ky * 7 + kx];
+        acc = fmaf(ld_any(x, ((b * H + iy) * W + ix) * C + c, x_dt), wv, acc);
+      }
+    }
+    st_any(y, i, y_dt, acc);
+  }
+}
+
+// dw[c,ky,kx] += sum_{b,y,x} dy[b,y,x,c] * x[b,y+ky-3,x+kx-3,c]; db[c] += sum dy.  CTA per image chunk, thread per channel.
+__global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const void* x, int x_dt, const void* dy, int dy_dt, int B, int H, int W, int C,
+                                                            int img_per_block, float* dw, float* db) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc[49];
+#pragma unroll
+  for (int j = 0; j < 49; ++j) acc[j] = 0.0f;
+  float sb = 0.0f;
+  const int b0 = blockIdx.x * img_per_block, b1 = min(B, b0 + img_per_block);
+  for (int b = b0; b < b1; ++b) {
+    for (int oy = 0; oy < H; ++oy) {
+      for (int ox = 0; ox < W; ++ox) {
+        const float g = ld_any(dy, (((long long)b * H + oy) * W + ox) * C + c, dy_dt);
+        sb += g;
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+          const int iy = oy + ky - 3;
+          if (iy < 0 || iy >= H) continue;
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx) {
+            const int ix = ox + kx - 3;
+            if (ix < 0 || ix >= W) continue;
+            acc[ky * 7 + kx] = fmaf(g, ld_any(x, (((long long)b * H + iy) * W + ix) * C + c, x_dt), acc[ky * 7 + kx]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 49; ++j) atomicAdd(dw + c * 49 + j, acc[j]);
+  atomicAdd(db + c, sb);
+}
+
+// 2x2/stride-2 patch gather (fwd) and its adjoint (bwd: rows/cols dropped by the floor get zero)
+__global__ void patch2_kernel(void* x, int x_dt, void* p, int p_dt, int B, int H, int W, int C, int adjoint) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long tot = (long long)B * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int ix = (int)(t % W);
+    t /= W;
+    const int iy = (int)(t % H);
+    const long long b = t / H;
+    const bool inside = iy < 2 * Ho && ix < 2 * Wo;
+    const long long pi = ((b * Ho + (iy >> 1)) * Wo + (ix >> 1)) * (4LL * C) + ((iy & 1) * 2 + (ix & 1)) * C + c;
+    if (!adjoint) {
+      if (inside) st_any(p, pi, p_dt, ld_any(x, i, x_dt));
+    } else {
+      st_any(x, i, x_dt, inside ? ld_any(p, pi, p_dt) : 0.0f);  // here x = dx (out), p = dpatches (in)
+    }
+  }
+}
+
+// mean over HW: y[b,c] = mean_i x[b,i,c] (fwd) ; dx[b,i,c] = dy[b,c]/HW (bwd)
+__global__ void gap_kernel(const void* x, int x_dt, float* y, int B, int HW, int C, int bwd, void* dx, int dx_dt) {
+  const long long tot = (long long)B * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long b = i / C;
+    if (!bwd) {
+      float s = 0.0f;
+      for (int k = 0; k < HW; ++k) s += ld_any(x, (b * HW + k) * C + c, x_dt);
+      y[i] = s / (float)HW;
+    } else {
+      const float g = y[i] / (float)HW;
+      for (int k = 0; k < HW; ++k) st_any(dx, (b * HW + k) * C + c, dx_dt, g);
+    }
+  }
+}
+
+// ================================ pooling backward ==================================================
+// window = 4: MaxPool1d(4) over L of [B,L,C] (grad to the first max of each window, zero elsewhere incl. the floor tail)
+// window = 0: global max over L
+__global__ void maxpool_bwd_kernel(const void* x, int x_dt, const void* dy, int dy_dt, void* dx, int dx_dt, int B, int L, int C, int window) {
+  const int Lo = window ? L / window : 1;
+  const int win = window ? window : L;
+  const long long tot = (long long)B * Lo * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long t = i / C;
+    const int lo = (int)(t % Lo);
+    const long long b = t / Lo;
+    const long long base = (b * L + (long long)lo * win) * C + c;
+    float m = -INFINITY;
+    int arg = 0;
+    for (int k = 0; k < win; ++k) {
+      const float v = ld_any(x, base + (long long)k * C, x_dt);
+      if (v > m) { m = v; arg = k; }
+    }
+    const float g = ld_any(dy, i, dy_dt);
+    for (int k = 0; k < win; ++k) st_any(dx, base + (long long)k * C, dx_dt, k == arg ? g : 0.0f);
+    if (window && lo == Lo - 1) {
+      for (int l = Lo * win; l < L; ++l) st_any(dx, (b * L + l) * C + c, dx_dt, 0.0f);
+    }
+  }
+}
+
+// ================================ MoE / L2 norm / losses / dropout ==================================
+__global__ void moe_combine_bwd_kernel(const float* gate, const float* eo, const float* dout, float* dgate, float* deo, int B, int E, int C) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B) return;
+  int i0 = 0;
+  float v0 = gate[(long long)r * E];
+  for (int e = 1; e < E; ++e) { const float v = gate[(long long)r * E + e]; if (v > v0) { v0 = v; i0 = e; } }
+  int i1 = -1;
+  float v1 = -INFINITY;
+  for (int e = 0; e < E; ++e) { if (e == i0) continue; const float v = gate[(long long)r * E + e]; if (v > v1) { v1 = v; i1 = e; } }
+  for (int e = 0; e < E; ++e) {
+    const bool sel = (e == i0) || (e == i1);
+    const float wv = e == i0 ? v0 : v1;
+    float dg = 0.0f;
+    for (int c = 0; c < C; ++c) {
+      const float go = dout[(long long)r * C + c];
+      const long long idx = ((long long)r * E + e) * C + c;
+      if (sel) dg = fmaf(go, eo[idx], dg);
+      deo[idx] = sel ? wv * go : 0.0f;
+    }
+    dgate[(long long)r * E + e] = sel ? dg : 0.0f;
+  }
+}
+
+// y = x / ||x||_2 per row (fwd) ; dx = (dy - y * (y.dy)) / ||x||  (bwd)
+__global__ void l2norm_kernel(const float* x, const float* dy, float* out, int rows, int C, int bwd) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float ss = 0.0f;
+  for (int c = lane; c < C; c += 32) { const float v = x[(long long)r * C + c]; ss += v * v; }
+  const float nrm = sqrtf(warp_sum(ss));
+  if (!bwd) {
+    for (int c = lane; c < C; c += 32) out[(long long)r * C + c] = x[(long long)r * C + c] / nrm;
+  } else {
+    float dot = 0.0f;
+    for (int c = lane; c < C; c += 32) dot += (x[(long long)r * C + c] / nrm) * dy[(long long)r * C + c];
+    dot = warp_sum(dot);
+    for (int c = lane; c < C; c += 32) out[(long long)r * C + c] = (dy[(long long)r * C + c] - (x[(long long)r * C + c] / nrm) * dot) / nrm;
+  }
+}
+
+// focal loss (gamma, mean reduction) with integer labels, or soft-target cross entropy (targets [B,C], mean):
+// loss_out[0] += per-row loss / B ; dlogits = d(mean loss)/d logits
+__global__ void loss_kernel(const float* logits, const long long* labels, const float* soft, float gamma, int B, int C, float* loss_out,
+                            float* dlogits) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  float lr = 0.0f;
+  if (r < B) {
+    const float* z = logits + (long long)r * C;
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, z[c]);
+    float s = 0.0f;
+    for (int c = 0; c < C; ++c) s += expf(z[c] - m);
+    const float lz = m + logf(s);
+    if (labels) {
+      const int y = (int)labels[r];
+      const float logp = z[y] - lz, p = expf(logp);
+      const float om = 1.0f - p;
+      const float fw = powf(om, gamma);
+      lr = -fw * logp;
+      // d/dlogp [-(1-p)^g logp] = g (1-p)^(g-1) p logp - (1-p)^g
+      const float dldlogp = gamma * powf(om, gamma - 1.0f) * p * logp - fw;
+      for (int c = 0; c < C; ++c) {
+        const float pc = expf(z[c] - lz);
+        dlogits[(long long)r * C + c] = dldlogp * ((c == y ? 1.0f : 0.0f) - pc) / (float)B;
+      }
+    } else {
+      const float* t = soft + (long long)r * C;
+      float ts = 0.0f;
+      for (int c = 0; c < C; ++c) { lr -= t[c] * (z[c] - lz); ts += t[c]; }
+      for (int c = 0; c < C; ++c) dlogits[(long long)r * C + c] = (expf(z[c] - lz) * ts - t[c]) / (float)B;
+    }
+    lr /= (float)B;
+  }
+  lr = warp_sum(lr);
+  if ((threadIdx.x & 31) == 0) atomicAdd(loss_out, lr);
+}
+
+__device__ __forceinline__ unsigned hash32(unsigned long long v) {
+  v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
+  return (unsigned)v;
+}
+// y = keep ? x / (1-p) : 0, keep decided by a counter-based hash of (seed, index); the same call with dy gives dx
+__global__ void dropout_kernel(const void* x, int x_dt, void* y, int y_dt, float p, unsigned long long seed, long long n) {
+  const float inv = 1.0f / (1.0f - p);
+  const unsigned thr = (unsigned)(p * 4294967296.0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const bool keep = hash32(seed * 0x9E3779B97F4A7C15ULL + (unsigned long long)i) >= thr;
+    st_any(y, i, y_dt, keep ? ld_any(x, i, x_dt) * inv : 0.0f);
+  }
+}
+
+// sum of squares (grad-norm) : out[0] += sum x^2
+__global__ void sumsq_kernel(const float* x, long long n, float* out) {
+  float s = 0.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += x[i] * x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+}  // namespace
+
+#define LAUNCHED(n)     \
+  ACB_LAUNCH_CHECK();   \
+  acb_count_launch(n);  \
+  return ACB_OK
+
+extern "C" {
+
+int acb_gemm_ex(const void* A, int a_dtype, const void* B, int b_dtype, float* C, int M, int N, int K, long long sam, long long sak,
+                long long sbn, long long sbk, int ldc, int convT, int conv_L, int conv_Cin, int conv_pad, int splits, int accumulate,
+                void* stream) {
+  ACB_CHECK(A && B && C && M > 0 && N > 0 && K > 0 && splits >= 1, "acb_gemm_ex: bad arguments");
+  GemmExArgs p{A, B, C, a_dtype, b_dtype, M, N, K, sam, sak, sbn, sbk, ldc, convT, conv_L, conv_Cin, conv_pad, 0, 0};
+  int chunk = (K + splits - 1) / splits;
+  chunk = ((chunk + 15) / 16) * 16;
+  splits = (K + chunk - 1) / chunk;
+  p.k_chunk = chunk;
+  p.atomic = (splits > 1 || accumulate) ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (splits > 1 && !accumulate) ACB_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, st));
+  dim3 grid(cdiv(M, 64), cdiv(N, 64), splits);
+  ACB_CHECK(grid.y <= 65535 && grid.z <= 65535, "acb_gemm_ex: grid too large");
+  gemm_ex_kernel<<<grid, 256, 0, st>>>(p);
+  LAUNCHED(1);
+}
+
+int acb_colsum(const void* a, int a_dtype, const void* b, int b_dtype, long long M, int N, long long ld, float* out, int accumulate,
+               void* stream) {
+  if (ld <= 0) ld = N;
+  ACB_CHECK(a && out && M > 0 && N > 0, "acb_colsum: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) ACB_CUDA(cudaMemsetAsync(out, 0, (size_t)N * 4, st));
+  const int rpb = 1024;
+  dim3 grid(cdiv(N, 32), cdiv(M, rpb));
+  colsum_kernel<<<grid, 256, 0, st>>>(a, a_dtype, b, b_dtype, M, N, ld, rpb, out);
+  LAUNCHED(1);
+}
+
+int acb_act_fwd(const void* x, int x_dtype, void* y, int y_dtype, int act, long long n, void* stream) {
+  ACB_CHECK(x && y && n >= 0, "acb_act_fwd: bad arguments");
+  if (n == 0) return ACB_OK;
+  act_fwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, y, y_dtype, act, n);
+  LAUNCHED(1);
+}
+
+int acb_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx, int dx_dtype, int act, long long n, void* stream) {
+  ACB_CHECK(dy && x && dx && n >= 0, "acb_act_bwd: bad arguments");
+  if (n == 0) return ACB_OK;
+  act_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, x, x_dtype, dx, dx_dtype, act, n);
+  LAUNCHED(1);
+}
+
+int acb_ew(const void* a, int a_dtype, const void* b, int b_dtype, const float* g, void* y, int y_dtype, int op, int C, float s0, float s1,
+           long long n, void* stream) {
+  ACB_CHECK(a && y && n >= 0 && C > 0, "acb_ew: bad arguments");
+  if (n == 0) return ACB_OK;
+  ew_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(a, a_dtype, b, b_dtype, g, y, y_dtype, op, C, s0, s1, n);
+  LAUNCHED(1);
+}
+
+int acb_copy2d(const void* src, int s_dtype, long long lds, void* dst, int d_dtype, long long ldd, long long rows, int cols, void* stream) {
+  ACB_CHECK(src && dst && rows >= 0 && cols > 0, "acb_copy2d: bad arguments");
+  if (rows == 0) return ACB_OK;
+  copy2d_kernel<<<grid_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(src, s_dtype, lds, dst, d_dtype, ldd, rows, cols);
+  LAUNCHED(1);
+}
+
+int acb_unpack_conv_wgrad(const float* G, float* dW, int Cout, int Cin, int k, void* stream) {
+  ACB_CHECK(G && dW && Cout > 0 && Cin > 0 && k > 0, "acb_unpack_conv_wgrad: bad arguments");
+  unpack_conv_wgrad_kernel<<<grid_for((long long)Cout * Cin * k), 256, 0, (cudaStream_t)stream>>>(G, dW, Cout, Cin, k);
+  LAUNCHED(1);
+}
+
+int acb_pack_conv_dgrad_weight(const float* w, void* out, int out_dtype, int Cout, int Cin, int k, void* stream) {
+  ACB_CHECK(w && out && Cout > 0 && Cin > 0 && k > 0, "acb_pack_conv_dgrad_weight: bad arguments");
+  pack_conv_dgrad_kernel<<<grid_for((long long)Cout * Cin * k), 256, 0, (cudaStream_t)stream>>>(w, out, out_dtype, Cout, Cin, k);
+  LAUNCHED(1);
+}
+
+int acb_gather_cols(const float* X, int ldx, const int* cols, int n, float* Y, long long rows, void* stream) {
+  ACB_CHECK(X && cols && Y && n > 0 && rows >= 0, "acb_gather_cols: bad arguments");
+  if (rows == 0) return ACB_OK;
+  gather_cols_kernel<<<grid_for(rows * n), 256, 0, (cudaStream_t)stream>>>(X, ldx, cols, n, Y, rows);
+  LAUNCHED(1);
+}
+
+int acb_layernorm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* w, void* dx, int dx_dtype, float* dw,
+                      float* db, long long rows, int C, float eps, void* stream) {
+  ACB_CHECK(x && dy && w && dx && dw && db && rows >= 0 && C > 0 && C <= 6000, "acb_layernorm_bwd: bad arguments");
+  if (rows == 0) return ACB_OK;
+  const int rpw = rows > (1 << 16) ? 16 : 1;
+  const long long warps = (rows + rpw - 1) / rpw;
+  layernorm_bwd_kernel<<<(unsigned)((warps + 7) / 8), 256, (size_t)2 * C * 4, (cudaStream_t)stream>>>(x, x_dtype, dy, dy_dtype, w, dx, dx_dtype,
+                                                                                                    dw, db, rows, C, eps, rpw);
+  LAUNCHED(1);
+}
+
+int acb_attention_varlen_bwd(const void* qkv, int dtype, const void* dout, int dout_dtype, const int* cu_seqlens, int B, int n_heads, int dh,
+                             int max_seqlen, float drop_p, long long seed, void* dqkv, int dqkv_dtype, void* stream) {
+  ACB_CHECK(qkv && dout && cu_seqlens && dqkv && B > 0 && dh == 16, "acb_attention_varlen_bwd: bad arguments (dh must be 16)");
+  const size_t smem = ((size_t)max_seqlen * dh * 4 + 2 * (size_t)max_seqlen) * 4;
+  ACB_CHECK(smem <= 200 * 1024, "acb_attention_varlen_bwd: max_seqlen %d too long", max_seqlen);
+  auto k = attention_bwd_kernel<16>;
+  ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  k<<<dim3(B, n_heads), 128, smem, (cudaStream_t)stream>>>(qkv, dtype, dout, dout_dtype, cu_seqlens, n_heads, drop_p, (unsigned long long)seed, dqkv, dqkv_dtype);
+  LAUNCHED(1);
+}
+
+int acb_photo_embed_bwd(const float* x, const int* src_idx, int T, int D, const void* dh, int dh_dtype, const float* w, const float* b,
+                        float* grads, void* stream) {
+  ACB_CHECK(x && src_idx && dh && w && b && grads && T >= 0 && D > 1 && D <= 128, "acb_photo_embed_bwd: bad arguments (D <= 128)");
+  cudaStream_t st = (cudaStream_t)stream;
+  ACB_CUDA(cudaMemsetAsync(grads, 0, (size_t)11 * D * 4, st));
+  if (T == 0) return ACB_OK;
+  const int tpb = 256;
+  photo_embed_bwd_kernel<<<cdiv(T, tpb), 128, 0, st>>>(x, src_idx, T, D, dh, dh_dtype, w, b, tpb, grads);
+  LAUNCHED(1);
+}
+
+int acb_scatter_cls(const float* dcls, const int* cu_seqlens, int B, int D, void* dh, int dh_dtype, long long total_tokens, void* stream) {
+  ACB_CHECK(dcls && cu_seqlens && dh && B > 0 && D > 0, "acb_scatter_cls: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ACB_CUDA(cudaMemsetAsync(dh, 0, (size_t)total_tokens * D * (dh_dtype == ACB_F32 ? 4 : 2), st));
+  scatter_cls_kernel<<<cdiv((long long)B * D, 256), 256, 0, st>>>(dcls, cu_seqlens, B, D, dh, dh_dtype);
+  LAUNCHED(1);
+}
+
+int acb_dwconv7(const void* x, int x_dtype, const float* w, const float* bias, int flip, void* y, int y_dtype, int B, int H, int W, int C,
+                void* stream) {
+  ACB_CHECK(x && w && y && B > 0 && H > 0 && W > 0 && C > 0, "acb_dwconv7: bad arguments");
+  dwconv7_kernel<<<grid_for((long long)B * H * W * C), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, w, bias, flip, y, y_dtype, B, H, W, C);
+  LAUNCHED(1);
+}
+
+int acb_dwconv7_wgrad(const void* x, int x_dtype, const void* dy, int dy_dtype, int B, int H, int W, int C, float* dw, float* db, int accumulate,
+                      void* stream) {
+  ACB_CHECK(x && dy && dw && db && B > 0 && C > 0, "acb_dwconv7_wgrad: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) {
+    ACB_CUDA(cudaMemsetAsync(dw, 0, (size_t)C * 49 * 4, st));
+    ACB_CUDA(cudaMemsetAsync(db, 0, (size_t)C * 4, st));
+  }
+  const int ipb = B > 2048 ? 8 : (B > 256 ? 2 : 1);
+  const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
+  dwconv7_wgrad_kernel<<<dim3(cdiv(B, ipb), cdiv(C, threads)), threads, 0, st>>>(x, x_dtype, dy, dy_dtype, B, H, W, C, ipb, dw, db);
+  LAUNCHED(1);
+}
+
+int acb_patch2(const void* x, int x_dtype, void* p, int p_dtype, int B, int H, int W, int C, int adjoint, void* stream) {
+  ACB_CHECK(x && p && B > 0 && H >= 2 && W >= 2 && C > 0, "acb_patch2: bad arguments");
+  patch2_kernel<<<grid_for((long long)B * H * W * C), 256, 0, (cudaStream_t)stream>>>(const_cast<void*>(x), x_dtype, p, p_dtype, B, H, W, C, adjoint);
+  LAUNCHED(1);
+}
+
+int acb_gap(const void* x, int x_dtype, float* y, int B, int HW, int C, int bwd, void* dx, int dx_dtype, void* stream) {
+  ACB_CHECK(y && B > 0 && HW > 0 && C > 0 && (bwd ? dx != nullptr : x != nullptr), "acb_gap: bad arguments");
+  gap_kernel<<<grid_for((long long)B * C), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, y, B, HW, C, bwd, dx, dx_dtype);
+  LAUNCHED(1);
+}
+
+int acb_maxpool_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, void* dx, int dx_dtype, int B, int L, int C, int window,
+                    void* stream) {
+  ACB_CHECK(x && dy && dx && B > 0 && L > 0 && C > 0 && (window == 0 || window == 4), "acb_maxpool_bwd: bad arguments");
+  const int Lo = window ? L / window : 1;
+  maxpool_bwd_kernel<<<grid_for((long long)B * Lo * C), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, dy, dy_dtype, dx, dx_dtype, B, L, C, window);
+  LAUNCHED(1);
+}
+
+int acb_moe_combine_bwd(const float* gate, const float* expert_out, const float* dout, float* dgate, float* dexpert_out, int B, int E, int C,
+                        void* stream) {
+  ACB_CHECK(gate && expert_out && dout && dgate && dexpert_out && B > 0 && E >= 2 && C > 0, "acb_moe_combine_bwd: bad arguments");
+  moe_combine_bwd_kernel<<<cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(gate, expert_out, dout, dgate, dexpert_out, B, E, C);
+  LAUNCHED(1);
+}
+
+int acb_l2norm(const float* x, const float* dy, float* out, int rows, int C, int bwd, void* stream) {
+  ACB_CHECK(x && out && rows > 0 && C > 0 && (!bwd || dy), "acb_l2norm: bad arguments");
+  l2norm_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, dy, out, rows, C, bwd);
+  LAUNCHED(1);
+}
+
+int acb_loss_fwd_bwd(const float* logits, const long long* labels, const float* soft_targets, float gamma, int B, int C, float* loss_out,
+                     float* dlogits, void* stream) {
+  ACB_CHECK(logits && loss_out && dlogits && B > 0 && C > 0 && ((labels != nullptr) != (soft_targets != nullptr)),
+            "acb_loss_fwd_bwd: pass exactly one of labels (focal) or soft_targets (cross entropy)");
+  cudaStream_t st = (cudaStream_t)stream;
+  ACB_CUDA(cudaMemsetAsync(loss_out, 0, 4, st));
+  loss_kernel<<<cdiv(B, 128), 128, 0, st>>>(logits, labels, soft_targets, gamma, B, C, loss_out, dlogits);
+  LAUNCHED(1);
+}
+
+int acb_dropout(const void* x, int x_dtype, void* y, int y_dtype, float p, long long seed, long long n, void* stream) {
+  ACB_CHECK(x && y && n >= 0 && p >= 0.0f && p < 1.0f, "acb_dropout: bad arguments");
+  if (n == 0) return ACB_OK;
+  dropout_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, y, y_dtype, p, (unsigned long long)seed, n);
+  LAUNCHED(1);
+}
+
+int acb_sumsq(const float* x, long long n, float* out, int accumulate, void* stream) {
+  ACB_CHECK(x && out && n >= 0, "acb_sumsq: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) ACB_CUDA(cudaMemsetAsync(out, 0, 4, st));
+  if (n == 0) return ACB_OK;
+  sumsq_kernel<<<grid_for(n), 256, 0, st>>>(x, n, out);
+  LAUNCHED(1);
+}
+
+}  // extern "C"

@@ -92,9 +92,16 @@ __global__ void __launch_bounds__(256) photo_embed_kernel(const float* __restric
 // ---- attention -----------------------------------------------------------------------------------
 // One CTA per (sequence, head). K/V of the head live in shared memory (fp32); every thread owns
 // query rows and runs an exact two-pass softmax (max, then exp/sum/PV) against broadcast K/V reads.
+__device__ __forceinline__ unsigned attn_hash(unsigned long long seed, int bh, int i, int j) {
+  unsigned long long v = seed * 0x9E3779B97F4A7C15ULL + (((unsigned long long)bh << 26) | ((unsigned long long)i << 13) | (unsigned long long)j);
+  v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
+  return (unsigned)v;
+}
+
 template <typename T, int DH>
 __global__ void __launch_bounds__(128) attention_varlen_kernel(const T* __restrict__ qkv, const int* __restrict__ cu,
-                                                               int n_heads, T* __restrict__ out) {
+                                                               int n_heads, float drop_p, unsigned long long seed,
+                                                               T* __restrict__ out) {
   extern __shared__ float smem[];
   const int b = blockIdx.x, h = blockIdx.y;
   const int t0 = cu[b], n = cu[b + 1] - t0;
@@ -109,6 +116,9 @@ __global__ void __launch_bounds__(128) attention_varlen_kernel(const T* __restri
   }
   __syncthreads();
   const float scale = rsqrtf((float)DH);
+  const float drop_inv = 1.0f / (1.0f - drop_p);
+  const unsigned drop_thr = (unsigned)(drop_p * 4294967296.0);
+  const int bh = b * n_heads + h;
   for (int r = threadIdx.x; r < n; r += blockDim.x) {
     const T* qrow = qkv + (long long)(t0 + r) * 3 * D + h * DH;
     float q[DH];
@@ -143,8 +153,9 @@ __global__ void __launch_bounds__(128) attention_varlen_kernel(const T* __restri
         s = fmaf(q[c4 * 4 + 2], k4.z, s);
         s = fmaf(q[c4 * 4 + 3], k4.w, s);
       }
-      const float p = expf(s - m);
+      float p = expf(s - m);
       l += p;
+      if (drop_p > 0.0f) p = attn_hash(seed, bh, r, j) >= drop_thr ? p * drop_inv : 0.0f;
 #pragma unroll
       for (int c4 = 0; c4 < DH / 4; ++c4) {
         const float4 v4 = vp[c4];
@@ -204,9 +215,10 @@ int acb_photo_embed(const float* x, const int* src_idx, const int* total_dev, in
 }
 
 int acb_attention_varlen(const void* qkv, int dtype, const int* cu_seqlens, int B, int n_heads, int dh, int max_seqlen,
-                         void* out, void* stream) {
+                         float drop_p, long long seed, void* out, void* stream) {
   ACB_CHECK(qkv && cu_seqlens && out && B > 0 && n_heads > 0, "acb_attention_varlen: bad arguments");
   ACB_CHECK(dh == 16, "acb_attention_varlen: head dim %d unsupported (16 only)", dh);
+  ACB_CHECK(drop_p >= 0.0f && drop_p < 1.0f && max_seqlen < 8192, "acb_attention_varlen: bad dropout / sequence length");
   const size_t smem = (size_t)max_seqlen * dh * 2 * sizeof(float);
   ACB_CHECK(smem <= 200 * 1024, "acb_attention_varlen: max_seqlen %d too long for the shared-memory K/V tile", max_seqlen);
   cudaStream_t st = (cudaStream_t)stream;
@@ -214,11 +226,11 @@ int acb_attention_varlen(const void* qkv, int dtype, const int* cu_seqlens, int 
   if (dtype == ACB_F32) {
     auto k = attention_varlen_kernel<float, 16>;
     if (smem > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 128, smem, st>>>((const float*)qkv, cu_seqlens, n_heads, (float*)out);
+    k<<<grid, 128, smem, st>>>((const float*)qkv, cu_seqlens, n_heads, drop_p, (unsigned long long)seed, (float*)out);
   } else {
     auto k = attention_varlen_kernel<bf16, 16>;
     if (smem > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 128, smem, st>>>((const bf16*)qkv, cu_seqlens, n_heads, (bf16*)out);
+    k<<<grid, 128, smem, st>>>((const bf16*)qkv, cu_seqlens, n_heads, drop_p, (unsigned long long)seed, (bf16*)out);
   }
   ACB_LAUNCH_CHECK();
   acb_count_launch();

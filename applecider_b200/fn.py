@@ -1,0 +1,483 @@
+"""Differentiable ops: torch.autograd.Function wrappers whose forward AND backward call the C-ABI kernels.
+
+torch autograd is only the tape; no torch arithmetic runs on activations here.  Conventions as in ops.py:
+activations are [rows, C] CUDA tensors (fp32 or bf16), parameters fp32.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+from ._lib import call, dtype_tag
+
+F32 = torch.float32
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _zeros(shape, dev):
+    return torch.zeros(shape, dtype=F32, device=dev)
+
+
+def gemm_ex(A, a_dt, B, b_dt, M, N, K, sam, sak, sbn, sbk, dev, convT=None, splits=1, out=None, accumulate=False):
+    """C[m,n] (+)= sum_k A(m,k) B(n,k) with element strides; returns fp32 [M,N]."""
+    if out is None:
+        out = torch.empty((M, N), dtype=F32, device=dev)
+    cv = convT or (0, 0, 0)
+    call("acb_gemm_ex", A, a_dt, B, b_dt, out, M, N, K, sam, sak, sbn, sbk, out.shape[-1], int(convT is not None), cv[0], cv[1], cv[2],
+         splits, int(accumulate))
+    return out
+
+
+def _splits(k):
+    return max(1, min(128, k // 2048))
+
+
+def colsum(a, b=None, M=None, N=None, ld=0, a_dt=None, dev=None):
+    """out[n] = sum_m a[m*ld+n] (* b[m*ld+n]); a may be a raw device pointer when M, N, ld, a_dt, dev are given."""
+    if M is None:
+        M, N = a.shape
+    out = torch.empty(N, dtype=F32, device=(dev if dev is not None else a.device))
+    call("acb_colsum", a, (a_dt if a_dt is not None else dtype_tag(a)), b, (dtype_tag(b) if b is not None else 0), M, N, ld, out, 0)
+    return out
+
+
+def ew(a, b, op, g=None, C=1, s0=1.0, s1=1.0, out_dtype=None):
+    y = torch.empty(a.shape, dtype=(out_dtype or a.dtype), device=a.device)
+    call("acb_ew", a, dtype_tag(a), b, (dtype_tag(b) if b is not None else 0), g, y, dtype_tag(y), op, C, s0, s1, a.numel())
+    return y
+
+
+def cast_to(x, dtype):
+    return ops.cast(_c(x), dtype)
+
+
+# ------------------------------------------------------------------------------------------------------
+class Linear(Function):
+    """y = x W^T + b  (x [M,K] fp32|bf16, W [N,K] fp32 parameter, b [N] or None); output dtype = x dtype
+    unless out_dtype is given."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, wcast, out_dtype):
+        x = _c(x)
+        w_use = W if x.dtype == F32 else wcast
+        y = ops.gemm(x, w_use, b, out_dtype=out_dtype)
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = _c(dy)
+        M, K = x.shape
+        N = W.shape[0]
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_ex(dy, dtype_tag(dy), W, 0, M, K, N, N, 1, 1, K, x.device)
+            dx = cast_to(dx, x.dtype)
+        if ctx.needs_input_grad[1]:
+            dW = gemm_ex(dy, dtype_tag(dy), x, dtype_tag(x), N, K, M, 1, N, 1, K, x.device, splits=_splits(M))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy)
+        return dx, dW, db, None, None
+
+
+def linear(x, W, b=None, wcast=None, out_dtype=None):
+    if x.dtype != F32 and wcast is None:
+        wcast = ops.cast(W.detach(), x.dtype)
+    return Linear.apply(x, W, b, wcast, out_dtype)
+
+
+class Act(Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        x = _c(x)
+        y = torch.empty_like(x)
+        call("acb_act_fwd", x, dtype_tag(x), y, dtype_tag(y), act, x.numel())
+        ctx.save_for_backward(x)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(x)
+        call("acb_act_bwd", dy, dtype_tag(dy), x, dtype_tag(x), dx, dtype_tag(dx), ctx.act, x.numel())
+        return dx, None
+
+
+def act(x, kind):
+    return Act.apply(x, kind)
+
+
+class LayerNorm(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps, out_dtype):
+        x = _c(x)
+        y = ops.layernorm(x, w, b, eps, out_dtype=out_dtype)
+        ctx.save_for_backward(x, w)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _c(dy)
+        C = x.shape[-1]
+        rows = x.numel() // C
+        dx = torch.empty_like(x)
+        dw, db = _zeros(C, x.device), _zeros(C, x.device)
+        call("acb_layernorm_bwd", x, dtype_tag(x), dy, dtype_tag(dy), w, dx, dtype_tag(dx), dw, db, rows, C, ctx.eps)
+        return dx, dw, db, None, None
+
+
+def layernorm(x, w, b, eps, out_dtype=None):
+    return LayerNorm.apply(x, w, b, eps, out_dtype)
+
+
+class Add(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return ew(_c(a), _c(b), 0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add(a, b):
+    return Add.apply(a, b)
+
+
+class Mul(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _c(a), _c(b)
+        ctx.save_for_backward(a, b)
+        return ew(a, b, 1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, b = ctx.saved_tensors
+        dy = _c(dy)
+        return ew(dy, b, 1, out_dtype=a.dtype), ew(dy, a, 1, out_dtype=b.dtype)
+
+
+def mul(a, b):
+    return Mul.apply(a, b)
+
+
+class ScaleAdd(Function):
+    """y = x + gamma[col] * v   (ConvNeXt layer scale + residual)."""
+
+    @staticmethod
+    def forward(ctx, x, v, gamma):
+        x, v = _c(x), _c(v)
+        ctx.save_for_backward(v, gamma)
+        return ew(x, v, 2, g=gamma, C=gamma.numel())
+
+    @staticmethod
+    def backward(ctx, dy):
+        v, gamma = ctx.saved_tensors
+        dy = _c(dy)
+        C = gamma.numel()
+        dv = ew(dy, None, 3, g=gamma, C=C, out_dtype=v.dtype)
+        dgamma = colsum(dy.view(-1, C), v.view(-1, C))
+        return dy, dv, dgamma
+
+
+def scale_add(x, v, gamma):
+    return ScaleAdd.apply(x, v, gamma)
+
+
+class Attention(Function):
+    @staticmethod
+    def forward(ctx, qkv, cu, B, H, dh, maxlen, drop_p, seed):
+        qkv = _c(qkv)
+        out = ops.attention_varlen(qkv, cu, B, H, dh, maxlen, drop_p, seed)
+        ctx.save_for_backward(qkv, cu)
+        ctx.cfg = (B, H, dh, maxlen, drop_p, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, cu = ctx.saved_tensors
+        B, H, dh, maxlen, drop_p, seed = ctx.cfg
+        dout = _c(dout)
+        dqkv = torch.empty_like(qkv)
+        call("acb_attention_varlen_bwd", qkv, dtype_tag(qkv), dout, dtype_tag(dout), cu, B, H, dh, maxlen, drop_p, seed, dqkv, dtype_tag(dqkv))
+        return dqkv, None, None, None, None, None, None, None
+
+
+def attention(qkv, cu, B, H, dh, maxlen, drop_p=0.0, seed=0):
+    return Attention.apply(qkv, cu, B, H, dh, maxlen, drop_p, seed)
+
+
+class PhotoEmbed(Function):
+    @staticmethod
+    def forward(ctx, x, src, T, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype):
+        h = ops.photo_embed(x, src, T, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype)
+        ctx.save_for_backward(x, src, w, b)
+        ctx.dims = (T, D, cls_tok.shape)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, src, w, b = ctx.saved_tensors
+        T, D, cls_shape = ctx.dims
+        dh = _c(dh)
+        g = torch.empty(11 * D, dtype=F32, device=x.device)
+        call("acb_photo_embed_bwd", x, src, T, D, dh, dtype_tag(dh), w, b, g)
+        return (None, None, None, None, g[: 7 * D].view(D, 7), g[7 * D: 8 * D], g[8 * D: 8 * D + 1], g[8 * D + 1: 8 * D + 2],
+                g[8 * D + 2: 9 * D + 1], g[9 * D + 1: 10 * D], g[10 * D: 11 * D].view(cls_shape), None)
+
+
+class GatherCls(Function):
+    @staticmethod
+    def forward(ctx, h, cu, B):
+        h = _c(h)
+        ctx.save_for_backward(cu)
+        ctx.meta = (h.shape, h.dtype, B)
+        return ops.gather_cls(h, cu, B)
+
+    @staticmethod
+    def backward(ctx, dcls):
+        (cu,) = ctx.saved_tensors
+        shape, dtype, B = ctx.meta
+        dh = torch.empty(shape, dtype=dtype, device=dcls.device)
+        call("acb_scatter_cls", _c(dcls), cu, B, shape[1], dh, dtype_tag(dh), shape[0])
+        return dh, None, None
+
+
+class DwConv7(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, dims):
+        x = _c(x)
+        B, H, W, C = dims
+        y = torch.empty_like(x)
+        call("acb_dwconv7", x, dtype_tag(x), w, b, 0, y, dtype_tag(y), B, H, W, C)
+        ctx.save_for_backward(x, w)
+        ctx.dims = dims
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        B, H, W, C = ctx.dims
+        dy = _c(dy)
+        dx = torch.empty_like(x)
+        call("acb_dwconv7", dy, dtype_tag(dy), w, None, 1, dx, dtype_tag(dx), B, H, W, C)
+        dw = torch.empty(w.shape, dtype=F32, device=x.device)
+        db = torch.empty(C, dtype=F32, device=x.device)
+        call("acb_dwconv7_wgrad", x, dtype_tag(x), dy, dtype_tag(dy), B, H, W, C, dw, db, 0)
+        return dx, dw, db, None
+
+
+class Patch2(Function):
+    @staticmethod
+    def forward(ctx, x, dims):
+        x = _c(x)
+        B, H, W, C = dims
+        p = torch.empty((B * (H // 2) * (W // 2), 4 * C), dtype=x.dtype, device=x.device)
+        call("acb_patch2", x, dtype_tag(x), p, dtype_tag(p), B, H, W, C, 0)
+        ctx.meta = (dims, x.shape)
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        (B, H, W, C), shape = ctx.meta
+        dp = _c(dp)
+        dx = torch.empty(shape, dtype=dp.dtype, device=dp.device)
+        call("acb_patch2", dx, dtype_tag(dx), dp, dtype_tag(dp), B, H, W, C, 1)
+        return dx, None
+
+
+class Gap(Function):
+    @staticmethod
+    def forward(ctx, x, B, HW, C):
+        x = _c(x)
+        y = torch.empty((B, C), dtype=F32, device=x.device)
+        call("acb_gap", x, dtype_tag(x), y, B, HW, C, 0, None, 0)
+        ctx.meta = (B, HW, C, x.shape, x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, HW, C, shape, dtype = ctx.meta
+        dx = torch.empty(shape, dtype=dtype, device=dy.device)
+        call("acb_gap", None, 0, _c(dy), B, HW, C, 1, dx, dtype_tag(dx))
+        return dx, None, None, None
+
+
+class MaxPool(Function):
+    """window 4: [B,L,C] -> [B,L//4,C]; window 0: global max -> [B,C] fp32."""
+
+    @staticmethod
+    def forward(ctx, x, B, L, C, window):
+        x = _c(x)
+        y = ops.maxpool4(x, B, L, C) if window else ops.globalmax(x, B, L, C)
+        ctx.save_for_backward(x)
+        ctx.meta = (B, L, C, window)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        B, L, C, window = ctx.meta
+        dy = _c(dy)
+        dx = torch.empty_like(x)
+        call("acb_maxpool_bwd", x, dtype_tag(x), dy, dtype_tag(dy), dx, dtype_tag(dx), B, L, C, window)
+        return dx, None, None, None, None
+
+
+class ConcatCols(Function):
+    @staticmethod
+    def forward(ctx, *parts):
+        rows = parts[0].shape[0]
+        widths = [p.shape[1] for p in parts]
+        out = torch.empty((rows, sum(widths)), dtype=F32, device=parts[0].device)
+        off = 0
+        for p, w in zip(parts, widths):
+            call("acb_copy2d", _c(p), dtype_tag(p), w, ops._offset_ptr(out, off), 0, out.shape[1], rows, w)
+            off += w
+        ctx.widths = widths
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        rows, tot = dy.shape
+        outs, off = [], 0
+        for w in ctx.widths:
+            g = torch.empty((rows, w), dtype=F32, device=dy.device)
+            call("acb_copy2d", ops._offset_ptr(dy, off), 0, tot, g, 0, w, rows, w)
+            outs.append(g)
+            off += w
+        return tuple(outs)
+
+
+def gather_cols(X, cols):
+    Y = torch.empty((X.shape[0], cols.numel()), dtype=F32, device=X.device)
+    call("acb_gather_cols", X, X.shape[1], cols, cols.numel(), Y, X.shape[0])
+    return Y
+
+
+class MoeCombine(Function):
+    @staticmethod
+    def forward(ctx, gate, eo, E, C):
+        gate, eo = _c(gate), _c(eo)
+        B = gate.shape[0]
+        out = torch.empty((B, C), dtype=F32, device=gate.device)
+        call("acb_moe_combine", gate, eo, out, None, B, E, C)
+        ctx.save_for_backward(gate, eo)
+        ctx.meta = (B, E, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        gate, eo = ctx.saved_tensors
+        B, E, C = ctx.meta
+        dgate, deo = torch.empty_like(gate), torch.empty_like(eo)
+        call("acb_moe_combine_bwd", gate, eo, _c(dout), dgate, deo, B, E, C)
+        return dgate, deo, None, None
+
+
+class L2Norm(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y = torch.empty_like(x)
+        call("acb_l2norm", x, None, y, x.shape[0], x.shape[1], 0)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        call("acb_l2norm", x, _c(dy), dx, x.shape[0], x.shape[1], 1)
+        return dx
+
+
+class Loss(Function):
+    """Focal loss (int64 labels) or soft-target cross entropy (float targets), mean reduction."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, soft, gamma):
+        logits = _c(logits.float())
+        B, C = logits.shape
+        loss = torch.empty(1, dtype=F32, device=logits.device)
+        dlogits = torch.empty_like(logits)
+        call("acb_loss_fwd_bwd", logits, labels, soft, gamma, B, C, loss, dlogits)
+        ctx.save_for_backward(dlogits)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return ew(dlogits, None, 5, g=_c(g.float().view(1))), None, None, None
+
+
+def focal_loss(logits, target, gamma=2.0, reduction="mean"):
+    if reduction != "mean":
+        raise NotImplementedError("only mean reduction is implemented")
+    return Loss.apply(logits, _c(target.long()), None, float(gamma))
+
+
+def soft_cross_entropy(logits, target):
+    return Loss.apply(logits, None, _c(target.float()), 0.0)
+
+
+class Dropout(Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        x = _c(x)
+        y = torch.empty_like(x)
+        call("acb_dropout", x, dtype_tag(x), y, dtype_tag(y), p, seed, x.numel())
+        ctx.meta = (p, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed = ctx.meta
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        call("acb_dropout", dy, dtype_tag(dy), dx, dtype_tag(dx), p, seed, dy.numel())
+        return dx, None, None
+
+
+class Mean3(Function):
+    """(a + b + c) / 3  (late-fusion 'avg', brew_cider.py:854)."""
+
+    @staticmethod
+    def forward(ctx, a, b, c):
+        t = ew(_c(a), _c(b), 0)
+        return ew(t, _c(c), 4, s0=1.0 / 3.0, s1=1.0 / 3.0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = ew(_c(dy), None, 4, s0=1.0 / 3.0, s1=0.0)
+        return g, g, g
+
+
+def ew_scaled_sum3(a, b, c):
+    return Mean3.apply(a, b, c)
+
+
+_seed_counter = [0x5EED]
+
+
+def next_seed():
+    _seed_counter[0] += 1
+    return _seed_counter[0]
+
+
+def dropout(x, p, training):
+    if not training or p <= 0.0:
+        return x
+    return Dropout.apply(x, float(p), next_seed())

@@ -66,7 +66,7 @@ class AppleCider(nn.Module):
         return emb[0], emb[1], emb[2]
 
     def forward(self, photometry, photometry_mask, metadata, images, spectra):
-        if self.training and torch.is_grad_enabled():
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .train import fusion_forward_train
 
             return fusion_forward_train(self, photometry, photometry_mask, metadata, images, spectra)

@@ -151,10 +151,10 @@ def photo_embed(x, src, total, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype):
     return out
 
 
-def attention_varlen(qkv, cu, B, n_heads, dh, max_seqlen):
+def attention_varlen(qkv, cu, B, n_heads, dh, max_seqlen, drop_p=0.0, seed=0):
     T = qkv.shape[0]
     out = torch.empty((T, n_heads * dh), dtype=qkv.dtype, device=qkv.device)
-    call("acb_attention_varlen", qkv, dtype_tag(qkv), cu, B, n_heads, dh, max_seqlen, out)
+    call("acb_attention_varlen", qkv, dtype_tag(qkv), cu, B, n_heads, dh, max_seqlen, drop_p, seed, out)
     return out
 
 

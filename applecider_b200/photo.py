@@ -111,7 +111,7 @@ class HyraxBaselineCLS(_PhotoEncoderBase):
 
     def forward(self, x):
         data, pad, _ = x
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .train import photo_forward_train
 
             return photo_forward_train(self, data, pad)

@@ -224,7 +224,7 @@ class SpectraNet(nn.Module):
 
     def forward(self, batch):
         x, _, _ = batch
-        if self.training and torch.is_grad_enabled():
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .train import spectra_forward_train
 
             return spectra_forward_train(self, x)

@@ -1,12 +1,311 @@
-"""Training path (backward kernels + optimizer glue).  Filled in incrementally; see DESIGN.md."""
+"""Training path: differentiable forward graphs of the drop-in modules (built from fn.py ops whose forward and
+backward are C-ABI kernels) and the reference's train_step semantics.
+
+Reference anchors: HyraxBaselineCLS.train_step (models/HyraxBaselineCLS.py:88-120: focal loss, clip-norm 1.0,
+Adam lr 1e-4), AstroMiNN.train_step (models/astrominn.py:308-326: soft-target CE, 11-group AdamW),
+SpectraNet.train_step (models/spectranet.py:172-184: injected optimizer/criterion).
+Dropout sites follow torch's nn.TransformerEncoderLayer / the reference modules and are active only in
+train() mode; eval() + autograd gives deterministic gradients (parity mode).
+"""
 from __future__ import annotations
 
+import numpy as np
+import torch
 
-def _todo(*a, **k):
-    raise NotImplementedError("applecider_b200: the training path of this module is not implemented yet")
+from . import fn, ops
+from .fn import focal_loss  # noqa: F401  (FocalLoss module in photo.py)
+
+F32 = torch.float32
 
 
-focal_loss = photo_forward_train = photo_train_step = _todo
-spectra_forward_train = spectra_train_step = _todo
-astrominn_forward_train = astrominn_train_step = _todo
-fusion_forward_train = _todo
+def _wc(cache, p, dtype):
+    if dtype == F32:
+        return None
+    return cache.get(("cast", id(p)), (p,), lambda: ops.cast(p.detach().contiguous(), dtype))
+
+
+# ---- photometry -------------------------------------------------------------------------------------------
+def photo_encode_train(model, data, pad, total_tokens=None):
+    """-> (B, d_model) fp32 LayerNorm(CLS) with an autograd graph."""
+    dtype = model.compute_dtype
+    tr = model.training
+    mc = model.config["model"]["HyraxBaselineCLS"] if hasattr(model, "config") else {"dropout": 0.0}
+    p_drop = float(mc.get("dropout", 0.0)) if tr else 0.0
+    B, L, _ = data.shape
+    data = data.contiguous().float()
+    pad = pad.contiguous()
+    if pad.dtype != torch.bool:
+        pad = pad != 0
+    cu, src = ops.photo_compact(pad)
+    T = int(cu[-1].item()) if total_tokens is None else int(total_tokens)
+    D, H = model.d_model, model.n_heads
+    t2v = model.time2vec
+    h = fn.PhotoEmbed.apply(data, src, T, D, model.in_proj.weight, model.in_proj.bias, t2v.w0, t2v.b0, t2v.w, t2v.b, model.cls_tok, dtype)
+    dc = model._derived
+    for lyr in model.encoder.layers:
+        sa = lyr.self_attn
+        qkv = fn.linear(h, sa.in_proj_weight, sa.in_proj_bias, _wc(dc, sa.in_proj_weight, dtype))
+        att = fn.attention(qkv, cu, B, H, D // H, L + 1, p_drop, fn.next_seed() if p_drop > 0 else 0)
+        o = fn.linear(att, sa.out_proj.weight, sa.out_proj.bias, _wc(dc, sa.out_proj.weight, dtype))
+        o = fn.dropout(o, p_drop, tr)
+        h1 = fn.layernorm(fn.add(h, o), lyr.norm1.weight, lyr.norm1.bias, lyr.norm1.eps)
+        f = fn.act(fn.linear(h1, lyr.linear1.weight, lyr.linear1.bias, _wc(dc, lyr.linear1.weight, dtype)), ops.ACT_RELU)
+        f = fn.dropout(f, p_drop, tr)
+        g = fn.linear(f, lyr.linear2.weight, lyr.linear2.bias, _wc(dc, lyr.linear2.weight, dtype))
+        g = fn.dropout(g, p_drop, tr)
+        h = fn.layernorm(fn.add(h1, g), lyr.norm2.weight, lyr.norm2.bias, lyr.norm2.eps)
+    cls = fn.GatherCls.apply(h, cu, B)
+    return fn.layernorm(cls, model.norm.weight, model.norm.bias, model.norm.eps)
+
+
+def photo_forward_train(model, data, pad):
+    out = photo_encode_train(model, data, pad)
+    if model.classification:
+        out = fn.linear(out, model.fc.weight, model.fc.bias)
+    if model.config["model"]["HyraxBaselineCLS"]["use_probabilities"]:
+        raise NotImplementedError("training through use_probabilities=True is not implemented")
+    return out
+
+
+def photo_train_step(model, batch):
+    """HyraxBaselineCLS.py:88-120."""
+    _, _, labels = batch
+    decoded = model.forward(batch)
+    loss = model.criterion(decoded, labels)
+    model.optimizer.zero_grad()
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+    model.optimizer.step()
+    return {"loss": loss.item(), "num_tdes": np.sum([labels.cpu().numpy() == 4])}
+
+
+# ---- SpectraNet -------------------------------------------------------------------------------------------
+class SpectraConvs(torch.autograd.Function):
+    """The three same-padded Conv1d of a SpectraNetBlock on a channels-last signal -> [B*L, 3*Cout].
+
+    forward: implicit-GEMM kernels of spectra.py; backward: dgrad = conv with flipped kernels (implicit GEMM),
+    wgrad = transposed-im2col GEMM with split-K, bias = column sums."""
+
+    @staticmethod
+    def forward(ctx, x, sig, blk, B, L, dtype, *params):
+        ctx.blk, ctx.dims, ctx.dtype = blk, (B, L), dtype
+        if dtype == F32:
+            y, Lr = blk._convs_f32(x, B, L), L
+        elif blk.in_channels == 1:
+            y, Lr = blk._convs_bf16_polyphase(sig, B, L)
+            if Lr != L:
+                y = y.view(B, Lr, -1)[:, :L].contiguous().view(B * L, -1)
+        else:
+            y, Lr = blk._convs_bf16(x, B, L), L
+        ctx.save_for_backward(x if x is not None else sig.view(B, L, 1))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        blk, (B, L), dtype = ctx.blk, ctx.dims, ctx.dtype
+        (x,) = ctx.saved_tensors
+        dy = fn._c(dy)
+        cin, cout, nk = blk.in_channels, blk.out_channels, blk.k
+        ldy = nk * cout
+        dev = dy.device
+        grads = []
+        dx = None
+        need_dx = ctx.needs_input_grad[0] and cin > 1
+        for j, conv in enumerate(blk.convs):
+            kj = blk.kernel_sizes[j]
+            # wgrad: G[(tap,ci), co] = sum_(b,l) X[b, l+tap-pad, ci] * dY[(b,l), j*cout+co]
+            G = fn.gemm_ex(x, fn.dtype_tag(x), ops._offset_ptr(dy, j * cout), fn.dtype_tag(dy), kj * cin, cout, B * L, 0, 0, 1, ldy, dev,
+                           convT=(L, cin, kj // 2), splits=fn._splits(B * L))
+            dW = torch.empty(conv.weight.shape, dtype=F32, device=dev)
+            fn.call("acb_unpack_conv_wgrad", G, dW, cout, cin, kj)
+            db = fn.colsum(ops._offset_ptr(dy, j * cout), None, M=B * L, N=cout, ld=ldy, a_dt=fn.dtype_tag(dy), dev=dev)
+            grads.append((dW, db))
+            if need_dx:
+                # dgrad: dX = sum_j conv(dY_j, flipped W_j^T)
+                wd = torch.empty((cin, kj * cout), dtype=F32, device=dev)
+                fn.call("acb_pack_conv_dgrad_weight", conv.weight, wd, 0, cout, cin, kj)
+                dyj = torch.empty((B, L, cout), dtype=F32, device=dev)
+                fn.call("acb_copy2d", ops._offset_ptr(dy, j * cout), fn.dtype_tag(dy), ldy, dyj, 0, cout, B * L, cout)
+                if dx is None:
+                    dx = ops.gemm(dyj, wd, None, conv=(kj, kj // 2))
+                else:
+                    ops.gemm(dyj, wd, None, conv=(kj, kj // 2), res=dx, res_mode=ops.RES_ADD, out=dx)
+        if dx is not None:
+            dx = fn.cast_to(dx.view(B, L, cin), x.dtype)
+        out = [dx, None, None, None, None, None]
+        for dW, _ in grads:
+            out.append(dW)
+        for _, db in grads:
+            out.append(db)
+        return tuple(out)
+
+
+def spectra_features_train(model, x):
+    dtype = model.compute_dtype
+    B, _, L = x.shape
+    sig = x.contiguous().float().view(B, L)
+    h = sig.view(B, L, 1) if dtype == F32 else None
+    for stage in model.all_stages:
+        for blk in stage:
+            params = [c.weight for c in blk.convs] + [c.bias for c in blk.convs]
+            y = SpectraConvs.apply(h, sig if h is None else None, blk, B, L, dtype, *params)
+            y = fn.act(fn.layernorm(y, blk.norm.weight, blk.norm.bias, blk.norm.eps), ops.ACT_GELU)
+            nc = blk.out_channels * blk.k
+            if blk.do_pool:
+                wd = blk.downsample.weight.view(blk.out_channels, nc)
+                z = fn.linear(y, wd, blk.downsample.bias, _wc(blk._derived, blk.downsample.weight, dtype) if dtype != F32 else None)
+                z = fn.MaxPool.apply(z.view(B, L, blk.out_channels), B, L, blk.out_channels, 4)
+                L = L // 4
+                h = z
+            else:
+                h = y.view(B, L, nc)
+    return fn.MaxPool.apply(h, B, L, h.shape[-1], 0)
+
+
+def spectra_forward_train(model, x):
+    feat = spectra_features_train(model, x)
+    head = model.regressor if model.redshift else model.classifier
+    tr = model.training
+    z = fn.linear(feat, head[0].weight, head[0].bias)
+    z = fn.act(fn.layernorm(z, head[1].weight, head[1].bias, head[1].eps), ops.ACT_GELU)
+    z = fn.dropout(z, head[3].p, tr)
+    out = fn.linear(z, head[4].weight, head[4].bias)
+    return out.squeeze(1) if model.redshift else out
+
+
+def spectra_train_step(model, batch):
+    """spectranet.py:172-184 (optimizer / criterion injected by the framework)."""
+    _, labels, redshifts = batch
+    model.optimizer.zero_grad()
+    outputs = model(batch)
+    loss = model.criterion(outputs, redshifts if model.redshift else labels)
+    loss.backward()
+    model.optimizer.step()
+    return {"loss": loss.item()}
+
+
+# ---- AstroMiNN ----------------------------------------------------------------------------------------------
+def _tower_train(tw, x, training):
+    """ResidualTowerBlock (astrominn.py:59-64) from differentiable ops; x fp32 [B, in]."""
+    s = fn.act(fn.linear(x, tw.start_path[0].weight, tw.start_path[0].bias), ops.ACT_GELU)
+    m = fn.layernorm(s, tw.main_path[0].weight, tw.main_path[0].bias, tw.main_path[0].eps)
+    m = fn.linear(fn.dropout(m, tw.main_path[1].p, training), tw.main_path[2].weight, tw.main_path[2].bias)
+    g = fn.layernorm(s, tw.activation[0].weight, tw.activation[0].bias, tw.activation[0].eps)
+    g = fn.act(fn.linear(fn.dropout(g, tw.activation[1].p, training), tw.activation[2].weight, tw.activation[2].bias), ops.ACT_SIGMOID)
+    skip = fn.linear(x, tw.skip_path.weight, tw.skip_path.bias) if isinstance(tw.skip_path, torch.nn.Linear) else x
+    return fn.add(fn.mul(m, g), skip)
+
+
+def convnext_features_train(bb, img, dtype):
+    B, Cin, H, W = img.shape
+    img = img.contiguous().float()
+    c0 = bb.dims[0]
+    a = ops.patchify(img, 4, dtype)
+    w0 = bb.stem[0].weight.view(c0, Cin * 16)
+    x = fn.linear(a, w0, bb.stem[0].bias, bb._w(bb.stem[0].weight, dtype, (c0, Cin * 16)) if dtype != F32 else None)
+    x = fn.layernorm(x, bb.stem[1].weight, bb.stem[1].bias, bb.stem[1].eps)
+    h, w = H // 4, W // 4
+    for si, st in enumerate(bb.stages):
+        C = bb.dims[si]
+        if si > 0:
+            cp = bb.dims[si - 1]
+            xn = fn.layernorm(x, st.downsample[0].weight, st.downsample[0].bias, st.downsample[0].eps)
+            p = fn.Patch2.apply(xn, (B, h, w, cp))
+            h, w = h // 2, w // 2
+            # conv weight (C, cp, 2, 2) viewed in the gather's (ky, kx, ci) column order
+            wds = PackDown.apply(st.downsample[1].weight)
+            x = fn.linear(p, wds, st.downsample[1].bias, ops.cast(wds.detach(), dtype) if dtype != F32 else None)
+        for blk in st.blocks:
+            y = fn.DwConv7.apply(x, blk.conv_dw.weight, blk.conv_dw.bias, (B, h, w, C))
+            y = fn.layernorm(y, blk.norm.weight, blk.norm.bias, blk.norm.eps)
+            hid = fn.act(fn.linear(y, blk.mlp.fc1.weight, blk.mlp.fc1.bias, bb._w(blk.mlp.fc1.weight, dtype) if dtype != F32 else None), ops.ACT_GELU)
+            v = fn.linear(hid, blk.mlp.fc2.weight, blk.mlp.fc2.bias, bb._w(blk.mlp.fc2.weight, dtype) if dtype != F32 else None)
+            x = fn.scale_add(x, v, blk.gamma)
+    g = fn.Gap.apply(x, B, h * w, bb.dims[-1])
+    return fn.layernorm(g, bb.head.norm.weight, bb.head.norm.bias, bb.head.norm.eps)
+
+
+class PackDown(torch.autograd.Function):
+    """(Cout, Cin, 2, 2) -> [Cout, (ky,kx,ci)] and the inverse re-layout for its gradient."""
+
+    @staticmethod
+    def forward(ctx, w):
+        ctx.shape = w.shape
+        return ops.pack_conv2d_weight(w.detach(), F32)
+
+    @staticmethod
+    def backward(ctx, g):
+        cout, cin, kh, kw = ctx.shape
+        # inverse of pack_conv2d_weight = the same kernel with the roles (cin <-> kh*kw) exchanged
+        out = torch.empty((cout, cin * kh * kw), dtype=F32, device=g.device)
+        fn.call("acb_pack_conv_weight", fn._c(g), out, 0, cout, kh * kw, cin, cin * kh * kw, 0)
+        return out.view(cout, cin, kh, kw)
+
+
+def image_tower_train(it, img, dtype, training):
+    feat = convnext_features_train(it.backbone, img, dtype)
+    hm, ha = it.head_main, it.head_aux
+    a = fn.layernorm(fn.act(feat, ops.ACT_GELU), hm[1].weight, hm[1].bias, hm[1].eps)
+    a = fn.act(fn.linear(a, hm[2].weight, hm[2].bias), ops.ACT_RELU)
+    a = fn.dropout(a, hm[4].p, training)
+    a = fn.linear(fn.linear(a, hm[5].weight, hm[5].bias), hm[6].weight, hm[6].bias)
+    x = fn.act(fn.linear(fn.layernorm(feat, ha[0].weight, ha[0].bias, ha[0].eps), ha[1].weight, ha[1].bias), ops.ACT_TANH)
+    return fn.mul(a, x)
+
+
+def astrominn_forward_train(model, metadata, image):
+    from .astrominn import CONCAT_ORDER
+
+    tr = model.training
+    metadata = metadata.contiguous().float()
+    parts = []
+    for n in CONCAT_ORDER:
+        if n == "image":
+            parts.append(image_tower_train(model.image_tower, image, model.compute_dtype, tr))
+        else:
+            tw = getattr(model, f"{n}_tower")
+            parts.append(_tower_train(tw, fn.gather_cols(metadata, getattr(model, f"_cols_{n}")), tr))
+    feats = fn.ConcatCols.apply(*parts)
+    r = model.fusion_router
+    g1 = fn.act(fn.linear(feats, r[0].weight, r[0].bias), ops.ACT_TANH)
+    gate = fn.act(fn.linear(fn.dropout(g1, r[2].p, tr), r[3].weight, r[3].bias), ops.ACT_SIGMOID)
+    eo = fn.ConcatCols.apply(*[_tower_train(ex, feats, tr) for ex in model.fusion_experts])
+    out = fn.MoeCombine.apply(gate, eo, model.num_mlp_experts, 5)
+    if model.config["model"]["AstroMiNN"]["use_probabilities"]:
+        raise NotImplementedError("training through use_probabilities=True is not implemented")
+    return out
+
+
+class _SoftCE(torch.nn.Module):
+    def forward(self, logits, target):
+        return fn.soft_cross_entropy(logits, target)
+
+
+def astrominn_train_step(model, batch):
+    """astrominn.py:308-326."""
+    _, _, labels = batch
+    model.this_optimizer.zero_grad()
+    logits = model.forward(batch)
+    crit = model.this_criterion
+    loss = fn.soft_cross_entropy(logits, labels) if isinstance(crit, torch.nn.CrossEntropyLoss) and labels.dtype.is_floating_point else crit(logits, labels)
+    model._update_stats(loss.item())
+    loss.backward()
+    model.this_optimizer.step()
+    return {"loss": model._calculate_stats()}
+
+
+# ---- fusion ---------------------------------------------------------------------------------------------------
+def fusion_forward_train(model, photometry, photometry_mask, metadata, images, spectra):
+    p = photo_encode_train(model.photometry_encoder, photometry, photometry_mask)
+    s = spectra_forward_train(model.spectra_encoder, spectra)
+    if s.dim() == 1:
+        s = s[:, None]
+    im = astrominn_forward_train(model.img_metadata_encoder, metadata, images)
+    pe = fn.L2Norm.apply(fn.linear(p, model.photometry_proj.weight, model.photometry_proj.bias))
+    ie = fn.L2Norm.apply(fn.linear(im, model.img_metadata_proj.weight, model.img_metadata_proj.bias))
+    se = fn.L2Norm.apply(fn.linear(s, model.spectra_proj.weight, model.spectra_proj.bias))
+    if model.fusion == "concat":
+        emb = fn.ConcatCols.apply(pe, ie, se)
+    else:
+        emb = fn.ew_scaled_sum3(pe, ie, se)
+    return fn.linear(emb, model.fc.weight, model.fc.bias)

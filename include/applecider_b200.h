@@ -108,10 +108,11 @@ int acb_photo_embed(const float* x, const int* src_idx, const int* total_dev, in
                     const float* b_in, const float* w0, const float* b0, const float* w, const float* b,
                     const float* cls_tok, void* out, int out_dtype, void* stream);
 /* fused masked varlen multi-head attention over packed tokens; qkv[T,3D] rows = [q|k|v], head h uses
- * columns h*dh..; softmax(q k^T / sqrt(dh)) v with fp32 math.  nn.MultiheadAttention inside
+ * columns h*dh..; softmax(q k^T / sqrt(dh)) v with fp32 math (drop_p > 0: training-time dropout on the
+ * probabilities, mask = counter hash of (seed, sequence, head, i, j), regenerated in the backward).  nn.MultiheadAttention inside
  * nn.TransformerEncoderLayer (HyraxBaselineCLS.py:26-33,78). dh must be 16. */
 int acb_attention_varlen(const void* qkv, int dtype, const int* cu_seqlens, int B, int n_heads, int dh,
-                         int max_seqlen, void* out, void* stream);
+                         int max_seqlen, float drop_p, long long seed, void* out, void* stream);
 /* out[b,:] = x[cu_seqlens[b],:]  (CLS read-out z[:,0], HyraxBaselineCLS.py:79) */
 int acb_gather_cls(const void* x, int dtype, const int* cu_seqlens, int B, int D, float* out, void* stream);
 
@@ -185,6 +186,64 @@ int acb_prep_cutout_norm(const float* img, int B, int C, int H, int W, int cutou
 /* P5  preprocess_multimodal.py:863-895.  Column mean and population std (clipped at 0) of data[rows,F] f32
  * from streamed sums / sums of squares (fp64 accumulation).  work = 2*F doubles of scratch. */
 int acb_feature_stats(const float* data, long long rows, int F, double* work, float* mean, float* stdv, void* stream);
+
+/* ---- backward / training kernels (gradients of the ops above; torch autograd is only the tape) ---------- */
+/* C[m,n] (+)= sum_k A(m,k) B(n,k) with arbitrary element strides (dgrad: B = W read column-wise; wgrad: A = dY,
+ * B = X read column-wise).  convT: A is the transposed im2col of X[nb, conv_L, conv_Cin] (conv wgrad:
+ * m = tap*Cin+ci, k = b*L+l).  splits > 1 splits K over grid.z with fp32 atomic accumulation. */
+int acb_gemm_ex(const void* A, int a_dtype, const void* B, int b_dtype, float* C, int M, int N, int K, long long sam,
+                long long sak, long long sbn, long long sbk, int ldc, int convT, int conv_L, int conv_Cin, int conv_pad,
+                int splits, int accumulate, void* stream);
+/* out[n] (+)= sum_m a[m*ld+n] * (b ? b[m*ld+n] : 1)   (bias / layer-scale gradients; ld <= 0 means N) */
+int acb_colsum(const void* a, int a_dtype, const void* b, int b_dtype, long long M, int N, long long ld, float* out,
+               int accumulate, void* stream);
+int acb_act_fwd(const void* x, int x_dtype, void* y, int y_dtype, int act, long long n, void* stream);
+/* dx = dy * act'(x), x = pre-activation */
+int acb_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx, int dx_dtype, int act, long long n,
+                void* stream);
+/* op 0: a+b; 1: a*b; 2: a + g[col]*b; 3: g[col]*a; 4: a*s0 + b*s1; 5: a * g[0] (device scalar) */
+int acb_ew(const void* a, int a_dtype, const void* b, int b_dtype, const float* g, void* y, int y_dtype, int op, int C,
+           float s0, float s1, long long n, void* stream);
+int acb_copy2d(const void* src, int s_dtype, long long lds, void* dst, int d_dtype, long long ldd, long long rows, int cols,
+               void* stream);
+int acb_gather_cols(const float* X, int ldx, const int* cols, int n, float* Y, long long rows, void* stream);
+/* dW[co,ci,tap] = G[(tap*Cin+ci)*Cout + co] (G = convT wgrad GEMM result) */
+int acb_unpack_conv_wgrad(const float* G, float* dW, int Cout, int Cin, int k, void* stream);
+/* out[ci*(k*Cout) + tap*Cout + co] = w[co,ci,k-1-tap]  (weights of the input-gradient convolution) */
+int acb_pack_conv_dgrad_weight(const float* w, void* out, int out_dtype, int Cout, int Cin, int k, void* stream);
+/* LayerNorm backward: dx, and dw += sum dy*xhat, db += sum dy (caller zeroes dw/db) */
+int acb_layernorm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* w, void* dx, int dx_dtype,
+                      float* dw, float* db, long long rows, int C, float eps, void* stream);
+int acb_attention_varlen_bwd(const void* qkv, int dtype, const void* dout, int dout_dtype, const int* cu_seqlens, int B,
+                             int n_heads, int dh, int max_seqlen, float drop_p, long long seed, void* dqkv, int dqkv_dtype,
+                             void* stream);
+/* grads = [d in_proj.weight (D*7) | d in_proj.bias (D) | dw0 | db0 | dw (D-1) | db (D-1) | d cls_tok (D)] */
+int acb_photo_embed_bwd(const float* x, const int* src_idx, int T, int D, const void* dh, int dh_dtype, const float* w,
+                        const float* b, float* grads, void* stream);
+int acb_scatter_cls(const float* dcls, const int* cu_seqlens, int B, int D, void* dh, int dh_dtype, long long total_tokens,
+                    void* stream);
+/* depthwise 7x7 without LayerNorm (training forward), flip=1: gradient w.r.t. the input */
+int acb_dwconv7(const void* x, int x_dtype, const float* w, const float* bias, int flip, void* y, int y_dtype, int B, int H,
+                int W, int C, void* stream);
+int acb_dwconv7_wgrad(const void* x, int x_dtype, const void* dy, int dy_dtype, int B, int H, int W, int C, float* dw,
+                      float* db, int accumulate, void* stream);
+/* 2x2/stride-2 patch gather x[B,H,W,C] -> p[B*(H/2)*(W/2), 4C] (adjoint=0) or its adjoint p -> x (adjoint=1) */
+int acb_patch2(const void* x, int x_dtype, void* p, int p_dtype, int B, int H, int W, int C, int adjoint, void* stream);
+/* mean over HW (bwd=0: y from x; bwd=1: dx from y) */
+int acb_gap(const void* x, int x_dtype, float* y, int B, int HW, int C, int bwd, void* dx, int dx_dtype, void* stream);
+/* window 4: MaxPool1d(4) backward; window 0: global max backward (gradient to the first maximum) */
+int acb_maxpool_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, void* dx, int dx_dtype, int B, int L, int C,
+                    int window, void* stream);
+int acb_moe_combine_bwd(const float* gate, const float* expert_out, const float* dout, float* dgate, float* dexpert_out, int B,
+                        int E, int C, void* stream);
+/* bwd=0: out = x/||x||; bwd=1: out = d x given dy */
+int acb_l2norm(const float* x, const float* dy, float* out, int rows, int C, int bwd, void* stream);
+/* focal loss (labels int64, gamma; HyraxBaselineCLS.py:177-191) or soft-target cross entropy (astrominn.py:147,315),
+ * mean reduction: loss_out[0] and dlogits = d loss / d logits */
+int acb_loss_fwd_bwd(const float* logits, const long long* labels, const float* soft_targets, float gamma, int B, int C,
+                     float* loss_out, float* dlogits, void* stream);
+int acb_dropout(const void* x, int x_dtype, void* y, int y_dtype, float p, long long seed, long long n, void* stream);
+int acb_sumsq(const float* x, long long n, float* out, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,181 @@
+"""GPU: every differentiable op in applecider_b200/fn.py (forward + backward kernels) against torch autograd
+on a plain fp32 statement of the same op."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(*shape, seed=0, scale=1.0, grad=False):
+    g = torch.Generator().manual_seed(seed)
+    t = (torch.randn(*shape, generator=g) * scale).to(DEV)
+    return t.requires_grad_(grad)
+
+
+def _check(got_out, ref_out, got_inputs, ref_inputs, tol=2e-5, seed=99):
+    assert_close(got_out, ref_out, tol, "forward")
+    go = _rand(*ref_out.shape, seed=seed)
+    got_out.backward(go.to(got_out.dtype))
+    ref_out.backward(go)
+    for i, (a, b) in enumerate(zip(got_inputs, ref_inputs)):
+        s = b.grad.abs().max().clamp_min(1e-12)
+        assert_close(a.grad / s, b.grad / s, tol, f"grad of input {i}")
+
+
+@pytest.mark.parametrize("M,N,K", [(2000, 64, 192), (2048, 64, 192), (130, 70, 50), (5000, 128, 128), (7, 5, 288)])
+def test_linear(M, N, K):
+    from applecider_b200 import fn
+
+    x, W, b = _rand(M, K, seed=1, grad=True), _rand(N, K, seed=2, scale=K**-0.5, grad=True), _rand(N, seed=3, grad=True)
+    x2, W2, b2 = [t.detach().clone().requires_grad_(True) for t in (x, W, b)]
+    _check(fn.linear(x, W, b), F.linear(x2, W2, b2), (x, W, b), (x2, W2, b2))
+
+
+@pytest.mark.parametrize("act,ref", [(1, torch.relu), (2, F.gelu), (3, torch.tanh), (4, torch.sigmoid)])
+def test_act(act, ref):
+    from applecider_b200 import fn
+
+    x = _rand(300, 37, seed=4, grad=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    _check(fn.act(x, act), ref(x2), (x,), (x2,))
+
+
+@pytest.mark.parametrize("rows,C", [(2000, 192), (33, 128), (5, 3072), (70000, 96)])
+def test_layernorm(rows, C):
+    from applecider_b200 import fn
+
+    x, w, b = _rand(rows, C, seed=5, scale=2.0, grad=True), (1 + 0.1 * _rand(C, seed=6)).requires_grad_(True), _rand(C, seed=7, grad=True)
+    x2, w2, b2 = [t.detach().clone().requires_grad_(True) for t in (x, w, b)]
+    _check(fn.layernorm(x, w, b, 1e-5), F.layer_norm(x2, (C,), w2, b2, 1e-5), (x, w, b), (x2, w2, b2), tol=5e-5)
+
+
+@pytest.mark.parametrize("B,L,C", [(2, 1000, 64), (2, 250, 128), (3, 15, 16), (2, 1024, 64)])
+def test_maxpool(B, L, C):
+    from applecider_b200 import fn
+
+    x = _rand(B, L, C, seed=8, grad=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    _check(fn.MaxPool.apply(x, B, L, C, 4), F.max_pool1d(x2.transpose(1, 2), 4).transpose(1, 2), (x,), (x2,), tol=1e-6)
+    x.grad = None
+    x2.grad = None
+    _check(fn.MaxPool.apply(x, B, L, C, 0), x2.amax(1), (x,), (x2,), tol=1e-6)
+
+
+@pytest.mark.parametrize("B,L,Cin,Cout,ks", [(2, 250, 64, 128, [3, 31, 251]), (2, 1000, 1, 64, [3, 61, 1021]), (3, 62, 16, 32, [3, 7, 13]), (2, 256, 64, 128, [3, 31, 251])])
+def test_spectra_convs(B, L, Cin, Cout, ks):
+    from applecider_b200.spectra import SpectraNetBlock
+    from applecider_b200.train import SpectraConvs
+
+    torch.manual_seed(0)
+    blk = SpectraNetBlock(Cin, Cout, ks, do_pool=True).to(DEV)
+    x = _rand(B, L, Cin, seed=9, grad=Cin > 1)
+    params = [c.weight for c in blk.convs] + [c.bias for c in blk.convs]
+    y = SpectraConvs.apply(x, None, blk, B, L, torch.float32, *params)
+    x2 = x.detach().clone().requires_grad_(Cin > 1)
+    ref = torch.cat([c(x2.transpose(1, 2)) for c in blk.convs], 1).transpose(1, 2).reshape(B * L, -1)
+    assert_close(y, ref, 2e-5, "convs forward")
+    go = _rand(*ref.shape, seed=10)
+    refs = torch.autograd.grad(ref, ([x2] if Cin > 1 else []) + params, go, retain_graph=True)
+    y.backward(go)
+    if Cin > 1:
+        assert_close(x.grad, refs[0], 3e-5, "dX")
+        refs = refs[1:]
+    for p, r in zip(params, refs):
+        s = r.abs().max().clamp_min(1e-12)
+        assert_close(p.grad / s, r / s, 3e-5, f"param grad {tuple(p.shape)}")
+        p.grad = None
+
+
+def test_dwconv_patch_gap():
+    from applecider_b200 import fn
+
+    B = 3
+    for (H, C) in [(15, 96), (7, 192), (3, 384), (1, 768)]:
+        x, w, b = _rand(B, H, H, C, seed=11, grad=True), _rand(C, 1, 7, 7, seed=12, scale=0.15, grad=True), _rand(C, seed=13, grad=True)
+        x2, w2, b2 = [t.detach().clone().requires_grad_(True) for t in (x, w, b)]
+        got = fn.DwConv7.apply(x.view(B * H * H, C), w, b, (B, H, H, C))
+        ref = F.conv2d(x2.permute(0, 3, 1, 2), w2, b2, padding=3, groups=C).permute(0, 2, 3, 1).reshape(B * H * H, C)
+        _check(got, ref, (x, w, b), (x2, w2, b2), tol=3e-5)
+        if H >= 2:
+            x3 = _rand(B * H * H, C, seed=14, grad=True)
+            x4 = x3.detach().clone().requires_grad_(True)
+            got = fn.Patch2.apply(x3, (B, H, H, C))
+            Ho = H // 2
+            v = x4.view(B, H, H, C)[:, : 2 * Ho, : 2 * Ho].reshape(B, Ho, 2, Ho, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * Ho * Ho, 4 * C)
+            _check(got, v, (x3,), (x4,), tol=1e-6)
+        x5 = _rand(B * H * H, C, seed=15, grad=True)
+        x6 = x5.detach().clone().requires_grad_(True)
+        _check(fn.Gap.apply(x5, B, H * H, C), x6.view(B, H * H, C).mean(1), (x5,), (x6,), tol=1e-6)
+
+
+def test_attention_backward():
+    from applecider_b200 import fn, ops, synth
+
+    _, pad, _ = synth.photometry_batch(7, seed=16, L=70)
+    cu, _ = ops.photo_compact(pad.to(DEV))
+    T, D, H = int(cu[-1]), 128, 8
+    qkv = _rand(T, 3 * D, seed=17, grad=True)
+    q2 = qkv.detach().clone().requires_grad_(True)
+    got = fn.attention(qkv, cu, 7, H, 16, 71)
+    outs = []
+    for bi in range(7):
+        s, e = int(cu[bi]), int(cu[bi + 1])
+        q, k, v = [z.view(e - s, H, 16).transpose(0, 1) for z in q2[s:e].split(D, 1)]
+        p = torch.softmax(q @ k.transpose(1, 2) / 4.0, -1)
+        outs.append((p @ v).transpose(0, 1).reshape(e - s, D))
+    _check(got, torch.cat(outs, 0), (qkv,), (q2,), tol=2e-5)
+
+
+def test_small_ops():
+    from applecider_b200 import fn
+
+    a, b, c = _rand(50, 32, seed=18, grad=True), _rand(50, 5, seed=19, grad=True), _rand(50, 64, seed=20, grad=True)
+    a2, b2, c2 = [t.detach().clone().requires_grad_(True) for t in (a, b, c)]
+    _check(fn.ConcatCols.apply(a, b, c), torch.cat([a2, b2, c2], 1), (a, b, c), (a2, b2, c2), tol=1e-6)
+    x, y = _rand(40, 24, seed=21, grad=True), _rand(40, 24, seed=22, grad=True)
+    x2, y2 = x.detach().clone().requires_grad_(True), y.detach().clone().requires_grad_(True)
+    _check(fn.add(fn.mul(x, y), x), x2 * y2 + x2, (x, y), (x2, y2), tol=1e-6)
+    v, g = _rand(90, 96, seed=23, grad=True), _rand(96, seed=24, grad=True)
+    x = _rand(90, 96, seed=25, grad=True)
+    v2, g2, x2 = [t.detach().clone().requires_grad_(True) for t in (v, g, x)]
+    _check(fn.scale_add(x, v, g), x2 + g2 * v2, (x, v, g), (x2, v2, g2), tol=2e-6)
+    z = _rand(33, 64, seed=26, grad=True)
+    z2 = z.detach().clone().requires_grad_(True)
+    _check(fn.L2Norm.apply(z), z2 / z2.norm(dim=-1, keepdim=True), (z,), (z2,), tol=2e-6)
+    gate = torch.sigmoid(_rand(64, 4, seed=27)).requires_grad_(True)
+    eo = _rand(64, 20, seed=28, grad=True)
+    gate2, eo2 = gate.detach().clone().requires_grad_(True), eo.detach().clone().requires_grad_(True)
+    tw, ti = torch.topk(gate2, 2, -1)
+    ref = sum((tw * (ti == e)).sum(-1, keepdim=True) * eo2.view(64, 4, 5)[:, e] for e in range(4))
+    _check(fn.MoeCombine.apply(gate, eo, 4, 5), ref, (gate, eo), (gate2, eo2), tol=2e-6)
+    p, q, r = _rand(9, 64, seed=29, grad=True), _rand(9, 64, seed=30, grad=True), _rand(9, 64, seed=31, grad=True)
+    p2, q2, r2 = [t.detach().clone().requires_grad_(True) for t in (p, q, r)]
+    _check(fn.ew_scaled_sum3(p, q, r), (p2 + q2 + r2) / 3, (p, q, r), (p2, q2, r2), tol=2e-6)
+
+
+def test_losses():
+    from applecider_b200 import fn
+    from oracle.models import focal_loss as oracle_focal
+
+    z = _rand(37, 5, seed=32, scale=2.0, grad=True)
+    z2 = z.detach().clone().requires_grad_(True)
+    y = torch.randint(0, 5, (37,), generator=torch.Generator().manual_seed(1)).to(DEV)
+    l1, l2 = fn.focal_loss(z, y), oracle_focal(z2, y)
+    assert_close(l1, l2, 1e-6, "focal loss")
+    (l1 * 3.0).backward()
+    (l2 * 3.0).backward()
+    assert_close(z.grad, z2.grad, 2e-6, "focal dlogits", atol=1e-8)
+    t = torch.softmax(_rand(37, 5, seed=33), -1)
+    z.grad = None
+    z2.grad = None
+    l1, l2 = fn.soft_cross_entropy(z, t), F.cross_entropy(z2, t)
+    assert_close(l1, l2, 1e-6, "soft CE")
+    l1.backward()
+    l2.backward()
+    assert_close(z.grad, z2.grad, 2e-6, "CE dlogits", atol=1e-8)
