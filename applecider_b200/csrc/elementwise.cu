@@ -275,6 +275,22 @@ __global__ void pad_signal_kernel(const float* in, void* out, int odt, int nb, i
   }
 }
 
+// out[c*R + r] = in[r*C + c]  (32x32 smem tiles, dtype-tagged; used for bf16 W^T copies of the dgrad GEMMs)
+__global__ void __launch_bounds__(256) transpose_kernel(const void* in, int idt, void* out, int odt, int R, int C) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    if (r < R && c < C) tile[i][tx] = ld_any(in, (long long)r * C + c, idt);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < R && c < C) st_any(out, (long long)c * R + r, odt, tile[tx][i]);
+  }
+}
+
 // ---- pooling over L of channels-last [B, L, C] ---------------------------------------------------
 template <typename T>
 __global__ void maxpool4_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int L, int C) {
@@ -351,6 +367,16 @@ int acb_cast(const void* in, int in_dtype, void* out, int out_dtype, long long n
   ACB_CHECK(in && out && n >= 0, "acb_cast: bad arguments");
   if (n == 0) return ACB_OK;
   cast_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(in, in_dtype, out, out_dtype, n);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+int acb_transpose(const void* in, int in_dtype, void* out, int out_dtype, int R, int C, void* stream) {
+  ACB_CHECK(in && out && R > 0 && C > 0, "acb_transpose: bad arguments");
+  dim3 grid(cdiv(C, 32), cdiv(R, 32));
+  ACB_CHECK(grid.y <= 65535, "acb_transpose: too many rows");
+  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, in_dtype, out, out_dtype, R, C);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;

@@ -411,6 +411,152 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args
   return ACB_OK;
 }
 
+
+// ======================================================================================================
+// Weight-gradient GEMM on tcgen05 with MN-major operands (no transposes):
+//   dW[m, n] += sum_{rows r} dY[r, a_col0 + m] * X(r, n)          m < M_out, n < taps*Cin
+// Both operands are the row-major activations themselves: a TMA box of [64 rows x 64 columns] is exactly
+// the canonical MN-major SWIZZLE_128B UMMA tile with K = rows (LBO = 8 KB between 64-column blocks,
+// SBO = 1 KB between 8-row groups).  For convolutions n = tap*Cin + ci and X(r, n) = X[b, l + tap - pad, ci]
+// (the 3-D TMA map shifts the row coordinate and zero-fills outside the sample).  grid.z splits the row
+// range; partial tiles are accumulated with fp32 atomics into a pre-zeroed dW.
+// ======================================================================================================
+struct TcWgradArgs {
+  int nb, L, cps;          // samples, rows per sample, 64-row chunks per sample
+  int Cin, pad, n_total;   // B-operand geometry (n_total = taps * Cin)
+  int a_col0, M_out;       // dY column slice
+  int chunks_per_split;
+  float* C;
+  int ldc;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr) {
+  // MN-major, SWIZZLE_128B: LBO = 8192 B (next 64-wide MN block), SBO = 1024 B (next 8 K rows)
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB,
+                                                              const __grid_constant__ TcWgradArgs p) {
+  constexpr uint32_t A_BYTES = 2 * 8192;          // two [64 x 64] boxes = 128 output rows
+  constexpr uint32_t B_BYTES = (BN / 64) * 8192;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);  // a_major = b_major = MN
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_holder;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  const int total_chunks = p.nb * p.cps;
+  const int c_begin = blockIdx.z * p.chunks_per_split;
+  const int c_end = min(total_chunks, c_begin + p.chunks_per_split);
+  const int nkb = c_end - c_begin;
+  if (nkb <= 0) return;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[STAGES]);
+  const uint32_t bar_acc = smem_u32(&bars[2 * STAGES]);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
+                 "r"((uint32_t)tmem_cols<BN>())
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        const int ch = c_begin + it;
+        const int b = ch / p.cps, l0 = (ch - b * p.cps) * 64;
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+        mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+        tma_load_3d(sa, &tmA, p.a_col0 + m0, l0, b, bar_full + 8 * s);
+        tma_load_3d(sa + 8192, &tmA, p.a_col0 + m0 + 64, l0, b, bar_full + 8 * s);
+#pragma unroll
+        for (int qn = 0; qn < BN / 64; ++qn) {
+          const int n = n0 + qn * 64;
+          const int tap = n / p.Cin, ci0 = n - tap * p.Cin;
+          tma_load_3d(sb + qn * 8192, &tmB, ci0, l0 + tap - p.pad, b, bar_full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 64 rows = 4 x UMMA_K(16); 16 rows = 2 KB
+          umma_bf16(tmem_base, make_smem_desc_mn(sa + k * 2048), make_smem_desc_mn(sb + k * 2048), IDESC, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_empty + 8 * s);
+      }
+      umma_commit(bar_acc);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.n_total) break;
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+      if (m < p.M_out) {
+        float* dst = p.C + (long long)m * p.ldc + n0 + c0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (n0 + c0 + i < p.n_total) atomicAdd(dst + i, __uint_as_float(raw[i]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols<BN>()) : "memory");
+  }
+}
+
+template <int BN, int STAGES>
+int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcWgradArgs& args, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (2 * 8192 + (BN / 64) * 8192) + 1024;
+  auto k = wgrad_tc_kernel<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  k<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, args);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
 }  // namespace
 
 extern "C" int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype, int nbatch, int L, int Cin, int taps,
@@ -496,5 +642,59 @@ extern "C" int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype
     case 64: return short_k ? launch_tc<64, 2>(tmA, tmB, args, grid, st) : launch_tc<64, 4>(tmA, tmB, args, grid, st);
     case 128: return short_k ? launch_tc<128, 2>(tmA, tmB, args, grid, st) : launch_tc<128, 3>(tmA, tmB, args, grid, st);
     default: return short_k ? launch_tc<256, 2>(tmA, tmB, args, grid, st) : launch_tc<256, 4>(tmA, tmB, args, grid, st);
+  }
+}
+
+
+extern "C" int acb_wgrad_bf16(const void* dY, int ldy, int a_col0, int M_out, const void* X, int nb, int L, int Cin, int taps, int pad,
+                              long long x_batch_stride, long long x_row_stride, float* dW, int ldc, int accumulate, void* stream) {
+  ACB_CHECK(dY && X && dW && nb > 0 && L > 0 && Cin > 0 && taps > 0 && M_out > 0, "acb_wgrad_bf16: bad arguments");
+  ACB_CHECK(taps == 1 || Cin % 64 == 0, "acb_wgrad_bf16: convolution weight gradients need Cin %% 64 == 0 (got %d)", Cin);
+  ACB_CHECK(((uintptr_t)dY % 16 == 0) && ((uintptr_t)X % 16 == 0) && ldy % 8 == 0 && x_row_stride % 8 == 0 && x_batch_stride % 8 == 0,
+            "acb_wgrad_bf16: operands must be 16-byte aligned with strides that are multiples of 8 elements");
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
+  ACB_CHECK(enc != nullptr, "acb_wgrad_bf16: cuTensorMapEncodeTiled unavailable");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_total = taps * Cin;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)ldy, (cuuint64_t)L, (cuuint64_t)nb};
+    cuuint64_t strides[2] = {(cuuint64_t)ldy * 2, (cuuint64_t)ldy * 2 * (cuuint64_t)L};
+    cuuint32_t box[3] = {64, 64, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(dY), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACB_CHECK(r == CUDA_SUCCESS, "acb_wgrad_bf16: cuTensorMapEncodeTiled(dY) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)L, (cuuint64_t)nb};
+    cuuint64_t strides[2] = {(cuuint64_t)x_row_stride * 2, (cuuint64_t)(nb > 1 ? x_batch_stride : x_row_stride * L) * 2};
+    cuuint32_t box[3] = {64, 64, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(X), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACB_CHECK(r == CUDA_SUCCESS, "acb_wgrad_bf16: cuTensorMapEncodeTiled(X) failed with %d", (int)r);
+  }
+  TcWgradArgs args;
+  args.nb = nb; args.L = L; args.cps = cdiv(L, 64);
+  args.Cin = Cin; args.pad = pad; args.n_total = n_total;
+  args.a_col0 = a_col0; args.M_out = M_out;
+  args.C = dW; args.ldc = ldc;
+  const int bn = n_total >= 256 ? 256 : (n_total > 64 ? 128 : 64);
+  const int mt = cdiv(M_out, TC_BM), ntl = cdiv(n_total, bn);
+  const long long total_chunks = (long long)nb * args.cps;
+  int splits = (int)((148LL * 4 + (long long)mt * ntl - 1) / ((long long)mt * ntl));
+  if (splits > total_chunks) splits = (int)total_chunks;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  args.chunks_per_split = (int)((total_chunks + splits - 1) / splits);
+  splits = (int)((total_chunks + args.chunks_per_split - 1) / args.chunks_per_split);
+  if (!accumulate) ACB_CUDA(cudaMemset2DAsync(dW, (size_t)ldc * 4, 0, (size_t)n_total * 4, M_out, st));
+  dim3 grid(mt, ntl, splits);
+  ACB_CHECK(ntl <= 65535, "acb_wgrad_bf16: too many column tiles");
+  switch (bn) {
+    case 64: return launch_wgrad<64, 4>(tmA, tmB, args, grid, st);
+    case 128: return launch_wgrad<128, 4>(tmA, tmB, args, grid, st);
+    default: return launch_wgrad<256, 3>(tmA, tmB, args, grid, st);
   }
 }

@@ -1,0 +1,78 @@
+"""Data-parallel training: identical replicas, one process per GPU, ONE collective per step — an all-reduce
+(average) of a persistent flat gradient buffer over NCCL/NVLink (gloo on CPU for the host-logic tests).
+
+Every parameter's ``.grad`` is a view into the flat buffer, so autograd accumulates straight into it: no
+pack/unpack copies, one memset + one collective per step.  The reference has no distributed code of its own
+(data parallelism comes from Hyrax/ignite); this is the B200-native equivalent for §8(e).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class FlatGradSync:
+    def __init__(self, module: torch.nn.Module, process_group=None):
+        self.module = module
+        self.group = process_group
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError("module has no trainable parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=dt, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off: off + n].view_as(p)
+            off += n
+        self.numel = total
+
+    @property
+    def world_size(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def zero(self) -> None:
+        """Replaces optimizer.zero_grad(): keeps the .grad views alive."""
+        self.flat.zero_()
+        for p in self.params:  # an optimizer.zero_grad(set_to_none=True) elsewhere would have dropped the views
+            if p.grad is None or p.grad.data_ptr() < self.flat.data_ptr() or p.grad.data_ptr() >= self.flat.data_ptr() + self.flat.numel() * self.flat.element_size():
+                self._rebind()
+                break
+
+    def _rebind(self) -> None:
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off: off + n].view_as(p)
+            off += n
+
+    def sync(self) -> None:
+        """Average gradients over all ranks (the single exchange step of the data-parallel path)."""
+        w = self.world_size
+        if w == 1:
+            return
+        if self.flat.is_cuda:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:  # gloo has no AVG
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.div_(w)
+
+
+def ddp_train_step(sync: FlatGradSync, forward_loss, optimizer, clip_norm=None):
+    """zero -> forward+loss -> backward -> all-reduce(avg) -> [clip] -> optimizer.step.  Returns the local loss tensor."""
+    sync.zero()
+    loss = forward_loss()
+    loss.backward()
+    sync.sync()
+    if clip_norm is not None:
+        torch.nn.utils.clip_grad_norm_(sync.params, max_norm=clip_norm)
+    optimizer.step()
+    return loss.detach()
+
+
+def shard_batch(n: int, rank: int, world: int):
+    """Contiguous alert shard [lo, hi) of rank `rank` (inference: independent shards, no collective)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

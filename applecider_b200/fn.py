@@ -55,6 +55,23 @@ def cast_to(x, dtype):
     return ops.cast(_c(x), dtype)
 
 
+def transpose(x, dtype):
+    R, C = x.shape
+    y = torch.empty((C, R), dtype=dtype, device=x.device)
+    call("acb_transpose", _c(x), dtype_tag(x), y, dtype_tag(y), R, C)
+    return y
+
+
+def wgrad_tc(dy, ldy, a_col0, M_out, x, nb, L, Cin, taps, pad, x_bstride, x_rstride, dev):
+    """tcgen05 weight gradient (bf16 operands, fp32 result [M_out, taps*Cin])."""
+    out = torch.empty((M_out, taps * Cin), dtype=F32, device=dev)
+    call("acb_wgrad_bf16", dy, ldy, a_col0, M_out, x, nb, L, Cin, taps, pad, x_bstride, x_rstride, out, taps * Cin, 0)
+    return out
+
+
+BF16 = torch.bfloat16
+
+
 # ------------------------------------------------------------------------------------------------------
 class Linear(Function):
     """y = x W^T + b  (x [M,K] fp32|bf16, W [N,K] fp32 parameter, b [N] or None); output dtype = x dtype
@@ -76,11 +93,17 @@ class Linear(Function):
         M, K = x.shape
         N = W.shape[0]
         dx = dW = db = None
+        tc = x.dtype == BF16 and dy.dtype == BF16 and N % 8 == 0 and K % 8 == 0 and M >= 64
         if ctx.needs_input_grad[0]:
-            dx = gemm_ex(dy, dtype_tag(dy), W, 0, M, K, N, N, 1, 1, K, x.device)
-            dx = cast_to(dx, x.dtype)
+            if tc:  # tcgen05 dgrad: dX = dY @ W through a bf16 W^T copy
+                dx = ops.gemm(dy, transpose(W.detach(), BF16), None)
+            else:
+                dx = cast_to(gemm_ex(dy, dtype_tag(dy), W, 0, M, K, N, N, 1, 1, K, x.device), x.dtype)
         if ctx.needs_input_grad[1]:
-            dW = gemm_ex(dy, dtype_tag(dy), x, dtype_tag(x), N, K, M, 1, N, 1, K, x.device, splits=_splits(M))
+            if tc:  # tcgen05 wgrad with MN-major operands (no activation transposes)
+                dW = wgrad_tc(dy, N, 0, N, x, 1, M, K, 1, 0, M * K, K, x.device)
+            else:
+                dW = gemm_ex(dy, dtype_tag(dy), x, dtype_tag(x), N, K, M, 1, N, 1, K, x.device, splits=_splits(M))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy)
         return dx, dW, db, None, None

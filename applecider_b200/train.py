@@ -111,16 +111,32 @@ class SpectraConvs(torch.autograd.Function):
         grads = []
         dx = None
         need_dx = ctx.needs_input_grad[0] and cin > 1
+        tc = dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and cin % 64 == 0 and cout % 8 == 0
         for j, conv in enumerate(blk.convs):
             kj = blk.kernel_sizes[j]
-            # wgrad: G[(tap,ci), co] = sum_(b,l) X[b, l+tap-pad, ci] * dY[(b,l), j*cout+co]
-            G = fn.gemm_ex(x, fn.dtype_tag(x), ops._offset_ptr(dy, j * cout), fn.dtype_tag(dy), kj * cin, cout, B * L, 0, 0, 1, ldy, dev,
-                           convT=(L, cin, kj // 2), splits=fn._splits(B * L))
             dW = torch.empty(conv.weight.shape, dtype=F32, device=dev)
-            fn.call("acb_unpack_conv_wgrad", G, dW, cout, cin, kj)
+            if tc:
+                # tcgen05 wgrad (MN-major operands): G[co, tap*Cin+ci]; unpack = pack with (Cin <-> k) exchanged
+                G = fn.wgrad_tc(dy, ldy, j * cout, cout, x, B, L, cin, kj, kj // 2, L * cin, cin, dev)
+                fn.call("acb_pack_conv_weight", G, dW, 0, cout, kj, cin, cin * kj, 0)
+            else:
+                # G[(tap,ci), co] = sum_(b,l) X[b, l+tap-pad, ci] * dY[(b,l), j*cout+co]
+                G = fn.gemm_ex(x, fn.dtype_tag(x), ops._offset_ptr(dy, j * cout), fn.dtype_tag(dy), kj * cin, cout, B * L, 0, 0, 1, ldy, dev,
+                               convT=(L, cin, kj // 2), splits=fn._splits(B * L))
+                fn.call("acb_unpack_conv_wgrad", G, dW, cout, cin, kj)
             db = fn.colsum(ops._offset_ptr(dy, j * cout), None, M=B * L, N=cout, ld=ldy, a_dt=fn.dtype_tag(dy), dev=dev)
             grads.append((dW, db))
-            if need_dx:
+            if need_dx and tc:
+                # tcgen05 dgrad: conv of the dY_j column slice with the flipped/transposed kernel, accumulated over j
+                wd = torch.empty((cin, kj * cout), dtype=torch.bfloat16, device=dev)
+                fn.call("acb_pack_conv_dgrad_weight", conv.weight, wd, 1, cout, cin, kj)
+                first = dx is None
+                if first:
+                    dx = torch.empty((B * L, cin), dtype=torch.bfloat16, device=dev)
+                fn.call("acb_gemm_bf16", ops._offset_ptr(dy, j * cout), wd, dx, 1, B, L, cout, kj, kj // 2, L * ldy, ldy, cin, kj * cout, cin,
+                        ops.pick_bn(cin), None, None, None, ops.ACT_NONE, (None if first else dx), 1, cin, None,
+                        (ops.RES_NONE if first else ops.RES_ADD), 0, None)
+            elif need_dx:
                 # dgrad: dX = sum_j conv(dY_j, flipped W_j^T)
                 wd = torch.empty((cin, kj * cout), dtype=F32, device=dev)
                 fn.call("acb_pack_conv_dgrad_weight", conv.weight, wd, 0, cout, cin, kj)

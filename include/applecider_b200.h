@@ -86,6 +86,8 @@ int acb_pack_conv_weight(const float* w, void* out, int out_dtype, int Cout, int
 int acb_pack_polyphase_weight(const float* w, void* out, int out_dtype, int Cout, int k, int phases, int halo,
                               int rows_per_phase, int row_off, long long row_stride, int Kp, void* stream);
 int acb_cast(const void* in, int in_dtype, void* out, int out_dtype, long long n, void* stream);
+/* out[c*R + r] = in[r*C + c] */
+int acb_transpose(const void* in, int in_dtype, void* out, int out_dtype, int R, int C, void* stream);
 /* out[b*out_stride + lead + i] = in[b*L + i] (bf16/f32), buffer pre-zeroed by the caller */
 int acb_pad_signal(const float* in, void* out, int out_dtype, int nb, int L, long long out_stride, int lead,
                    void* stream);
@@ -194,6 +196,11 @@ int acb_feature_stats(const float* data, long long rows, int F, double* work, fl
 int acb_gemm_ex(const void* A, int a_dtype, const void* B, int b_dtype, float* C, int M, int N, int K, long long sam,
                 long long sak, long long sbn, long long sbk, int ldc, int convT, int conv_L, int conv_Cin, int conv_pad,
                 int splits, int accumulate, void* stream);
+/* tcgen05 weight gradient with MN-major operands (no transposes), fp32 atomic accumulation over row splits:
+ *   dW[m, tap*Cin+ci] (+)= sum_{b,l} dY[(b*L+l)*ldy + a_col0 + m] * X[b, l+tap-pad, ci]       (bf16 operands)
+ * Linear layers: nb=1, L=rows, taps=1, pad=0.  Convolutions need Cin % 64 == 0. */
+int acb_wgrad_bf16(const void* dY, int ldy, int a_col0, int M_out, const void* X, int nb, int L, int Cin, int taps, int pad,
+                   long long x_batch_stride, long long x_row_stride, float* dW, int ldc, int accumulate, void* stream);
 /* out[n] (+)= sum_m a[m*ld+n] * (b ? b[m*ld+n] : 1)   (bias / layer-scale gradients; ld <= 0 means N) */
 int acb_colsum(const void* a, int a_dtype, const void* b, int b_dtype, long long M, int N, long long ld, float* out,
                int accumulate, void* stream);

@@ -179,3 +179,57 @@ def test_losses():
     l1.backward()
     l2.backward()
     assert_close(z.grad, z2.grad, 2e-6, "CE dlogits", atol=1e-8)
+
+
+# ---- tcgen05 backward paths (bf16 operands, MN-major UMMA descriptors) ---------------------------------
+@pytest.mark.parametrize("M,N,K", [(5000, 384, 96), (2048, 128, 512), (300, 96, 384), (70000, 512, 128), (64, 32, 768)])
+def test_wgrad_tc_linear(M, N, K):
+    from applecider_b200 import fn
+
+    dy = _rand(M, N, seed=40).to(torch.bfloat16)
+    x = _rand(M, K, seed=41).to(torch.bfloat16)
+    got = fn.wgrad_tc(dy, N, 0, N, x, 1, M, K, 1, 0, M * K, K, DEV)
+    ref = dy.float().T @ x.float()
+    assert_close(got / ref.abs().max(), ref / ref.abs().max(), 2e-5, f"wgrad_tc {M}x{N}x{K}")
+    t = fn.transpose(_rand(77, 130, seed=42), torch.bfloat16)
+    assert torch.equal(t, _rand(77, 130, seed=42).T.contiguous().to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("M,N,K", [(5000, 384, 96), (1000, 128, 512)])
+def test_linear_bf16_backward(M, N, K):
+    from applecider_b200 import fn
+
+    x = _rand(M, K, seed=43).to(torch.bfloat16).requires_grad_(True)
+    W, b = _rand(N, K, seed=44, scale=K**-0.5, grad=True), _rand(N, seed=45, grad=True)
+    y = fn.linear(x, W, b)
+    go = _rand(M, N, seed=46).to(torch.bfloat16)
+    y.backward(go)
+    x2 = x.detach().float().requires_grad_(True)
+    W2 = W.detach().to(torch.bfloat16).float().requires_grad_(True)
+    F.linear(x2, W2, b.detach()).backward(go.float())
+    assert_close(x.grad.float() / x2.grad.abs().max(), x2.grad / x2.grad.abs().max(), 1e-2, "bf16 dX")
+    assert_close(W.grad / W2.grad.abs().max(), W2.grad / W2.grad.abs().max(), 2e-5, "bf16 dW (fp32 accumulate)")
+    assert_close(b.grad, go.float().sum(0), 1e-5, "bf16 db")
+
+
+@pytest.mark.parametrize("B,L,Cin,Cout,ks", [(3, 200, 64, 128, [3, 5, 9]), (2, 250, 64, 128, [3, 31, 251]), (5, 62, 128, 256, [3, 15, 61]), (9, 13, 512, 256, [3, 7, 13])])
+def test_spectra_convs_bf16_backward(B, L, Cin, Cout, ks):
+    from applecider_b200.spectra import SpectraNetBlock
+    from applecider_b200.train import SpectraConvs
+
+    torch.manual_seed(0)
+    blk = SpectraNetBlock(Cin, Cout, ks, do_pool=True).to(DEV)
+    x = _rand(B, L, Cin, seed=47).to(torch.bfloat16).requires_grad_(True)
+    params = [c.weight for c in blk.convs] + [c.bias for c in blk.convs]
+    y = SpectraConvs.apply(x, None, blk, B, L, torch.bfloat16, *params)
+    go = _rand(B * L, 3 * Cout, seed=48).to(torch.bfloat16)
+    y.backward(go)
+    x2 = x.detach().float().requires_grad_(True)
+    ws = [c.weight.detach().to(torch.bfloat16).float().requires_grad_(True) for c in blk.convs]
+    ref = torch.cat([F.conv1d(x2.transpose(1, 2), w, c.bias.detach(), padding=k // 2) for w, c, k in zip(ws, blk.convs, ks)], 1).transpose(1, 2).reshape(B * L, -1)
+    assert_close(y.float(), ref, 1e-2, "bf16 convs forward")
+    ref.backward(go.float())
+    assert_close(x.grad.float() / x2.grad.abs().max(), x2.grad / x2.grad.abs().max(), 2e-2, "bf16 conv dX")
+    for c, w in zip(blk.convs, ws):
+        s = w.grad.abs().max()
+        assert_close(c.weight.grad / s, w.grad / s, 3e-5, f"bf16 conv dW k={c.kernel_size[0]}")
