@@ -143,10 +143,18 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=32, dest="cpu_sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "cnn_train", "preprocess"],
+                    help="infer = headline (BASELINE configs[1]); train = fusion DP training (configs[3]); cnn_train = AstroMiNN training "
+                         "(configs[2]); preprocess = P1-P5 sweep (configs[4])")
     args = ap.parse_args()
 
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload != "infer":
+        from bench_extra import run_extra
+
+        run_extra(args, load_peaks(), ClockSampler)
         return
 
     import applecider_b200 as ab
