@@ -1,0 +1,252 @@
+// SpectraNet block front half as ONE tcgen05 kernel (stages whose 3*C_out*groups fit TMEM):
+//   three same-padded Conv1d (implicit GEMM, 3-D TMA, per-conv K-block ranges)  ->  + bias
+//   ->  LayerNorm over the 3*C concatenated channels of every position  ->  GELU  ->  bf16 [B*L, 3*C]
+// The 128 x 384 fp32 accumulator tile lives in TMEM (three 128-column sub-tiles, one per kernel size); an
+// accumulator row is one thread of the epilogue, so the LayerNorm statistics are thread-local.
+//   stage 1 (C_in 64 -> 3 x 128):  sub-tile j = conv j, one LN group of 384 columns per row.
+//   stage 0 (1 -> 3 x 64, polyphase): a GEMM row is 8 positions; one CTA owns two phases, sub-tile j holds
+//   [conv j phase r0 | conv j phase r0+1], two LN groups (one per phase) of 3 x 64 columns per row.
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+// A pipeline item is (K block, sub-tile): A tile + ONE 128-row weight sub-tile (32 KB), 6 stages deep.  K blocks
+// where several kernel sizes are active (12 % of them) re-load the A tile once per active sub-tile.
+constexpr int CL_STAGES = 6;
+constexpr uint32_t CL_A_BYTES = TC_BM * TC_BK * 2;       // 16 KB
+constexpr uint32_t CL_SUB_BYTES = 128 * TC_BK * 2;       // 16 KB per 128-row weight sub-tile
+constexpr uint32_t CL_STAGE_BYTES = CL_A_BYTES + CL_SUB_BYTES;
+
+struct ConvLnArgs {
+  int Lbox, Bbox, tps, nbatch, L;     // A tile geometry (as in gemm_tc)
+  int taps, pad, cpt, Cin;
+  int kb_lo[3], kb_hi[3];             // K-block range of every sub-tile (nested in sub-tile 2's range)
+  int brow_base[3], brow_stride_y;    // packed-weight row of sub-tile j for blockIdx.y
+  int ng;                             // LayerNorm groups per accumulator row (1 | 2); group width gw = 128 / ng per sub-tile
+  long long row_mul, row_add_y;       // output row = m * row_mul + blockIdx.y * row_add_y + g
+  long long out_rows;                 // valid output rows (positions)
+  int ldc;                            // 3 * gw
+  const float* bias;                  // packed like the weight rows
+  const float* gamma;                 // [3*gw] LayerNorm weight (channel order conv0|conv1|conv2)
+  const float* beta;
+  float eps;
+  bf16* out;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ ConvLnArgs p) {
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * CL_STAGES + 1];
+  __shared__ uint32_t tmem_holder;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x;
+  const int sample0 = (mt / p.tps) * p.Bbox;
+  const int l0 = (mt % p.tps) * p.Lbox;
+  const int kb_lo = p.kb_lo[2], kb_hi = p.kb_hi[2];
+  const int nkb = kb_hi - kb_lo;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[CL_STAGES]);
+  const uint32_t bar_acc = smem_u32(&bars[2 * CL_STAGES]);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CL_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t a_box_bytes = (uint32_t)TC_BK * 2u * (uint32_t)p.Lbox * (uint32_t)p.Bbox;
+      int it = 0;
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        const int tap = kb / p.cpt, cc = kb - tap * p.cpt;
+        for (int j = 2; j >= 0; --j) {
+          if (kb < p.kb_lo[j] || kb >= p.kb_hi[j]) continue;
+          const int s = it % CL_STAGES;
+          const uint32_t ph = (uint32_t)(it / CL_STAGES) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          const uint32_t sa = smem_base + s * CL_STAGE_BYTES;
+          mbar_expect_tx(bar_full + 8 * s, a_box_bytes + CL_SUB_BYTES);
+          tma_load_3d(sa, &tmA, cc * TC_BK, l0 + tap - p.pad, sample0, bar_full + 8 * s);
+          tma_load_2d(sa + CL_A_BYTES, &tmB, tap * p.Cin + cc * TC_BK, p.brow_base[j] + (int)blockIdx.y * p.brow_stride_y, bar_full + 8 * s);
+          ++it;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int it = 0;
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        for (int j = 2; j >= 0; --j) {
+          if (kb < p.kb_lo[j] || kb >= p.kb_hi[j]) continue;
+          const int s = it % CL_STAGES;
+          const uint32_t ph = (uint32_t)(it / CL_STAGES) & 1u;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * CL_STAGE_BYTES;
+          const uint32_t sb = sa + CL_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(tmem_base + 128u * j, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), IDESC, (kb > p.kb_lo[j] || k > 0) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * s);
+          ++it;
+        }
+      }
+      umma_commit(bar_acc);
+    }
+  } else {
+    // ===================== epilogue: bias -> LayerNorm(3*gw) -> GELU -> bf16 =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int s_in_tile = r / p.Lbox;
+    const int l = l0 + (r - s_in_tile * p.Lbox);
+    const int sample = sample0 + s_in_tile;
+    const long long m = (long long)sample * p.L + l;
+    const bool valid_row = (s_in_tile < p.Bbox) && (sample < p.nbatch) && (l < p.L);
+    mbar_wait_sleep(bar_acc, 0);
+    tc_fence_after();
+    const int gw = 128 / p.ng;
+    const float inv_n = 1.0f / (float)(3 * gw);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int g = 0; g < p.ng; ++g) {
+      const long long orow = m * p.row_mul + (long long)blockIdx.y * p.row_add_y + g;
+      const bool valid = valid_row && orow < p.out_rows;
+      // pass 1: statistics of (acc + bias) over the 3*gw channels of this position
+      float sum = 0.0f, sq = 0.0f;
+      for (int j = 0; j < 3; ++j) {
+        const int brow = p.brow_base[j] + (int)blockIdx.y * p.brow_stride_y + g * gw;
+        for (int c0 = 0; c0 < gw; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(lane_base + (uint32_t)(128 * j + g * gw + c0), raw);
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + brow + c0);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 bb = __ldg(b4 + i4);
+            const float v0 = __uint_as_float(raw[i4 * 4 + 0]) + bb.x, v1 = __uint_as_float(raw[i4 * 4 + 1]) + bb.y;
+            const float v2 = __uint_as_float(raw[i4 * 4 + 2]) + bb.z, v3 = __uint_as_float(raw[i4 * 4 + 3]) + bb.w;
+            sum += (v0 + v1) + (v2 + v3);
+            sq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+          }
+        }
+      }
+      const float mean = sum * inv_n;
+      const float rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.0f) + p.eps);
+      // pass 2: normalise, affine, GELU, pack to bf16 and store this thread's own row (64 contiguous bytes per chunk)
+      bf16* orow_ptr = p.out + orow * p.ldc;
+      for (int j = 0; j < 3; ++j) {
+        const int brow = p.brow_base[j] + (int)blockIdx.y * p.brow_stride_y + g * gw;
+        for (int c0 = 0; c0 < gw; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(lane_base + (uint32_t)(128 * j + g * gw + c0), raw);
+          const int ch = j * gw + c0;  // channel inside the concatenated 3*gw row
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + brow + c0);
+          const float4* g4 = reinterpret_cast<const float4*>(p.gamma + ch);
+          const float4* e4 = reinterpret_cast<const float4*>(p.beta + ch);
+          uint32_t pk[16];
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 bb = __ldg(b4 + i4), gg = __ldg(g4 + i4), ee = __ldg(e4 + i4);
+            const float y0 = gelu_fast((__uint_as_float(raw[i4 * 4 + 0]) + bb.x - mean) * rstd * gg.x + ee.x);
+            const float y1 = gelu_fast((__uint_as_float(raw[i4 * 4 + 1]) + bb.y - mean) * rstd * gg.y + ee.y);
+            const float y2 = gelu_fast((__uint_as_float(raw[i4 * 4 + 2]) + bb.z - mean) * rstd * gg.z + ee.z);
+            const float y3 = gelu_fast((__uint_as_float(raw[i4 * 4 + 3]) + bb.w - mean) * rstd * gg.w + ee.w);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
+            pk[i4 * 2 + 0] = *reinterpret_cast<uint32_t*>(&h0);
+            pk[i4 * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(orow_ptr + ch);
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) dst[v4] = make_uint4(pk[v4 * 4 + 0], pk[v4 * 4 + 1], pk[v4 * 4 + 2], pk[v4 * 4 + 3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+extern "C" int acb_spectra_conv_ln_bf16(const void* A, const void* Bw, void* out, int nbatch, int L, int Cin, int taps, int pad,
+                                        long long a_batch_stride, long long a_row_stride, int ldb, int b_rows, const int* kb_ranges_host,
+                                        const int* brow_base_host, int brow_stride_y, int grid_y, int ng, long long row_mul,
+                                        long long row_add_y, long long out_rows, const float* bias, const float* gamma,
+                                        const float* beta, float eps, void* stream) {
+  ACB_CHECK(A && Bw && out && bias && gamma && beta && kb_ranges_host && brow_base_host, "acb_spectra_conv_ln_bf16: null argument");
+  ACB_CHECK(nbatch > 0 && L > 0 && Cin > 0 && taps > 0 && (ng == 1 || ng == 2) && grid_y >= 1, "acb_spectra_conv_ln_bf16: bad shape");
+  ACB_CHECK(((uintptr_t)A % 16 == 0) && ((uintptr_t)Bw % 16 == 0) && ((uintptr_t)out % 16 == 0) && a_row_stride % 8 == 0 && a_batch_stride % 8 == 0 && ldb % 8 == 0,
+            "acb_spectra_conv_ln_bf16: alignment");
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
+  ACB_CHECK(enc != nullptr, "acb_spectra_conv_ln_bf16: cuTensorMapEncodeTiled unavailable");
+  ConvLnArgs args;
+  memset(&args, 0, sizeof(args));
+  args.Lbox = L >= TC_BM ? TC_BM : L;
+  args.Bbox = L >= TC_BM ? 1 : (TC_BM / L);
+  args.tps = L >= TC_BM ? cdiv(L, TC_BM) : 1;
+  args.nbatch = nbatch; args.L = L; args.taps = taps; args.pad = pad; args.cpt = cdiv(Cin, TC_BK); args.Cin = Cin;
+  const int kb_total = taps * args.cpt;
+  for (int j = 0; j < 3; ++j) {
+    args.kb_lo[j] = kb_ranges_host[2 * j];
+    args.kb_hi[j] = kb_ranges_host[2 * j + 1];
+    args.brow_base[j] = brow_base_host[j];
+    ACB_CHECK(args.kb_lo[j] >= 0 && args.kb_hi[j] <= kb_total && args.kb_lo[j] < args.kb_hi[j], "acb_spectra_conv_ln_bf16: bad K range %d", j);
+  }
+  ACB_CHECK(args.kb_lo[2] <= args.kb_lo[0] && args.kb_lo[2] <= args.kb_lo[1] && args.kb_hi[2] >= args.kb_hi[0] && args.kb_hi[2] >= args.kb_hi[1],
+            "acb_spectra_conv_ln_bf16: sub-tile 2 must span the other K ranges");
+  args.brow_stride_y = brow_stride_y; args.ng = ng; args.row_mul = row_mul; args.row_add_y = row_add_y; args.out_rows = out_rows;
+  args.ldc = 3 * (128 / ng); args.bias = bias; args.gamma = gamma; args.beta = beta; args.eps = eps; args.out = (bf16*)out;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)L, (cuuint64_t)nbatch};
+    cuuint64_t strides[2] = {(cuuint64_t)a_row_stride * 2, (cuuint64_t)(nbatch > 1 ? a_batch_stride : (long long)a_row_stride * L) * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)args.Lbox, (cuuint32_t)args.Bbox};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(A), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACB_CHECK(r == CUDA_SUCCESS, "acb_spectra_conv_ln_bf16: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)((long long)taps * Cin), (cuuint64_t)b_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ldb * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(Bw), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACB_CHECK(r == CUDA_SUCCESS, "acb_spectra_conv_ln_bf16: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  constexpr size_t smem = (size_t)CL_STAGES * CL_STAGE_BYTES + 1024;
+  static bool configured = false;
+  if (!configured) {
+    ACB_CUDA(cudaFuncSetAttribute(conv_ln_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const long long MT = (long long)cdiv(nbatch, args.Bbox) * args.tps;
+  ACB_CHECK(MT < (1LL << 31) && grid_y <= 65535, "acb_spectra_conv_ln_bf16: grid too large");
+  conv_ln_tc_kernel<<<dim3((unsigned)MT, (unsigned)grid_y), TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, args);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}

@@ -77,6 +77,17 @@ int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype, int nbatc
                   int res_dtype, int ldr, const float* gamma, int res_mode, int pool4, const int* m_valid_dev,
                   void* stream);
 
+/* SpectraNet block front half fused on tcgen05 (spectranet.py:29-35): three same-padded Conv1d (implicit GEMM, packed
+ * weights Bw [b_rows, ldb], per-conv K-block ranges kb_ranges_host[3][2]) + bias + LayerNorm over the concatenated
+ * channels of every position + GELU -> bf16 out[out_rows, 3*(128/ng)].  Sub-tile j (= conv j, 128 accumulator columns)
+ * reads weight rows brow_base_host[j] + blockIdx.y*brow_stride_y; ng = LayerNorm groups per GEMM row (stage 0 polyphase:
+ * 2 phases per CTA, output row = m*row_mul + blockIdx.y*row_add_y + g).  A geometry as in acb_gemm_bf16. */
+int acb_spectra_conv_ln_bf16(const void* A, const void* Bw, void* out, int nbatch, int L, int Cin, int taps, int pad,
+                             long long a_batch_stride, long long a_row_stride, int ldb, int b_rows, const int* kb_ranges_host,
+                             const int* brow_base_host, int brow_stride_y, int grid_y, int ng, long long row_mul,
+                             long long row_add_y, long long out_rows, const float* bias, const float* gamma,
+                             const float* beta, float eps, void* stream);
+
 /* Weight packing (derived, non-persistent buffers; refreshed after load_state_dict / optimizer step).
  * out[co*row_stride + (tap + tap_off)*Cin + ci] = w[co, ci, tap]     (w = PyTorch (Cout, Cin, k)) */
 int acb_pack_conv_weight(const float* w, void* out, int out_dtype, int Cout, int Cin, int k, long long row_stride,

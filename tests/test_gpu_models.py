@@ -216,3 +216,19 @@ def test_fusion_matches_golden(golden_dir, fusion, dtype, tol):
         assert_close(p, g["p_emb"], tol, "photometry embedding")
         assert_close(im, g["im_emb"], tol, "image+metadata embedding")
         assert_close(s, g["s_emb"], tol, "spectra embedding")
+
+
+def test_spectra_fused_stage1_path(golden_dir):
+    """The opt-in fused conv+LN+GELU kernel for the 64->3x128 stage gives the same logits."""
+    from applecider_b200 import spectra as sp
+
+    g = load_golden(golden_dir, "spectra")
+    prod, _ = _pair("SpectraNet", dtype="bf16")
+    old = sp.FUSE_STAGE1
+    sp.FUSE_STAGE1 = True
+    try:
+        with torch.no_grad():
+            got = prod((g["s4096"].to(DEV), None, None))
+    finally:
+        sp.FUSE_STAGE1 = old
+    assert_close(got, g["logits4096"], BF16_TOL, "spectra bf16 with fused stage 1")
