@@ -612,6 +612,8 @@ __global__ void sumsq_kernel(const float* x, long long n, float* out) {
 
 }  // namespace
 
+int acb_dwconv7_fast(const void* x, int dtype, const float* w, const float* bias, int flip, void* y, int B, int H, int W, int C, cudaStream_t st);
+
 #define LAUNCHED(n)     \
   ACB_LAUNCH_CHECK();   \
   acb_count_launch(n);  \
@@ -741,6 +743,10 @@ int acb_scatter_cls(const float* dcls, const int* cu_seqlens, int B, int D, void
 int acb_dwconv7(const void* x, int x_dtype, const float* w, const float* bias, int flip, void* y, int y_dtype, int B, int H, int W, int C,
                 void* stream) {
   ACB_CHECK(x && w && y && B > 0 && H > 0 && W > 0 && C > 0, "acb_dwconv7: bad arguments");
+  if (x_dtype == y_dtype) {
+    const int rc = acb_dwconv7_fast(x, x_dtype, w, bias, flip, y, B, H, W, C, (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
   dwconv7_kernel<<<grid_for((long long)B * H * W * C), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, w, bias, flip, y, y_dtype, B, H, W, C);
   LAUNCHED(1);
 }

@@ -82,7 +82,7 @@ template <typename T, int W>
 __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, const float* __restrict__ ln_w,
                                                            const float* __restrict__ ln_b, float eps, T* __restrict__ y,
-                                                           int H, int C, int R, int use_wsm) {
+                                                           int H, int C, int R, int use_wsm, int do_ln, int flip) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int strips = (H + R - 1) / R;
   const int b = blockIdx.x / strips, oy0 = (blockIdx.x % strips) * R;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const
   if (use_wsm) {
     for (int i = tid; i < 49 * C; i += nthr) {
       const int cc = i / 49, j = i - cc * 49;
-      wsm[j * (C + 1) + cc] = __ldg(w + i);
+      wsm[(flip ? 48 - j : j) * (C + 1) + cc] = __ldg(w + i);
     }
   }
   __syncthreads();
@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const
   float bc = 0.0f;
   if (c < C) {
 #pragma unroll
-    for (int j = 0; j < 49; ++j) wr[j] = use_wsm ? wsm[j * (C + 1) + c] : __ldg(w + c * 49 + j);
-    bc = bias[c];
+    for (int j = 0; j < 49; ++j) wr[j] = use_wsm ? wsm[j * (C + 1) + c] : __ldg(w + c * 49 + (flip ? 48 - j : j));
+    bc = bias ? bias[c] : 0.0f;
   }
   const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
   for (int r = 0; r < rows; ++r) {
@@ -140,9 +140,16 @@ __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const
           }
         }
       }
+      if (!do_ln) {
+        T* o = y + (((long long)b * H + oy0 + r) * W) * C + c;
 #pragma unroll
-      for (int ox = 0; ox < W; ++ox) cv[ox * C + c] = acc[ox];
+        for (int ox = 0; ox < W; ++ox) o[ox * C] = from_f<T>(acc[ox]);
+      } else {
+#pragma unroll
+        for (int ox = 0; ox < W; ++ox) cv[ox * C + c] = acc[ox];
+      }
     }
+    if (!do_ln) continue;  // uniform for the whole CTA
     __syncthreads();
     for (int ox = wid; ox < W; ox += nw) {
       const float* v = cv + ox * C;
@@ -177,7 +184,7 @@ __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const
 
 template <typename T, int W>
 int launch_dwconv_w(const void* x, const float* w, const float* b, const float* ln_w, const float* ln_b, float eps, void* y,
-                    int B, int H, int C, cudaStream_t st) {
+                    int B, int H, int C, cudaStream_t st, int do_ln = 1, int flip = 0) {
   const int R = W >= 15 ? 5 : (W >= 7 ? 7 : (W >= 3 ? 3 : 1));
   const int use_wsm = C <= 192 ? 1 : 0;
   const size_t in_bytes = (((size_t)(R + 6) * W * C * sizeof(T)) + 15) & ~(size_t)15;
@@ -187,7 +194,7 @@ int launch_dwconv_w(const void* x, const float* w, const float* b, const float* 
   const int threads = ((C + 31) / 32) * 32;
   if (threads > dw_max_threads<W>() || smem > 200 * 1024) return 1;  // fall back to the generic kernel
   const unsigned grid = (unsigned)((long long)B * ((H + R - 1) / R));
-  k<<<grid, threads, smem, st>>>((const T*)x, w, b, ln_w, ln_b, eps, (T*)y, H, C, R, use_wsm);
+  k<<<grid, threads, smem, st>>>((const T*)x, w, b, ln_w, ln_b, eps, (T*)y, H, C, R, use_wsm, do_ln, flip);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;
@@ -195,12 +202,12 @@ int launch_dwconv_w(const void* x, const float* w, const float* b, const float* 
 
 template <typename T>
 int dispatch_dwconv_w(int W, const void* x, const float* w, const float* b, const float* ln_w, const float* ln_b, float eps,
-                      void* y, int B, int H, int C, cudaStream_t st) {
+                      void* y, int B, int H, int C, cudaStream_t st, int do_ln = 1, int flip = 0) {
   switch (W) {
-    case 15: return launch_dwconv_w<T, 15>(x, w, b, ln_w, ln_b, eps, y, B, H, C, st);
-    case 7: return launch_dwconv_w<T, 7>(x, w, b, ln_w, ln_b, eps, y, B, H, C, st);
-    case 3: return launch_dwconv_w<T, 3>(x, w, b, ln_w, ln_b, eps, y, B, H, C, st);
-    case 1: return launch_dwconv_w<T, 1>(x, w, b, ln_w, ln_b, eps, y, B, H, C, st);
+    case 15: return launch_dwconv_w<T, 15>(x, w, b, ln_w, ln_b, eps, y, B, H, C, st, do_ln, flip);
+    case 7: return launch_dwconv_w<T, 7>(x, w, b, ln_w, ln_b, eps, y, B, H, C, st, do_ln, flip);
+    case 3: return launch_dwconv_w<T, 3>(x, w, b, ln_w, ln_b, eps, y, B, H, C, st, do_ln, flip);
+    case 1: return launch_dwconv_w<T, 1>(x, w, b, ln_w, ln_b, eps, y, B, H, C, st, do_ln, flip);
   }
   return 1;  // not specialised
 }
@@ -269,6 +276,14 @@ inline unsigned grid_for(long long n, int block = 256) {
 }
 
 }  // namespace
+
+// plain depthwise conv (no LayerNorm) through the register-window kernel; returns 1 when the shape is not specialised
+int acb_dwconv7_fast(const void* x, int dtype, const float* w, const float* bias, int flip, void* y, int B, int H, int W, int C, cudaStream_t st) {
+  const bool aligned = (((uintptr_t)x | (uintptr_t)y) % 16 == 0);
+  if (!((W == 15 || W == 7 || W == 3 || W == 1) && H == W && C % 8 == 0 && C <= 768 && aligned)) return 1;
+  return dtype == ACB_F32 ? dispatch_dwconv_w<float>(W, x, w, bias, nullptr, nullptr, 0.0f, y, B, H, C, st, 0, flip)
+                          : dispatch_dwconv_w<bf16>(W, x, w, bias, nullptr, nullptr, 0.0f, y, B, H, C, st, 0, flip);
+}
 
 extern "C" {
 

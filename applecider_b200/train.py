@@ -112,6 +112,32 @@ class SpectraConvs(torch.autograd.Function):
         dx = None
         need_dx = ctx.needs_input_grad[0] and cin > 1
         tc = dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and cin % 64 == 0 and cout % 8 == 0
+        if dy.dtype == torch.bfloat16 and cin == 1 and L % 8 == 0 and cout % 64 == 0:
+            # stage 0 (1 input channel): polyphase weight gradient on tcgen05.  dY is viewed as [B, L/8, 8*3C] (a GEMM row =
+            # 8 positions), X as the overlapping-row view of the zero-padded signal; the 8 phases accumulate (fp32 atomics)
+            # into one buffer per kernel size because the output pointer is shifted by (8 - r) columns.
+            from .spectra import _HALO, _PHASES
+
+            kp = ((_HALO + blk._kmax() // 2 + _PHASES + 63) // 64) * 64
+            stride = L + kp
+            xp = torch.zeros((B, stride), dtype=torch.bfloat16, device=dev)
+            fn.call("acb_pad_signal", x.view(B, L).float() if x.dtype != F32 else x.view(B, L), xp, 1, B, L, stride, _HALO)
+            out = [None] * 6
+            for j, conv in enumerate(blk.convs):
+                kj = blk.kernel_sizes[j]
+                padj = kj // 2
+                n_start = ((_HALO - padj) // 8) * 8
+                width = ((_HALO + padj + _PHASES - n_start + 63) // 64) * 64
+                width = min(width, kp - n_start)
+                G = torch.zeros((cout, width + 8), dtype=F32, device=dev)
+                for r in range(_PHASES):
+                    fn.call("acb_wgrad_bf16", dy, _PHASES * ldy, r * ldy + j * cout, cout, ops._offset_ptr(xp, n_start), B, L // _PHASES, width, 1, 0,
+                            stride, _PHASES, ops._offset_ptr(G, _PHASES - r), width + 8, 1)
+                dW = torch.empty(conv.weight.shape, dtype=F32, device=dev)
+                fn.call("acb_copy2d", ops._offset_ptr(G, _HALO - padj - n_start + _PHASES), 0, width + 8, dW, 0, kj, cout, kj)
+                out[j] = dW
+                out[3 + j] = fn.colsum(ops._offset_ptr(dy, j * cout), None, M=B * L, N=cout, ld=ldy, a_dt=fn.dtype_tag(dy), dev=dev)
+            return (None, None, None, None, None, None, *out)
         for j, conv in enumerate(blk.convs):
             kj = blk.kernel_sizes[j]
             dW = torch.empty(conv.weight.shape, dtype=F32, device=dev)

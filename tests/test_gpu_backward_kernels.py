@@ -233,3 +233,28 @@ def test_spectra_convs_bf16_backward(B, L, Cin, Cout, ks):
     for c, w in zip(blk.convs, ws):
         s = w.grad.abs().max()
         assert_close(c.weight.grad / s, w.grad / s, 3e-5, f"bf16 conv dW k={c.kernel_size[0]}")
+
+
+@pytest.mark.parametrize("L", [1024, 4096, 1000])
+def test_spectra_stage0_bf16_wgrad(L):
+    """Stage-0 (1 input channel, k up to 1021) weight gradients through the polyphase tcgen05 wgrad."""
+    from applecider_b200.spectra import SpectraNetBlock
+    from applecider_b200.train import SpectraConvs
+
+    torch.manual_seed(0)
+    B = 2
+    blk = SpectraNetBlock(1, 64, [3, 61, 1021], do_pool=True).to(DEV)
+    sig = _rand(B, L, seed=50)
+    params = [c.weight for c in blk.convs] + [c.bias for c in blk.convs]
+    y = SpectraConvs.apply(None, sig, blk, B, L, torch.bfloat16, *params)
+    go = _rand(B * L, 192, seed=51).to(torch.bfloat16)
+    y.backward(go)
+    xb = sig.to(torch.bfloat16).float()[:, None, :]
+    ws = [c.weight.detach().clone().requires_grad_(True) for c in blk.convs]
+    bs = [c.bias.detach().clone().requires_grad_(True) for c in blk.convs]
+    ref = torch.cat([F.conv1d(xb, w, b, padding=w.shape[-1] // 2) for w, b in zip(ws, bs)], 1).transpose(1, 2).reshape(B * L, -1)
+    ref.backward(go.float())
+    for c, w, b in zip(blk.convs, ws, bs):
+        s = w.grad.abs().max()
+        assert_close(c.weight.grad / s, w.grad / s, 5e-5, f"stage-0 dW k={c.kernel_size[0]} L={L}")
+        assert_close(c.bias.grad, b.grad, 1e-5, "stage-0 db")
