@@ -80,6 +80,20 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float cdf = x >= 0.0f ? 1.0f - 0.5f * erfc_z : 0.5f * erfc_z;
   return x * cdf;
 }
+// bf16-output GELU: x * Phi(x) through the hardware tanh (MUFU.TANH), 7 instructions / 1 MUFU.  |error| <= 4.8e-4
+// against the exact erf form, below the bf16 rounding of the O(1) activations it feeds; used only where the result is
+// rounded to bf16 (define ACB_EXACT_GELU_BF16 to fall back to the 1.5e-7-accurate rational).
+__device__ __forceinline__ float gelu_bf16(float x) {
+#ifdef ACB_EXACT_GELU_BF16
+  return gelu_fast(x);
+#else
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);  // sqrt(2/pi) * (x + 0.044715 x^3)
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+#endif
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float apply_act(float v, int act) {

@@ -10,11 +10,17 @@
 
 using namespace tc;
 
+// optional phase timing (clock64 deltas summed over CTAs): [0] prologue, [1] main loop until the accumulator is ready,
+// [2] epilogue, [3] CTA count.  Enabled by acb_debug_timing(1); read + reset by acb_debug_timing_read().
+__device__ unsigned long long g_cl_timing[4];
+__device__ int g_cl_timing_on = 0;
+
 namespace {
 
-// A pipeline item is (K block, sub-tile): A tile + ONE 128-row weight sub-tile (32 KB), 6 stages deep.  K blocks
+// A pipeline item is (K block, sub-tile): A tile + ONE 128-row weight sub-tile (32 KB), 5 stages deep.  K blocks
 // where several kernel sizes are active (12 % of them) re-load the A tile once per active sub-tile.
-constexpr int CL_STAGES = 6;
+constexpr int CL_STAGES = 5;
+constexpr uint32_t CL_STG_BYTES = 32 * 144;  // per-warp 32 x 64 bf16 transpose tile (row pitch 128 + 16 bytes)
 constexpr uint32_t CL_A_BYTES = TC_BM * TC_BK * 2;       // 16 KB
 constexpr uint32_t CL_SUB_BYTES = 128 * TC_BK * 2;       // 16 KB per 128-row weight sub-tile
 constexpr uint32_t CL_STAGE_BYTES = CL_A_BYTES + CL_SUB_BYTES;
@@ -35,14 +41,19 @@ struct ConvLnArgs {
   bf16* out;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+constexpr int CL_THREADS = 64 + 256;  // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+
+__global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ ConvLnArgs p) {
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * CL_STAGES + 1];
   __shared__ uint32_t tmem_holder;
+  __shared__ float part[2][2][128][2];  // [group][half][row][sum, sumsq] partial LayerNorm statistics
+  __shared__ __align__(16) float s_bias[384], s_gamma[384], s_beta[384];  // staged once per CTA while the main loop runs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_start = clock64();
   const int mt = blockIdx.x;
   const int sample0 = (mt / p.tps) * p.Bbox;
   const int l0 = (mt % p.tps) * p.Lbox;
@@ -70,6 +81,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
+  const long long t_pro = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -113,7 +125,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
     }
   } else {
     // ===================== epilogue: bias -> LayerNorm(3*gw) -> GELU -> bf16 =====================
+    {  // stage the per-channel parameters (the epilogue warps are idle during the main loop)
+      const int gw0 = 128 / p.ng;
+      for (int i = threadIdx.x - 64; i < 384; i += 256) {
+        const int j = i >> 7, c = i & 127;  // accumulator column 128*j + c  <->  (group g = c / gw, channel c % gw)
+        s_bias[i] = __ldg(p.bias + p.brow_base[j] + (int)blockIdx.y * p.brow_stride_y + c);
+        const int g = c / gw0, cc = c - g * gw0;
+        s_gamma[i] = __ldg(p.gamma + j * gw0 + cc);
+        s_beta[i] = __ldg(p.beta + j * gw0 + cc);
+      }
+      asm volatile("bar.sync 9, 256;" ::: "memory");  // the 8 epilogue warps
+    }
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;  // which of the two warps serving this lane quarter
     const int r = q * 32 + lane;
     const int s_in_tile = r / p.Lbox;
     const int l = l0 + (r - s_in_tile * p.Lbox);
@@ -122,6 +146,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
     const bool valid_row = (s_in_tile < p.Bbox) && (sample < p.nbatch) && (l < p.L);
     mbar_wait_sleep(bar_acc, 0);
     tc_fence_after();
+    const long long t_acc = clock64();
     const int gw = 128 / p.ng;
     const float inv_n = 1.0f / (float)(3 * gw);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -133,12 +158,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
       for (int j = 0; j < 3; ++j) {
         const int brow = p.brow_base[j] + (int)blockIdx.y * p.brow_stride_y + g * gw;
         for (int c0 = 0; c0 < gw; c0 += 32) {
+          if ((((g * 3 * gw + j * gw + c0) >> 6) & 1) != half) continue;  // 64-column blocks alternate between the two warps
           uint32_t raw[32];
           tmem_ld32(lane_base + (uint32_t)(128 * j + g * gw + c0), raw);
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + brow + c0);
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + 128 * j + g * gw + c0);
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 bb = __ldg(b4 + i4);
+            const float4 bb = b4[i4];
             const float v0 = __uint_as_float(raw[i4 * 4 + 0]) + bb.x, v1 = __uint_as_float(raw[i4 * 4 + 1]) + bb.y;
             const float v2 = __uint_as_float(raw[i4 * 4 + 2]) + bb.z, v3 = __uint_as_float(raw[i4 * 4 + 3]) + bb.w;
             sum += (v0 + v1) + (v2 + v3);
@@ -146,38 +172,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
           }
         }
       }
+      part[g][half][r][0] = sum;
+      part[g][half][r][1] = sq;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the two warps of this quarter
+      sum += part[g][half ^ 1][r][0];
+      sq += part[g][half ^ 1][r][1];
       const float mean = sum * inv_n;
       const float rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.0f) + p.eps);
-      // pass 2: normalise, affine, GELU, pack to bf16 and store this thread's own row (64 contiguous bytes per chunk)
-      bf16* orow_ptr = p.out + orow * p.ldc;
+      // pass 2: normalise, affine, GELU, pack to bf16; 32 x 64 tiles go through a per-warp smem transpose so that every
+      // store instruction writes four full 128-byte lines (uncoalesced per-row stores cost 32 L1 wavefronts each)
+      uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)CL_STAGES * CL_STAGE_BYTES + (size_t)(warp - 2) * CL_STG_BYTES;
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
       for (int j = 0; j < 3; ++j) {
-        const int brow = p.brow_base[j] + (int)blockIdx.y * p.brow_stride_y + g * gw;
-        for (int c0 = 0; c0 < gw; c0 += 32) {
-          uint32_t raw[32];
-          tmem_ld32(lane_base + (uint32_t)(128 * j + g * gw + c0), raw);
-          const int ch = j * gw + c0;  // channel inside the concatenated 3*gw row
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + brow + c0);
-          const float4* g4 = reinterpret_cast<const float4*>(p.gamma + ch);
-          const float4* e4 = reinterpret_cast<const float4*>(p.beta + ch);
-          uint32_t pk[16];
+        for (int cb = 0; cb < gw; cb += 64) {
+          if ((((g * 3 * gw + j * gw + cb) >> 6) & 1) != half) continue;
 #pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 bb = __ldg(b4 + i4), gg = __ldg(g4 + i4), ee = __ldg(e4 + i4);
-            const float y0 = gelu_fast((__uint_as_float(raw[i4 * 4 + 0]) + bb.x - mean) * rstd * gg.x + ee.x);
-            const float y1 = gelu_fast((__uint_as_float(raw[i4 * 4 + 1]) + bb.y - mean) * rstd * gg.y + ee.y);
-            const float y2 = gelu_fast((__uint_as_float(raw[i4 * 4 + 2]) + bb.z - mean) * rstd * gg.z + ee.z);
-            const float y3 = gelu_fast((__uint_as_float(raw[i4 * 4 + 3]) + bb.w - mean) * rstd * gg.w + ee.w);
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
-            pk[i4 * 2 + 0] = *reinterpret_cast<uint32_t*>(&h0);
-            pk[i4 * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
-          }
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(orow_ptr + ch);
+          for (int hh = 0; hh < 2; ++hh) {
+            const int c0 = cb + hh * 32;
+            uint32_t raw[32];
+            tmem_ld32(lane_base + (uint32_t)(128 * j + g * gw + c0), raw);
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + 128 * j + g * gw + c0);
+            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + 128 * j + g * gw + c0);
+            const float4* e4 = reinterpret_cast<const float4*>(s_beta + 128 * j + g * gw + c0);
+            uint32_t pk[16];
 #pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) dst[v4] = make_uint4(pk[v4 * 4 + 0], pk[v4 * 4 + 1], pk[v4 * 4 + 2], pk[v4 * 4 + 3]);
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 bb = b4[i4], gg = g4[i4], ee = e4[i4];
+              const float y0 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 0]) + bb.x - mean) * rstd * gg.x + ee.x);
+              const float y1 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 1]) + bb.y - mean) * rstd * gg.y + ee.y);
+              const float y2 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 2]) + bb.z - mean) * rstd * gg.z + ee.z);
+              const float y3 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 3]) + bb.w - mean) * rstd * gg.w + ee.w);
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
+              pk[i4 * 2 + 0] = *reinterpret_cast<uint32_t*>(&h0);
+              pk[i4 * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            }
+            uint4* srow = reinterpret_cast<uint4*>(stg + lane * 144 + hh * 64);
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) srow[v4] = make_uint4(pk[v4 * 4 + 0], pk[v4 * 4 + 1], pk[v4 * 4 + 2], pk[v4 * 4 + 3]);
           }
+          __syncwarp();
+          const int ch = j * gw + cb;  // first channel of this 64-wide block inside the concatenated row
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {  // 8 lanes x 16 B = one 128-byte row segment, 4 rows per instruction
+            const int rr = it * 4 + (lane >> 3), cg = lane & 7;
+            const long long orr = __shfl_sync(0xffffffffu, orow, rr);
+            if ((vmask >> rr) & 1u) {
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 144 + cg * 16);
+              *reinterpret_cast<uint4*>(p.out + orr * p.ldc + ch + cg * 8) = val;
+            }
+          }
+          __syncwarp();
         }
       }
+    }
+    if (g_cl_timing_on && warp == 2 && lane == 0) {
+      const long long t_end = clock64();
+      atomicAdd(&g_cl_timing[0], (unsigned long long)(t_pro - t_start));
+      atomicAdd(&g_cl_timing[1], (unsigned long long)(t_acc - t_pro));
+      atomicAdd(&g_cl_timing[2], (unsigned long long)(t_end - t_acc));
+      atomicAdd(&g_cl_timing[3], 1ull);
     }
   }
   tc_fence_before();
@@ -237,7 +290,7 @@ extern "C" int acb_spectra_conv_ln_bf16(const void* A, const void* Bw, void* out
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ACB_CHECK(r == CUDA_SUCCESS, "acb_spectra_conv_ln_bf16: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   }
-  constexpr size_t smem = (size_t)CL_STAGES * CL_STAGE_BYTES + 1024;
+  constexpr size_t smem = (size_t)CL_STAGES * CL_STAGE_BYTES + 8 * CL_STG_BYTES + 1024;
   static bool configured = false;
   if (!configured) {
     ACB_CUDA(cudaFuncSetAttribute(conv_ln_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -245,8 +298,21 @@ extern "C" int acb_spectra_conv_ln_bf16(const void* A, const void* Bw, void* out
   }
   const long long MT = (long long)cdiv(nbatch, args.Bbox) * args.tps;
   ACB_CHECK(MT < (1LL << 31) && grid_y <= 65535, "acb_spectra_conv_ln_bf16: grid too large");
-  conv_ln_tc_kernel<<<dim3((unsigned)MT, (unsigned)grid_y), TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, args);
+  conv_ln_tc_kernel<<<dim3((unsigned)MT, (unsigned)grid_y), CL_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, args);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
+  return ACB_OK;
+}
+
+
+extern "C" int acb_debug_timing(int enable, unsigned long long* out4_host) {
+  // enable != 0: switch the conv+LN phase timers on/off; out4_host != NULL: copy + reset the accumulators
+  ACB_CUDA(cudaDeviceSynchronize());
+  ACB_CUDA(cudaMemcpyToSymbol(g_cl_timing_on, &enable, sizeof(int)));
+  if (out4_host) {
+    ACB_CUDA(cudaMemcpyFromSymbol(out4_host, g_cl_timing, sizeof(unsigned long long) * 4));
+    unsigned long long z[4] = {0, 0, 0, 0};
+    ACB_CUDA(cudaMemcpyToSymbol(g_cl_timing, z, sizeof(z)));
+  }
   return ACB_OK;
 }

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) layernorm_cached_kernel(const TX* __restr
       o[3] = (v[k][3] - mean) * rstd * w4.w + b4.w;
       if (post_act == ACB_ACT_GELU) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = FAST ? gelu_fast(o[i]) : gelu_erf(o[i]);
+        for (int i = 0; i < 4; ++i) o[i] = FAST ? gelu_bf16(o[i]) : gelu_erf(o[i]);
       } else if (post_act != ACB_ACT_NONE) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[i] = apply_act(o[i], post_act);

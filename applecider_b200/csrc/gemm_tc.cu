@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
   __shared__ uint32_t tmem_holder;
+  __shared__ __align__(16) float s_bias[BN], s_gamma[BN];  // staged by the epilogue warps while the main loop runs
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
@@ -128,6 +129,12 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     // ===================== epilogue =====================
     // TMEM -> registers (thread = output row) -> bias/act/residual/pool -> per-warp smem transpose
     // (the pipeline stages are idle by now) -> row-contiguous 16-byte global stores.
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {  // global parameter loads miss the small L1 (long-scoreboard stalls)
+      const int n = n0 + i;
+      s_bias[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
+      s_gamma[i] = (p.gamma && n < p.N) ? __ldg(p.gamma + n) : 1.0f;
+    }
+    asm volatile("bar.sync 9, 128;" ::: "memory");  // the 4 epilogue warps
     const int q = warp & 3;  // TMEM lane quarter accessible to this warp
     const int r = q * 32 + lane;
     const int s_in_tile = r / p.Lbox;
@@ -163,17 +170,11 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
       const int out_col = (p.has_coloff ? p.col_off[n_first >> 6] : (n_first & ~63)) + (n_first & 63);
       const int ncols = min(32, p.N - n_first);
       if (p.bias) {
-        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(p.bias + n_first) & 15) == 0)) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_first);
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 t = __ldg(b4 + g);
-            v[g * 4 + 0] += t.x; v[g * 4 + 1] += t.y; v[g * 4 + 2] += t.z; v[g * 4 + 3] += t.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < ncols) v[i] += __ldg(p.bias + n_first + i);
+        for (int g = 0; g < 8; ++g) {
+          const float4 t = b4[g];
+          v[g * 4 + 0] += t.x; v[g * 4 + 1] += t.y; v[g * 4 + 2] += t.z; v[g * 4 + 3] += t.w;
         }
       }
       switch (p.act) {  // warp-uniform: one branch per 32-column chunk, not per element
@@ -182,8 +183,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
           break;
         case ACB_ACT_GELU:
+          if (p.c_dtype == ACB_BF16) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+            for (int i = 0; i < 32; ++i) v[i] = gelu_bf16(v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+          }
           break;
         case ACB_ACT_TANH:
 #pragma unroll
@@ -231,7 +237,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         if (p.res_mode == ACB_RES_ADD) {
           if (p.gamma) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = rv[i] + ((i < ncols) ? __ldg(p.gamma + n_first + i) : 0.0f) * v[i];
+            for (int i = 0; i < 32; ++i) v[i] = rv[i] + s_gamma[c0 + i] * v[i];
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = rv[i] + v[i];

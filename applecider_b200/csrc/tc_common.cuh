@@ -32,22 +32,34 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// bounded wait: a protocol bug traps (-> launch failure reported to the host) instead of hanging the GPU
+// bounded wait: a protocol bug traps (-> launch failure reported to the host) instead of hanging the GPU.
+// The clock is sampled only every 4096 polls: CS2R issues on the XU pipe, and a spinning TMA/MMA thread that reads
+// it every iteration starves the epilogue's MUFU (exp/rcp) work on the same SM (ncu: pipe_xu at 105 %).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if ((++polls & 4095u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) __trap();
+    }
   }
 }
-// long waits (epilogue warps waiting for a whole main loop): back off so the spinning warps do not steal issue
+// long waits (epilogue warps waiting for a whole main loop): back off so the waiting warps do not steal issue
 // slots from the single TMA / MMA threads that share their schedulers
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(200);
-    if (clock64() - t0 > 4000000000LL) __trap();
+    __nanosleep(128);
+    if ((++polls & 1023u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) __trap();
+    }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {

@@ -17,3 +17,13 @@ with torch.no_grad():
     e1.record(); torch.cuda.synchronize()
     reg = ops.profile_stop()
 print("B", B, "ms/fwd", e0.elapsed_time(e1) / 3, {k: sum(v) / len(v) for k, v in reg.items()})
+import ctypes
+from applecider_b200 import _lib
+l = _lib.lib()
+buf = (ctypes.c_ulonglong * 4)()
+l.acb_debug_timing(1, buf)
+with torch.no_grad():
+    m((x, None, None))
+l.acb_debug_timing(0, buf)
+n = max(1, buf[3])
+print("conv_ln phases (cycles/CTA): prologue %.0f  mainloop %.0f  epilogue %.0f  ctas %d" % (buf[0] / n, buf[1] / n, buf[2] / n, buf[3]))
