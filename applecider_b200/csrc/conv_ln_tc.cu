@@ -39,16 +39,26 @@ struct ConvLnArgs {
   const float* beta;
   float eps;
   bf16* out;
+  // HANKEL mode (stage 0, polyphase): the A operand is never materialised.  A(m', chunk c) = W16[m' + c] in 16-byte
+  // units of the zero-padded signal, so the UMMA descriptor (K-major, no swizzle: rows 16 B apart, SBO 128 B, LBO 16 B)
+  // reads overlapping core matrices straight from one 4 KB window of the signal in shared memory.
+  const bf16* xwin;            // padded signal [nbatch, a_batch_stride]
+  long long xwin_stride;       // elements per sample
+  long long xwin_total;        // elements in the whole buffer
 };
 
 constexpr int CL_THREADS = 64 + 256;  // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 
+template <bool HANKEL>
 __global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ ConvLnArgs p) {
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * CL_STAGES + 1];
+  constexpr int NST = HANKEL ? 2 * CL_STAGES : CL_STAGES;            // HANKEL stages hold only a 16 KB weight sub-tile
+  constexpr uint32_t STAGE_BYTES = HANKEL ? CL_SUB_BYTES : CL_STAGE_BYTES;
+  constexpr uint32_t WIN_BYTES = (128 + 8 * 17 + 8) * 16;            // 128 rows + 17 K blocks of 8 chunks (+ slack)
+  __shared__ __align__(8) uint64_t bars[2 * NST + 2];
   __shared__ uint32_t tmem_holder;
   __shared__ float part[2][2][128][2];  // [group][half][row][sum, sumsq] partial LayerNorm statistics
   __shared__ __align__(16) float s_bias[384], s_gamma[384], s_beta[384];  // staged once per CTA while the main loop runs
@@ -62,14 +72,19 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_tc_kernel(const __grid_
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = smem_u32(&bars[0]);
-  const uint32_t bar_empty = smem_u32(&bars[CL_STAGES]);
-  const uint32_t bar_acc = smem_u32(&bars[2 * CL_STAGES]);
+  const uint32_t bar_empty = smem_u32(&bars[NST]);
+  const uint32_t bar_acc = smem_u32(&bars[2 * NST]);
+  const uint32_t bar_win = smem_u32(&bars[2 * NST + 1]);
+  // smem carve-up: [pipeline stages][8 per-warp transpose tiles][signal window (HANKEL)]
+  const uint32_t stg_off = (uint32_t)CL_STAGES * CL_STAGE_BYTES;  // both modes use the same pipeline footprint
+  const uint32_t win_off = stg_off + 8 * CL_STG_BYTES;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < CL_STAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_acc, 1);
+    mbar_init(bar_win, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -84,45 +99,68 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_tc_kernel(const __grid_
   const long long t_pro = clock64();
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t a_box_bytes = (uint32_t)TC_BK * 2u * (uint32_t)p.Lbox * (uint32_t)p.Bbox;
-      int it = 0;
-      for (int kb = kb_lo; kb < kb_hi; ++kb) {
-        const int tap = kb / p.cpt, cc = kb - tap * p.cpt;
-        for (int j = 2; j >= 0; --j) {
-          if (kb < p.kb_lo[j] || kb >= p.kb_hi[j]) continue;
-          const int s = it % CL_STAGES;
-          const uint32_t ph = (uint32_t)(it / CL_STAGES) & 1u;
-          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-          const uint32_t sa = smem_base + s * CL_STAGE_BYTES;
-          mbar_expect_tx(bar_full + 8 * s, a_box_bytes + CL_SUB_BYTES);
-          tma_load_3d(sa, &tmA, cc * TC_BK, l0 + tap - p.pad, sample0, bar_full + 8 * s);
-          tma_load_2d(sa + CL_A_BYTES, &tmB, tap * p.Cin + cc * TC_BK, p.brow_base[j] + (int)blockIdx.y * p.brow_stride_y, bar_full + 8 * s);
-          ++it;
+    const uint32_t a_box_bytes = (uint32_t)TC_BK * 2u * (uint32_t)p.Lbox * (uint32_t)p.Bbox;
+    if (HANKEL && elect_one_sync()) {
+      const long long e0 = (long long)sample0 * p.xwin_stride + 8LL * l0;  // first element of the window
+      long long nbytes = (p.xwin_total - e0) * 2;
+      if (nbytes > (long long)WIN_BYTES) nbytes = WIN_BYTES;
+      nbytes &= ~15LL;
+      mbar_expect_tx(bar_win, (uint32_t)nbytes);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_base + win_off),
+                   "l"(p.xwin + e0), "r"((uint32_t)nbytes), "r"(bar_win)
+                   : "memory");
+    }
+    __syncwarp();
+    int it = 0;
+    for (int kb = kb_lo; kb < kb_hi; ++kb) {
+      const int tap = kb / p.cpt, cc = kb - tap * p.cpt;
+      for (int j = 2; j >= 0; --j) {
+        if (kb < p.kb_lo[j] || kb >= p.kb_hi[j]) continue;
+        const int s = it % NST;
+        const uint32_t ph = (uint32_t)(it / NST) & 1u;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        if (elect_one_sync()) {
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          if (HANKEL) {
+            mbar_expect_tx(bar_full + 8 * s, CL_SUB_BYTES);
+            tma_load_2d(sa, &tmB, tap * p.Cin + cc * TC_BK, p.brow_base[j] + (int)blockIdx.y * p.brow_stride_y, bar_full + 8 * s);
+          } else {
+            mbar_expect_tx(bar_full + 8 * s, a_box_bytes + CL_SUB_BYTES);
+            tma_load_3d(sa, &tmA, cc * TC_BK, l0 + tap - p.pad, sample0, bar_full + 8 * s);
+            tma_load_2d(sa + CL_A_BYTES, &tmB, tap * p.Cin + cc * TC_BK, p.brow_base[j] + (int)blockIdx.y * p.brow_stride_y, bar_full + 8 * s);
+          }
         }
+        __syncwarp();
+        ++it;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int it = 0;
-      for (int kb = kb_lo; kb < kb_hi; ++kb) {
-        for (int j = 2; j >= 0; --j) {
-          if (kb < p.kb_lo[j] || kb >= p.kb_hi[j]) continue;
-          const int s = it % CL_STAGES;
-          const uint32_t ph = (uint32_t)(it / CL_STAGES) & 1u;
-          mbar_wait(bar_full + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t sa = smem_base + s * CL_STAGE_BYTES;
-          const uint32_t sb = sa + CL_A_BYTES;
+    if (HANKEL) mbar_wait(bar_win, 0);
+    int it = 0;
+    for (int kb = kb_lo; kb < kb_hi; ++kb) {
+      for (int j = 2; j >= 0; --j) {
+        if (kb < p.kb_lo[j] || kb >= p.kb_hi[j]) continue;
+        const int s = it % NST;
+        const uint32_t ph = (uint32_t)(it / NST) & 1u;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t sb = HANKEL ? sa : sa + CL_A_BYTES;
+          // HANKEL: chunk index of MMA k = 8*kb + 2*k; no-swizzle K-major descriptor, LBO = 16 B, SBO = 128 B
+          const uint64_t da = HANKEL ? ((uint64_t)(((smem_base + win_off + (uint32_t)(8 * kb) * 16u) & 0x3FFFFu) >> 4) | (1ull << 16) | (8ull << 32) | (1ull << 46))
+                                     : make_smem_desc(sa);
+          const uint64_t db = make_smem_desc(sb);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            umma_bf16(tmem_base + 128u * j, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), IDESC, (kb > p.kb_lo[j] || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_base + 128u * j, da + 2 * k, db + 2 * k, IDESC, (kb > p.kb_lo[j] || k > 0) ? 1u : 0u);
           umma_commit(bar_empty + 8 * s);
-          ++it;
         }
+        __syncwarp();
+        ++it;
       }
-      umma_commit(bar_acc);
     }
+    if (elect_one_sync()) umma_commit(bar_acc);
+    __syncwarp();
   } else {
     // ===================== epilogue: bias -> LayerNorm(3*gw) -> GELU -> bf16 =====================
     {  // stage the per-channel parameters (the epilogue warps are idle during the main loop)
@@ -181,7 +219,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_tc_kernel(const __grid_
       const float rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.0f) + p.eps);
       // pass 2: normalise, affine, GELU, pack to bf16; 32 x 64 tiles go through a per-warp smem transpose so that every
       // store instruction writes four full 128-byte lines (uncoalesced per-row stores cost 32 L1 wavefronts each)
-      uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)CL_STAGES * CL_STAGE_BYTES + (size_t)(warp - 2) * CL_STG_BYTES;
+      uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + stg_off + (size_t)(warp - 2) * CL_STG_BYTES;
       const unsigned vmask = __ballot_sync(0xffffffffu, valid);
       for (int j = 0; j < 3; ++j) {
         for (int cb = 0; cb < gw; cb += 64) {
@@ -290,15 +328,22 @@ extern "C" int acb_spectra_conv_ln_bf16(const void* A, const void* Bw, void* out
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ACB_CHECK(r == CUDA_SUCCESS, "acb_spectra_conv_ln_bf16: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   }
-  constexpr size_t smem = (size_t)CL_STAGES * CL_STAGE_BYTES + 8 * CL_STG_BYTES + 1024;
+  constexpr size_t smem = (size_t)CL_STAGES * CL_STAGE_BYTES + 8 * CL_STG_BYTES + 4608 + 1024;
   static bool configured = false;
   if (!configured) {
-    ACB_CUDA(cudaFuncSetAttribute(conv_ln_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ACB_CUDA(cudaFuncSetAttribute(conv_ln_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ACB_CUDA(cudaFuncSetAttribute(conv_ln_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
+  // polyphase view (rows overlap by construction: row stride 8 samples, 1 tap, Cin = window length): A straight from smem
+  const bool hankel = taps == 1 && a_row_stride == 8 && ng == 2 && Cin <= 64 * 17 && L % 128 == 0;
+  args.xwin = (const bf16*)A; args.xwin_stride = a_batch_stride; args.xwin_total = (long long)nbatch * a_batch_stride;
   const long long MT = (long long)cdiv(nbatch, args.Bbox) * args.tps;
   ACB_CHECK(MT < (1LL << 31) && grid_y <= 65535, "acb_spectra_conv_ln_bf16: grid too large");
-  conv_ln_tc_kernel<<<dim3((unsigned)MT, (unsigned)grid_y), CL_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, args);
+  if (hankel)
+    conv_ln_tc_kernel<true><<<dim3((unsigned)MT, (unsigned)grid_y), CL_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, args);
+  else
+    conv_ln_tc_kernel<false><<<dim3((unsigned)MT, (unsigned)grid_y), CL_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, args);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;

@@ -91,13 +91,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   const uint32_t tmem_base = tmem_holder;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      const uint32_t a_box_bytes = (uint32_t)TC_BK * 2u * (uint32_t)p.Lbox * (uint32_t)p.Bbox;
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+    // ===================== TMA producer (whole warp waits, one elected lane issues) =====================
+    const uint32_t a_box_bytes = (uint32_t)TC_BK * 2u * (uint32_t)p.Lbox * (uint32_t)p.Bbox;
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+      if (elect_one_sync()) {
         const int kb = kb_lo + it;
         const int tap = kb / p.cpt, cc = kb - tap * p.cpt;
         const uint32_t sa = smem_base + s * STAGE_BYTES;
@@ -106,25 +106,27 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         tma_load_3d(sa, &tmA, cc * TC_BK, l0 + tap - p.pad, sample0, bar_full + 8 * s);
         tma_load_2d(sb, &tmB, tap * p.Cin + cc * TC_BK, n0, bar_full + 8 * s);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(bar_full + 8 * s, ph);
-        tc_fence_after();
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(bar_full + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
         const uint32_t sa = smem_base + s * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
+        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          umma_bf16(tmem_base, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), IDESC, (it > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, IDESC, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(bar_empty + 8 * s);  // frees the smem stage once these MMAs retire
       }
-      umma_commit(bar_acc);  // accumulator complete
+      __syncwarp();
     }
+    if (elect_one_sync()) umma_commit(bar_acc);  // accumulator complete
+    __syncwarp();
   } else {
     // ===================== epilogue =====================
     // TMEM -> registers (thread = output row) -> bias/act/residual/pool -> per-warp smem transpose
@@ -383,11 +385,11 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
   const uint32_t tmem_base = tmem_holder;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+      if (elect_one_sync()) {
         const int ch = c_begin + it;
         const int b = ch / p.cps, l0 = (ch - b * p.cps) * 64;
         const uint32_t sa = smem_base + s * STAGE_BYTES;
@@ -402,24 +404,27 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
           tma_load_3d(sb + qn * 8192, &tmB, ci0, l0 + tap - p.pad, b, bar_full + 8 * s);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(bar_full + 8 * s, ph);
-        tc_fence_after();
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(bar_full + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
         const uint32_t sa = smem_base + s * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
+        const uint64_t da = make_smem_desc_mn(sa), db = make_smem_desc_mn(sb);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 64 rows = 4 x UMMA_K(16); 16 rows = 2 KB
-          umma_bf16(tmem_base, make_smem_desc_mn(sa + k * 2048), make_smem_desc_mn(sb + k * 2048), IDESC, (it > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < 4; ++k)  // 64 rows = 4 x UMMA_K(16); 16 rows = 2 KB = 128 descriptor units
+          umma_bf16(tmem_base, da + 128 * k, db + 128 * k, IDESC, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(bar_empty + 8 * s);
       }
-      umma_commit(bar_acc);
+      __syncwarp();
     }
+    if (elect_one_sync()) umma_commit(bar_acc);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;

@@ -62,6 +62,20 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// One lane of a converged warp, chosen by the hardware.  Unlike `if (lane == 0)`, the compiler knows the guarded
+// region is warp-uniform, so TMA / tcgen05 operands go to uniform registers directly instead of through a
+// R2UR.BROADCAST + BRA.U.ANY loop per instruction (which made the single MMA-issuing thread the bottleneck).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
