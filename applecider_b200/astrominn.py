@@ -150,7 +150,7 @@ class ResidualTowerBlock(nn.Module):
         self.activation = nn.Sequential(nn.LayerNorm(hidden_dim), nn.Dropout(0.25), nn.Linear(hidden_dim, output_dim), nn.Sigmoid())
         self.skip_path = nn.Linear(input_dim, output_dim) if input_dim != output_dim else nn.Identity()
 
-    def run(self, X, cols, Y, y_off):
+    def run(self, X, cols, Y, y_off, s_pre=None, s_off=0):
         skip = self.skip_path if isinstance(self.skip_path, nn.Linear) else None
         ops.call(
             "acb_tower_fwd", X, X.shape[1], cols, self.input_dim, self.hidden_dim, self.output_dim,
@@ -158,6 +158,7 @@ class ResidualTowerBlock(nn.Module):
             self.main_path[2].weight, self.main_path[2].bias, self.activation[0].weight, self.activation[0].bias,
             self.activation[2].weight, self.activation[2].bias, (skip.weight if skip is not None else None),
             (skip.bias if skip is not None else None), Y, Y.shape[1], y_off, X.shape[0],
+            s_pre, (s_pre.shape[1] if s_pre is not None else 0), s_off,
         )
 
     def forward(self, x):
@@ -204,6 +205,7 @@ class AstroMiNN(nn.Module):
         self.total_loss, self.total_correct_predictions, self.total_predictions = [], 0, 0
         self.this_criterion = nn.CrossEntropyLoss()
         self.compute_dtype = resolve_dtype(ac.get("compute_dtype"))
+        self._derived = ops.DerivedCache()
         for n, c in TOWER_COLS.items():
             self.register_buffer(f"_cols_{n}", torch.tensor(c, dtype=torch.int32), persistent=False)
         self.this_optimizer = self._make_optimizer(ac)
@@ -255,8 +257,14 @@ class AstroMiNN(nn.Module):
         g1 = ops.gemm(feats, r[0].weight, r[0].bias, act=ops.ACT_TANH)
         gate = ops.gemm(g1, r[3].weight, r[3].bias, act=ops.ACT_SIGMOID)
         eo = torch.empty((B, E * 5), dtype=torch.float32, device=feats.device)
+        # all expert start paths (288 -> 128, GELU) as ONE GEMM; the per-expert kernel then only does LN + heads + skip
+        hid = self.fusion_hidden_dims
+        w0, b0 = self._derived.get("experts_w0", [ex.start_path[0].weight for ex in self.fusion_experts] + [ex.start_path[0].bias for ex in self.fusion_experts],
+                                   lambda: (torch.cat([ex.start_path[0].weight.detach() for ex in self.fusion_experts], 0).contiguous(),
+                                            torch.cat([ex.start_path[0].bias.detach() for ex in self.fusion_experts], 0).contiguous()))
+        s_all = ops.gemm(feats, w0, b0, act=ops.ACT_GELU)
         for e, ex in enumerate(self.fusion_experts):
-            ex.run(feats, None, eo, e * 5)
+            ex.run(feats, None, eo, e * 5, s_pre=s_all, s_off=e * hid)
         out = torch.empty((B, 5), dtype=torch.float32, device=feats.device)
         ops.call("acb_moe_combine", gate, eo, out, None, B, E, 5)
         if self.config["model"]["AstroMiNN"]["use_probabilities"]:

@@ -12,6 +12,7 @@ struct TowerArgs {
   const float* X; int ldx; const int* cols; int in_dim, hid, out_dim;
   const float *W0, *b0, *ln1w, *ln1b, *W1, *b1, *ln2w, *ln2b, *W2, *b2, *Ws, *bs;
   float* Y; int ldy, y_off, rows;
+  const float* S_pre; int lds, s_off;  // optional precomputed gelu(W0 x + b0) (experts: one GEMM for all start paths)
 };
 
 __global__ void __launch_bounds__(TOWER_WARPS * 32) tower_fwd_kernel(const TowerArgs p) {
@@ -27,10 +28,15 @@ __global__ void __launch_bounds__(TOWER_WARPS * 32) tower_fwd_kernel(const Tower
   // start_path: s = gelu(W0 x + b0)
   float sum = 0.0f;
   for (int h = lane; h < p.hid; h += 32) {
-    const float* wr = p.W0 + (long long)h * p.in_dim;
-    float a = p.b0[h];
-    for (int i = 0; i < p.in_dim; ++i) a = fmaf(__ldg(wr + i), x[i], a);
-    a = gelu_erf(a);
+    float a;
+    if (p.S_pre) {
+      a = p.S_pre[(long long)row * p.lds + p.s_off + h];
+    } else {
+      const float* wr = p.W0 + (long long)h * p.in_dim;
+      a = p.b0[h];
+      for (int i = 0; i < p.in_dim; ++i) a = fmaf(__ldg(wr + i), x[i], a);
+      a = gelu_erf(a);
+    }
     s[h] = a;
     sum += a;
   }
@@ -159,13 +165,13 @@ extern "C" {
 int acb_tower_fwd(const float* X, int ldx, const int* cols, int in_dim, int hid, int out_dim, const float* W0,
                   const float* b0, const float* ln1w, const float* ln1b, const float* W1, const float* b1,
                   const float* ln2w, const float* ln2b, const float* W2, const float* b2, const float* Ws,
-                  const float* bs, float* Y, int ldy, int y_off, int rows, void* stream) {
-  ACB_CHECK(X && Y && W0 && b0 && ln1w && ln1b && W1 && b1 && ln2w && ln2b && W2 && b2, "acb_tower_fwd: null argument");
+                  const float* bs, float* Y, int ldy, int y_off, int rows, const float* S_pre, int lds, int s_off, void* stream) {
+  ACB_CHECK(X && Y && (S_pre || (W0 && b0)) && ln1w && ln1b && W1 && b1 && ln2w && ln2b && W2 && b2, "acb_tower_fwd: null argument");
   ACB_CHECK(in_dim > 0 && in_dim <= TOWER_MAX_IN && hid > 0 && hid <= TOWER_MAX_HID && out_dim > 0,
             "acb_tower_fwd: dims out of range (in=%d hid=%d out=%d)", in_dim, hid, out_dim);
   ACB_CHECK(Ws != nullptr || in_dim == out_dim, "acb_tower_fwd: identity skip needs in_dim == out_dim");
   if (rows == 0) return ACB_OK;
-  TowerArgs p{X, ldx, cols, in_dim, hid, out_dim, W0, b0, ln1w, ln1b, W1, b1, ln2w, ln2b, W2, b2, Ws, bs, Y, ldy, y_off, rows};
+  TowerArgs p{X, ldx, cols, in_dim, hid, out_dim, W0, b0, ln1w, ln1b, W1, b1, ln2w, ln2b, W2, b2, Ws, bs, Y, ldy, y_off, rows, S_pre, lds, s_off};
   tower_fwd_kernel<<<cdiv(rows, TOWER_WARPS), TOWER_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
   ACB_LAUNCH_CHECK();
   acb_count_launch();

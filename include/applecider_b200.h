@@ -151,11 +151,12 @@ int acb_globalmax_cl(const void* x, int dtype, float* y, int B, int L, int C, vo
 
 /* ---- metadata towers / MoE / fusion head -------------------------------------------------------- */
 /* ResidualTowerBlock (astrominn.py:44-64), eval: s = gelu(W0 x + b0); y = (W1 ln1(s) + b1) * sigmoid(W2 ln2(s) + b2)
- * + (Ws x + bs | x).  x = X[r, cols[i]] (cols == NULL: identity), Y[r, y_off + o].  hid <= 256, in <= 512, out <= 32 */
+ * + (Ws x + bs | x).  x = X[r, cols[i]] (cols == NULL: identity), Y[r, y_off + o].  hid <= 256, in <= 512, out <= 32.
+ * S_pre (optional): precomputed s = gelu(W0 x + b0) at S_pre[r*lds + s_off + h] (one GEMM for all experts). */
 int acb_tower_fwd(const float* X, int ldx, const int* cols, int in_dim, int hid, int out_dim, const float* W0,
                   const float* b0, const float* ln1w, const float* ln1b, const float* W1, const float* b1,
                   const float* ln2w, const float* ln2b, const float* W2, const float* b2, const float* Ws,
-                  const float* bs, float* Y, int ldy, int y_off, int rows, void* stream);
+                  const float* bs, float* Y, int ldy, int y_off, int rows, const float* S_pre, int lds, int s_off, void* stream);
 /* top-2-of-E sigmoid-gated mixture (astrominn.py:270-295): gate[B,E], expert_out[E][B,C] (stride E*C per row:
  * expert_out[r*E*C + e*C + c]) -> out[B,C]; also writes the selected indices (top_idx[B,2]) for parity checks. */
 int acb_moe_combine(const float* gate, const float* expert_out, float* out, int* top_idx, int B, int E, int C,

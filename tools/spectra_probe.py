@@ -4,6 +4,8 @@ import torch
 import applecider_b200 as ab
 from applecider_b200 import synth, ops
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+from applecider_b200 import spectra as _sp
+_sp.FUSE_STAGE1 = len(sys.argv) > 2 and sys.argv[2] == 'fuse1'
 cfg = ab.default_config(); cfg["model"]["SpectraNet"]["compute_dtype"] = "bf16"
 m = ab.SpectraNet(cfg); m.load_state_dict(synth.det_state_dict(m, 0)); m = m.cuda().eval()
 x = synth.spectra(B, seed=1).cuda()
