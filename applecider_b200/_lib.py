@@ -101,23 +101,47 @@ def _ptr(a):
     raise TypeError(f"cannot pass {type(a)} as a pointer")
 
 
+_FN_CACHE = {}
+_raw_stream = None
+
+
+def _current_stream() -> int:
+    global _raw_stream
+    if _raw_stream is None:
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or False
+    if _raw_stream:
+        return _raw_stream(torch.cuda.current_device())
+    return torch.cuda.current_stream().cuda_stream
+
+
 def call(name: str, *args):
-    l = lib()
-    sig = SIGNATURES[name]
+    ent = _FN_CACHE.get(name)
+    if ent is None:
+        l = lib()
+        ent = _FN_CACHE[name] = (getattr(l, name), SIGNATURES[name], l.acb_last_error)
+    fn, sig, last_error = ent
     if len(args) != len(sig):
         raise TypeError(f"{name}: expected {len(sig)} arguments, got {len(args)}")
     conv = []
     for k, a in zip(sig, args):
         if k == "p":
-            conv.append(_ptr(a))
-        elif k in ("f", "d"):
-            conv.append(float(a))
-        else:
+            if a is None or type(a) is int:
+                conv.append(a)
+            elif isinstance(a, torch.Tensor):
+                if not a.is_cuda:
+                    raise RuntimeError("applecider_b200: tensors must live on a CUDA device (no CPU fallback)")
+                if not a.is_contiguous():
+                    raise RuntimeError("applecider_b200: tensors must be contiguous")
+                conv.append(a.data_ptr())
+            else:
+                conv.append(_ptr(a))
+        elif k == "i" or k == "l":
             conv.append(int(a))
-    stream = torch.cuda.current_stream().cuda_stream
-    rc = getattr(l, name)(*conv, stream)
+        else:
+            conv.append(float(a))
+    rc = fn(*conv, _current_stream())
     if rc != 0:
-        raise RuntimeError(f"{name} failed ({rc}): {l.acb_last_error().decode()}")
+        raise RuntimeError(f"{name} failed ({rc}): {last_error().decode()}")
 
 
 def launch_count() -> int:

@@ -151,9 +151,15 @@ def photo_embed(x, src, total, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype):
     return out
 
 
+USE_TC_ATTENTION = True
+
+
 def attention_varlen(qkv, cu, B, n_heads, dh, max_seqlen, drop_p=0.0, seed=0):
     T = qkv.shape[0]
     out = torch.empty((T, n_heads * dh), dtype=qkv.dtype, device=qkv.device)
+    if qkv.dtype == torch.bfloat16 and USE_TC_ATTENTION and max_seqlen <= 480 and dh == 16:
+        call("acb_attention_varlen_tc", qkv, cu, B, n_heads, dh, max_seqlen, drop_p, seed, out)
+        return out
     call("acb_attention_varlen", qkv, dtype_tag(qkv), cu, B, n_heads, dh, max_seqlen, drop_p, seed, out)
     return out
 

@@ -126,6 +126,10 @@ int acb_photo_embed(const float* x, const int* src_idx, const int* total_dev, in
  * nn.TransformerEncoderLayer (HyraxBaselineCLS.py:26-33,78). dh must be 16. */
 int acb_attention_varlen(const void* qkv, int dtype, const int* cu_seqlens, int B, int n_heads, int dh,
                          int max_seqlen, float drop_p, long long seed, void* out, void* stream);
+/* the same attention on tcgen05 for bf16 tokens: S = QK^T is one UMMA per (head, 128-query tile) into TMEM, fp32 softmax
+ * per accumulator row, P V accumulated in TMEM; operands are no-swizzle K-major core matrices written by the CTA. */
+int acb_attention_varlen_tc(const void* qkv, const int* cu_seqlens, int B, int n_heads, int dh, int max_seqlen, float drop_p,
+                            long long seed, void* out, void* stream);
 /* out[b,:] = x[cu_seqlens[b],:]  (CLS read-out z[:,0], HyraxBaselineCLS.py:79) */
 int acb_gather_cls(const void* x, int dtype, const int* cu_seqlens, int B, int D, float* out, void* stream);
 

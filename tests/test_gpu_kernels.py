@@ -320,3 +320,28 @@ def test_tower_moe_fusion_head():
         sel = (ti == e)
         ref += (tw * sel).sum(-1, keepdim=True) * eo.view(64, 4, 5)[:, e] * sel.any(-1, keepdim=True)
     assert_close(out, ref, 1e-6, "moe_combine")
+
+
+@pytest.mark.parametrize("lens", [[1, 5, 16, 17, 33, 64, 100], [128, 129, 200, 257, 258], [300, 470, 3]])
+def test_attention_tc_matches_reference(lens):
+    """tcgen05 attention (bf16) vs fp32 torch on the same bf16-rounded q/k/v, incl. > 128 queries and > 256 keys."""
+    ops = _ops()
+    B, H, D = len(lens), 8, 128
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=DEV)
+    T = int(cu[-1])
+    qkv = _bf(_rand(T, 3 * D, seed=sum(lens)))
+    got = ops.attention_varlen(qkv, cu, B, H, 16, max(lens))
+    ref = torch.empty(T, D, device=DEV)
+    f = qkv.float()
+    for bi in range(B):
+        s, e = int(cu[bi]), int(cu[bi + 1])
+        q, k, v = [z.view(e - s, H, 16).transpose(0, 1) for z in f[s:e].split(D, 1)]
+        p = torch.softmax(q @ k.transpose(1, 2) / 4.0, -1)
+        ref[s:e] = (p @ v).transpose(0, 1).reshape(e - s, D)
+    assert_close(got, ref, 1.2e-2, f"tc attention lens={lens}")
+    ops.USE_TC_ATTENTION = False
+    try:
+        old = ops.attention_varlen(qkv, cu, B, H, 16, max(lens))
+    finally:
+        ops.USE_TC_ATTENTION = True
+    assert_close(got, old.float(), 1.2e-2, "tc vs CUDA-core attention")
