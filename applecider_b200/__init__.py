@@ -14,7 +14,7 @@ def __getattr__(name):
     import importlib
 
     table = {
-        "HyraxBaselineCLS": "photo", "BaselineCLS": "photo", "Time2Vec": "photo", "FocalLoss": "photo",
+        "HyraxBaselineCLS": "photo", "MPTModel": "photo", "BaselineCLS": "photo", "Time2Vec": "photo", "FocalLoss": "photo",
         "SpectraNet": "spectra", "SpectraNetBlock": "spectra",
         "AstroMiNN": "astrominn", "SplitHeadConvNeXt": "astrominn", "ResidualTowerBlock": "astrominn", "ConvNeXtTiny": "astrominn",
         "AppleCider": "fusion", "fusion_collate": "fusion",

@@ -351,8 +351,11 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const void* qkv, int
 // grads[0:7D] d in_proj.weight (D,7) | [7D:8D] d in_proj.bias | [8D] dw0 | [8D+1] db0 | [8D+2 : 9D+1] dw (D-1)
 // | [9D+1 : 10D] db (D-1) | [10D : 11D] d cls_tok
 __global__ void __launch_bounds__(128) photo_embed_bwd_kernel(const float* x, const int* src, int T, int D, const void* dh, int dh_dt,
-                                                              const float* w, const float* bb, int tok_per_block, float* grads) {
+                                                              const float* w, const float* bb, int tok_per_block, float te_drop_p,
+                                                              unsigned long long te_seed, float* grads) {
   const int c = threadIdx.x;  // channel
+  const float drop_inv = 1.0f / (1.0f - te_drop_p);
+  const unsigned drop_thr = (unsigned)(te_drop_p * 4294967296.0);
   const int t0 = blockIdx.x * tok_per_block, t1 = min(T, t0 + tok_per_block);
   if (c >= D) return;
   float gw[7] = {}, gb = 0.f, g0 = 0.f, g1 = 0.f, gc = 0.f;
@@ -365,8 +368,10 @@ __global__ void __launch_bounds__(128) photo_embed_bwd_kernel(const float* x, co
     for (int j = 0; j < 7; ++j) gw[j] = fmaf(g, xr[j], gw[j]);
     gb += g;
     const float tt = xr[0];
-    if (c == 0) { g0 += g * tt; g1 += g; }
-    else { const float cs = cosf(tt * w[c - 1] + bb[c - 1]); g0 += g * cs * tt; g1 += g * cs; }
+    float gt = g;  // gradient reaching the Time2Vec term (dropout mask regenerated from the hash)
+    if (te_drop_p > 0.0f) gt = (te_hash(te_seed, t, c) < drop_thr) ? 0.0f : g * drop_inv;
+    if (c == 0) { g0 += gt * tt; g1 += gt; }
+    else { const float cs = cosf(tt * w[c - 1] + bb[c - 1]); g0 += gt * cs * tt; g1 += gt * cs; }
   }
 #pragma unroll
   for (int j = 0; j < 7; ++j) atomicAdd(grads + c * 7 + j, gw[j]);
@@ -722,13 +727,13 @@ int acb_attention_varlen_bwd(const void* qkv, int dtype, const void* dout, int d
 }
 
 int acb_photo_embed_bwd(const float* x, const int* src_idx, int T, int D, const void* dh, int dh_dtype, const float* w, const float* b,
-                        float* grads, void* stream) {
+                        float te_drop_p, long long te_seed, float* grads, void* stream) {
   ACB_CHECK(x && src_idx && dh && w && b && grads && T >= 0 && D > 1 && D <= 128, "acb_photo_embed_bwd: bad arguments (D <= 128)");
   cudaStream_t st = (cudaStream_t)stream;
   ACB_CUDA(cudaMemsetAsync(grads, 0, (size_t)11 * D * 4, st));
   if (T == 0) return ACB_OK;
   const int tpb = 256;
-  photo_embed_bwd_kernel<<<cdiv(T, tpb), 128, 0, st>>>(x, src_idx, T, D, dh, dh_dtype, w, b, tpb, grads);
+  photo_embed_bwd_kernel<<<cdiv(T, tpb), 128, 0, st>>>(x, src_idx, T, D, dh, dh_dtype, w, b, tpb, te_drop_p, (unsigned long long)te_seed, grads);
   LAUNCHED(1);
 }
 

@@ -106,6 +106,13 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// counter hash for the Time2Vec dropout of the masked pre-training path (same mask in forward and backward)
+__device__ __forceinline__ unsigned te_hash(unsigned long long seed, int t, int c) {
+  unsigned long long v = seed * 0x9E3779B97F4A7C15ULL + (((unsigned long long)(unsigned)t << 10) | (unsigned long long)c);
+  v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
+  return (unsigned)v;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -64,9 +64,12 @@ __global__ void __launch_bounds__(256) photo_embed_kernel(const float* __restric
                                                           const float* __restrict__ w_in, const float* __restrict__ b_in,
                                                           const float* __restrict__ w0, const float* __restrict__ b0,
                                                           const float* __restrict__ w, const float* __restrict__ bb,
-                                                          const float* __restrict__ cls, T* __restrict__ out) {
+                                                          const float* __restrict__ cls, float te_drop_p,
+                                                          unsigned long long te_seed, T* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const float drop_inv = 1.0f / (1.0f - te_drop_p);
+  const unsigned drop_thr = (unsigned)(te_drop_p * 4294967296.0);
   const int total = total_dev ? min(*total_dev, max_tokens) : max_tokens;
   if (t >= total) return;
   const int s = src[t];
@@ -84,7 +87,8 @@ __global__ void __launch_bounds__(256) photo_embed_kernel(const float* __restric
     float h = b_in[c];
 #pragma unroll
     for (int j = 0; j < 7; ++j) h = fmaf(w_in[c * 7 + j], xr[j], h);
-    const float te = (c == 0) ? (w0[0] * tt + b0[0]) : sinf(tt * w[c - 1] + bb[c - 1]);
+    float te = (c == 0) ? (w0[0] * tt + b0[0]) : sinf(tt * w[c - 1] + bb[c - 1]);
+    if (te_drop_p > 0.0f) te = (te_hash(te_seed, t, c) < drop_thr) ? 0.0f : te * drop_inv;  // MPTModel: F.dropout(te) (:248)
     o[c] = from_f<T>(h + te);
   }
 }
@@ -200,15 +204,16 @@ int acb_photo_compact(const uint8_t* pad, int B, int L, int* cu_seqlens, int* sr
 
 int acb_photo_embed(const float* x, const int* src_idx, const int* total_dev, int max_tokens, int D, const float* w_in,
                     const float* b_in, const float* w0, const float* b0, const float* w, const float* b,
-                    const float* cls_tok, void* out, int out_dtype, void* stream) {
+                    const float* cls_tok, float te_drop_p, long long te_seed, void* out, int out_dtype, void* stream) {
   ACB_CHECK(x && src_idx && out && max_tokens >= 0 && D > 1, "acb_photo_embed: bad arguments");
+  ACB_CHECK(te_drop_p >= 0.0f && te_drop_p < 1.0f, "acb_photo_embed: dropout %g out of range", (double)te_drop_p);
   if (max_tokens == 0) return ACB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = cdiv(max_tokens, 8);
   if (out_dtype == ACB_F32)
-    photo_embed_kernel<float><<<grid, 256, 0, st>>>(x, src_idx, total_dev, max_tokens, D, w_in, b_in, w0, b0, w, b, cls_tok, (float*)out);
+    photo_embed_kernel<float><<<grid, 256, 0, st>>>(x, src_idx, total_dev, max_tokens, D, w_in, b_in, w0, b0, w, b, cls_tok, te_drop_p, (unsigned long long)te_seed, (float*)out);
   else
-    photo_embed_kernel<bf16><<<grid, 256, 0, st>>>(x, src_idx, total_dev, max_tokens, D, w_in, b_in, w0, b0, w, b, cls_tok, (bf16*)out);
+    photo_embed_kernel<bf16><<<grid, 256, 0, st>>>(x, src_idx, total_dev, max_tokens, D, w_in, b_in, w0, b0, w, b, cls_tok, te_drop_p, (unsigned long long)te_seed, (bf16*)out);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;

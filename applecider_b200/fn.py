@@ -243,21 +243,21 @@ def attention(qkv, cu, B, H, dh, maxlen, drop_p=0.0, seed=0):
 
 class PhotoEmbed(Function):
     @staticmethod
-    def forward(ctx, x, src, T, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype):
-        h = ops.photo_embed(x, src, T, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype)
+    def forward(ctx, x, src, T, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype, te_drop_p=0.0, te_seed=0):
+        h = ops.photo_embed(x, src, T, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype, te_drop_p, te_seed)
         ctx.save_for_backward(x, src, w, b)
-        ctx.dims = (T, D, cls_tok.shape)
+        ctx.dims = (T, D, cls_tok.shape, te_drop_p, te_seed)
         return h
 
     @staticmethod
     def backward(ctx, dh):
         x, src, w, b = ctx.saved_tensors
-        T, D, cls_shape = ctx.dims
+        T, D, cls_shape, te_drop_p, te_seed = ctx.dims
         dh = _c(dh)
         g = torch.empty(11 * D, dtype=F32, device=x.device)
-        call("acb_photo_embed_bwd", x, src, T, D, dh, dtype_tag(dh), w, b, g)
+        call("acb_photo_embed_bwd", x, src, T, D, dh, dtype_tag(dh), w, b, te_drop_p, te_seed, g)
         return (None, None, None, None, g[: 7 * D].view(D, 7), g[7 * D: 8 * D], g[8 * D: 8 * D + 1], g[8 * D + 1: 8 * D + 2],
-                g[8 * D + 2: 9 * D + 1], g[9 * D + 1: 10 * D], g[10 * D: 11 * D].view(cls_shape), None)
+                g[8 * D + 2: 9 * D + 1], g[9 * D + 1: 10 * D], g[10 * D: 11 * D].view(cls_shape), None, None, None)
 
 
 class GatherCls(Function):
@@ -444,6 +444,28 @@ class Loss(Function):
     def backward(ctx, g):
         (dlogits,) = ctx.saved_tensors
         return ew(dlogits, None, 5, g=_c(g.float().view(1))), None, None, None
+
+
+class MptLoss(Function):
+    """Masked-event pre-training loss (HyraxBaselineCLS.py:262-278): product of the three masked-token losses."""
+
+    @staticmethod
+    def forward(ctx, pred, src, x, masked, L, lam):
+        pred = _c(pred)
+        T = pred.shape[0]
+        losses = torch.empty(4, dtype=F32, device=pred.device)
+        dpred = torch.empty((T, 5), dtype=F32, device=pred.device)
+        ws = torch.empty(4, dtype=F32, device=pred.device)
+        call("acb_mpt_loss_fwd_bwd", pred, dtype_tag(pred), src, T, x, masked, L, lam[0], lam[1], lam[2], losses, dpred, ws)
+        ctx.save_for_backward(dpred)
+        ctx.pdtype = pred.dtype
+        ctx.mark_non_differentiable(losses)
+        return losses[0].view(()).clone(), losses
+
+    @staticmethod
+    def backward(ctx, g, _):
+        (dpred,) = ctx.saved_tensors
+        return ew(dpred, None, 5, g=_c(g.float().view(1)), out_dtype=ctx.pdtype), None, None, None, None, None
 
 
 def focal_loss(logits, target, gamma=2.0, reduction="mean"):

@@ -145,9 +145,9 @@ def photo_compact(pad):
     return cu, src
 
 
-def photo_embed(x, src, total, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype):
+def photo_embed(x, src, total, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype, te_drop_p=0.0, te_seed=0):
     out = torch.empty((total, D), dtype=dtype, device=x.device)
-    call("acb_photo_embed", x, src, None, total, D, w_in, b_in, w0, b0, w, b, cls_tok, out, dtype_tag(out))
+    call("acb_photo_embed", x, src, None, total, D, w_in, b_in, w0, b0, w, b, cls_tok, te_drop_p, te_seed, out, dtype_tag(out))
     return out
 
 

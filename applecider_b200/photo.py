@@ -144,6 +144,51 @@ class HyraxBaselineCLS(_PhotoEncoderBase):
         return (photo_tensor, false_mask, label_tensor)
 
 
+class MPTModel(_PhotoEncoderBase):
+    """Masked-event pre-training of the same encoder (HyraxBaselineCLS.py:194-319): heads flux(1)/band(3)/dt(1),
+    loss = lambda_f*L_f * lambda_b*L_b * lambda_dt*L_dt (a product, as in the reference)."""
+
+    def __init__(self, config, data_sample=None):
+        super().__init__()
+        self.config = config
+        mc = config["model"]["HyraxBaselineCLS"]
+        self._build(mc["d_model"], mc["n_heads"], mc["n_layers"], mc["dropout"])
+        d = mc["d_model"]
+        self.head_flux = nn.Linear(d, 1)
+        self.head_band = nn.Linear(d, 3)
+        self.head_dt = nn.Linear(d, 1)
+        self.compute_dtype = resolve_dtype(mc.get("compute_dtype"))
+        self.optimizer = torch.optim.AdamW(self.parameters(), lr=1e-4)
+
+    def forward(self, z):
+        """z [..., d_model] -> (flux, band logits, dt) like the reference's forward (:238-239)."""
+        if not z.is_cuda:
+            raise RuntimeError("applecider_b200: inputs must be CUDA tensors (no CPU fallback)")
+        lead = z.shape[:-1]
+        z2 = z.reshape(-1, z.shape[-1]).float().contiguous()
+        w = torch.cat([self.head_flux.weight, self.head_band.weight, self.head_dt.weight]).detach().contiguous()
+        b = torch.cat([self.head_flux.bias, self.head_band.bias, self.head_dt.bias]).detach().contiguous()
+        o = ops.gemm(z2, w, b).view(*lead, 5)
+        return o[..., 0:1], o[..., 1:4], o[..., 4:5]
+
+    def mask_batch(self, data, pad, seed=None):
+        """Device version of _mask_batch (:283-319): zeroes channels 2:7 of the drawn tokens IN PLACE, returns the mask."""
+        from . import fn
+
+        B, L, _ = data.shape
+        masked = torch.empty((B, L), dtype=torch.bool, device=data.device)
+        mp = float(self.config["model"]["HyraxBaselineCLS"]["mask_p"])
+        ops.call("acb_mpt_mask", data, pad.view(torch.uint8), B, L, mp, fn.next_seed() if seed is None else int(seed), masked.view(torch.uint8))
+        return masked
+
+    def train_step(self, batch, masked=None):
+        from .train import mpt_train_step
+
+        return mpt_train_step(self, batch, masked)
+
+    to_tensor = staticmethod(HyraxBaselineCLS.to_tensor)
+
+
 class BaselineCLS(_PhotoEncoderBase):
     """Legacy signature forward(x, pad_mask) -> head(norm(z[:,0])) (Time2Vec.py:80-124)."""
 

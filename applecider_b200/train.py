@@ -25,8 +25,8 @@ def _wc(cache, p, dtype):
 
 
 # ---- photometry -------------------------------------------------------------------------------------------
-def photo_encode_train(model, data, pad, total_tokens=None):
-    """-> (B, d_model) fp32 LayerNorm(CLS) with an autograd graph."""
+def photo_encode_train(model, data, pad, total_tokens=None, tokens=False, te_dropout=False):
+    """-> (B, d_model) fp32 LayerNorm(CLS) with an autograd graph; tokens=True: (h [T,D] fp32, cu, src) instead."""
     dtype = model.compute_dtype
     tr = model.training
     mc = model.config["model"]["HyraxBaselineCLS"] if hasattr(model, "config") else {"dropout": 0.0}
@@ -40,9 +40,12 @@ def photo_encode_train(model, data, pad, total_tokens=None):
     T = int(cu[-1].item()) if total_tokens is None else int(total_tokens)
     D, H = model.d_model, model.n_heads
     t2v = model.time2vec
-    h = fn.PhotoEmbed.apply(data, src, T, D, model.in_proj.weight, model.in_proj.bias, t2v.w0, t2v.b0, t2v.w, t2v.b, model.cls_tok, dtype)
+    te_p = float(mc.get("dropout", 0.0)) if te_dropout else 0.0  # MPTModel: F.dropout(te) is always active (:248)
+    h = fn.PhotoEmbed.apply(data, src, T, D, model.in_proj.weight, model.in_proj.bias, t2v.w0, t2v.b0, t2v.w, t2v.b, model.cls_tok, dtype,
+                            te_p, fn.next_seed() if te_p > 0 else 0)
     dc = model._derived
-    for lyr in model.encoder.layers:
+    n_layers = len(model.encoder.layers)
+    for li, lyr in enumerate(model.encoder.layers):
         sa = lyr.self_attn
         qkv = fn.linear(h, sa.in_proj_weight, sa.in_proj_bias, _wc(dc, sa.in_proj_weight, dtype))
         att = fn.attention(qkv, cu, B, H, D // H, L + 1, p_drop, fn.next_seed() if p_drop > 0 else 0)
@@ -53,7 +56,10 @@ def photo_encode_train(model, data, pad, total_tokens=None):
         f = fn.dropout(f, p_drop, tr)
         g = fn.linear(f, lyr.linear2.weight, lyr.linear2.bias, _wc(dc, lyr.linear2.weight, dtype))
         g = fn.dropout(g, p_drop, tr)
-        h = fn.layernorm(fn.add(h1, g), lyr.norm2.weight, lyr.norm2.bias, lyr.norm2.eps)
+        h = fn.layernorm(fn.add(h1, g), lyr.norm2.weight, lyr.norm2.bias, lyr.norm2.eps,
+                         out_dtype=(F32 if tokens and li == n_layers - 1 else None))
+    if tokens:
+        return h, cu, src
     cls = fn.GatherCls.apply(h, cu, B)
     return fn.layernorm(cls, model.norm.weight, model.norm.bias, model.norm.eps)
 
@@ -77,6 +83,39 @@ def photo_train_step(model, batch):
     torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
     model.optimizer.step()
     return {"loss": loss.item(), "num_tdes": np.sum([labels.cpu().numpy() == 4])}
+
+
+def mpt_losses(model, data, pad, masked, total_tokens=None):
+    """data must already be masked (channels 2:7 of masked tokens zeroed).  -> (loss, [loss, L_f, L_b, L_dt])."""
+    mc = model.config["model"]["HyraxBaselineCLS"]
+    B, L, _ = data.shape
+    data = data.contiguous().float()
+    h, cu, src = photo_encode_train(model, data, pad, total_tokens, tokens=True, te_dropout=True)
+    w = torch.cat([model.head_flux.weight, model.head_band.weight, model.head_dt.weight])
+    b = torch.cat([model.head_flux.bias, model.head_band.bias, model.head_dt.bias])
+    pred = fn.linear(h, w, b)  # [T,5] fp32; CLS rows are ignored by the loss
+    m8 = masked.contiguous().view(torch.uint8) if masked.dtype == torch.bool else masked.contiguous()
+    return fn.MptLoss.apply(pred, src, data, m8, L, (float(mc["lambda_f"]), float(mc["lambda_b"]), float(mc["lambda_dt"])))
+
+
+def mpt_train_step(model, batch, masked=None):
+    """HyraxBaselineCLS.py:241-281: mask -> encode -> three heads -> product loss -> clip 1.0 -> AdamW."""
+    data, pad = batch[0], batch[1]
+    if not data.is_cuda:
+        raise RuntimeError("applecider_b200: inputs must be CUDA tensors (no CPU fallback)")
+    if pad.dtype != torch.bool:
+        pad = pad != 0
+    pad = pad.contiguous()
+    if masked is None:
+        if data.dtype != F32 or not data.is_contiguous():
+            raise RuntimeError("applecider_b200: MPTModel.train_step masks `data` in place and needs a contiguous fp32 tensor")
+        masked = model.mask_batch(data, pad)
+    loss, _ = mpt_losses(model, data, pad, masked)
+    model.optimizer.zero_grad()
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+    model.optimizer.step()
+    return {"loss": loss.item()}
 
 
 # ---- SpectraNet -------------------------------------------------------------------------------------------

@@ -119,7 +119,7 @@ int acb_photo_compact(const uint8_t* pad, int B, int L, int* cu_seqlens, int* sr
  * Time2Vec.py:63-72).  D = d_model. */
 int acb_photo_embed(const float* x, const int* src_idx, const int* total_dev, int max_tokens, int D, const float* w_in,
                     const float* b_in, const float* w0, const float* b0, const float* w, const float* b,
-                    const float* cls_tok, void* out, int out_dtype, void* stream);
+                    const float* cls_tok, float te_drop_p, long long te_seed, void* out, int out_dtype, void* stream);
 /* fused masked varlen multi-head attention over packed tokens; qkv[T,3D] rows = [q|k|v], head h uses
  * columns h*dh..; softmax(q k^T / sqrt(dh)) v with fp32 math (drop_p > 0: training-time dropout on the
  * probabilities, mask = counter hash of (seed, sequence, head, i, j), regenerated in the backward).  nn.MultiheadAttention inside
@@ -242,7 +242,7 @@ int acb_attention_varlen_bwd(const void* qkv, int dtype, const void* dout, int d
                              void* stream);
 /* grads = [d in_proj.weight (D*7) | d in_proj.bias (D) | dw0 | db0 | dw (D-1) | db (D-1) | d cls_tok (D)] */
 int acb_photo_embed_bwd(const float* x, const int* src_idx, int T, int D, const void* dh, int dh_dtype, const float* w,
-                        const float* b, float* grads, void* stream);
+                        const float* b, float te_drop_p, long long te_seed, float* grads, void* stream);
 int acb_scatter_cls(const float* dcls, const int* cu_seqlens, int B, int D, void* dh, int dh_dtype, long long total_tokens,
                     void* stream);
 /* depthwise 7x7 without LayerNorm (training forward), flip=1: gradient w.r.t. the input */
@@ -267,6 +267,20 @@ int acb_loss_fwd_bwd(const float* logits, const long long* labels, const float* 
                      float* loss_out, float* dlogits, void* stream);
 int acb_dropout(const void* x, int x_dtype, void* y, int y_dtype, float p, long long seed, long long n, void* stream);
 int acb_sumsq(const float* x, long long n, float* out, int accumulate, void* stream);
+
+/* ---- masked-event pre-training (MPTModel, HyraxBaselineCLS.py:194-319) ---------------------------- */
+/* _mask_batch (:283-319) on the device: per light curve k = max(int(n_valid*mask_p), 3) tokens, k/3 per band
+ * (band = argmax of channels 4:7) drawn uniformly without replacement plus k%3 extras from the remaining valid
+ * tokens; channels 2:7 of the chosen rows of x[B,L,7] are zeroed IN PLACE and masked[B,L] set.  The draw is a
+ * counter hash of (seed, light curve, token), not torch.randperm: same distribution, different stream. */
+int acb_mpt_mask(float* x, const uint8_t* pad, int B, int L, double mask_p, long long seed, uint8_t* masked, void* stream);
+/* pred[T,5] = (flux, band logits x3, dt) of the packed tokens (CLS rows ignored); targets are read from the
+ * already-masked x exactly as the reference does (:264-272); losses[4] = {lambda_f*L_f*lambda_b*L_b*lambda_dt*L_dt,
+ * L_f (MSE), L_b (CE), L_dt (MSE)} as means over masked tokens; dpred[T,5] (optional) = d losses[0] / d pred.
+ * workspace: 4 floats. */
+int acb_mpt_loss_fwd_bwd(const void* pred, int pred_dtype, const int* src_idx, int T, const float* x, const uint8_t* masked, int L,
+                         float lambda_f, float lambda_b, float lambda_dt, float* losses, float* dpred, float* workspace,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -147,6 +147,79 @@ class HyraxBaselineCLS(nn.Module):
         return out
 
 
+class MPTModel(nn.Module):
+    """Masked-event pre-training restated (HyraxBaselineCLS.py:194-319), dropout off.
+
+    mask_batch follows _mask_batch (:283-319) draw for draw (same torch.randperm calls, so the same global
+    seed gives the reference's mask); losses() follows train_step (:241-278) up to the loss, including the
+    reference's quirks: targets are read from the ALREADY masked data, and the loss is a product.
+    """
+
+    def __init__(self, config, data_sample=None):
+        super().__init__()
+        self.config = config
+        mc = config["model"]["HyraxBaselineCLS"]
+        d = mc["d_model"]
+        self.n_heads = mc["n_heads"]
+        layer = nn.TransformerEncoderLayer(d, mc["n_heads"], d * 4, mc["dropout"], batch_first=True)
+        self.encoder = nn.TransformerEncoder(layer, mc["n_layers"])  # parameter container
+        self.in_proj = nn.Linear(7, d)
+        self.cls_tok = nn.Parameter(torch.zeros(1, 1, d))
+        self.time2vec = Time2Vec(d)
+        self.head_flux = nn.Linear(d, 1)
+        self.head_band = nn.Linear(d, 3)
+        self.head_dt = nn.Linear(d, 1)
+
+    def forward(self, z):
+        return self.head_flux(z), self.head_band(z), self.head_dt(z)
+
+    def mask_batch(self, x, pad_mask):
+        mask_p = self.config["model"]["HyraxBaselineCLS"]["mask_p"]
+        masked = torch.zeros_like(pad_mask)
+        for b in range(x.shape[0]):
+            valid = (~pad_mask[b]).nonzero(as_tuple=True)[0]
+            k = max(int(len(valid) * mask_p), 3)
+            each, extras = k // 3, k - 3 * (k // 3)
+            bands = x[b, :, 4:7].argmax(-1)
+            chosen = []
+            for band in (0, 1, 2):
+                vb = valid[bands[valid] == band]
+                if len(vb) > 0:
+                    chosen.append(vb[torch.randperm(len(vb))[: min(len(vb), each)]])
+            if extras > 0:
+                taken = torch.cat(chosen) if chosen else valid[:0]
+                pool = valid[~torch.isin(valid, taken)]
+                if len(pool) > 0:
+                    chosen.append(pool[torch.randperm(len(pool))[:extras]])
+            if chosen:
+                idx = torch.cat(chosen)
+                if len(idx) > 0:
+                    x[b, idx, 2:7] = 0.0
+                    masked[b, idx] = True
+        return masked
+
+    def losses(self, data, pad, masked):
+        """data already masked. -> (loss, loss_f, loss_b, loss_dt)."""
+        mc = self.config["model"]["HyraxBaselineCLS"]
+        B = data.shape[0]
+        h = self.in_proj(data) + self.time2vec(data[..., 0])
+        h = torch.cat([self.cls_tok.expand(B, -1, -1), h], dim=1)
+        kp = F.pad(pad, (1, 0), value=False)
+        for lyr in self.encoder.layers:
+            h = _encoder_layer_math(h, kp, lyr, self.n_heads)
+        z = h[:, 1:, :]
+        f_hat, b_hat, dt_hat = self.forward(z)
+        mf = masked.reshape(-1)
+        loss_f = F.mse_loss(f_hat.reshape(-1)[mf], data[..., 2].reshape(-1)[mf])
+        true_b = data[..., 4:7].argmax(-1).reshape(-1)
+        loss_b = F.cross_entropy(b_hat.reshape(-1, 3)[mf], true_b[mf])
+        dt_gt = torch.roll(data[..., 1], -1, dims=1).clone()
+        dt_gt[:, -1] = 0.0
+        loss_dt = F.mse_loss(dt_hat[..., 0].reshape(-1)[mf], dt_gt.reshape(-1)[mf])
+        loss = mc["lambda_f"] * loss_f * mc["lambda_b"] * loss_b * mc["lambda_dt"] * loss_dt
+        return loss, loss_f, loss_b, loss_dt
+
+
 def focal_loss(logits, target, gamma=2.0):
     """HyraxBaselineCLS.py:177-191 with alpha=None, eps=0, reduction='mean'."""
     logp = F.log_softmax(logits, dim=1)

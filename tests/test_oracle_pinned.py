@@ -156,3 +156,39 @@ def test_product_state_dict_schema_matches_oracle():
         assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in a), name
     a, b = ab.AppleCider(ab.default_config()).state_dict(), om.AppleCider(om.default_config()).state_dict()
     assert list(a) == list(b)
+
+
+def _clip_grads(named_grads, max_norm=1.0):
+    """torch.nn.utils.clip_grad_norm_ arithmetic on a dict of gradients."""
+    total = torch.sqrt(sum((g.float() ** 2).sum() for g in named_grads.values()))
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    return {k: g * coef for k, g in named_grads.items()}, total * coef
+
+
+def test_oracle_mpt_vs_golden(golden_dir):
+    """MPTModel restatement vs the unmodified reference train_step (tests/golden/make_golden_mpt.py)."""
+    from applecider_b200 import synth
+    from oracle import models as om
+
+    g = load_golden(golden_dir, "mpt")
+    cfg = om.default_config()
+    cfg["model"]["HyraxBaselineCLS"]["dropout"] = 0.0
+    m = om.MPTModel(cfg).train()
+    m.load_state_dict(synth.det_state_dict(m, 0))
+    # same seed -> same torch.randperm draws -> the reference's mask, bit for bit
+    torch.manual_seed(123)
+    x = g["x"].clone()
+    masked = m.mask_batch(x, g["pad"])
+    assert torch.equal(masked, g["masked"])
+    assert torch.equal(x, g["x_masked"])
+    loss, lf, lb, ldt = m.losses(x, g["pad"], masked)
+    assert_close(loss, g["loss"], 1e-5, "mpt loss")
+    mc = cfg["model"]["HyraxBaselineCLS"]
+    assert_close(mc["lambda_f"] * lf * mc["lambda_b"] * lb * mc["lambda_dt"] * ldt, g["loss"], 1e-5, "mpt loss product")
+    loss.backward()
+    grads, norm = _clip_grads({n: p.grad for n, p in m.named_parameters() if p.grad is not None})
+    assert_close(norm, g["clipped_grad_norm"], 1e-5, "clipped grad norm")
+    for k in g:
+        if k.startswith("g_"):
+            name = [n for n in grads if n.replace(".", "_") == k[2:]][0]
+            assert_close(grads[name], g[k], 2e-4, "d " + name, atol=1e-6)
