@@ -12,21 +12,25 @@ import torch.distributed as dist
 
 
 class FlatGradSync:
-    def __init__(self, module: torch.nn.Module, process_group=None):
+    def __init__(self, module, process_group=None, offsets=None, numel=None):
+        """module: an nn.Module or a list of parameters; offsets/numel: an explicit (aligned) flat layout."""
         self.module = module
         self.group = process_group
-        self.params = [p for p in module.parameters() if p.requires_grad]
+        plist = module.parameters() if isinstance(module, torch.nn.Module) else module
+        self.params = [p for p in plist if p.requires_grad]
         if not self.params:
             raise ValueError("module has no trainable parameters")
         dev, dt = self.params[0].device, self.params[0].dtype
-        total = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(total, dtype=dt, device=dev)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off: off + n].view_as(p)
-            off += n
-        self.numel = total
+        if offsets is None:
+            offsets, off = [], 0
+            for p in self.params:
+                offsets.append(off)
+                off += p.numel()
+            numel = off
+        self.offsets = list(offsets)
+        self.flat = torch.zeros(numel, dtype=dt, device=dev)
+        self.numel = numel
+        self._rebind()
 
     @property
     def world_size(self) -> int:
@@ -41,11 +45,8 @@ class FlatGradSync:
                 break
 
     def _rebind(self) -> None:
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off: off + n].view_as(p)
-            off += n
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.flat[off: off + p.numel()].view_as(p)
 
     def sync(self) -> None:
         """Average gradients over all ranks (the single exchange step of the data-parallel path)."""
@@ -60,11 +61,18 @@ class FlatGradSync:
 
 
 def ddp_train_step(sync: FlatGradSync, forward_loss, optimizer, clip_norm=None):
-    """zero -> forward+loss -> backward -> all-reduce(avg) -> [clip] -> optimizer.step.  Returns the local loss tensor."""
+    """zero -> forward+loss -> backward -> all-reduce(avg) -> [clip] -> optimizer.step.  Returns the local loss tensor.
+
+    With an optim.FusedAdam (whose ``grads`` is the FlatGradSync) clip + update are two kernels and nothing syncs."""
     sync.zero()
     loss = forward_loss()
     loss.backward()
     sync.sync()
+    if hasattr(optimizer, "flat_p"):  # optim.FusedAdam: the clip is part of the fused step
+        if clip_norm is not None and optimizer.max_grad_norm != clip_norm:
+            optimizer.max_grad_norm = clip_norm
+        optimizer.step()
+        return loss.detach()
     if clip_norm is not None:
         torch.nn.utils.clip_grad_norm_(sync.params, max_norm=clip_norm)
     optimizer.step()

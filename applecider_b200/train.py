@@ -21,6 +21,9 @@ F32 = torch.float32
 def _wc(cache, p, dtype):
     if dtype == F32:
         return None
+    sh = getattr(p, "_acb_bf16", None)  # bf16 shadow kept current by optim.FusedAdam
+    if sh is not None and dtype == torch.bfloat16 and sh[1] == p._version:
+        return sh[0]
     return cache.get(("cast", id(p)), (p,), lambda: ops.cast(p.detach().contiguous(), dtype))
 
 

@@ -56,8 +56,15 @@ def run_extra(args, peaks, ClockSampler):
         flops = FLOPS_ASTROMINN_TRAIN
     model.load_state_dict(synth.det_state_dict(model, 0), strict=True)
     model = model.cuda().train()
-    sync = FlatGradSync(model)
-    optimizer = opt_fn(sync.params) if opt_fn else model.this_optimizer
+    topt = opt_fn([p for p in model.parameters() if p.requires_grad]) if opt_fn else model.this_optimizer
+    if getattr(args, "torch_optim", False):
+        sync = FlatGradSync(model)
+        optimizer = topt
+    else:  # fused step: two kernels over flat buffers, bf16 weight shadow refreshed in the same pass
+        from applecider_b200.optim import fused_from_torch
+
+        optimizer = fused_from_torch(topt, bf16_shadow=(args.dtype == "bf16"))
+        sync = optimizer.grads
 
     x, pad, lens = synth.photometry_batch(B, seed=1337 + rank)
     host = {"x": x, "pad": pad, "meta": synth.metadata(B, seed=1337 + rank), "img": synth.cutouts(B, seed=1337 + rank),
@@ -113,7 +120,8 @@ def run_extra(args, peaks, ClockSampler):
             "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{args.workload}_b{B}_per_gpu_{args.dtype}", "global_batch": B * world,
-                       "step": "forward + backward (C-ABI kernels) + NCCL all-reduce(avg) of the flat gradient + torch optimizer step; dropout on",
+                       "step": "forward + backward (C-ABI kernels) + NCCL all-reduce(avg) of the flat gradient + "
+                               + ("torch optimizer step" if getattr(args, "torch_optim", False) else "fused Adam kernel (acb_adam_step)") + "; dropout on",
                        "optimizer": "Adam(lr 1e-3, wd 0.01)" if args.workload == "train" else "AdamW 11 groups (astrominn.py:151-218)",
                        "grad_elements": sync.numel, "parallelism": f"dp{world}",
                        "fraction_of_tensor_roofline": value / world * flops / (peaks["tf_sustained"] * 1e12)},

@@ -282,6 +282,17 @@ int acb_mpt_loss_fwd_bwd(const void* pred, int pred_dtype, const int* src_idx, i
                          float lambda_f, float lambda_b, float lambda_dt, float* losses, float* dpred, float* workspace,
                          void* stream);
 
+/* ---- fused optimiser step ------------------------------------------------------------ */
+/* One pass over flat fp32 buffers p/g/m/v[n] (16-byte aligned, n % 4 == 0): optional torch-style gradient-norm
+ * clip (gnorm_sq = device scalar holding sum(g^2), e.g. from acb_sumsq; coef = min(1, max_norm/(norm+1e-6))),
+ * gradient scaling, then Adam (L2 weight decay joins the gradient) or AdamW (decoupled) with per-group
+ * hyper-parameters; group i covers [group_end[i-1], group_end[i]) and hyper[6*i..] = {lr, beta1, beta2, eps,
+ * weight_decay, decoupled}; both arrays live on the HOST.  step >= 1 is the 1-based step count (bias correction).
+ * p_bf16 (optional) receives the bf16 copy of the updated weights.  Replaces clip_grad_norm_ + optimizer.step at
+ * HyraxBaselineCLS.py:108-120,228,279-280, astrominn.py:151-218,311-326, brew_cider.py:1211. */
+int acb_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, int n_groups, const long long* group_end,
+                  const float* hyper, int step, const float* gnorm_sq, float max_norm, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
