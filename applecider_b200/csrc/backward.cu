@@ -242,6 +242,125 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* x, int x
   }
 }
 
+// Register-resident variant for C = 32*VEC*NCH <= 768 and one dtype for x/dy/dx: every row is read ONCE (vector
+// loads), dw/db partial sums stay in registers over the warp's rows, then one shared-memory pass + one global
+// atomic per channel and CTA.
+template <typename T, int NCH, int VEC>
+__global__ void __launch_bounds__(256) layernorm_bwd_reg_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ w,
+                                                                T* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
+                                                                long long rows, float eps, int rows_per_warp) {
+  constexpr int C = 32 * VEC * NCH, NE = NCH * VEC;
+  __shared__ float shacc[2 * C];
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) shacc[i] = 0.0f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float wv[NE], aw[NE], ab[NE];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      wv[k * VEC + e] = w[(k * 32 + lane) * VEC + e];
+      aw[k * VEC + e] = 0.0f;
+      ab[k * VEC + e] = 0.0f;
+    }
+  const long long row0 = ((long long)blockIdx.x * nw + wid) * rows_per_warp;
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const long long row = row0 + rr;
+    if (row >= rows) break;
+    float xv[NE], gv[NE];
+    const T* xr = x + row * C;
+    const T* gr = dy + row * C;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c0 = (k * 32 + lane) * VEC;
+      if constexpr (VEC == 2 && sizeof(T) == 2) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + c0));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gr + c0));
+        xv[k * 2] = a.x; xv[k * 2 + 1] = a.y; gv[k * 2] = b.x; gv[k * 2 + 1] = b.y;
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          xv[k * VEC + e] = to_f<T>(xr[c0 + e]);
+          gv[k * VEC + e] = to_f<T>(gr[c0 + e]);
+        }
+      }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) s += xv[i];
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) { xv[i] -= mean; q += xv[i] * xv[i]; }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    float sg = 0.0f, sgx = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      xv[i] *= rstd;  // xhat
+      const float g = gv[i] * wv[i];
+      sg += g;
+      sgx += g * xv[i];
+      aw[i] = fmaf(gv[i], xv[i], aw[i]);
+      ab[i] += gv[i];
+    }
+    sg = warp_sum(sg) / (float)C;
+    sgx = warp_sum(sgx) / (float)C;
+    T* dr = dx + row * C;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c0 = (k * 32 + lane) * VEC;
+      if constexpr (VEC == 2 && sizeof(T) == 2) {
+        const float o0 = rstd * (gv[k * 2] * wv[k * 2] - sg - xv[k * 2] * sgx);
+        const float o1 = rstd * (gv[k * 2 + 1] * wv[k * 2 + 1] - sg - xv[k * 2 + 1] * sgx);
+        *reinterpret_cast<__nv_bfloat162*>(dr + c0) = __floats2bfloat162_rn(o0, o1);
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const int i = k * VEC + e;
+          dr[c0 + e] = from_f<T>(rstd * (gv[i] * wv[i] - sg - xv[i] * sgx));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int c = (k * 32 + lane) * VEC + e;
+      atomicAdd(&shacc[c], aw[k * VEC + e]);
+      atomicAdd(&shacc[C + c], ab[k * VEC + e]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dw + i, shacc[i]);
+    atomicAdd(db + i, shacc[C + i]);
+  }
+}
+
+template <typename T>
+static bool launch_ln_bwd_reg(const void* x, const void* dy, const float* w, void* dx, float* dw, float* db, long long rows, int C, float eps,
+                              cudaStream_t st) {
+  const int rpw = rows > (1 << 18) ? 64 : (rows > (1 << 14) ? 16 : (rows > 2048 ? 4 : 1));
+  const long long warps = (rows + rpw - 1) / rpw;
+  const unsigned grid = (unsigned)((warps + 7) / 8);
+#define LNB(NCH, VEC)                                                                                                              \
+  layernorm_bwd_reg_kernel<T, NCH, VEC><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, w, (T*)dx, dw, db, rows, eps, rpw); \
+  return true
+  switch (C) {
+    case 32: LNB(1, 1);
+    case 64: LNB(1, 2);
+    case 96: LNB(3, 1);
+    case 128: LNB(2, 2);
+    case 192: LNB(3, 2);
+    case 256: LNB(4, 2);
+    case 384: LNB(6, 2);
+    case 512: LNB(8, 2);
+    case 768: LNB(12, 2);
+    default: return false;
+  }
+#undef LNB
+}
+
 // ================================ attention backward ================================================
 // CTA per (sequence, head); Q, K, V, dO in shared memory; pass A (thread per query): lse, D, dQ;
 // pass B (thread per key): dK, dV.
@@ -447,6 +566,79 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const void* x, int x
 #pragma unroll
   for (int j = 0; j < 49; ++j) atomicAdd(dw + c * 49 + j, acc[j]);
   atomicAdd(db + c, sb);
+}
+
+// Row-register variant for the square ConvNeXt maps (W = H in {15, 7, 3}): thread = (channel, row phase); the dy row
+// and one x row live in registers, so every x value loaded feeds up to 7 taps (loads : FMAs = 1 : 7 instead of 1 : 1);
+// partial sums are merged in shared memory before the global atomics.
+template <typename T, int W>
+__global__ void __launch_bounds__(512) dwconv7_wgrad_w_kernel(const T* __restrict__ x, const T* __restrict__ dy, int B, int C, int cc,
+                                                              int rowsplit, int img_per_block, float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ float red[];  // [cc][50]
+  for (int i = threadIdx.x; i < cc * 50; i += blockDim.x) red[i] = 0.0f;
+  __syncthreads();
+  const int cl = threadIdx.x % cc, part = threadIdx.x / cc;
+  const int c = blockIdx.y * cc + cl;
+  if (c < C) {
+    float acc[49];
+#pragma unroll
+    for (int j = 0; j < 49; ++j) acc[j] = 0.0f;
+    float sb = 0.0f;
+    const int b0 = blockIdx.x * img_per_block, b1 = min(B, b0 + img_per_block);
+    for (int b = b0; b < b1; ++b) {
+      const T* xb = x + (long long)b * W * W * C + c;
+      const T* gb = dy + (long long)b * W * W * C + c;
+      for (int oy = part; oy < W; oy += rowsplit) {
+        float g[W];
+#pragma unroll
+        for (int ox = 0; ox < W; ++ox) {
+          g[ox] = to_f<T>(gb[(long long)(oy * W + ox) * C]);
+          sb += g[ox];
+        }
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+          const int iy = oy + ky - 3;
+          if (iy < 0 || iy >= W) continue;
+          float xr[W];
+#pragma unroll
+          for (int ix = 0; ix < W; ++ix) xr[ix] = to_f<T>(xb[(long long)(iy * W + ix) * C]);
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx) {
+#pragma unroll
+            for (int ox = 0; ox < W; ++ox) {
+              const int ix = ox + kx - 3;
+              if (ix >= 0 && ix < W) acc[ky * 7 + kx] = fmaf(g[ox], xr[ix], acc[ky * 7 + kx]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 49; ++j) atomicAdd(&red[cl * 50 + j], acc[j]);
+    atomicAdd(&red[cl * 50 + 49], sb);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cc * 50; i += blockDim.x) {
+    const int l = i / 50, j = i - l * 50, ch = blockIdx.y * cc + l;
+    if (ch >= C) continue;
+    if (j < 49) atomicAdd(dw + ch * 49 + j, red[i]);
+    else atomicAdd(db + ch, red[i]);
+  }
+}
+
+template <typename T>
+static bool launch_dwconv7_wgrad_w(const void* x, const void* dy, int B, int H, int W, int C, float* dw, float* db, cudaStream_t st) {
+  if (H != W || !(W == 15 || W == 7 || W == 3)) return false;
+  const int cc = C >= 128 ? 128 : ((C + 31) / 32) * 32;
+  const int rowsplit = min(W, 512 / cc);
+  int ipb = 1;
+  while (ipb < 16 && (long long)cdiv(B, ipb * 2) * cdiv(C, cc) >= 2 * 148) ipb *= 2;
+  const dim3 grid(cdiv(B, ipb), cdiv(C, cc));
+  const size_t smem = (size_t)cc * 50 * 4;
+  if (W == 15) dwconv7_wgrad_w_kernel<T, 15><<<grid, cc * rowsplit, smem, st>>>((const T*)x, (const T*)dy, B, C, cc, rowsplit, ipb, dw, db);
+  else if (W == 7) dwconv7_wgrad_w_kernel<T, 7><<<grid, cc * rowsplit, smem, st>>>((const T*)x, (const T*)dy, B, C, cc, rowsplit, ipb, dw, db);
+  else dwconv7_wgrad_w_kernel<T, 3><<<grid, cc * rowsplit, smem, st>>>((const T*)x, (const T*)dy, B, C, cc, rowsplit, ipb, dw, db);
+  return true;
 }
 
 // 2x2/stride-2 patch gather (fwd) and its adjoint (bwd: rows/cols dropped by the floor get zero)
@@ -708,6 +900,11 @@ int acb_layernorm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, 
                       float* db, long long rows, int C, float eps, void* stream) {
   ACB_CHECK(x && dy && w && dx && dw && db && rows >= 0 && C > 0 && C <= 6000, "acb_layernorm_bwd: bad arguments");
   if (rows == 0) return ACB_OK;
+  if (x_dtype == dy_dtype && x_dtype == dx_dtype) {
+    const bool done = x_dtype == ACB_F32 ? launch_ln_bwd_reg<float>(x, dy, w, dx, dw, db, rows, C, eps, (cudaStream_t)stream)
+                                         : launch_ln_bwd_reg<bf16>(x, dy, w, dx, dw, db, rows, C, eps, (cudaStream_t)stream);
+    if (done) { LAUNCHED(1); }
+  }
   const int rpw = rows > (1 << 16) ? 16 : 1;
   const long long warps = (rows + rpw - 1) / rpw;
   layernorm_bwd_kernel<<<(unsigned)((warps + 7) / 8), 256, (size_t)2 * C * 4, (cudaStream_t)stream>>>(x, x_dtype, dy, dy_dtype, w, dx, dx_dtype,
@@ -763,6 +960,10 @@ int acb_dwconv7_wgrad(const void* x, int x_dtype, const void* dy, int dy_dtype, 
   if (!accumulate) {
     ACB_CUDA(cudaMemsetAsync(dw, 0, (size_t)C * 49 * 4, st));
     ACB_CUDA(cudaMemsetAsync(db, 0, (size_t)C * 4, st));
+  }
+  if (x_dtype == dy_dtype) {
+    const bool done = x_dtype == ACB_F32 ? launch_dwconv7_wgrad_w<float>(x, dy, B, H, W, C, dw, db, st) : launch_dwconv7_wgrad_w<bf16>(x, dy, B, H, W, C, dw, db, st);
+    if (done) { LAUNCHED(1); }
   }
   const int ipb = B > 2048 ? 8 : (B > 256 ? 2 : 1);
   const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
