@@ -384,6 +384,82 @@ class ConcatCols(Function):
         return tuple(outs)
 
 
+class TowerGroup(Function):
+    """N ResidualTowerBlocks in one forward and one backward launch (acb_tower_group_fwd/bwd).
+
+    spec = dict(towers=[dict(cols=int32 tensor|None, in_dim, hid, out_dim, y_off, a_off)], ldy, lda, drop_p, seed,
+    need_dx, extra_off); X [rows, ldx] fp32; A_pre [rows, lda] fp32 or None (then every tower has its start path W0);
+    extra: optional [rows, w] tensor copied into Y at column extra_off (the image features inside the 288-wide concat);
+    params: 12 per tower (W0, b0, ln1w, ln1b, W1, b1, ln2w, ln2b, W2, b2, Ws, bs), None where absent."""
+
+    @staticmethod
+    def _tables(spec, params, grads):
+        import ctypes
+
+        n = len(spec["towers"])
+        ptrs = (ctypes.c_longlong * (25 * n))()
+        dims = (ctypes.c_int * (5 * n))()
+        for t, tw in enumerate(spec["towers"]):
+            ptrs[25 * t] = tw["cols"].data_ptr() if tw["cols"] is not None else 0
+            for j in range(12):
+                p = params[12 * t + j]
+                ptrs[25 * t + 1 + j] = p.data_ptr() if p is not None else 0
+                g = grads[12 * t + j] if grads is not None else None
+                ptrs[25 * t + 13 + j] = g.data_ptr() if g is not None else 0
+            dims[5 * t: 5 * t + 5] = [tw["in_dim"], tw["hid"], tw["out_dim"], tw["y_off"], tw["a_off"]]
+        return n, ptrs, dims
+
+    @staticmethod
+    def forward(ctx, spec, X, A_pre, extra, *params):
+        X = _c(X)
+        rows = X.shape[0]
+        Y = torch.empty((rows, spec["ldy"]), dtype=F32, device=X.device)
+        A = _c(A_pre) if A_pre is not None else torch.empty((rows, spec["lda"]), dtype=F32, device=X.device)
+        pd = [None if p is None else p.detach() for p in params]
+        n, ptrs, dims = TowerGroup._tables(spec, pd, None)
+        call("acb_tower_group_fwd", X, X.shape[1], rows, n, ptrs, dims, Y, spec["ldy"], A, spec["lda"], spec["drop_p"], spec["seed"])
+        if extra is not None:
+            call("acb_copy2d", _c(extra), dtype_tag(extra), extra.shape[1], ops._offset_ptr(Y, spec["extra_off"]), 0, spec["ldy"], rows, extra.shape[1])
+            ctx.extra_w = extra.shape[1]
+        ctx.spec, ctx.has_apre, ctx.has_extra = spec, A_pre is not None, extra is not None
+        ctx.save_for_backward(X, A, *[p for p in pd if p is not None])
+        ctx.present = [p is not None for p in pd]
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        spec = ctx.spec
+        X, A = ctx.saved_tensors[:2]
+        it = iter(ctx.saved_tensors[2:])
+        params = [next(it) if pres else None for pres in ctx.present]
+        dY = _c(dY)
+        rows = X.shape[0]
+        sizes = [0 if p is None else (p.numel() + 3) // 4 * 4 for p in params]
+        flat = torch.zeros(sum(sizes), dtype=F32, device=X.device)
+        grads, off = [], 0
+        for p, sz in zip(params, sizes):
+            grads.append(None if p is None else flat[off: off + p.numel()].view(p.shape))
+            off += sz
+        n, ptrs, dims = TowerGroup._tables(spec, params, grads)
+        dA = torch.empty_like(A) if ctx.has_apre else None
+        dX = torch.empty_like(X) if spec["need_dx"] else None
+        call("acb_tower_group_bwd", X, X.shape[1], rows, n, ptrs, dims, A, spec["lda"], dY, spec["ldy"], dA, dX, spec["drop_p"], spec["seed"])
+        dextra = None
+        if ctx.has_extra:
+            dextra = torch.empty((rows, ctx.extra_w), dtype=F32, device=X.device)
+            call("acb_copy2d", ops._offset_ptr(dY, spec["extra_off"]), 0, spec["ldy"], dextra, 0, ctx.extra_w, rows, ctx.extra_w)
+        return (None, dX, dA, dextra, *grads)
+
+
+def tower_params(tw, with_start=True):
+    """The 12 parameter slots of a ResidualTowerBlock in acb_tower_group order."""
+    skip = isinstance(tw.skip_path, torch.nn.Linear)
+    return [tw.start_path[0].weight if with_start else None, tw.start_path[0].bias if with_start else None,
+            tw.main_path[0].weight, tw.main_path[0].bias, tw.main_path[2].weight, tw.main_path[2].bias,
+            tw.activation[0].weight, tw.activation[0].bias, tw.activation[2].weight, tw.activation[2].bias,
+            tw.skip_path.weight if skip else None, tw.skip_path.bias if skip else None]
+
+
 def gather_cols(X, cols):
     Y = torch.empty((X.shape[0], cols.numel()), dtype=F32, device=X.device)
     call("acb_gather_cols", X, X.shape[1], cols, cols.numel(), Y, X.shape[0])

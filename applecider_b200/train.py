@@ -337,23 +337,78 @@ def image_tower_train(it, img, dtype, training):
     return fn.mul(a, x)
 
 
+FUSE_TOWERS = True  # tower groups as one forward + one backward launch (acb_tower_group_*)
+
+
+def _dims(tw):
+    return tw.start_path[0].in_features, tw.start_path[0].out_features, tw.main_path[2].out_features
+
+
+def _towers_fused(model, metadata, image_feats, tr):
+    """The 8 metadata towers + the image features -> the 288-wide concat (astrominn.py:249-267), one launch each way."""
+    from .astrominn import CONCAT_ORDER
+
+    towers, params, y_off, a_off, extra_off = [], [], 0, 0, 0
+    p_drop = 0.0
+    for n in CONCAT_ORDER:
+        if n == "image":
+            extra_off = y_off
+            y_off += image_feats.shape[1]
+            continue
+        tw = getattr(model, f"{n}_tower")
+        i, h, o = _dims(tw)
+        towers.append(dict(cols=getattr(model, f"_cols_{n}"), in_dim=i, hid=h, out_dim=o, y_off=y_off, a_off=a_off))
+        params += fn.tower_params(tw)
+        y_off += o
+        a_off += h
+        p_drop = tw.main_path[1].p if tr else 0.0
+    spec = dict(towers=towers, ldy=y_off, lda=a_off, drop_p=float(p_drop), seed=(fn.next_seed() if p_drop > 0 else 0), need_dx=False,
+                extra_off=extra_off)
+    return fn.TowerGroup.apply(spec, metadata, None, image_feats, *params)
+
+
+def _experts_fused(model, feats, tr):
+    """The 4 experts: start paths as ONE GEMM (pre-GELU), the rest as one fused launch -> [B, 4*5]."""
+    exs = list(model.fusion_experts)
+    w0 = torch.cat([ex.start_path[0].weight for ex in exs], 0)
+    b0 = torch.cat([ex.start_path[0].bias for ex in exs], 0)
+    a_pre = fn.linear(feats, w0, b0)
+    towers, params, y_off, a_off = [], [], 0, 0
+    for ex in exs:
+        i, h, o = _dims(ex)
+        towers.append(dict(cols=None, in_dim=i, hid=h, out_dim=o, y_off=y_off, a_off=a_off))
+        params += fn.tower_params(ex, with_start=False)
+        y_off += o
+        a_off += h
+    p_drop = exs[0].main_path[1].p if tr else 0.0
+    spec = dict(towers=towers, ldy=y_off, lda=a_off, drop_p=float(p_drop), seed=(fn.next_seed() if p_drop > 0 else 0), need_dx=True, extra_off=0)
+    return fn.TowerGroup.apply(spec, feats, a_pre, None, *params)
+
+
 def astrominn_forward_train(model, metadata, image):
     from .astrominn import CONCAT_ORDER
 
     tr = model.training
     metadata = metadata.contiguous().float()
-    parts = []
-    for n in CONCAT_ORDER:
-        if n == "image":
-            parts.append(image_tower_train(model.image_tower, image, model.compute_dtype, tr))
-        else:
-            tw = getattr(model, f"{n}_tower")
-            parts.append(_tower_train(tw, fn.gather_cols(metadata, getattr(model, f"_cols_{n}")), tr))
-    feats = fn.ConcatCols.apply(*parts)
+    fuse = FUSE_TOWERS and len(model.fusion_experts) <= 8
+    if fuse:
+        feats = _towers_fused(model, metadata, image_tower_train(model.image_tower, image, model.compute_dtype, tr), tr)
+    else:
+        parts = []
+        for n in CONCAT_ORDER:
+            if n == "image":
+                parts.append(image_tower_train(model.image_tower, image, model.compute_dtype, tr))
+            else:
+                tw = getattr(model, f"{n}_tower")
+                parts.append(_tower_train(tw, fn.gather_cols(metadata, getattr(model, f"_cols_{n}")), tr))
+        feats = fn.ConcatCols.apply(*parts)
     r = model.fusion_router
     g1 = fn.act(fn.linear(feats, r[0].weight, r[0].bias), ops.ACT_TANH)
     gate = fn.act(fn.linear(fn.dropout(g1, r[2].p, tr), r[3].weight, r[3].bias), ops.ACT_SIGMOID)
-    eo = fn.ConcatCols.apply(*[_tower_train(ex, feats, tr) for ex in model.fusion_experts])
+    if fuse:
+        eo = _experts_fused(model, feats, tr)
+    else:
+        eo = fn.ConcatCols.apply(*[_tower_train(ex, feats, tr) for ex in model.fusion_experts])
     out = fn.MoeCombine.apply(gate, eo, model.num_mlp_experts, 5)
     if model.config["model"]["AstroMiNN"]["use_probabilities"]:
         raise NotImplementedError("training through use_probabilities=True is not implemented")

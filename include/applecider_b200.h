@@ -293,6 +293,23 @@ int acb_mpt_loss_fwd_bwd(const void* pred, int pred_dtype, const int* src_idx, i
 int acb_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, int n_groups, const long long* group_end,
                   const float* hyper, int step, const float* gnorm_sq, float max_norm, float grad_scale, void* stream);
 
+/* ---- tower groups, training path (ResidualTowerBlock x N in one launch; astrominn.py:44-64,264-300) ---- */
+/* ptrs: HOST array, 25 device addresses per tower = {cols (int*, or 0 = columns 0..in-1 of X),
+ *   W0, b0, ln1w, ln1b, W1, b1, ln2w, ln2b, W2, b2, Ws, bs,           (parameters, torch (out,in) layout; W0/b0 = 0:
+ *                                                                      the pre-GELU start path is supplied in A;
+ *                                                                      Ws/bs = 0: identity skip)
+ *   gW0, gb0, gln1w, gln1b, gW1, gb1, gln2w, gln2b, gW2, gb2, gWs, gbs} (gradient buffers, backward only: ACCUMULATED)
+ * dims: HOST array, 5 ints per tower = {in_dim, hidden, out_dim (<= 32), y_off (column of Y / dY), a_off (column of A / dA)}.
+ * fwd: Y[rows, ldy] columns y_off.. = tower(X); A[rows, lda] receives (W0 given) or supplies (W0 = 0) the pre-GELU
+ * activations -- the only tensor the backward needs.  Dropout (p = drop_p on both LayerNorm outputs, training only)
+ * is a counter hash of (seed, tower, row, column), regenerated in the backward.
+ * bwd: parameter gradients accumulated into the g* buffers; dA (optional, layout of A) = d loss / d pre-GELU;
+ * dX (optional, [rows, ldx], overwritten) = d loss / d X summed over the towers of the group. */
+int acb_tower_group_fwd(const float* X, int ldx, int rows, int n_towers, const long long* ptrs, const int* dims, float* Y, int ldy,
+                        float* A, int lda, float drop_p, long long seed, void* stream);
+int acb_tower_group_bwd(const float* X, int ldx, int rows, int n_towers, const long long* ptrs, const int* dims, const float* A, int lda,
+                        const float* dY, int ldy, float* dA, float* dX, float drop_p, long long seed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
