@@ -199,8 +199,8 @@ __global__ void pack_conv_dgrad_kernel(const float* w, void* out, int odt, int C
 // ================================ LayerNorm backward ================================================
 // warp per row; dx = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*w; dw += dy*xhat, db += dy (atomics per block)
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* x, int x_dt, const void* dy, int dy_dt, const float* w,
-                                                            void* dx, int dx_dt, float* dw, float* db, long long rows, int C,
-                                                            float eps, int rows_per_warp) {
+                                                            const float* bias, int gelu, void* dx, int dx_dt, float* dw, float* db,
+                                                            long long rows, int C, float eps, int rows_per_warp) {
   extern __shared__ float shacc[];  // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) shacc[i] = 0.0f;
   __syncthreads();
@@ -221,7 +221,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* x, int x
     float sg = 0.0f, sgx = 0.0f;
     for (int c = lane; c < C; c += 32) {
       const float xh = (ld_any(x, row * C + c, x_dt) - mean) * rstd;
-      const float g = ld_any(dy, row * C + c, dy_dt) * w[c];
+      float dyv = ld_any(dy, row * C + c, dy_dt);
+      if (gelu) dyv *= gelu_erf_grad(fmaf(xh, w[c], bias[c]));  // y = gelu(LN(x)): chain through the activation
+      const float g = dyv * w[c];
       sg += g;
       sgx += g * xh;
     }
@@ -229,7 +231,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* x, int x
     sgx = warp_sum(sgx) / (float)C;
     for (int c = lane; c < C; c += 32) {
       const float xh = (ld_any(x, row * C + c, x_dt) - mean) * rstd;
-      const float dyv = ld_any(dy, row * C + c, dy_dt);
+      float dyv = ld_any(dy, row * C + c, dy_dt);
+      if (gelu) dyv *= gelu_erf_grad(fmaf(xh, w[c], bias[c]));
       st_any(dx, row * C + c, dx_dt, rstd * (dyv * w[c] - sg - xh * sgx));
       atomicAdd(&shacc[c], dyv * xh);
       atomicAdd(&shacc[C + c], dyv);
@@ -247,19 +250,21 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* x, int x
 // atomic per channel and CTA.
 template <typename T, int NCH, int VEC>
 __global__ void __launch_bounds__(256) layernorm_bwd_reg_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ w,
-                                                                T* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
-                                                                long long rows, float eps, int rows_per_warp) {
+                                                                const float* __restrict__ bias, int gelu, T* __restrict__ dx,
+                                                                float* __restrict__ dw, float* __restrict__ db, long long rows, float eps,
+                                                                int rows_per_warp) {
   constexpr int C = 32 * VEC * NCH, NE = NCH * VEC;
   __shared__ float shacc[2 * C];
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) shacc[i] = 0.0f;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float wv[NE], aw[NE], ab[NE];
+  float wv[NE], bv[NE], aw[NE], ab[NE];
 #pragma unroll
   for (int k = 0; k < NCH; ++k)
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       wv[k * VEC + e] = w[(k * 32 + lane) * VEC + e];
+      bv[k * VEC + e] = gelu ? bias[(k * 32 + lane) * VEC + e] : 0.0f;
       aw[k * VEC + e] = 0.0f;
       ab[k * VEC + e] = 0.0f;
     }
@@ -297,6 +302,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_reg_kernel(const T* __restr
 #pragma unroll
     for (int i = 0; i < NE; ++i) {
       xv[i] *= rstd;  // xhat
+      if (gelu) gv[i] *= gelu_erf_grad(fmaf(xv[i], wv[i], bv[i]));
       const float g = gv[i] * wv[i];
       sg += g;
       sgx += g * xv[i];
@@ -338,13 +344,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_reg_kernel(const T* __restr
 }
 
 template <typename T>
-static bool launch_ln_bwd_reg(const void* x, const void* dy, const float* w, void* dx, float* dw, float* db, long long rows, int C, float eps,
-                              cudaStream_t st) {
+static bool launch_ln_bwd_reg(const void* x, const void* dy, const float* w, const float* bias, int gelu, void* dx, float* dw, float* db,
+                              long long rows, int C, float eps, cudaStream_t st) {
   const int rpw = rows > (1 << 18) ? 64 : (rows > (1 << 14) ? 16 : (rows > 2048 ? 4 : 1));
   const long long warps = (rows + rpw - 1) / rpw;
   const unsigned grid = (unsigned)((warps + 7) / 8);
 #define LNB(NCH, VEC)                                                                                                              \
-  layernorm_bwd_reg_kernel<T, NCH, VEC><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, w, (T*)dx, dw, db, rows, eps, rpw); \
+  layernorm_bwd_reg_kernel<T, NCH, VEC><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, w, bias, gelu, (T*)dx, dw, db, rows, eps, rpw); \
   return true
   switch (C) {
     case 32: LNB(1, 1);
@@ -896,19 +902,21 @@ int acb_gather_cols(const float* X, int ldx, const int* cols, int n, float* Y, l
   LAUNCHED(1);
 }
 
-int acb_layernorm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* w, void* dx, int dx_dtype, float* dw,
-                      float* db, long long rows, int C, float eps, void* stream) {
+int acb_layernorm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* w, const float* b, int post_act, void* dx,
+                      int dx_dtype, float* dw, float* db, long long rows, int C, float eps, void* stream) {
   ACB_CHECK(x && dy && w && dx && dw && db && rows >= 0 && C > 0 && C <= 6000, "acb_layernorm_bwd: bad arguments");
+  ACB_CHECK(post_act == ACB_ACT_NONE || (post_act == ACB_ACT_GELU && b), "acb_layernorm_bwd: post_act must be none or GELU (with the LayerNorm bias)");
+  const int gelu = post_act == ACB_ACT_GELU;
   if (rows == 0) return ACB_OK;
   if (x_dtype == dy_dtype && x_dtype == dx_dtype) {
-    const bool done = x_dtype == ACB_F32 ? launch_ln_bwd_reg<float>(x, dy, w, dx, dw, db, rows, C, eps, (cudaStream_t)stream)
-                                         : launch_ln_bwd_reg<bf16>(x, dy, w, dx, dw, db, rows, C, eps, (cudaStream_t)stream);
+    const bool done = x_dtype == ACB_F32 ? launch_ln_bwd_reg<float>(x, dy, w, b, gelu, dx, dw, db, rows, C, eps, (cudaStream_t)stream)
+                                         : launch_ln_bwd_reg<bf16>(x, dy, w, b, gelu, dx, dw, db, rows, C, eps, (cudaStream_t)stream);
     if (done) { LAUNCHED(1); }
   }
   const int rpw = rows > (1 << 16) ? 16 : 1;
   const long long warps = (rows + rpw - 1) / rpw;
-  layernorm_bwd_kernel<<<(unsigned)((warps + 7) / 8), 256, (size_t)2 * C * 4, (cudaStream_t)stream>>>(x, x_dtype, dy, dy_dtype, w, dx, dx_dtype,
-                                                                                                    dw, db, rows, C, eps, rpw);
+  layernorm_bwd_kernel<<<(unsigned)((warps + 7) / 8), 256, (size_t)2 * C * 4, (cudaStream_t)stream>>>(x, x_dtype, dy, dy_dtype, w, b, gelu, dx,
+                                                                                                    dx_dtype, dw, db, rows, C, eps, rpw);
   LAUNCHED(1);
 }
 

@@ -139,28 +139,31 @@ def act(x, kind):
 
 
 class LayerNorm(Function):
+    """y = [gelu](LN(x)); the optional GELU is fused in both directions (its input is recomputed from x)."""
+
     @staticmethod
-    def forward(ctx, x, w, b, eps, out_dtype):
+    def forward(ctx, x, w, b, eps, out_dtype, post_act=ops.ACT_NONE):
         x = _c(x)
-        y = ops.layernorm(x, w, b, eps, out_dtype=out_dtype)
-        ctx.save_for_backward(x, w)
-        ctx.eps = eps
+        y = ops.layernorm(x, w, b, eps, out_dtype=out_dtype, post_act=post_act)
+        ctx.save_for_backward(x, w, b)
+        ctx.eps, ctx.post_act = eps, post_act
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w = ctx.saved_tensors
+        x, w, b = ctx.saved_tensors
         dy = _c(dy)
         C = x.shape[-1]
         rows = x.numel() // C
         dx = torch.empty_like(x)
-        dw, db = _zeros(C, x.device), _zeros(C, x.device)
-        call("acb_layernorm_bwd", x, dtype_tag(x), dy, dtype_tag(dy), w, dx, dtype_tag(dx), dw, db, rows, C, ctx.eps)
-        return dx, dw, db, None, None
+        dwb = _zeros(2 * C, x.device)
+        dw, db = dwb[:C], dwb[C:]
+        call("acb_layernorm_bwd", x, dtype_tag(x), dy, dtype_tag(dy), w, b, ctx.post_act, dx, dtype_tag(dx), dw, db, rows, C, ctx.eps)
+        return dx, dw, db, None, None, None
 
 
-def layernorm(x, w, b, eps, out_dtype=None):
-    return LayerNorm.apply(x, w, b, eps, out_dtype)
+def layernorm(x, w, b, eps, out_dtype=None, post_act=ops.ACT_NONE):
+    return LayerNorm.apply(x, w, b, eps, out_dtype, post_act)
 
 
 class Add(Function):

@@ -233,7 +233,7 @@ def spectra_features_train(model, x):
         for blk in stage:
             params = [c.weight for c in blk.convs] + [c.bias for c in blk.convs]
             y = SpectraConvs.apply(h, sig if h is None else None, blk, B, L, dtype, *params)
-            y = fn.act(fn.layernorm(y, blk.norm.weight, blk.norm.bias, blk.norm.eps), ops.ACT_GELU)
+            y = fn.layernorm(y, blk.norm.weight, blk.norm.bias, blk.norm.eps, post_act=ops.ACT_GELU)
             nc = blk.out_channels * blk.k
             if blk.do_pool:
                 wd = blk.downsample.weight.view(blk.out_channels, nc)
@@ -251,7 +251,7 @@ def spectra_forward_train(model, x):
     head = model.regressor if model.redshift else model.classifier
     tr = model.training
     z = fn.linear(feat, head[0].weight, head[0].bias)
-    z = fn.act(fn.layernorm(z, head[1].weight, head[1].bias, head[1].eps), ops.ACT_GELU)
+    z = fn.layernorm(z, head[1].weight, head[1].bias, head[1].eps, post_act=ops.ACT_GELU)
     z = fn.dropout(z, head[3].p, tr)
     out = fn.linear(z, head[4].weight, head[4].bias)
     return out.squeeze(1) if model.redshift else out

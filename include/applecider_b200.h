@@ -234,9 +234,11 @@ int acb_gather_cols(const float* X, int ldx, const int* cols, int n, float* Y, l
 int acb_unpack_conv_wgrad(const float* G, float* dW, int Cout, int Cin, int k, void* stream);
 /* out[ci*(k*Cout) + tap*Cout + co] = w[co,ci,k-1-tap]  (weights of the input-gradient convolution) */
 int acb_pack_conv_dgrad_weight(const float* w, void* out, int out_dtype, int Cout, int Cin, int k, void* stream);
-/* LayerNorm backward: dx, and dw += sum dy*xhat, db += sum dy (caller zeroes dw/db) */
-int acb_layernorm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* w, void* dx, int dx_dtype,
-                      float* dw, float* db, long long rows, int C, float eps, void* stream);
+/* LayerNorm backward: dx, and dw += sum dy*xhat, db += sum dy (caller zeroes dw/db).  post_act = ACB_ACT_GELU (b = the
+ * LayerNorm bias): backward of y = gelu(LN(x)) in one pass, the pre-activation is recomputed from x
+ * (SpectraNetBlock norm + GELU, spectranet.py:36-38). */
+int acb_layernorm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* w, const float* b, int post_act,
+                      void* dx, int dx_dtype, float* dw, float* db, long long rows, int C, float eps, void* stream);
 int acb_attention_varlen_bwd(const void* qkv, int dtype, const void* dout, int dout_dtype, const int* cu_seqlens, int B,
                              int n_heads, int dh, int max_seqlen, float drop_p, long long seed, void* dqkv, int dqkv_dtype,
                              void* stream);
