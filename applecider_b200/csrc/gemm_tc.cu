@@ -591,9 +591,22 @@ extern "C" int acb_wgrad_bf16(const void* dY, int ldy, int a_col0, int M_out, co
   const int bn = n_total >= 256 ? 256 : (n_total > 64 ? 128 : 64);
   const int mt = cdiv(M_out, TC_BM), ntl = cdiv(n_total, bn);
   const long long total_chunks = (long long)nb * args.cps;
-  int splits = (int)((148LL * 4 + (long long)mt * ntl - 1) / ((long long)mt * ntl));
-  if (splits > total_chunks) splits = (int)total_chunks;
-  if (splits < 1) splits = 1;
+  // split-K choice: every split adds M_out * n_total fp32 atomics (the L2 retires ~150 G atomics/s, so one 128x256 tile
+  // costs as much as ~60 K-chunks of tensor-core work), while too few splits leave SMs idle.  Minimise the modelled time
+  //   waves(tiles * s) * chunks_per_split * t_chunk  +  s * M_out * n_total / atomic_rate      over s.
+  const long long tiles = (long long)mt * ntl;
+  const double t_chunk_us = 0.5 * bn / 256.0, atomics_per_us = 150e3;
+  int splits = 1;
+  double best = 1e30;
+  const int s_max = (int)std::min<long long>(total_chunks, 2048);
+  for (int sidx = 1; sidx <= s_max; ++sidx) {
+    const long long cps = (total_chunks + sidx - 1) / sidx;
+    const long long s_eff = (total_chunks + cps - 1) / cps;
+    if (s_eff != sidx) continue;
+    const long long waves = (tiles * s_eff + 147) / 148;
+    const double t = (double)waves * (double)cps * t_chunk_us + (double)s_eff * (double)M_out * (double)n_total / atomics_per_us;
+    if (t < best) { best = t; splits = sidx; }
+  }
   if (splits > 65535) splits = 65535;
   args.chunks_per_split = (int)((total_chunks + splits - 1) / splits);
   splits = (int)((total_chunks + args.chunks_per_split - 1) / args.chunks_per_split);
