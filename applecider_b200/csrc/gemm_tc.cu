@@ -8,6 +8,8 @@
 // tensor map (channel, row, sample): a conv tap only shifts the row coordinate of the box and the TMA
 // unit zero-fills rows outside [0, L) — the im2col matrix never exists in memory.  Element strides of
 // the map may overlap (polyphase view of the 1-channel input signal for SpectraNet stage 0).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -35,108 +37,16 @@ struct TcArgs {
   int col_off[TC_MAX_CB];
 };
 
-// ---- the kernel --------------------------------------------------------------------------------------
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                             const __grid_constant__ CUtensorMap tmB,
-                                                             const __grid_constant__ TcArgs p) {
-  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
-  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
-  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
-  __shared__ uint32_t tmem_holder;
-  __shared__ __align__(16) float s_bias[BN], s_gamma[BN];  // staged by the epilogue warps while the main loop runs
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x, nt = blockIdx.y;
+// ---- epilogue of one 128 x BN tile (called by the 4 epilogue warps) ------------------------------------
+// TMEM -> registers (thread = output row) -> bias/act/residual/pool -> per-warp smem transpose (stg: 32 x 33 floats
+// per warp) -> row-contiguous 16-byte global stores.
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_tile(const TcArgs& p, bool have_acc, uint32_t tmem_acc, int mt, int nt, float* stg,
+                                                 const float* s_bias, const float* s_gamma, int warp, int lane) {
   const int n0 = nt * BN;
-
   const int sample0 = (mt / p.tps) * p.Bbox;
   const int l0 = (mt % p.tps) * p.Lbox;
-  if (p.m_valid_dev) {
-    if ((long long)sample0 * p.L + l0 >= (long long)(*p.m_valid_dev)) return;
-  }
-
-  const int kb_total = p.taps * p.cpt;
-  const int kb_lo = p.has_ranges ? p.kb_lo[nt] : 0;
-  const int kb_hi = p.has_ranges ? p.kb_hi[nt] : kb_total;
-  const int nkb = kb_hi - kb_lo;
-
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_full = smem_u32(&bars[0]);
-  const uint32_t bar_empty = smem_u32(&bars[STAGES]);
-  const uint32_t bar_acc = smem_u32(&bars[2 * STAGES]);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
-    }
-    mbar_init(bar_acc, 1);
-    fence_barrier_init();
-    fence_proxy_async();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
-                 "r"((uint32_t)tmem_cols<BN>())
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_holder;
-
-  if (warp == 0) {
-    // ===================== TMA producer (whole warp waits, one elected lane issues) =====================
-    const uint32_t a_box_bytes = (uint32_t)TC_BK * 2u * (uint32_t)p.Lbox * (uint32_t)p.Bbox;
-    for (int it = 0; it < nkb; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-      if (elect_one_sync()) {
-        const int kb = kb_lo + it;
-        const int tap = kb / p.cpt, cc = kb - tap * p.cpt;
-        const uint32_t sa = smem_base + s * STAGE_BYTES;
-        const uint32_t sb = sa + A_BYTES;
-        mbar_expect_tx(bar_full + 8 * s, a_box_bytes + B_BYTES);
-        tma_load_3d(sa, &tmA, cc * TC_BK, l0 + tap - p.pad, sample0, bar_full + 8 * s);
-        tma_load_2d(sb, &tmB, tap * p.Cin + cc * TC_BK, n0, bar_full + 8 * s);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    for (int it = 0; it < nkb; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-      mbar_wait(bar_full + 8 * s, ph);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint32_t sa = smem_base + s * STAGE_BYTES;
-        const uint32_t sb = sa + A_BYTES;
-        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
-#pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, IDESC, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(bar_empty + 8 * s);  // frees the smem stage once these MMAs retire
-      }
-      __syncwarp();
-    }
-    if (elect_one_sync()) umma_commit(bar_acc);  // accumulator complete
-    __syncwarp();
-  } else {
-    // ===================== epilogue =====================
-    // TMEM -> registers (thread = output row) -> bias/act/residual/pool -> per-warp smem transpose
-    // (the pipeline stages are idle by now) -> row-contiguous 16-byte global stores.
-    for (int i = threadIdx.x - 64; i < BN; i += 128) {  // global parameter loads miss the small L1 (long-scoreboard stalls)
-      const int n = n0 + i;
-      s_bias[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
-      s_gamma[i] = (p.gamma && n < p.N) ? __ldg(p.gamma + n) : 1.0f;
-    }
-    asm volatile("bar.sync 9, 128;" ::: "memory");  // the 4 epilogue warps
+  {
     const int q = warp & 3;  // TMEM lane quarter accessible to this warp
     const int r = q * 32 + lane;
     const int s_in_tile = r / p.Lbox;
@@ -145,11 +55,6 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     const long long m = (long long)sample * p.L + l;
     bool valid = (s_in_tile < p.Bbox) && (sample < p.nbatch) && (l < p.L);
     if (p.m_valid_dev) valid = valid && (m < (long long)(*p.m_valid_dev));
-    if (nkb > 0) {
-      mbar_wait_sleep(bar_acc, 0);
-      tc_fence_after();
-    }
-    float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + (warp - 2) * (32 * 33);
     const long long out_row = p.pool4 ? (m >> 2) : m;
     const bool writer = valid && (!p.pool4 || (lane & 3) == 0);
     const unsigned wmask = __ballot_sync(0xffffffffu, writer);
@@ -160,8 +65,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
       const int n_first = n0 + c0;
       if (n_first >= p.N) break;  // warp-uniform
       uint32_t raw[32];
-      if (nkb > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+      if (have_acc) {
+        tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) raw[i] = 0u;
@@ -291,6 +196,117 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
       }
     }
   }
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB,
+                                                             const __grid_constant__ TcArgs p) {
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
+  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_holder;
+  __shared__ __align__(16) float s_bias[BN], s_gamma[BN];  // staged by the epilogue warps while the main loop runs
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x, nt = blockIdx.y;
+  const int n0 = nt * BN;
+
+  const int sample0 = (mt / p.tps) * p.Bbox;
+  const int l0 = (mt % p.tps) * p.Lbox;
+  if (p.m_valid_dev) {
+    if ((long long)sample0 * p.L + l0 >= (long long)(*p.m_valid_dev)) return;
+  }
+
+  const int kb_total = p.taps * p.cpt;
+  const int kb_lo = p.has_ranges ? p.kb_lo[nt] : 0;
+  const int kb_hi = p.has_ranges ? p.kb_hi[nt] : kb_total;
+  const int nkb = kb_hi - kb_lo;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[STAGES]);
+  const uint32_t bar_acc = smem_u32(&bars[2 * STAGES]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
+                 "r"((uint32_t)tmem_cols<BN>())
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp waits, one elected lane issues) =====================
+    const uint32_t a_box_bytes = (uint32_t)TC_BK * 2u * (uint32_t)p.Lbox * (uint32_t)p.Bbox;
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+      if (elect_one_sync()) {
+        const int kb = kb_lo + it;
+        const int tap = kb / p.cpt, cc = kb - tap * p.cpt;
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+        mbar_expect_tx(bar_full + 8 * s, a_box_bytes + B_BYTES);
+        tma_load_3d(sa, &tmA, cc * TC_BK, l0 + tap - p.pad, sample0, bar_full + 8 * s);
+        tma_load_2d(sb, &tmB, tap * p.Cin + cc * TC_BK, n0, bar_full + 8 * s);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(bar_full + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar_empty + 8 * s);  // frees the smem stage once these MMAs retire
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) umma_commit(bar_acc);  // accumulator complete
+    __syncwarp();
+  } else {
+    // ===================== epilogue =====================
+    // TMEM -> registers (thread = output row) -> bias/act/residual/pool -> per-warp smem transpose
+    // (the pipeline stages are idle by now) -> row-contiguous 16-byte global stores.
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {  // global parameter loads miss the small L1 (long-scoreboard stalls)
+      const int n = n0 + i;
+      s_bias[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
+      s_gamma[i] = (p.gamma && n < p.N) ? __ldg(p.gamma + n) : 1.0f;
+    }
+    asm volatile("bar.sync 9, 128;" ::: "memory");  // the 4 epilogue warps
+    if (nkb > 0) {
+      mbar_wait_sleep(bar_acc, 0);
+      tc_fence_after();
+    }
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + (warp - 2) * (32 * 33);
+    tc_epilogue_tile<BN>(p, nkb > 0, tmem_base, mt, nt, stg, s_bias, s_gamma, warp, lane);
+  }
 
   tc_fence_before();
   __syncthreads();
@@ -311,6 +327,180 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args
     configured = true;
   }
   k<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, args);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+
+// ---- persistent variant for short-K problems ---------------------------------------------------------------
+// A tile with <= a few K blocks is over before its epilogue has started, so the non-persistent kernel is bound by
+// CTA set-up (barrier init, TMEM allocation) plus an unoverlapped epilogue.  Here one CTA walks tiles t = blockIdx.x,
+// + gridDim.x, ...: the TMA ring runs ahead across tile boundaries and the accumulator is DOUBLE-BUFFERED in TMEM
+// (2 x BN columns), so the epilogue warps drain tile i while the MMA warp already fills tile i+1.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                     const __grid_constant__ CUtensorMap tmB,
+                                                                     const __grid_constant__ TcArgs p, int MT, int n_tiles) {
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
+  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  __shared__ uint32_t tmem_holder;
+  __shared__ __align__(16) float s_bias[2][BN], s_gamma[2][BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[STAGES]);
+  const uint32_t bar_acc_full = smem_u32(&bars[2 * STAGES]);
+  const uint32_t bar_acc_empty = smem_u32(&bars[2 * STAGES + 2]);
+  const int kb_total = p.taps * p.cpt;
+  const long long m_valid = p.m_valid_dev ? (long long)(*p.m_valid_dev) : (1LL << 62);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc_full + 8 * b, 1);
+      mbar_init(bar_acc_empty + 8 * b, 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
+                 "r"((uint32_t)tmem_cols<2 * BN>())
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  // every role walks the same tile sequence and skips the same tiles
+  auto tile_live = [&](int t, int& mt, int& nt, int& kb_lo, int& nkb) {
+    mt = t % MT;
+    nt = t / MT;
+    const int sample0 = (mt / p.tps) * p.Bbox, l0 = (mt % p.tps) * p.Lbox;
+    kb_lo = p.has_ranges ? p.kb_lo[nt] : 0;
+    nkb = (p.has_ranges ? p.kb_hi[nt] : kb_total) - kb_lo;
+    return (long long)sample0 * p.L + l0 < m_valid;
+  };
+
+  if (warp == 0) {
+    const uint32_t a_box_bytes = (uint32_t)TC_BK * 2u * (uint32_t)p.Lbox * (uint32_t)p.Bbox;
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      int mt, nt, kb_lo, nkb;
+      if (!tile_live(t, mt, nt, kb_lo, nkb)) continue;
+      const int sample0 = (mt / p.tps) * p.Bbox, l0 = (mt % p.tps) * p.Lbox, n0 = nt * BN;
+      for (int k = 0; k < nkb; ++k, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        if (elect_one_sync()) {
+          const int kb = kb_lo + k;
+          const int tap = kb / p.cpt, cc = kb - tap * p.cpt;
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+          mbar_expect_tx(bar_full + 8 * s, a_box_bytes + B_BYTES);
+          tma_load_3d(sa, &tmA, cc * TC_BK, l0 + tap - p.pad, sample0, bar_full + 8 * s);
+          tma_load_2d(sb, &tmB, tap * p.Cin + cc * TC_BK, n0, bar_full + 8 * s);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    int it = 0, lt = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      int mt, nt, kb_lo, nkb;
+      if (!tile_live(t, mt, nt, kb_lo, nkb) || nkb == 0) continue;
+      const int buf = lt & 1;
+      mbar_wait(bar_acc_empty + 8 * buf, (((uint32_t)lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+      for (int k = 0; k < nkb; ++k, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 16; ++kk) umma_bf16(acc, da + 2 * kk, db + 2 * kk, IDESC, (k > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * s);
+        }
+        __syncwarp();
+      }
+      if (elect_one_sync()) umma_commit(bar_acc_full + 8 * buf);
+      __syncwarp();
+      ++lt;
+    }
+  } else {
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES) + (warp - 2) * (32 * 33);
+    int lt = 0, ti = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      int mt, nt, kb_lo, nkb;
+      if (!tile_live(t, mt, nt, kb_lo, nkb)) continue;
+      const int pb = ti & 1;  // parameter staging buffer (a warp is never more than one tile ahead of the others)
+      ++ti;
+      for (int i = threadIdx.x - 64; i < BN; i += 128) {
+        const int n = nt * BN + i;
+        s_bias[pb][i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
+        s_gamma[pb][i] = (p.gamma && n < p.N) ? __ldg(p.gamma + n) : 1.0f;
+      }
+      asm volatile("bar.sync 9, 128;" ::: "memory");
+      const int buf = lt & 1;
+      if (nkb > 0) {
+        mbar_wait_sleep(bar_acc_full + 8 * buf, ((uint32_t)lt >> 1) & 1u);
+        tc_fence_after();
+      }
+      tc_epilogue_tile<BN>(p, nkb > 0, tmem_base + (uint32_t)(buf * BN), mt, nt, stg, s_bias[pb], s_gamma[pb], warp, lane);
+      if (nkb > 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+        ++lt;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols<2 * BN>()) : "memory");
+  }
+}
+
+template <int BN, int STAGES>
+int launch_tc_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, long long MT, int NT, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024 + 4 * 32 * 33 * sizeof(float);
+  auto k = gemm_tc_persist_kernel<BN, STAGES>;
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int by_smem = (int)((227 * 1024) / (smem + 2 * 1024));
+    int by_tmem = 512 / tmem_cols<2 * BN>();
+    ctas_per_sm = by_smem < by_tmem ? by_smem : by_tmem;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  const long long n_tiles = MT * NT;
+  const int grid = (int)(n_tiles < 148LL * ctas_per_sm ? n_tiles : 148LL * ctas_per_sm);
+  k<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, args, (int)MT, (int)n_tiles);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;
@@ -546,6 +736,18 @@ extern "C" int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype
     for (int i = 0; i < NT; ++i) max_kb = args.kb_hi[i] - args.kb_lo[i] > max_kb ? args.kb_hi[i] - args.kb_lo[i] : max_kb;
   }
   const bool short_k = max_kb <= 4;
+  static int persist_kb = -1;  // K blocks per tile up to which the persistent (overlapped-epilogue) kernel is used
+  if (persist_kb < 0) {
+    const char* e = getenv("ACB_PERSIST_KB");
+    persist_kb = e ? atoi(e) : 0;  // measured on B200: no gain over 2-3 co-resident non-persistent CTAs, opt-in
+  }
+  if (max_kb <= persist_kb && MT * NT < (1LL << 31) && MT * NT > 148) {
+    switch (bn) {
+      case 64: return launch_tc_persist<64, 2>(tmA, tmB, args, MT, NT, st);
+      case 128: return launch_tc_persist<128, 2>(tmA, tmB, args, MT, NT, st);
+      default: return launch_tc_persist<256, 2>(tmA, tmB, args, MT, NT, st);
+    }
+  }
   switch (bn) {
     case 64: return short_k ? launch_tc<64, 2>(tmA, tmB, args, grid, st) : launch_tc<64, 4>(tmA, tmB, args, grid, st);
     case 128: return short_k ? launch_tc<128, 2>(tmA, tmB, args, grid, st) : launch_tc<128, 3>(tmA, tmB, args, grid, st);

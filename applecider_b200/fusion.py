@@ -74,6 +74,70 @@ class AppleCider(nn.Module):
         return self._head(p, im, s, False)[0]
 
 
+    @torch.no_grad()
+    def predict_batches(self, host_batches):
+        """Streaming inference over HOST batches: yields one pinned (B, num_classes) fp32 logits tensor per batch.
+
+        host_batches: iterable of (photometry, photometry_mask, metadata, images, spectra) CPU tensors (pinned memory
+        makes the copies asynchronous).  The host->device copy of batch i+1 runs on a side stream while batch i is being
+        computed (two device slots); the logits come back with an asynchronous device->host copy and are yielded one
+        batch late, after their own event -- nothing blocks the device queue.
+        """
+        dev = self.fc.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("applecider_b200: the model must live on a CUDA device (no CPU fallback)")
+        compute = torch.cuda.current_stream(dev)
+        copy_stream = getattr(self, "_copy_stream", None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream(dev)
+        slots = [None, None]            # device input buffers, reused every other batch
+        h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+        slot_free = [None, None]        # compute finished reading the slot
+        outs = [None, None]
+        out_done = [None, None]
+
+        def stage(i, batch):
+            k = i & 1
+            with torch.cuda.stream(copy_stream):
+                if slot_free[k] is not None:
+                    copy_stream.wait_event(slot_free[k])
+                if slots[k] is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(slots[k], batch)):
+                    slots[k] = [torch.empty(h.shape, dtype=h.dtype, device=dev) for h in batch]
+                for d, h in zip(slots[k], batch):
+                    d.copy_(h, non_blocking=True)
+                h2d_done[k].record(copy_stream)
+
+        it = iter(host_batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        stage(0, nxt)
+        i = 0
+        pending = None
+        while nxt is not None:
+            k = i & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                stage(i + 1, nxt)  # overlaps with the compute of batch i
+            compute.wait_event(h2d_done[k])
+            d = slots[k]
+            logits = self.forward(d[0], d[1], d[2], d[3], d[4])
+            slot_free[k] = torch.cuda.Event()
+            slot_free[k].record(compute)
+            if outs[k] is None or outs[k].shape != logits.shape:
+                outs[k] = torch.empty(logits.shape, dtype=torch.float32).pin_memory()
+            outs[k].copy_(logits, non_blocking=True)
+            out_done[k] = torch.cuda.Event()
+            out_done[k].record(compute)
+            if pending is not None:
+                out_done[pending].synchronize()
+                yield outs[pending]
+            pending = k
+            i += 1
+        out_done[pending].synchronize()
+        yield outs[pending]
+
+
 def fusion_collate(batch, mean, std, device="cuda"):
     """Fusion collate contract of models/Time2Vec.py:18-45 with the hard-coded stats path turned into
     arguments: batch of (photo[L,7], metadata, image, spectra[1,Ls], label) ->

@@ -222,14 +222,20 @@ def main():
         regions = ops.profile_stop()
         clocks = sampler.stop() if rank == 0 else None
         # ---- end to end through the public API with host buffers ("e2e") ----
-        for _ in range(2):
-            step_e2e()
+        # model.predict_batches: the public streaming call -- per step one H2D copy of the pinned host batch (on a side
+        # stream, overlapping the previous batch's compute) and one D2H read of that step's logits, all inside the timed region
+        host_batch = (pinned["x"], pinned["pad"], pinned["meta"], pinned["img"], pinned["spec"])
+        for _ in model.predict_batches([host_batch] * 2):
+            pass
+        step_e2e()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(K):
-            step_e2e()
+        n_out = 0
+        for lg in model.predict_batches(host_batch for _ in range(K)):
+            n_out += lg.shape[0]
         barrier()
         e2e_s = time.perf_counter() - t0
+        assert n_out == K * B
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:

@@ -232,3 +232,25 @@ def test_spectra_fused_stage1_path(golden_dir):
     finally:
         sp.FUSE_STAGE1 = old
     assert_close(got, g["logits4096"], BF16_TOL, "spectra bf16 with fused stage 1")
+
+
+def test_predict_batches_streams_host_batches_and_matches_forward():
+    """AppleCider.predict_batches (double-buffered H2D on a side stream) returns the logits of forward(), in order."""
+    import applecider_b200 as ab
+    from applecider_b200 import synth
+
+    model = ab.AppleCider(ab.default_config(), hidden_dim=64, fusion="avg", compute_dtype="bf16")
+    model.load_state_dict(synth.det_state_dict(model, 0), strict=True)
+    model = model.cuda().eval()
+    batches = []
+    for i, B in enumerate([5, 5, 3, 5]):  # a shape change in the middle re-allocates the slot
+        x, pad, _ = synth.photometry_batch(B, seed=50 + i)
+        batches.append(tuple(t.pin_memory() for t in (x, pad, synth.metadata(B, seed=50 + i), synth.cutouts(B, seed=50 + i),
+                                                     synth.spectra(B, seed=50 + i, L=4096))))
+    got = [o.clone() for o in model.predict_batches(iter(batches))]
+    assert len(got) == len(batches)
+    with torch.no_grad():
+        for b, g in zip(batches, got):
+            ref = model(*[t.cuda() for t in b]).float().cpu()
+            assert torch.equal(g, ref)
+    assert list(model.predict_batches([])) == []
