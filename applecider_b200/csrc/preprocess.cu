@@ -444,6 +444,26 @@ __global__ void feature_finalize_kernel(const double* __restrict__ sums, long lo
   stdv[c] = sqrtf(fmaxf(var, 0.0f));
 }
 
+// ---- pad_collate dict format -> model inputs (SURVEY 8b collate contract iii / 8f-2) ------------------------------
+// events[B,T,Fe] (Fe = 14 columns of build_event_features), events_mask[B,T] TRUE = VALID  ->
+// x[B,T,7] = selected columns (dt, dt_prev, logflux, logflux_err, band one-hot x3), optional log1p on the two time
+// columns, channels 0..3 normalised (x - mean)/(std + 1e-8) on EVERY row (padding included, as the Hyrax collate
+// does), and pad[B,T] TRUE = PADDING (the polarity the encoder expects).
+__global__ void __launch_bounds__(256) collate_events_kernel(const float* __restrict__ ev, const uint8_t* __restrict__ valid, long long rows,
+                                                             int Fe, const int* __restrict__ cols, int log1p_dt,
+                                                             const float* __restrict__ mean, const float* __restrict__ stdv,
+                                                             float* __restrict__ x, uint8_t* __restrict__ pad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 7) return;
+  const long long r = i / 7;
+  const int c = (int)(i - r * 7);
+  float v = ev[r * Fe + cols[c]];
+  if (log1p_dt && c < 2) v = log1pf(v);
+  if (c < 4) v = (v - mean[c]) / (stdv[c] + 1e-8f);
+  x[i] = v;
+  if (c == 0) pad[r] = valid[r] ? 0 : 1;
+}
+
 }  // namespace
 
 extern "C" {
@@ -518,6 +538,16 @@ int acb_feature_stats(const float* data, long long rows, int F, double* work, fl
   feature_finalize_kernel<<<cdiv(F, 64), 64, 0, st>>>(work, rows, F, mean, stdv);
   ACB_LAUNCH_CHECK();
   acb_count_launch(2);
+  return ACB_OK;
+}
+
+int acb_collate_events(const float* events, const uint8_t* valid_mask, int B, int T, int Fe, const int* cols, int log1p_dt,
+                       const float* mean, const float* stdv, float* x, uint8_t* pad, void* stream) {
+  ACB_CHECK(events && valid_mask && cols && mean && stdv && x && pad && B > 0 && T > 0 && Fe > 0, "acb_collate_events: bad arguments");
+  const long long rows = (long long)B * T;
+  collate_events_kernel<<<cdiv(rows * 7, 256), 256, 0, (cudaStream_t)stream>>>(events, valid_mask, rows, Fe, cols, log1p_dt, mean, stdv, x, pad);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
   return ACB_OK;
 }
 

@@ -158,3 +158,31 @@ def fusion_collate(batch, mean, std, device="cuda"):
     return (to(x), to(mask), to(torch.stack([torch.as_tensor(m, dtype=torch.float32) for m in meta])),
             to(torch.stack([torch.as_tensor(i, dtype=torch.float32) for i in img])),
             to(torch.stack([torch.as_tensor(s, dtype=torch.float32) for s in spec])), to(torch.as_tensor(labels)))
+
+
+EVENT_COLUMNS = ["dt", "dt_prev", "band_id", "logflux", "logflux_err", "band_ztfg", "band_ztfr", "band_ztfi",
+                 "g_r", "g_r_err", "r_i", "r_i_err", "has_g_r", "has_r_i"]  # build_event_features minus obj_id/jd/fid (:680)
+MODEL_EVENT_COLUMNS = ["dt", "dt_prev", "logflux", "logflux_err", "band_ztfg", "band_ztfr", "band_ztfi"]
+
+
+def from_pad_collate(batch, mean, std, event_columns=None, log1p_dt=False, n_meta=24, device="cuda"):
+    """MultiModalDataset.pad_collate dict (events[B,T,14], events_mask True=valid, image, metadata[B,46], label) ->
+    (photometry[B,T,7] normalised, pad_mask[B,T] True=pad, metadata[B,n_meta], image, label) on the device.
+
+    The column gather, the optional log1p of the time columns, the normalisation and the mask polarity flip run in one
+    kernel (acb_collate_events); AstroMiNN's 24 metadata columns are the first 24 of ALERT_META_KEEP
+    (preprocess_multimodal.py:615-640, consistent with the tower comments astrominn.py:249-254)."""
+    names = list(event_columns) if event_columns is not None else EVENT_COLUMNS
+    cols = torch.tensor([names.index(c) for c in MODEL_EVENT_COLUMNS], dtype=torch.int32, device=device)
+    ev = batch["events"].to(device, non_blocking=True).float().contiguous()
+    valid = batch["events_mask"].to(device, non_blocking=True).contiguous()
+    B, T, Fe = ev.shape
+    if Fe != len(names):
+        raise ValueError(f"events have {Fe} columns, expected {len(names)}")
+    x = torch.empty((B, T, 7), dtype=torch.float32, device=device)
+    pad = torch.empty((B, T), dtype=torch.bool, device=device)
+    m = torch.as_tensor(mean, dtype=torch.float32).to(device).contiguous()
+    sd = torch.as_tensor(std, dtype=torch.float32).to(device).contiguous()
+    ops.call("acb_collate_events", ev, valid.view(torch.uint8), B, T, Fe, cols, int(log1p_dt), m, sd, x, pad.view(torch.uint8))
+    meta = batch["metadata"].to(device, non_blocking=True).float()[:, :n_meta].contiguous()
+    return x, pad, meta, batch["image"].to(device, non_blocking=True).float().contiguous(), batch["label"].to(device, non_blocking=True)

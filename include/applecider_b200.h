@@ -312,6 +312,14 @@ int acb_tower_group_fwd(const float* X, int ldx, int rows, int n_towers, const l
 int acb_tower_group_bwd(const float* X, int ldx, int rows, int n_towers, const long long* ptrs, const int* dims, const float* A, int lda,
                         const float* dY, int ldy, float* dA, float* dX, float drop_p, long long seed, void* stream);
 
+/* MultiModalDataset.pad_collate dict format (docs/pre_executed/Fusion_Dataset.ipynb cell 0) -> encoder inputs:
+ * events[B,T,Fe] + events_mask[B,T] (nonzero = VALID) -> x[B,T,7] = columns cols[0..6] (dt, dt_prev, logflux,
+ * logflux_err, band_ztfg, band_ztfr, band_ztfi of build_event_features, preprocess_multimodal.py:315-336), optional
+ * log1p on the two time columns (photo_dataset.py:85-101), channels 0..3 normalised with (x - mean)/(std + 1e-8)
+ * (HyraxBaselineCLS.py:157) and pad[B,T] with nonzero = PADDING (the polarity of forward()). */
+int acb_collate_events(const float* events, const uint8_t* valid_mask, int B, int T, int Fe, const int* cols, int log1p_dt,
+                       const float* mean, const float* stdv, float* x, uint8_t* pad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

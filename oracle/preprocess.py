@@ -179,3 +179,34 @@ def feature_stats(chunks):
     mean = s / total
     std = np.sqrt(np.clip(sq / total - mean**2, 0, None))
     return mean.astype(np.float32), std.astype(np.float32)
+
+
+# ---- pad_collate dict format -> model inputs (Fusion_Dataset.ipynb cell 0) ---------------------------
+EVENT_COLUMNS = ["dt", "dt_prev", "band_id", "logflux", "logflux_err", "band_ztfg", "band_ztfr", "band_ztfi",
+                 "g_r", "g_r_err", "r_i", "r_i_err", "has_g_r", "has_r_i"]  # preprocess_multimodal.py:324-365 minus :680's drops
+
+
+def pad_collate(samples, pad_value=0.0):
+    """MultiModalDataset.pad_collate restated with numpy: list of dicts(events[T,Fe], image, metadata, label)."""
+    B = len(samples)
+    Tmax = max(s["events"].shape[0] for s in samples)
+    Fe = samples[0]["events"].shape[1]
+    ev = np.full((B, Tmax, Fe), pad_value, dtype=np.float32)
+    mask = np.zeros((B, Tmax), dtype=bool)
+    for i, s in enumerate(samples):
+        T = s["events"].shape[0]
+        ev[i, :T] = s["events"]
+        mask[i, :T] = True
+    return {"events": ev, "events_mask": mask, "image": np.stack([s["image"] for s in samples]),
+            "metadata": np.stack([s["metadata"] for s in samples]), "label": np.asarray([s["label"] for s in samples])}
+
+
+def pad_collate_to_model_inputs(batch, mean, std, log1p_dt=False, n_meta=24):
+    """The 7 model channels of the 14 event columns, normalised like HyraxBaselineCLS.to_tensor (:157), and the
+    key-padding mask in the encoder's polarity (True = padding)."""
+    idx = [EVENT_COLUMNS.index(c) for c in ("dt", "dt_prev", "logflux", "logflux_err", "band_ztfg", "band_ztfr", "band_ztfi")]
+    x = batch["events"][..., idx].astype(np.float32).copy()
+    if log1p_dt:
+        x[..., :2] = np.log1p(x[..., :2])
+    x[..., :4] = (x[..., :4] - np.asarray(mean, np.float32)) / (np.asarray(std, np.float32) + np.float32(1e-8))
+    return x, ~batch["events_mask"], batch["metadata"][:, :n_meta].astype(np.float32), batch["image"].astype(np.float32)

@@ -5,6 +5,8 @@ import numpy as np
 import pytest
 import torch
 
+from util import assert_close  # noqa: E402
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
@@ -130,3 +132,28 @@ def test_p5_feature_stats(g):
     m, s = pp.feature_stats(big)
     np.testing.assert_allclose(m.cpu().numpy(), big.double().mean(0).float().cpu().numpy(), rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(s.cpu().numpy(), big.double().std(0, unbiased=False).float().cpu().numpy(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("log1p_dt", [False, True])
+def test_pad_collate_dict_to_model_inputs(log1p_dt):
+    """acb_collate_events vs the numpy restatement: gather of the 7 model channels, normalisation, mask polarity (bit-exact mask)."""
+    import numpy as np
+    from applecider_b200.fusion import from_pad_collate
+    from oracle import preprocess as op
+
+    rng = np.random.default_rng(3)
+    samples = []
+    for T in [1, 17, 108, 40, 0 + 5]:
+        ev = rng.normal(size=(T, 14)).astype(np.float32)
+        ev[:, 0] = np.sort(rng.uniform(0, 100, T)); ev[:, 1] = np.abs(rng.normal(size=T))
+        samples.append({"events": ev, "image": rng.normal(size=(3, 63, 63)).astype(np.float32), "metadata": rng.normal(size=46).astype(np.float32), "label": T % 5})
+    batch = op.pad_collate(samples)
+    mean, std = rng.normal(size=4).astype(np.float32), np.abs(rng.normal(size=4)).astype(np.float32) + 0.1
+    rx, rpad, rmeta, rimg = op.pad_collate_to_model_inputs(batch, mean, std, log1p_dt=log1p_dt)
+    tb = {k: torch.from_numpy(v) for k, v in batch.items()}
+    x, pad, meta, img, label = from_pad_collate(tb, mean, std, log1p_dt=log1p_dt)
+    assert torch.equal(pad.cpu(), torch.from_numpy(rpad))
+    assert torch.equal(x[..., 4:].cpu(), torch.from_numpy(rx[..., 4:]))  # one-hot columns pass through untouched
+    assert_close(x, torch.from_numpy(rx), 2e-6, "normalised channels")
+    assert torch.equal(meta.cpu(), torch.from_numpy(rmeta)) and torch.equal(img.cpu(), torch.from_numpy(rimg))
+    assert meta.shape == (5, 24) and label.tolist() == [s["label"] for s in samples]
