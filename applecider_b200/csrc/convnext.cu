@@ -75,6 +75,35 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const T* __restrict__ x
 // registers, one input row segment (W values) is loaded per ky and reused by all W x 7 taps (register
 // sliding window), so shared-memory traffic drops 5x against the generic kernel; out-of-range taps vanish
 // at compile time.  LayerNorm: conv row -> smem -> warp per pixel, channel pairs per lane.
+// LayerNorm of the W pixels of one conv row held in shared memory (cv[W][C] fp32): warp per pixel, NPL = C/32 values
+// per lane in registers (read once), affine parameters from shared memory, two-pass statistics.
+template <typename T, int NPL>
+__device__ __forceinline__ void dw_ln_row(const float* __restrict__ cv, const float* __restrict__ s_lnw, const float* __restrict__ s_lnb,
+                                          float eps, T* __restrict__ yrow, int Wpix, int wid, int nw, int lane) {
+  constexpr int C = NPL * 32;
+  for (int ox = wid; ox < Wpix; ox += nw) {
+    const float* v = cv + ox * C;
+    float t[NPL];
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+      t[k] = v[lane + 32 * k];
+      s += t[k];
+    }
+    const float mean = warp_sum(s) * (1.0f / (float)C);
+    float q = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+      t[k] -= mean;
+      q = fmaf(t[k], t[k], q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / (float)C) + eps);
+    T* o = yrow + (long long)ox * C;
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) o[lane + 32 * k] = from_f<T>(fmaf(t[k] * rstd, s_lnw[lane + 32 * k], s_lnb[lane + 32 * k]));
+  }
+}
+
 template <int W>
 constexpr int dw_max_threads() { return W >= 15 ? 256 : (W >= 7 ? 512 : 768); }
 
@@ -92,23 +121,27 @@ __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const
   const size_t in_bytes = (((size_t)(R + 6) * WC * sizeof(T)) + 15) & ~(size_t)15;
   float* cv = reinterpret_cast<float*>(smraw + in_bytes);
   float* wsm = cv + WC;
+  float* s_lnw = wsm + (use_wsm ? 49 * (C + 1) : 0);
+  float* s_lnb = s_lnw + C;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  if (do_ln)
+    for (int i = tid; i < C; i += nthr) {
+      s_lnw[i] = ln_w[i];
+      s_lnb[i] = ln_b[i];
+    }
   {  // stage input rows oy0-3 .. oy0+rows+2 (16-byte copies; rows outside the image are zero)
     const int v_per_row = (int)((size_t)WC * sizeof(T) / 16);
-    const int nvec = (rows + 6) * v_per_row;
     const uint4* xg = reinterpret_cast<const uint4*>(x + (long long)b * H * WC);
     uint4* ins = reinterpret_cast<uint4*>(in);
-    for (int i = tid; i < nvec; i += nthr) {
+    const int nvec = (rows + 6) * v_per_row;
+    for (int i = tid; i < nvec; i += nthr) {  // flat loop: many independent loads in flight per thread
       const int rr = i / v_per_row, rem = i - rr * v_per_row;
       const int iy = oy0 + rr - 3;
       ins[i] = (iy >= 0 && iy < H) ? __ldg(xg + (long long)iy * v_per_row + rem) : make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  if (use_wsm) {
-    for (int i = tid; i < 49 * C; i += nthr) {
-      const int cc = i / 49, j = i - cc * 49;
-      wsm[(flip ? 48 - j : j) * (C + 1) + cc] = __ldg(w + i);
-    }
+  if (use_wsm) {  // straight coalesced copy [C][49]: the odd row stride makes the per-thread reads below conflict-free
+    for (int i = tid; i < 49 * C; i += nthr) wsm[i] = __ldg(w + i);
   }
   __syncthreads();
   const int c = tid;
@@ -116,7 +149,7 @@ __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const
   float bc = 0.0f;
   if (c < C) {
 #pragma unroll
-    for (int j = 0; j < 49; ++j) wr[j] = use_wsm ? wsm[j * (C + 1) + c] : __ldg(w + c * 49 + (flip ? 48 - j : j));
+    for (int j = 0; j < 49; ++j) wr[j] = use_wsm ? wsm[c * 49 + (flip ? 48 - j : j)] : __ldg(w + c * 49 + (flip ? 48 - j : j));
     bc = bias ? bias[c] : 0.0f;
   }
   const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
@@ -151,6 +184,21 @@ __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const
     }
     if (!do_ln) continue;  // uniform for the whole CTA
     __syncthreads();
+    {
+      T* yrow = y + (((long long)b * H + oy0 + r) * W) * C;
+      bool done = true;
+      switch (C) {
+        case 96: dw_ln_row<T, 3>(cv, s_lnw, s_lnb, eps, yrow, W, wid, nw, lane); break;
+        case 192: dw_ln_row<T, 6>(cv, s_lnw, s_lnb, eps, yrow, W, wid, nw, lane); break;
+        case 384: dw_ln_row<T, 12>(cv, s_lnw, s_lnb, eps, yrow, W, wid, nw, lane); break;
+        case 768: dw_ln_row<T, 24>(cv, s_lnw, s_lnb, eps, yrow, W, wid, nw, lane); break;
+        default: done = false;
+      }
+      if (done) {
+        __syncthreads();
+        continue;
+      }
+    }
     for (int ox = wid; ox < W; ox += nw) {
       const float* v = cv + ox * C;
       float s = 0.0f;
@@ -188,7 +236,7 @@ int launch_dwconv_w(const void* x, const float* w, const float* b, const float* 
   const int R = W >= 15 ? 5 : (W >= 7 ? 7 : (W >= 3 ? 3 : 1));
   const int use_wsm = C <= 192 ? 1 : 0;
   const size_t in_bytes = (((size_t)(R + 6) * W * C * sizeof(T)) + 15) & ~(size_t)15;
-  const size_t smem = in_bytes + (size_t)W * C * 4 + (use_wsm ? (size_t)49 * (C + 1) * 4 : 0);
+  const size_t smem = in_bytes + (size_t)W * C * 4 + (use_wsm ? (size_t)49 * (C + 1) * 4 : 0) + (size_t)2 * C * 4;
   auto k = dwconv7_ln_w_kernel<T, W>;
   ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int threads = ((C + 31) / 32) * 32;
