@@ -6,6 +6,8 @@
 //   stage 1 (C_in 64 -> 3 x 128):  sub-tile j = conv j, one LN group of 384 columns per row.
 //   stage 0 (1 -> 3 x 64, polyphase): a GEMM row is 8 positions; one CTA owns two phases, sub-tile j holds
 //   [conv j phase r0 | conv j phase r0+1], two LN groups (one per phase) of 3 x 64 columns per row.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -46,6 +48,101 @@ struct ConvLnArgs {
   long long xwin_stride;       // elements per sample
   long long xwin_total;        // elements in the whole buffer
 };
+
+// ---- epilogue of one tile: bias -> LayerNorm(3*gw) -> GELU -> bf16, executed by the 8 epilogue warps ---------------
+// Sub-tiles 0 and 1 sit at TMEM columns 0 and 128; sub-tile 2 at col2 (256, or 384 in the persistent kernel's odd tiles).
+__device__ __forceinline__ void cl_epilogue_tile(const ConvLnArgs& p, int mt, int y, uint32_t tmem_base, uint32_t col2, const float* s_bias,
+                                                 const float* s_gamma, const float* s_beta, float (*part)[2][128][2], uint8_t* stg,
+                                                 int warp, int lane) {
+  const int sample0 = (mt / p.tps) * p.Bbox;
+  const int l0 = (mt % p.tps) * p.Lbox;
+  {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;  // which of the two warps serving this lane quarter
+    const int r = q * 32 + lane;
+    const int s_in_tile = r / p.Lbox;
+    const int l = l0 + (r - s_in_tile * p.Lbox);
+    const int sample = sample0 + s_in_tile;
+    const long long m = (long long)sample * p.L + l;
+    const bool valid_row = (s_in_tile < p.Bbox) && (sample < p.nbatch) && (l < p.L);
+    const int gw = 128 / p.ng;
+    const float inv_n = 1.0f / (float)(3 * gw);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int g = 0; g < p.ng; ++g) {
+      const long long orow = m * p.row_mul + (long long)y * p.row_add_y + g;
+      const bool valid = valid_row && orow < p.out_rows;
+      // pass 1: statistics of (acc + bias) over the 3*gw channels of this position
+      float sum = 0.0f, sq = 0.0f;
+      for (int j = 0; j < 3; ++j) {
+        for (int c0 = 0; c0 < gw; c0 += 32) {
+          if ((((g * 3 * gw + j * gw + c0) >> 6) & 1) != half) continue;  // 64-column blocks alternate between the two warps
+          uint32_t raw[32];
+          tmem_ld32(lane_base + (j == 2 ? col2 : (uint32_t)(128 * j)) + (uint32_t)(g * gw + c0), raw);
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + 128 * j + g * gw + c0);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 bb = b4[i4];
+            const float v0 = __uint_as_float(raw[i4 * 4 + 0]) + bb.x, v1 = __uint_as_float(raw[i4 * 4 + 1]) + bb.y;
+            const float v2 = __uint_as_float(raw[i4 * 4 + 2]) + bb.z, v3 = __uint_as_float(raw[i4 * 4 + 3]) + bb.w;
+            sum += (v0 + v1) + (v2 + v3);
+            sq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+          }
+        }
+      }
+      part[g][half][r][0] = sum;
+      part[g][half][r][1] = sq;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the two warps of this quarter
+      sum += part[g][half ^ 1][r][0];
+      sq += part[g][half ^ 1][r][1];
+      const float mean = sum * inv_n;
+      const float rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.0f) + p.eps);
+      // pass 2: normalise, affine, GELU, pack to bf16; 32 x 64 tiles go through a per-warp smem transpose so that every
+      // store instruction writes four full 128-byte lines (uncoalesced per-row stores cost 32 L1 wavefronts each)
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      for (int j = 0; j < 3; ++j) {
+        for (int cb = 0; cb < gw; cb += 64) {
+          if ((((g * 3 * gw + j * gw + cb) >> 6) & 1) != half) continue;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int c0 = cb + hh * 32;
+            uint32_t raw[32];
+            tmem_ld32(lane_base + (j == 2 ? col2 : (uint32_t)(128 * j)) + (uint32_t)(g * gw + c0), raw);
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + 128 * j + g * gw + c0);
+            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + 128 * j + g * gw + c0);
+            const float4* e4 = reinterpret_cast<const float4*>(s_beta + 128 * j + g * gw + c0);
+            uint32_t pk[16];
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 bb = b4[i4], gg = g4[i4], ee = e4[i4];
+              const float y0 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 0]) + bb.x - mean) * rstd * gg.x + ee.x);
+              const float y1 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 1]) + bb.y - mean) * rstd * gg.y + ee.y);
+              const float y2 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 2]) + bb.z - mean) * rstd * gg.z + ee.z);
+              const float y3 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 3]) + bb.w - mean) * rstd * gg.w + ee.w);
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
+              pk[i4 * 2 + 0] = *reinterpret_cast<uint32_t*>(&h0);
+              pk[i4 * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            }
+            uint4* srow = reinterpret_cast<uint4*>(stg + lane * 144 + hh * 64);
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) srow[v4] = make_uint4(pk[v4 * 4 + 0], pk[v4 * 4 + 1], pk[v4 * 4 + 2], pk[v4 * 4 + 3]);
+          }
+          __syncwarp();
+          const int ch = j * gw + cb;  // first channel of this 64-wide block inside the concatenated row
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {  // 8 lanes x 16 B = one 128-byte row segment, 4 rows per instruction
+            const int rr = it * 4 + (lane >> 3), cg = lane & 7;
+            const long long orr = __shfl_sync(0xffffffffu, orow, rr);
+            if ((vmask >> rr) & 1u) {
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 144 + cg * 16);
+              *reinterpret_cast<uint4*>(p.out + orr * p.ldc + ch + cg * 8) = val;
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+}
 
 constexpr int CL_THREADS = 64 + 256;  // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 
@@ -174,101 +271,177 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_tc_kernel(const __grid_
       }
       asm volatile("bar.sync 9, 256;" ::: "memory");  // the 8 epilogue warps
     }
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;  // which of the two warps serving this lane quarter
-    const int r = q * 32 + lane;
-    const int s_in_tile = r / p.Lbox;
-    const int l = l0 + (r - s_in_tile * p.Lbox);
-    const int sample = sample0 + s_in_tile;
-    const long long m = (long long)sample * p.L + l;
-    const bool valid_row = (s_in_tile < p.Bbox) && (sample < p.nbatch) && (l < p.L);
     mbar_wait_sleep(bar_acc, 0);
     tc_fence_after();
     const long long t_acc = clock64();
-    const int gw = 128 / p.ng;
-    const float inv_n = 1.0f / (float)(3 * gw);
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int g = 0; g < p.ng; ++g) {
-      const long long orow = m * p.row_mul + (long long)blockIdx.y * p.row_add_y + g;
-      const bool valid = valid_row && orow < p.out_rows;
-      // pass 1: statistics of (acc + bias) over the 3*gw channels of this position
-      float sum = 0.0f, sq = 0.0f;
-      for (int j = 0; j < 3; ++j) {
-        const int brow = p.brow_base[j] + (int)blockIdx.y * p.brow_stride_y + g * gw;
-        for (int c0 = 0; c0 < gw; c0 += 32) {
-          if ((((g * 3 * gw + j * gw + c0) >> 6) & 1) != half) continue;  // 64-column blocks alternate between the two warps
-          uint32_t raw[32];
-          tmem_ld32(lane_base + (uint32_t)(128 * j + g * gw + c0), raw);
-          const float4* b4 = reinterpret_cast<const float4*>(s_bias + 128 * j + g * gw + c0);
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 bb = b4[i4];
-            const float v0 = __uint_as_float(raw[i4 * 4 + 0]) + bb.x, v1 = __uint_as_float(raw[i4 * 4 + 1]) + bb.y;
-            const float v2 = __uint_as_float(raw[i4 * 4 + 2]) + bb.z, v3 = __uint_as_float(raw[i4 * 4 + 3]) + bb.w;
-            sum += (v0 + v1) + (v2 + v3);
-            sq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
-          }
-        }
-      }
-      part[g][half][r][0] = sum;
-      part[g][half][r][1] = sq;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the two warps of this quarter
-      sum += part[g][half ^ 1][r][0];
-      sq += part[g][half ^ 1][r][1];
-      const float mean = sum * inv_n;
-      const float rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.0f) + p.eps);
-      // pass 2: normalise, affine, GELU, pack to bf16; 32 x 64 tiles go through a per-warp smem transpose so that every
-      // store instruction writes four full 128-byte lines (uncoalesced per-row stores cost 32 L1 wavefronts each)
-      uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + stg_off + (size_t)(warp - 2) * CL_STG_BYTES;
-      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-      for (int j = 0; j < 3; ++j) {
-        for (int cb = 0; cb < gw; cb += 64) {
-          if ((((g * 3 * gw + j * gw + cb) >> 6) & 1) != half) continue;
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int c0 = cb + hh * 32;
-            uint32_t raw[32];
-            tmem_ld32(lane_base + (uint32_t)(128 * j + g * gw + c0), raw);
-            const float4* b4 = reinterpret_cast<const float4*>(s_bias + 128 * j + g * gw + c0);
-            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + 128 * j + g * gw + c0);
-            const float4* e4 = reinterpret_cast<const float4*>(s_beta + 128 * j + g * gw + c0);
-            uint32_t pk[16];
-#pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-              const float4 bb = b4[i4], gg = g4[i4], ee = e4[i4];
-              const float y0 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 0]) + bb.x - mean) * rstd * gg.x + ee.x);
-              const float y1 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 1]) + bb.y - mean) * rstd * gg.y + ee.y);
-              const float y2 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 2]) + bb.z - mean) * rstd * gg.z + ee.z);
-              const float y3 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 3]) + bb.w - mean) * rstd * gg.w + ee.w);
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
-              pk[i4 * 2 + 0] = *reinterpret_cast<uint32_t*>(&h0);
-              pk[i4 * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
-            }
-            uint4* srow = reinterpret_cast<uint4*>(stg + lane * 144 + hh * 64);
-#pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) srow[v4] = make_uint4(pk[v4 * 4 + 0], pk[v4 * 4 + 1], pk[v4 * 4 + 2], pk[v4 * 4 + 3]);
-          }
-          __syncwarp();
-          const int ch = j * gw + cb;  // first channel of this 64-wide block inside the concatenated row
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {  // 8 lanes x 16 B = one 128-byte row segment, 4 rows per instruction
-            const int rr = it * 4 + (lane >> 3), cg = lane & 7;
-            const long long orr = __shfl_sync(0xffffffffu, orow, rr);
-            if ((vmask >> rr) & 1u) {
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 144 + cg * 16);
-              *reinterpret_cast<uint4*>(p.out + orr * p.ldc + ch + cg * 8) = val;
-            }
-          }
-          __syncwarp();
-        }
-      }
-    }
+    cl_epilogue_tile(p, mt, (int)blockIdx.y, tmem_base, 256u, s_bias, s_gamma, s_beta, part,
+                     smem_raw + (smem_base - smem_u32(smem_raw)) + stg_off + (size_t)(warp - 2) * CL_STG_BYTES, warp, lane);
     if (g_cl_timing_on && warp == 2 && lane == 0) {
       const long long t_end = clock64();
       atomicAdd(&g_cl_timing[0], (unsigned long long)(t_pro - t_start));
       atomicAdd(&g_cl_timing[1], (unsigned long long)(t_acc - t_pro));
       atomicAdd(&g_cl_timing[2], (unsigned long long)(t_end - t_acc));
       atomicAdd(&g_cl_timing[3], 1ull);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- persistent stage-0 (HANKEL) kernel with a ROTATING TMEM layout ------------------------------------------------
+// One CTA per SM walks the tiles (signal window mt, phase pair y).  A tile needs 384 accumulator columns, so TMEM
+// (512 columns) cannot hold two tiles -- but the k=1021 conv (sub-tile 2) is 17 of the 20 K blocks of a tile, and the
+// 128 spare columns can hold ITS next accumulator: sub-tile 2 alternates between columns [256,384) and [384,512).
+// The MMA warp therefore runs sub-tile 2 of tile n+1 while the 8 epilogue warps still normalise tile n, waits for
+// them, and only then issues the 3 short K blocks of sub-tiles 1 and 0 into the shared columns [0,256).
+// Steady state per tile ~ max(main loop, epilogue) instead of their sum, and no per-tile CTA set-up.
+__device__ __forceinline__ void cl_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+constexpr int CLP_NST = 2 * CL_STAGES;                      // 16 KB weight sub-tile stages
+constexpr uint32_t CLP_WIN_BYTES = (128 + 8 * 17 + 8) * 16;  // 4352 B signal window
+
+__global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_hankel_persist_kernel(const __grid_constant__ CUtensorMap tmB,
+                                                                               const __grid_constant__ ConvLnArgs p, int MT, int NY) {
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * CLP_NST + 6];
+  __shared__ uint32_t tmem_holder;
+  __shared__ float part[2][2][128][2];
+  __shared__ __align__(16) float s_bias[4][384], s_gamma[384], s_beta[384];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[CLP_NST]);
+  const uint32_t bar_acc = smem_u32(&bars[2 * CLP_NST]);           // accumulators of a tile complete (MMA -> epilogue)
+  const uint32_t bar_epi = smem_u32(&bars[2 * CLP_NST + 1]);       // epilogue has drained a tile (8 warps -> MMA)
+  const uint32_t bar_win_full = smem_u32(&bars[2 * CLP_NST + 2]);  // [2] signal window landed
+  const uint32_t bar_win_free = smem_u32(&bars[2 * CLP_NST + 4]);  // [2] all MMAs reading the window have retired
+  const uint32_t stg_off = (uint32_t)CLP_NST * CL_SUB_BYTES;
+  const uint32_t win_off = stg_off + 8 * CL_STG_BYTES;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CLP_NST; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_epi, 8);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_win_full + 8 * b, 1);
+      mbar_init(bar_win_free + 8 * b, 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    // ===================== producer: signal windows + weight sub-tiles in MMA order =====================
+    int it = 0, wi = 0;
+    for (int mt = blockIdx.x; mt < MT; mt += gridDim.x, ++wi) {
+      const int wb = wi & 1;
+      mbar_wait(bar_win_free + 8 * wb, (((uint32_t)wi >> 1) & 1u) ^ 1u);
+      if (elect_one_sync()) {
+        const int sample0 = (mt / p.tps) * p.Bbox, l0 = (mt % p.tps) * p.Lbox;
+        const long long e0 = (long long)sample0 * p.xwin_stride + 8LL * l0;
+        long long nbytes = (p.xwin_total - e0) * 2;
+        if (nbytes > (long long)CLP_WIN_BYTES) nbytes = CLP_WIN_BYTES;
+        nbytes &= ~15LL;
+        mbar_expect_tx(bar_win_full + 8 * wb, (uint32_t)nbytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_base + win_off + wb * CLP_WIN_BYTES),
+                     "l"(p.xwin + e0), "r"((uint32_t)nbytes), "r"(bar_win_full + 8 * wb)
+                     : "memory");
+      }
+      __syncwarp();
+      for (int y = 0; y < NY; ++y) {
+        for (int jj = 0; jj < 3; ++jj) {
+          const int j = 2 - jj;  // sub-tile 2 first (it overlaps the previous tile's epilogue)
+          for (int kb = p.kb_lo[j]; kb < p.kb_hi[j]; ++kb, ++it) {
+            const int s = it % CLP_NST;
+            const uint32_t ph = (uint32_t)(it / CLP_NST) & 1u;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            if (elect_one_sync()) {
+              mbar_expect_tx(bar_full + 8 * s, CL_SUB_BYTES);
+              tma_load_2d(smem_base + s * CL_SUB_BYTES, &tmB, kb * TC_BK, p.brow_base[j] + y * p.brow_stride_y, bar_full + 8 * s);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int it = 0, wi = 0, n = 0;
+    for (int mt = blockIdx.x; mt < MT; mt += gridDim.x, ++wi) {
+      const int wb = wi & 1;
+      mbar_wait(bar_win_full + 8 * wb, ((uint32_t)wi >> 1) & 1u);
+      const uint32_t win = smem_base + win_off + wb * CLP_WIN_BYTES;
+      for (int y = 0; y < NY; ++y, ++n) {
+        for (int jj = 0; jj < 3; ++jj) {
+          const int j = 2 - jj;
+          if (jj == 1 && n > 0) {  // columns [0,256) are shared with the previous tile: wait for its epilogue
+            mbar_wait(bar_epi, ((uint32_t)(n - 1)) & 1u);
+            tc_fence_after();
+          }
+          const uint32_t acc = tmem_base + (j == 2 ? 256u + 128u * (uint32_t)(n & 1) : 128u * (uint32_t)j);
+          for (int kb = p.kb_lo[j]; kb < p.kb_hi[j]; ++kb, ++it) {
+            const int s = it % CLP_NST;
+            const uint32_t ph = (uint32_t)(it / CLP_NST) & 1u;
+            mbar_wait(bar_full + 8 * s, ph);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              const uint64_t da = (uint64_t)(((win + (uint32_t)(8 * kb) * 16u) & 0x3FFFFu) >> 4) | (1ull << 16) | (8ull << 32) | (1ull << 46);
+              const uint64_t db = make_smem_desc(smem_base + s * CL_SUB_BYTES);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, IDESC, (kb > p.kb_lo[j] || k > 0) ? 1u : 0u);
+              umma_commit(bar_empty + 8 * s);
+            }
+            __syncwarp();
+          }
+        }
+        if (elect_one_sync()) {
+          umma_commit(bar_acc);
+          if (y == NY - 1) umma_commit(bar_win_free + 8 * wb);  // the window may be overwritten once these MMAs retire
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    {
+      const int gw0 = 128 / p.ng;
+      for (int i = threadIdx.x - 64; i < 384; i += 256) {
+        const int j = i >> 7, c = i & 127;
+        for (int y = 0; y < NY; ++y) s_bias[y][i] = __ldg(p.bias + p.brow_base[j] + y * p.brow_stride_y + c);
+        const int g = c / gw0, cc = c - g * gw0;
+        s_gamma[i] = __ldg(p.gamma + j * gw0 + cc);
+        s_beta[i] = __ldg(p.beta + j * gw0 + cc);
+      }
+      asm volatile("bar.sync 9, 256;" ::: "memory");
+    }
+    uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + stg_off + (size_t)(warp - 2) * CL_STG_BYTES;
+    int n = 0;
+    for (int mt = blockIdx.x; mt < MT; mt += gridDim.x) {
+      for (int y = 0; y < NY; ++y, ++n) {
+        mbar_wait_sleep(bar_acc, (uint32_t)n & 1u);
+        tc_fence_after();
+        cl_epilogue_tile(p, mt, y, tmem_base, 256u + 128u * (uint32_t)(n & 1), s_bias[y], s_gamma, s_beta, part, stg, warp, lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) cl_mbar_arrive(bar_epi);
+      }
     }
   }
   tc_fence_before();
@@ -340,7 +513,20 @@ extern "C" int acb_spectra_conv_ln_bf16(const void* A, const void* Bw, void* out
   args.xwin = (const bf16*)A; args.xwin_stride = a_batch_stride; args.xwin_total = (long long)nbatch * a_batch_stride;
   const long long MT = (long long)cdiv(nbatch, args.Bbox) * args.tps;
   ACB_CHECK(MT < (1LL << 31) && grid_y <= 65535, "acb_spectra_conv_ln_bf16: grid too large");
-  if (hankel)
+  static int persist = -1;
+  if (persist < 0) {
+    const char* e = getenv("ACB_CONVLN_PERSIST");
+    persist = e ? atoi(e) : 1;
+  }
+  if (hankel && persist && grid_y <= 4 && MT >= 148 && args.kb_hi[2] - args.kb_lo[2] <= 17) {
+    constexpr size_t psmem = (size_t)CLP_NST * CL_SUB_BYTES + 8 * CL_STG_BYTES + 2 * CLP_WIN_BYTES + 1024;
+    static bool pconf = false;
+    if (!pconf) {
+      ACB_CUDA(cudaFuncSetAttribute(conv_ln_hankel_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      pconf = true;
+    }
+    conv_ln_hankel_persist_kernel<<<148, CL_THREADS, psmem, (cudaStream_t)stream>>>(tmB, args, (int)MT, grid_y);
+  } else if (hankel)
     conv_ln_tc_kernel<true><<<dim3((unsigned)MT, (unsigned)grid_y), CL_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, args);
   else
     conv_ln_tc_kernel<false><<<dim3((unsigned)MT, (unsigned)grid_y), CL_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, args);

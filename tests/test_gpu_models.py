@@ -254,3 +254,32 @@ def test_predict_batches_streams_host_batches_and_matches_forward():
             ref = model(*[t.cuda() for t in b]).float().cpu()
             assert torch.equal(g, ref)
     assert list(model.predict_batches([])) == []
+
+
+def test_spectra_stage0_persistent_kernel_matches_per_tile_kernel():
+    """Stage-0 conv+LN: B=40 takes the persistent rotating-TMEM kernel (>= 148 signal windows), chunks of 8 take the
+    one-CTA-per-tile kernel; both accumulate every K block in the same order, so the results are bit-identical."""
+    import applecider_b200 as ab
+    from applecider_b200 import synth
+
+    cfg = ab.default_config()
+    cfg["model"]["SpectraNet"]["compute_dtype"] = "bf16"
+    m = ab.SpectraNet(cfg)
+    m.load_state_dict(synth.det_state_dict(m, 0), strict=True)
+    m = m.cuda().eval()
+    x = synth.spectra(40, seed=77, L=4096).cuda()
+    blk = m.all_stages[0][0]
+    with torch.no_grad():
+        big, L8 = blk._conv_ln_fused_bf16(None, 40, 4096, x.view(40, 4096))
+        torch.cuda.synchronize()
+        parts = [blk._conv_ln_fused_bf16(None, 8, 4096, x[i: i + 8].contiguous().view(8, 4096))[0] for i in range(0, 40, 8)]
+    assert torch.isfinite(big.float()).all()
+    assert torch.equal(big, torch.cat(parts, 0))
+    # and the whole network still matches the fp32 oracle-grade path within the bf16 bound
+    cfg32 = ab.default_config()
+    cfg32["model"]["SpectraNet"]["compute_dtype"] = "fp32"
+    m32 = ab.SpectraNet(cfg32)
+    m32.load_state_dict(synth.det_state_dict(m32, 0), strict=True)
+    m32 = m32.cuda().eval()
+    with torch.no_grad():
+        assert_close(m((x.view(40, 1, 4096), None, None)), m32((x.view(40, 1, 4096), None, None)), 3e-2, "persistent stage 0 through the network")
