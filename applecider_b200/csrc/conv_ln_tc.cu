@@ -51,14 +51,15 @@ struct ConvLnArgs {
 
 // ---- epilogue of one tile: bias -> LayerNorm(3*gw) -> GELU -> bf16, executed by the 8 epilogue warps ---------------
 // Sub-tiles 0 and 1 sit at TMEM columns 0 and 128; sub-tile 2 at col2 (256, or 384 in the persistent kernel's odd tiles).
+template <int NPQ>  // epilogue warps per TMEM lane quarter: the 64-column blocks of a row are dealt round-robin to them
 __device__ __forceinline__ void cl_epilogue_tile(const ConvLnArgs& p, int mt, int y, uint32_t tmem_base, uint32_t col2, const float* s_bias,
-                                                 const float* s_gamma, const float* s_beta, float (*part)[2][128][2], uint8_t* stg,
+                                                 const float* s_gamma, const float* s_beta, float (*part)[NPQ][128][2], uint8_t* stg,
                                                  int warp, int lane) {
   const int sample0 = (mt / p.tps) * p.Bbox;
   const int l0 = (mt % p.tps) * p.Lbox;
   {
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;  // which of the two warps serving this lane quarter
+    const int half = (warp - 2) >> 2;  // which of the NPQ warps serving this lane quarter
     const int r = q * 32 + lane;
     const int s_in_tile = r / p.Lbox;
     const int l = l0 + (r - s_in_tile * p.Lbox);
@@ -75,7 +76,7 @@ __device__ __forceinline__ void cl_epilogue_tile(const ConvLnArgs& p, int mt, in
       float sum = 0.0f, sq = 0.0f;
       for (int j = 0; j < 3; ++j) {
         for (int c0 = 0; c0 < gw; c0 += 32) {
-          if ((((g * 3 * gw + j * gw + c0) >> 6) & 1) != half) continue;  // 64-column blocks alternate between the two warps
+          if ((((g * 3 * gw + j * gw + c0) >> 6) % NPQ) != half) continue;  // 64-column blocks are dealt round-robin to the warps
           uint32_t raw[32];
           tmem_ld32(lane_base + (j == 2 ? col2 : (uint32_t)(128 * j)) + (uint32_t)(g * gw + c0), raw);
           const float4* b4 = reinterpret_cast<const float4*>(s_bias + 128 * j + g * gw + c0);
@@ -91,9 +92,13 @@ __device__ __forceinline__ void cl_epilogue_tile(const ConvLnArgs& p, int mt, in
       }
       part[g][half][r][0] = sum;
       part[g][half][r][1] = sq;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the two warps of this quarter
-      sum += part[g][half ^ 1][r][0];
-      sq += part[g][half ^ 1][r][1];
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * NPQ) : "memory");  // the warps of this quarter
+#pragma unroll
+      for (int o = 1; o < NPQ; ++o) {
+        const int oh = (half + o) % NPQ;
+        sum += part[g][oh][r][0];
+        sq += part[g][oh][r][1];
+      }
       const float mean = sum * inv_n;
       const float rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.0f) + p.eps);
       // pass 2: normalise, affine, GELU, pack to bf16; 32 x 64 tiles go through a per-warp smem transpose so that every
@@ -101,7 +106,7 @@ __device__ __forceinline__ void cl_epilogue_tile(const ConvLnArgs& p, int mt, in
       const unsigned vmask = __ballot_sync(0xffffffffu, valid);
       for (int j = 0; j < 3; ++j) {
         for (int cb = 0; cb < gw; cb += 64) {
-          if ((((g * 3 * gw + j * gw + cb) >> 6) & 1) != half) continue;
+          if ((((g * 3 * gw + j * gw + cb) >> 6) % NPQ) != half) continue;
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             const int c0 = cb + hh * 32;
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_tc_kernel(const __grid_
     mbar_wait_sleep(bar_acc, 0);
     tc_fence_after();
     const long long t_acc = clock64();
-    cl_epilogue_tile(p, mt, (int)blockIdx.y, tmem_base, 256u, s_bias, s_gamma, s_beta, part,
+    cl_epilogue_tile<2>(p, mt, (int)blockIdx.y, tmem_base, 256u, s_bias, s_gamma, s_beta, part,
                      smem_raw + (smem_base - smem_u32(smem_raw)) + stg_off + (size_t)(warp - 2) * CL_STG_BYTES, warp, lane);
     if (g_cl_timing_on && warp == 2 && lane == 0) {
       const long long t_end = clock64();
@@ -303,16 +308,19 @@ __device__ __forceinline__ void cl_mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-constexpr int CLP_NST = 2 * CL_STAGES;                      // 16 KB weight sub-tile stages
+constexpr int CLP_NST = 2 * CL_STAGES;                       // 16 KB weight sub-tile stages
+constexpr int CLP_NPQ = 2;                                   // epilogue warps per TMEM lane quarter (3 was measured: no gain, and
+                                                             // 2 keeps the statistics' summation order of the per-tile kernel)
+constexpr int CLP_THREADS = 64 + 128 * CLP_NPQ;
 constexpr uint32_t CLP_WIN_BYTES = (128 + 8 * 17 + 8) * 16;  // 4352 B signal window
 
-__global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_hankel_persist_kernel(const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(CLP_THREADS, 1) conv_ln_hankel_persist_kernel(const __grid_constant__ CUtensorMap tmB,
                                                                                const __grid_constant__ ConvLnArgs p, int MT, int NY) {
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * CLP_NST + 6];
   __shared__ uint32_t tmem_holder;
-  __shared__ float part[2][2][128][2];
+  __shared__ float part[2][CLP_NPQ][128][2];
   __shared__ __align__(16) float s_bias[4][384], s_gamma[384], s_beta[384];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -323,14 +331,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_hankel_persist_kernel(c
   const uint32_t bar_win_full = smem_u32(&bars[2 * CLP_NST + 2]);  // [2] signal window landed
   const uint32_t bar_win_free = smem_u32(&bars[2 * CLP_NST + 4]);  // [2] all MMAs reading the window have retired
   const uint32_t stg_off = (uint32_t)CLP_NST * CL_SUB_BYTES;
-  const uint32_t win_off = stg_off + 8 * CL_STG_BYTES;
+  const uint32_t win_off = stg_off + 4 * CLP_NPQ * CL_STG_BYTES;
   if (threadIdx.x == 0) {
     for (int s = 0; s < CLP_NST; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_acc, 1);
-    mbar_init(bar_epi, 8);
+    mbar_init(bar_epi, 4 * CLP_NPQ);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_win_full + 8 * b, 1);
       mbar_init(bar_win_free + 8 * b, 1);
@@ -371,7 +379,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_hankel_persist_kernel(c
           for (int kb = p.kb_lo[j]; kb < p.kb_hi[j]; ++kb, ++it) {
             const int s = it % CLP_NST;
             const uint32_t ph = (uint32_t)(it / CLP_NST) & 1u;
-            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            mbar_wait_sleep(bar_empty + 8 * s, ph ^ 1u);  // sleeps: a spinning warp steals issue slots from the epilogue warps
             if (elect_one_sync()) {
               mbar_expect_tx(bar_full + 8 * s, CL_SUB_BYTES);
               tma_load_2d(smem_base + s * CL_SUB_BYTES, &tmB, kb * TC_BK, p.brow_base[j] + y * p.brow_stride_y, bar_full + 8 * s);
@@ -392,7 +400,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_hankel_persist_kernel(c
         for (int jj = 0; jj < 3; ++jj) {
           const int j = 2 - jj;
           if (jj == 1 && n > 0) {  // columns [0,256) are shared with the previous tile: wait for its epilogue
-            mbar_wait(bar_epi, ((uint32_t)(n - 1)) & 1u);
+            mbar_wait_sleep(bar_epi, ((uint32_t)(n - 1)) & 1u);
             tc_fence_after();
           }
           const uint32_t acc = tmem_base + (j == 2 ? 256u + 128u * (uint32_t)(n & 1) : 128u * (uint32_t)j);
@@ -422,14 +430,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_hankel_persist_kernel(c
     // ===================== epilogue warps =====================
     {
       const int gw0 = 128 / p.ng;
-      for (int i = threadIdx.x - 64; i < 384; i += 256) {
+      for (int i = threadIdx.x - 64; i < 384; i += 128 * CLP_NPQ) {
         const int j = i >> 7, c = i & 127;
         for (int y = 0; y < NY; ++y) s_bias[y][i] = __ldg(p.bias + p.brow_base[j] + y * p.brow_stride_y + c);
         const int g = c / gw0, cc = c - g * gw0;
         s_gamma[i] = __ldg(p.gamma + j * gw0 + cc);
         s_beta[i] = __ldg(p.beta + j * gw0 + cc);
       }
-      asm volatile("bar.sync 9, 256;" ::: "memory");
+      asm volatile("bar.sync 9, %0;" ::"r"(128 * CLP_NPQ) : "memory");
     }
     uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + stg_off + (size_t)(warp - 2) * CL_STG_BYTES;
     int n = 0;
@@ -437,7 +445,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_hankel_persist_kernel(c
       for (int y = 0; y < NY; ++y, ++n) {
         mbar_wait_sleep(bar_acc, (uint32_t)n & 1u);
         tc_fence_after();
-        cl_epilogue_tile(p, mt, y, tmem_base, 256u + 128u * (uint32_t)(n & 1), s_bias[y], s_gamma, s_beta, part, stg, warp, lane);
+        cl_epilogue_tile<CLP_NPQ>(p, mt, y, tmem_base, 256u + 128u * (uint32_t)(n & 1), s_bias[y], s_gamma, s_beta, part, stg, warp, lane);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) cl_mbar_arrive(bar_epi);
@@ -519,13 +527,13 @@ extern "C" int acb_spectra_conv_ln_bf16(const void* A, const void* Bw, void* out
     persist = e ? atoi(e) : 1;
   }
   if (hankel && persist && grid_y <= 4 && MT >= 148 && args.kb_hi[2] - args.kb_lo[2] <= 17) {
-    constexpr size_t psmem = (size_t)CLP_NST * CL_SUB_BYTES + 8 * CL_STG_BYTES + 2 * CLP_WIN_BYTES + 1024;
+    constexpr size_t psmem = (size_t)CLP_NST * CL_SUB_BYTES + 4 * CLP_NPQ * CL_STG_BYTES + 2 * CLP_WIN_BYTES + 1024;
     static bool pconf = false;
     if (!pconf) {
       ACB_CUDA(cudaFuncSetAttribute(conv_ln_hankel_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
       pconf = true;
     }
-    conv_ln_hankel_persist_kernel<<<148, CL_THREADS, psmem, (cudaStream_t)stream>>>(tmB, args, (int)MT, grid_y);
+    conv_ln_hankel_persist_kernel<<<148, CLP_THREADS, psmem, (cudaStream_t)stream>>>(tmB, args, (int)MT, grid_y);
   } else if (hankel)
     conv_ln_tc_kernel<true><<<dim3((unsigned)MT, (unsigned)grid_y), CL_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, args);
   else
