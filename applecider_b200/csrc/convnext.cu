@@ -111,10 +111,10 @@ template <typename T, int W>
 __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, const float* __restrict__ ln_w,
                                                            const float* __restrict__ ln_b, float eps, T* __restrict__ y,
-                                                           int H, int C, int R, int use_wsm, int do_ln, int flip) {
+                                                           int B, int H, int C, int R, int ipb, int use_wsm, int do_ln, int flip) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int strips = (H + R - 1) / R;
-  const int b = blockIdx.x / strips, oy0 = (blockIdx.x % strips) * R;
+  const int b0 = (blockIdx.x / strips) * ipb, oy0 = (blockIdx.x % strips) * R;  // ipb > 1 only when one strip covers the image
   const int rows = min(R, H - oy0);
   const int WC = W * C;
   T* in = reinterpret_cast<T*>(smraw);
@@ -129,6 +129,22 @@ __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const
       s_lnw[i] = ln_w[i];
       s_lnb[i] = ln_b[i];
     }
+  if (use_wsm) {  // straight coalesced copy [C][49]: the odd row stride makes the per-thread reads below conflict-free
+    for (int i = tid; i < 49 * C; i += nthr) wsm[i] = __ldg(w + i);
+    __syncthreads();
+  }
+  const int c = tid;
+  float wr[49];
+  float bc = 0.0f;
+  if (c < C) {  // the 49 taps of this thread's channel stay in registers for every image of the CTA
+#pragma unroll
+    for (int j = 0; j < 49; ++j) wr[j] = use_wsm ? wsm[c * 49 + (flip ? 48 - j : j)] : __ldg(w + c * 49 + (flip ? 48 - j : j));
+    bc = bias ? bias[c] : 0.0f;
+  }
+  const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+  for (int bi = 0; bi < ipb; ++bi) {
+  const int b = b0 + bi;
+  if (b >= B) break;  // uniform
   {  // stage input rows oy0-3 .. oy0+rows+2 (16-byte copies; rows outside the image are zero)
     const int v_per_row = (int)((size_t)WC * sizeof(T) / 16);
     const uint4* xg = reinterpret_cast<const uint4*>(x + (long long)b * H * WC);
@@ -140,19 +156,7 @@ __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const
       ins[i] = (iy >= 0 && iy < H) ? __ldg(xg + (long long)iy * v_per_row + rem) : make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  if (use_wsm) {  // straight coalesced copy [C][49]: the odd row stride makes the per-thread reads below conflict-free
-    for (int i = tid; i < 49 * C; i += nthr) wsm[i] = __ldg(w + i);
-  }
   __syncthreads();
-  const int c = tid;
-  float wr[49];
-  float bc = 0.0f;
-  if (c < C) {
-#pragma unroll
-    for (int j = 0; j < 49; ++j) wr[j] = use_wsm ? wsm[c * 49 + (flip ? 48 - j : j)] : __ldg(w + c * 49 + (flip ? 48 - j : j));
-    bc = bias ? bias[c] : 0.0f;
-  }
-  const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
   for (int r = 0; r < rows; ++r) {
     if (c < C) {
       float acc[W];
@@ -228,6 +232,8 @@ __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const
     }
     __syncthreads();
   }
+  if (!do_ln) __syncthreads();  // the next image overwrites the staged rows
+  }
 }
 
 template <typename T, int W>
@@ -241,8 +247,12 @@ int launch_dwconv_w(const void* x, const float* w, const float* b, const float* 
   ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int threads = ((C + 31) / 32) * 32;
   if (threads > dw_max_threads<W>() || smem > 200 * 1024) return 1;  // fall back to the generic kernel
-  const unsigned grid = (unsigned)((long long)B * ((H + R - 1) / R));
-  k<<<grid, threads, smem, st>>>((const T*)x, w, b, ln_w, ln_b, eps, (T*)y, H, C, R, use_wsm, do_ln, flip);
+  const int strips = (H + R - 1) / R;
+  // small maps: several images per CTA so the 49 taps per channel are fetched once per CTA, not once per image
+  int ipb = 1;
+  if (strips == 1) while (ipb < 16 && (long long)(B / (ipb * 2)) >= 148 * 4) ipb *= 2;
+  const unsigned grid = (unsigned)((long long)((B + ipb - 1) / ipb) * strips);
+  k<<<grid, threads, smem, st>>>((const T*)x, w, b, ln_w, ln_b, eps, (T*)y, B, H, C, R, ipb, use_wsm, do_ln, flip);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;

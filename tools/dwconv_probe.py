@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from applecider_b200 import ops  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-for (H, C) in [(15, 96), (7, 192), (3, 384)]:
+for (H, C) in [(15, 96), (7, 192), (3, 384), (1, 768)]:
     x = torch.randn(B * H * H, C, device="cuda").to(torch.bfloat16)
     w = torch.randn(C, 1, 7, 7, device="cuda") * 0.1
     b = torch.randn(C, device="cuda") * 0.1
