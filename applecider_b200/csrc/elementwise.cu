@@ -199,12 +199,101 @@ __global__ void __launch_bounds__(256) layernorm_cached_kernel(const TX* __restr
   }
 }
 
+// Streaming variant for the large bf16 activations (SpectraNet LayerNorm+GELU, >= 64 K rows): a warp owns RPW rows
+// and issues the loads of ALL of them before touching the first (RPW x C x 2 bytes in flight per warp -- one row per
+// warp leaves HBM latency-bound at ~2.6 TB/s), affine parameters live in registers across the rows.
+template <int NC, int RPW>
+__global__ void __launch_bounds__(256) layernorm_stream_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ b, bf16* __restrict__ y, long long rows, float eps,
+                                                               int post_act) {
+  constexpr int C = NC * 128;
+  const int lane = threadIdx.x & 31;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (row0 >= rows) return;
+  uint2 raw[RPW][NC];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const long long row = row0 + r < rows ? row0 + r : rows - 1;  // clamp: tail rows recompute the last row, stores are guarded
+#pragma unroll
+    for (int k = 0; k < NC; ++k) raw[r][k] = __ldcs(reinterpret_cast<const uint2*>(x + row * C + lane * 4 + k * 128));
+  }
+  constexpr bool WREG = NC <= 6;  // wide rows re-read the affine parameters from L1 instead of pinning 8*NC registers
+  float4 wv[WREG ? NC : 1], bv[WREG ? NC : 1];
+  if constexpr (WREG) {
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      wv[k] = *reinterpret_cast<const float4*>(w + lane * 4 + k * 128);
+      bv[k] = *reinterpret_cast<const float4*>(b + lane * 4 + k * 128);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    float v[NC][4];
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw[r][k].x);
+      const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(&raw[r][k].y);
+      v[k][0] = __low2float(a); v[k][1] = __high2float(a); v[k][2] = __low2float(c); v[k][3] = __high2float(c);
+      s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
+    }
+    const float mean = warp_sum(s) / (float)C;  // same arithmetic as layernorm_cached_kernel: results do not depend on the row count
+    float q = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NC; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        q += (v[k][i] - mean) * (v[k][i] - mean);
+      }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    if (row0 + r < rows) {
+      bf16* yr = y + (row0 + r) * C;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        float o[4];
+        const float4 w4 = WREG ? wv[WREG ? k : 0] : *reinterpret_cast<const float4*>(w + lane * 4 + k * 128);
+        const float4 b4 = WREG ? bv[WREG ? k : 0] : *reinterpret_cast<const float4*>(b + lane * 4 + k * 128);
+        o[0] = (v[k][0] - mean) * rstd * w4.x + b4.x;
+        o[1] = (v[k][1] - mean) * rstd * w4.y + b4.y;
+        o[2] = (v[k][2] - mean) * rstd * w4.z + b4.z;
+        o[3] = (v[k][3] - mean) * rstd * w4.w + b4.w;
+        if (post_act == ACB_ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = gelu_bf16(o[i]);
+        } else if (post_act != ACB_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = apply_act(o[i], post_act);
+        }
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+        uint2 t;
+        t.x = *reinterpret_cast<uint32_t*>(&h0);
+        t.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(yr + lane * 4 + k * 128) = t;
+      }
+    }
+  }
+}
+
 template <typename TX, typename TR, typename TY>
 int launch_ln(const void* x, const void* res, const float* w, const float* b, void* y, long long rows, int C,
               float eps, int pre_gelu, int post_act, cudaStream_t st) {
   const int wpb = 8;
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
   const bool vec = (C % 4 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)w | (uintptr_t)b) % 16 == 0);
+  if constexpr (sizeof(TX) == 2 && sizeof(TY) == 2) {
+    if (vec && !res && !pre_gelu && rows >= 65536 && (C == 128 || C == 256 || C == 384 || C == 768 || C == 1536)) {
+      constexpr int RPW = 4;
+      const unsigned g = (unsigned)((rows + (long long)wpb * RPW - 1) / ((long long)wpb * RPW));
+      if (C == 128) layernorm_stream_kernel<1, 8><<<(unsigned)((rows + wpb * 8LL - 1) / (wpb * 8LL)), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
+      else if (C == 256) layernorm_stream_kernel<2, RPW><<<g, wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
+      else if (C == 384) layernorm_stream_kernel<3, RPW><<<g, wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
+      else if (C == 768) layernorm_stream_kernel<6, 2><<<(unsigned)((rows + wpb * 2LL - 1) / (wpb * 2LL)), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
+      else layernorm_stream_kernel<12, 1><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
+      ACB_LAUNCH_CHECK();
+      acb_count_launch();
+      return ACB_OK;
+    }
+  }
   if (vec && C <= 256)
     layernorm_cached_kernel<TX, TR, TY, 2><<<grid, wpb * 32, 0, st>>>((const TX*)x, (const TR*)res, w, b, (TY*)y, rows, C, eps, pre_gelu, post_act);
   else if (vec && C <= 768)
