@@ -269,16 +269,44 @@ __global__ void __launch_bounds__(256) layernorm_bwd_reg_kernel(const T* __restr
       ab[k * VEC + e] = 0.0f;
     }
   const long long row0 = ((long long)blockIdx.x * nw + wid) * rows_per_warp;
+  constexpr bool PREFETCH = VEC == 2 && sizeof(T) == 2;  // software prefetch of the next row: twice the bytes in flight per warp
+  uint32_t px[PREFETCH ? NCH : 1], pg[PREFETCH ? NCH : 1];
+  if constexpr (PREFETCH) {
+    if (row0 < rows) {
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        px[k] = *reinterpret_cast<const uint32_t*>(x + row0 * C + (k * 32 + lane) * 2);
+        pg[k] = *reinterpret_cast<const uint32_t*>(dy + row0 * C + (k * 32 + lane) * 2);
+      }
+    }
+  }
   for (int rr = 0; rr < rows_per_warp; ++rr) {
     const long long row = row0 + rr;
     if (row >= rows) break;
     float xv[NE], gv[NE];
     const T* xr = x + row * C;
     const T* gr = dy + row * C;
+    if constexpr (PREFETCH) {
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&px[k]));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pg[k]));
+        xv[k * 2] = a.x; xv[k * 2 + 1] = a.y; gv[k * 2] = b.x; gv[k * 2 + 1] = b.y;
+      }
+      if (rr + 1 < rows_per_warp && row + 1 < rows) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          px[k] = *reinterpret_cast<const uint32_t*>(xr + C + (k * 32 + lane) * 2);
+          pg[k] = *reinterpret_cast<const uint32_t*>(gr + C + (k * 32 + lane) * 2);
+        }
+      }
+    }
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int c0 = (k * 32 + lane) * VEC;
-      if constexpr (VEC == 2 && sizeof(T) == 2) {
+      if constexpr (PREFETCH) {
+        (void)c0;
+      } else if constexpr (VEC == 2 && sizeof(T) == 2) {
         const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + c0));
         const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gr + c0));
         xv[k * 2] = a.x; xv[k * 2 + 1] = a.y; gv[k * 2] = b.x; gv[k * 2 + 1] = b.y;

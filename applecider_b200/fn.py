@@ -55,6 +55,23 @@ def cast_to(x, dtype):
     return ops.cast(_c(x), dtype)
 
 
+class Cast(Function):
+    """Differentiable dtype change (gradient is cast back to the input dtype)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src = x.dtype
+        return ops.cast(_c(x), dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.cast(_c(dy), ctx.src), None
+
+
+def cast(x, dtype):
+    return x if x.dtype == dtype else Cast.apply(x, dtype)
+
+
 def transpose(x, dtype):
     R, C = x.shape
     y = torch.empty((C, R), dtype=dtype, device=x.device)
@@ -93,6 +110,8 @@ class Linear(Function):
         M, K = x.shape
         N = W.shape[0]
         dx = dW = db = None
+        if x.dtype == BF16 and dy.dtype == F32 and N % 8 == 0 and K % 8 == 0 and M >= 64:
+            dy = cast_to(dy, BF16)  # fp32 output of a bf16 GEMM: the gradient GEMMs run on the tensor cores too
         tc = x.dtype == BF16 and dy.dtype == BF16 and N % 8 == 0 and K % 8 == 0 and M >= 64
         if ctx.needs_input_grad[0]:
             if tc:  # tcgen05 dgrad: dX = dY @ W through a bf16 W^T copy

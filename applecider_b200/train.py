@@ -250,7 +250,11 @@ def spectra_forward_train(model, x):
     feat = spectra_features_train(model, x)
     head = model.regressor if model.redshift else model.classifier
     tr = model.training
-    z = fn.linear(feat, head[0].weight, head[0].bias)
+    if model.compute_dtype != F32 and feat.shape[0] >= 64:  # Linear(3072 -> 384) on the tensor cores, fp32 result
+        f16 = fn.cast(feat, model.compute_dtype)
+        z = fn.linear(f16, head[0].weight, head[0].bias, _wc(model._derived, head[0].weight, model.compute_dtype), out_dtype=F32)
+    else:
+        z = fn.linear(feat, head[0].weight, head[0].bias)
     z = fn.layernorm(z, head[1].weight, head[1].bias, head[1].eps, post_act=ops.ACT_GELU)
     z = fn.dropout(z, head[3].p, tr)
     out = fn.linear(z, head[4].weight, head[4].bias)
