@@ -128,7 +128,7 @@ __global__ void act_bwd_kernel(const void* dy, int dy_dt, const void* x, int x_d
     float d;
     switch (act) {
       case ACB_ACT_RELU: d = v > 0.0f ? 1.0f : 0.0f; break;
-      case ACB_ACT_GELU: d = gelu_erf_grad(v); break;
+      case ACB_ACT_GELU: d = (x_dt == ACB_BF16 && dx_dt == ACB_BF16) ? gelu_bf16_grad(v) : gelu_erf_grad(v); break;  // bf16 forward = tanh form
       case ACB_ACT_TANH: { const float t = tanhf(v); d = 1.0f - t * t; break; }
       case ACB_ACT_SIGMOID: { const float s = sigmoidf_(v); d = s * (1.0f - s); break; }
       default: d = 1.0f;
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_reg_kernel(const T* __restr
 #pragma unroll
     for (int i = 0; i < NE; ++i) {
       xv[i] *= rstd;  // xhat
-      if (gelu) gv[i] *= gelu_erf_grad(fmaf(xv[i], wv[i], bv[i]));
+      if (gelu) gv[i] *= (sizeof(T) == 2 ? gelu_bf16_grad(fmaf(xv[i], wv[i], bv[i])) : gelu_erf_grad(fmaf(xv[i], wv[i], bv[i])));
       const float g = gv[i] * wv[i];
       sg += g;
       sgx += g * xv[i];
@@ -405,7 +405,7 @@ __device__ __forceinline__ unsigned attn_hash(unsigned long long seed, int bh, i
 }
 
 template <int DH>
-__global__ void __launch_bounds__(128) attention_bwd_kernel(const void* qkv, int dt, const void* dout, int do_dt, const int* cu,
+__global__ void __launch_bounds__(512) attention_bwd_kernel(const void* qkv, int dt, const void* dout, int do_dt, const int* cu,
                                                             int n_heads, float drop_p, unsigned long long seed, void* dqkv, int dq_dt) {
   extern __shared__ float sm[];
   const int b = blockIdx.x, h = blockIdx.y;
@@ -955,7 +955,11 @@ int acb_attention_varlen_bwd(const void* qkv, int dtype, const void* dout, int d
   ACB_CHECK(smem <= 200 * 1024, "acb_attention_varlen_bwd: max_seqlen %d too long", max_seqlen);
   auto k = attention_bwd_kernel<16>;
   ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  k<<<dim3(B, n_heads), 128, smem, (cudaStream_t)stream>>>(qkv, dtype, dout, dout_dtype, cu_seqlens, n_heads, drop_p, (unsigned long long)seed, dqkv, dqkv_dtype);
+  // thread = query (pass A) / key (pass B): one round for every sequence up to 512 tokens (258 = 2 x 128 + 2 would otherwise
+  // run a third round with two active threads)
+  int threads = ((max_seqlen + 31) / 32) * 32;
+  threads = threads < 128 ? 128 : (threads > 512 ? 512 : threads);
+  k<<<dim3(B, n_heads), threads, smem, (cudaStream_t)stream>>>(qkv, dtype, dout, dout_dtype, cu_seqlens, n_heads, drop_p, (unsigned long long)seed, dqkv, dqkv_dtype);
   LAUNCHED(1);
 }
 

@@ -94,6 +94,19 @@ __device__ __forceinline__ float gelu_bf16(float x) {
   return fmaf(hx, t, hx);
 #endif
 }
+// derivative of gelu_bf16 (the tanh form the bf16 forward evaluates): ~10 instructions against ~40 for the erf/exp form
+__device__ __forceinline__ float gelu_bf16_grad(float x) {
+#ifdef ACB_EXACT_GELU_BF16
+  return gelu_erf_grad(x);
+#else
+  const float x2 = x * x;
+  const float u = x * fmaf(0.0356774081f, x2, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float du = fmaf(0.1070322243f, x2, 0.7978845608f);
+  return fmaf(0.5f * x * (1.0f - t * t), du, 0.5f * (1.0f + t));
+#endif
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float apply_act(float v, int act) {

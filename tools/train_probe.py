@@ -38,9 +38,12 @@ for _ in range(2):
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+import time
 e0.record()
+t0 = time.perf_counter()
 loss = ddp_train_step(opt.grads, loss_fn, opt)
+cpu_ms = (time.perf_counter() - t0) * 1e3
 e1.record()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-print("step ms", e0.elapsed_time(e1), "loss", float(loss))
+print("step ms", e0.elapsed_time(e1), "cpu launch ms", cpu_ms, "loss", float(loss))
