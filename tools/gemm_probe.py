@@ -34,3 +34,6 @@ if __name__ == "__main__":
         run(921600, 96, 384, res=True)
         run(8192, 8192, 8192, bn=256)
         run(8192, 8192, 8192, bn=128)
+    if which == "cnx":  # ConvNeXt stage-0 MLP pair (for ncu: first launch after warm-up)
+        run(921600, 384, 96, act=2)
+        run(921600, 96, 384, res=True)
