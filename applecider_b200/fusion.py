@@ -41,13 +41,52 @@ class AppleCider(nn.Module):
         self.img_metadata_proj = nn.Linear(5, hidden_dim)
         self.fc = nn.Linear(hidden_dim * 3 if fusion == "concat" else hidden_dim, num_classes)
 
+    # inference: the three encoders are independent and can run on three streams (measured +1.8 % throughput at B=4096, but the
+    # co-running small kernels slow the tensor-bound spectra convs by ~5 %, which muddies per-kernel timing) -> opt-in
+    CONCURRENT_ENCODERS = False
+
     def _encode(self, photometry, photometry_mask, metadata, images, spectra):
+        if self.CONCURRENT_ENCODERS and not torch.is_grad_enabled() and spectra.is_cuda:
+            return self._encode_concurrent(photometry, photometry_mask, metadata, images, spectra)
         p = self.photometry_encoder((photometry, photometry_mask, None))
         s = self.spectra_encoder((spectra, None, None))
         if s.dim() == 1:
             s = s[:, None].contiguous()
         im = self.img_metadata_encoder((metadata, images, None))
         return p, im, s
+
+    def _encode_concurrent(self, photometry, photometry_mask, metadata, images, spectra):
+        """Spectra on the caller's stream (it is 70 % of the work), photometry and image+metadata on two side streams."""
+        dev = spectra.device
+        main = torch.cuda.current_stream(dev)
+        side = getattr(self, "_side_streams", None)
+        if side is None:
+            side = self._side_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        start = torch.cuda.Event()
+        start.record(main)
+        outs = [None, None]
+        done = []
+        for k, st in enumerate(side):
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                if k == 0:
+                    outs[0] = self.photometry_encoder((photometry, photometry_mask, None))
+                else:
+                    outs[1] = self.img_metadata_encoder((metadata, images, None))
+                ev = torch.cuda.Event()
+                ev.record(st)
+                done.append(ev)
+        s = self.spectra_encoder((spectra, None, None))
+        if s.dim() == 1:
+            s = s[:, None].contiguous()
+        for ev, o in zip(done, outs):
+            main.wait_event(ev)
+            o.record_stream(main)
+        for t in (photometry, photometry_mask, metadata, images):  # inputs were produced on `main`, read on the side streams
+            if t is not None:
+                t.record_stream(side[0])
+                t.record_stream(side[1])
+        return outs[0], outs[1], s
 
     def _head(self, p, im, s, want_emb):
         B = p.shape[0]
