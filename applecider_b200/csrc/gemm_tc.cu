@@ -32,6 +32,7 @@ struct TcArgs {
   const float* gamma;
   int res_mode, pool4;
   const int* m_valid_dev;
+  void* pre_out;  // optional second bf16 output: the value after the bias, before activation / residual (same ldc, columns)
   int has_ranges, has_coloff;
   int kb_lo[TC_MAX_NT], kb_hi[TC_MAX_NT];
   int col_off[TC_MAX_CB];
@@ -82,6 +83,14 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& p, bool have_acc,
         for (int g = 0; g < 8; ++g) {
           const float4 t = b4[g];
           v[g * 4 + 0] += t.x; v[g * 4 + 1] += t.y; v[g * 4 + 2] += t.z; v[g * 4 + 3] += t.w;
+        }
+      }
+      uint32_t pre_pk[16];
+      if (p.pre_out) {  // warp-uniform
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+          pre_pk[i] = *reinterpret_cast<uint32_t*>(&h);
         }
       }
       switch (p.act) {  // warp-uniform: one branch per 32-column chunk, not per element
@@ -175,9 +184,12 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& p, bool have_acc,
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = rv[i] + v[i];
           }
-        } else {
+        } else if (p.res_mode == ACB_RES_MUL) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = rv[i] * v[i];
+        } else {  // ACB_RES_MUL_GELU_GRAD: back through h = gelu(u), res = the saved pre-activation u
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= gelu_bf16_grad(rv[i]);
         }
       }
       if (p.pool4) {
@@ -212,6 +224,21 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& p, bool have_acc,
             *reinterpret_cast<uint4*>(cbase + (size_t)orow * p.ldc * 2) = *reinterpret_cast<const uint4*>(sb + rr * 80 + piece * 16);
         }
         __syncwarp();
+        if (p.pre_out) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(sb + lane * 80 + j * 16) = make_uint4(pre_pk[4 * j], pre_pk[4 * j + 1], pre_pk[4 * j + 2], pre_pk[4 * j + 3]);
+          __syncwarp();
+          uint8_t* pbase = reinterpret_cast<uint8_t*>(p.pre_out) + ((size_t)out_col + piece * 8) * 2;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + r8;
+            const long long orow = __shfl_sync(0xffffffffu, out_row, rr);
+            if ((wmask >> rr) & 1u)
+              *reinterpret_cast<uint4*>(pbase + (size_t)orow * p.ldc * 2) = *reinterpret_cast<const uint4*>(sb + rr * 80 + piece * 16);
+          }
+          __syncwarp();
+        }
       } else if (cvec) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = v[i];
@@ -711,13 +738,17 @@ extern "C" int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype
                              int pad, long long a_batch_stride, long long a_row_stride, int N, int ldb, int ldc, int bn,
                              const int* tile_kb_host, const int* colblk_off_host, const float* bias, int act,
                              const void* res, int res_dtype, int ldr, const float* gamma, int res_mode, int pool4,
-                             const int* m_valid_dev, void* stream) {
+                             const int* m_valid_dev, void* pre_out, void* stream) {
   ACB_CHECK(A && Bw && C, "acb_gemm_bf16: null operand");
   ACB_CHECK(nbatch > 0 && L > 0 && Cin > 0 && taps > 0 && N > 0, "acb_gemm_bf16: bad shape");
   ACB_CHECK(bn == 64 || bn == 128 || bn == 256, "acb_gemm_bf16: bn must be 64, 128 or 256 (got %d)", bn);
   ACB_CHECK(((uintptr_t)A % 16 == 0) && ((uintptr_t)Bw % 16 == 0), "acb_gemm_bf16: operands must be 16-byte aligned");
   ACB_CHECK(a_row_stride % 8 == 0 && a_batch_stride % 8 == 0 && ldb % 8 == 0, "acb_gemm_bf16: strides must be multiples of 8 elements");
   ACB_CHECK(res_mode == ACB_RES_NONE || res != nullptr, "acb_gemm_bf16: res_mode set without res");
+  ACB_CHECK(res_mode >= ACB_RES_NONE && res_mode <= ACB_RES_MUL_GELU_GRAD, "acb_gemm_bf16: bad res_mode %d", res_mode);
+  if (pre_out)
+    ACB_CHECK(c_dtype == ACB_BF16 && !pool4 && N % 32 == 0 && ldc % 8 == 0 && ((uintptr_t)C % 16 == 0) && ((uintptr_t)pre_out % 16 == 0) && !colblk_off_host,
+              "acb_gemm_bf16: pre_out needs a bf16, 16-byte aligned, unpooled output with N %% 32 == 0");
   const int cpt = cdiv(Cin, TC_BK);
   const int NT = cdiv(N, bn);
   ACB_CHECK(NT <= TC_MAX_NT || !tile_kb_host, "acb_gemm_bf16: too many N tiles for K ranges");
@@ -736,7 +767,7 @@ extern "C" int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype
   args.taps = taps; args.pad = pad; args.cpt = cpt; args.Cin = Cin;
   args.N = N; args.ldc = ldc; args.c_dtype = c_dtype; args.C = C;
   args.bias = bias; args.act = act; args.res = res; args.res_dtype = res_dtype; args.ldr = ldr; args.gamma = gamma;
-  args.res_mode = res_mode; args.pool4 = pool4; args.m_valid_dev = m_valid_dev;
+  args.res_mode = res_mode; args.pool4 = pool4; args.m_valid_dev = m_valid_dev; args.pre_out = pre_out;
   const int kb_total = taps * cpt;
   if (tile_kb_host) {
     args.has_ranges = 1;

@@ -240,6 +240,42 @@ def scale_add(x, v, gamma):
     return ScaleAdd.apply(x, v, gamma)
 
 
+class MlpBlock(Function):
+    """ConvNeXt block tail (bf16): out = xres + gamma * fc2(gelu(fc1(y))).
+
+    forward : GEMM1 writes h = gelu(u) AND u (pre_out) from one epilogue; GEMM2 adds bias, scales by gamma, adds the
+              residual in its epilogue and also writes v = fc2(h) (needed for d gamma).
+    backward: dv = gamma * dy; d h -> d u inside the dgrad GEMM (ACB_RES_MUL_GELU_GRAD with res = u); tcgen05 wgrads."""
+
+    @staticmethod
+    def forward(ctx, xres, y, W1, b1, W2, b2, gamma, w1c, w2c):
+        xres, y = _c(xres), _c(y)
+        M = y.shape[0]
+        H, C = W1.shape[0], W2.shape[0]
+        u = torch.empty((M, H), dtype=BF16, device=y.device)
+        h = ops.gemm(y, w1c, b1, act=ops.ACT_GELU, pre_out=u)
+        v = torch.empty((M, C), dtype=BF16, device=y.device)
+        out = ops.gemm(h, w2c, b2, res=xres, gamma=gamma, res_mode=ops.RES_ADD, pre_out=v)
+        ctx.save_for_backward(y, u, h, v, W1, W2, gamma)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, u, h, v, W1, W2, gamma = ctx.saved_tensors
+        dy = _c(dy)
+        M = y.shape[0]
+        H, C = W1.shape[0], W2.shape[0]
+        dgamma = colsum(dy.view(-1, C), v.view(-1, C))
+        dv = ew(dy, None, 3, g=gamma, C=C, out_dtype=BF16)
+        db2 = colsum(dv)
+        dW2 = wgrad_tc(dv, C, 0, C, h, 1, M, H, 1, 0, M * H, H, y.device)
+        du = ops.gemm(dv, transpose(W2.detach(), BF16), None, res=u, res_mode=ops.RES_MUL_GELU_GRAD)  # [M,H] = (dv W2) * gelu'(u)
+        db1 = colsum(du)
+        dW1 = wgrad_tc(du, H, 0, H, y, 1, M, C, 1, 0, M * C, C, y.device)
+        dyin = ops.gemm(du, transpose(W1.detach(), BF16), None)
+        return dy, dyin, dW1, db1, dW2, db2, dgamma, None, None
+
+
 class Attention(Function):
     @staticmethod
     def forward(ctx, qkv, cu, B, H, dh, maxlen, drop_p, seed):

@@ -6,7 +6,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, BF16, F32, RES_ADD, RES_MUL, RES_NONE, call, dtype_tag  # noqa: F401
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, BF16, F32, RES_ADD, RES_MUL, RES_MUL_GELU_GRAD, RES_NONE, call, dtype_tag  # noqa: F401
 
 
 # ---- optional per-region CUDA-event timing (bench.py roofline; off by default) ----------------------
@@ -68,7 +68,7 @@ def pick_bn(n: int) -> int:
 
 
 def gemm(a, w, bias=None, act=ACT_NONE, res=None, gamma=None, res_mode=RES_NONE, out=None, out_dtype=None,
-         out_col=0, conv=None, pool4=False, bn=None, tile_kb=None, colblk_off=None, a_view=None):
+         out_col=0, conv=None, pool4=False, bn=None, tile_kb=None, colblk_off=None, a_view=None, pre_out=None):
     """C = epilogue(A @ W^T).  a: [M,K] (or [B,L,Cin] with conv=(taps,pad)); w: [N,K'] row-major.
 
     f32 operands run the CUDA-core kernel, bf16 operands the tcgen05 kernel.
@@ -98,7 +98,7 @@ def gemm(a, w, bias=None, act=ACT_NONE, res=None, gamma=None, res_mode=RES_NONE,
     c_ptr = _offset_ptr(out, out_col)
     ldr = res.shape[-1] if res is not None else 0
     if a.dtype == torch.float32:
-        assert w.dtype == torch.float32 and out.dtype == torch.float32 and not pool4 and a_view is None
+        assert w.dtype == torch.float32 and out.dtype == torch.float32 and not pool4 and a_view is None and pre_out is None
         assert res is None or res.dtype == torch.float32
         call("acb_gemm_f32", a, w, c_ptr, M, N, K, cin, ldb, ldc, (L if conv is not None else 0), (cin if conv is not None else 0), pad,
              bias, act, res, ldr, gamma, res_mode)
@@ -113,7 +113,7 @@ def gemm(a, w, bias=None, act=ACT_NONE, res=None, gamma=None, res_mode=RES_NONE,
         kb = _int_array(tile_kb) if tile_kb is not None else None
         co = _int_array(colblk_off) if colblk_off is not None else None
         call("acb_gemm_bf16", a, w, c_ptr, dtype_tag(out), nb, L, cin, taps, pad, bstride, rstride, N, ldb, ldc, bn, kb, co,
-             bias, act, res, (dtype_tag(res) if res is not None else 0), ldr, gamma, res_mode, int(pool4), None)
+             bias, act, res, (dtype_tag(res) if res is not None else 0), ldr, gamma, res_mode, int(pool4), None, pre_out)
     else:
         raise TypeError(f"gemm: unsupported dtype {a.dtype}")
     return out

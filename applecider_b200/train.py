@@ -203,7 +203,7 @@ class SpectraConvs(torch.autograd.Function):
                     dx = torch.empty((B * L, cin), dtype=torch.bfloat16, device=dev)
                 fn.call("acb_gemm_bf16", ops._offset_ptr(dy, j * cout), wd, dx, 1, B, L, cout, kj, kj // 2, L * ldy, ldy, cin, kj * cout, cin,
                         ops.pick_bn(cin), None, None, None, ops.ACT_NONE, (None if first else dx), 1, cin, None,
-                        (ops.RES_NONE if first else ops.RES_ADD), 0, None)
+                        (ops.RES_NONE if first else ops.RES_ADD), 0, None, None)
             elif need_dx:
                 # dgrad: dX = sum_j conv(dY_j, flipped W_j^T)
                 wd = torch.empty((cin, kj * cout), dtype=F32, device=dev)
@@ -306,6 +306,12 @@ def convnext_features_train(bb, img, dtype):
         for blk in st.blocks:
             y = fn.DwConv7.apply(x, blk.conv_dw.weight, blk.conv_dw.bias, (B, h, w, C))
             y = fn.layernorm(y, blk.norm.weight, blk.norm.bias, blk.norm.eps)
+            if dtype == torch.bfloat16 and FUSE_MLP_BLOCK:
+                # fc1 + GELU (pre-activation saved by the same epilogue), fc2 + layer scale + residual in the epilogue, and in
+                # the backward the GELU derivative inside the fc2 dgrad GEMM: 2 launches forward instead of 4
+                x = fn.MlpBlock.apply(x, y, blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias, blk.gamma,
+                                      bb._w(blk.mlp.fc1.weight, dtype), bb._w(blk.mlp.fc2.weight, dtype))
+                continue
             hid = fn.act(fn.linear(y, blk.mlp.fc1.weight, blk.mlp.fc1.bias, bb._w(blk.mlp.fc1.weight, dtype) if dtype != F32 else None), ops.ACT_GELU)
             v = fn.linear(hid, blk.mlp.fc2.weight, blk.mlp.fc2.bias, bb._w(blk.mlp.fc2.weight, dtype) if dtype != F32 else None)
             x = fn.scale_add(x, v, blk.gamma)
@@ -341,6 +347,7 @@ def image_tower_train(it, img, dtype, training):
     return fn.mul(a, x)
 
 
+FUSE_MLP_BLOCK = True  # ConvNeXt MLP + layer scale + residual as one autograd node with fused epilogues (bf16)
 FUSE_TOWERS = True  # tower groups as one forward + one backward launch (acb_tower_group_*)
 
 

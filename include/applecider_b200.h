@@ -37,6 +37,7 @@ extern "C" {
 #define ACB_RES_NONE 0
 #define ACB_RES_ADD 1 /* C = res + gamma[n] * v   (gamma may be NULL = 1) */
 #define ACB_RES_MUL 2 /* C = res * v */
+#define ACB_RES_MUL_GELU_GRAD 3 /* C = v * gelu'(res): gradient GEMM fused with the backward of h = gelu(res) (bf16 path) */
 
 #define ACB_OK 0
 #define ACB_ERR_INVALID (-1)
@@ -70,12 +71,14 @@ int acb_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, int K,
  * N tile to a range of 64-wide K blocks (zero weights outside are never touched).
  * colblk_off_host (optional, host memory, [N/64]) remaps each 64-column block of the result to
  * column offset colblk_off[j] of C (default j*64).  pool4 != 0 max-pools groups of 4 consecutive rows.
- * m_valid_dev (optional) holds the number of valid rows on the device (tiles beyond it exit). */
+ * m_valid_dev (optional) holds the number of valid rows on the device (tiles beyond it exit).
+ * pre_out (optional, bf16, layout of C): second output = accumulator + bias BEFORE the activation / residual (training:
+ * the tensor the backward of the activation needs, written by the same epilogue instead of a separate kernel). */
 int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype, int nbatch, int L, int Cin, int taps, int pad,
                   long long a_batch_stride, long long a_row_stride, int N, int ldb, int ldc, int bn,
                   const int* tile_kb_host, const int* colblk_off_host, const float* bias, int act, const void* res,
                   int res_dtype, int ldr, const float* gamma, int res_mode, int pool4, const int* m_valid_dev,
-                  void* stream);
+                  void* pre_out, void* stream);
 
 /* SpectraNet block front half fused on tcgen05 (spectranet.py:29-35): three same-padded Conv1d (implicit GEMM, packed
  * weights Bw [b_rows, ldb], per-conv K-block ranges kb_ranges_host[3][2]) + bias + LayerNorm over the concatenated

@@ -345,3 +345,35 @@ def test_attention_tc_matches_reference(lens):
     finally:
         ops.USE_TC_ATTENTION = True
     assert_close(got, old.float(), 1.2e-2, "tc vs CUDA-core attention")
+
+
+def test_gemm_bf16_pre_out_and_gelu_grad_epilogue():
+    """Training epilogues of the tcgen05 GEMM: (a) pre_out = acc + bias next to the activated output, (b) ACB_RES_MUL_GELU_GRAD:
+    out = (A W^T) * gelu'(res).  Reference: torch fp32 on the bf16-rounded operands; tolerance = bf16 rounding of the result."""
+    from applecider_b200 import ops
+
+    torch.manual_seed(0)
+    M, K, N = 1000, 96, 384
+    a = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) * K ** -0.5).to(torch.bfloat16)
+    b = torch.randn(N, device=DEV)
+    u = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    h = ops.gemm(a, w, b, act=ops.ACT_GELU, pre_out=u)
+    ref_u = a.float() @ w.float().t() + b
+    assert_close(u, ref_u, 1e-2, "pre_out (acc + bias)")
+    assert_close(h, torch.nn.functional.gelu(ref_u, approximate="tanh"), 1.5e-2, "gelu(acc + bias)")
+    # residual + layer scale with the un-scaled value as second output
+    g = torch.rand(N, device=DEV) + 0.5
+    r = torch.randn(M, N, device=DEV).to(torch.bfloat16)
+    v = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    o = ops.gemm(a, w, b, res=r, gamma=g, res_mode=ops.RES_ADD, pre_out=v)
+    assert_close(v, ref_u, 1e-2, "pre_out with residual epilogue")
+    assert_close(o, r.float() + g * ref_u, 1.5e-2, "res + gamma * v")
+    # gradient GEMM fused with the GELU backward
+    x = torch.randn(M, N, device=DEV).to(torch.bfloat16)  # plays d h
+    wt = (torch.randn(K, N, device=DEV) * N ** -0.5).to(torch.bfloat16)  # [K_out, N]
+    pre = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    du = ops.gemm(x, wt, None, res=pre, res_mode=ops.RES_MUL_GELU_GRAD)
+    pf = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(pf, approximate="tanh").sum().backward()
+    assert_close(du, (x.float() @ wt.float().t()) * pf.grad, 1.5e-2, "(A W^T) * gelu'(res)")
