@@ -18,7 +18,7 @@ import torch
 from ._lib import call
 from .ddp import FlatGradSync
 
-_ALIGN = 4  # elements: every tensor starts 16-byte aligned inside the flat buffers
+_ALIGN = 8  # elements: every tensor starts 16-byte aligned in the bf16 shadow too (TMA needs it), 32-byte in fp32
 
 
 class FusedAdam:

@@ -336,14 +336,22 @@ class PackDown(torch.autograd.Function):
         return out.view(cout, cin, kh, kw)
 
 
+def _lin(x, lin, dtype, cache, out_dtype=None):
+    """Linear on the tensor cores when the model runs in bf16 and the batch is large enough for a 128-row tile to pay."""
+    if dtype != F32 and x.shape[0] >= 64 and lin.in_features % 8 == 0 and lin.out_features % 8 == 0:
+        return fn.linear(fn.cast(x, dtype), lin.weight, lin.bias, _wc(cache, lin.weight, dtype), out_dtype=out_dtype)
+    return fn.linear(x, lin.weight, lin.bias)
+
+
 def image_tower_train(it, img, dtype, training):
     feat = convnext_features_train(it.backbone, img, dtype)
     hm, ha = it.head_main, it.head_aux
+    dc = it.backbone._derived
     a = fn.layernorm(fn.act(feat, ops.ACT_GELU), hm[1].weight, hm[1].bias, hm[1].eps)
-    a = fn.act(fn.linear(a, hm[2].weight, hm[2].bias), ops.ACT_RELU)
+    a = fn.act(_lin(a, hm[2], dtype, dc), ops.ACT_RELU)
     a = fn.dropout(a, hm[4].p, training)
-    a = fn.linear(fn.linear(a, hm[5].weight, hm[5].bias), hm[6].weight, hm[6].bias)
-    x = fn.act(fn.linear(fn.layernorm(feat, ha[0].weight, ha[0].bias, ha[0].eps), ha[1].weight, ha[1].bias), ops.ACT_TANH)
+    a = _lin(_lin(a, hm[5], dtype, dc), hm[6], dtype, dc, out_dtype=F32)
+    x = fn.act(_lin(fn.layernorm(feat, ha[0].weight, ha[0].bias, ha[0].eps), ha[1], dtype, dc, out_dtype=F32), ops.ACT_TANH)
     return fn.mul(a, x)
 
 
@@ -383,7 +391,10 @@ def _experts_fused(model, feats, tr):
     exs = list(model.fusion_experts)
     w0 = torch.cat([ex.start_path[0].weight for ex in exs], 0)
     b0 = torch.cat([ex.start_path[0].bias for ex in exs], 0)
-    a_pre = fn.linear(feats, w0, b0)
+    if model.compute_dtype != F32 and feats.shape[0] >= 64:  # [B,288] x [512,288]^T on the tensor cores, fp32 result
+        a_pre = fn.linear(fn.cast(feats, model.compute_dtype), w0, b0, None, out_dtype=F32)
+    else:
+        a_pre = fn.linear(feats, w0, b0)
     towers, params, y_off, a_off = [], [], 0, 0
     for ex in exs:
         i, h, o = _dims(ex)
@@ -414,7 +425,7 @@ def astrominn_forward_train(model, metadata, image):
                 parts.append(_tower_train(tw, fn.gather_cols(metadata, getattr(model, f"_cols_{n}")), tr))
         feats = fn.ConcatCols.apply(*parts)
     r = model.fusion_router
-    g1 = fn.act(fn.linear(feats, r[0].weight, r[0].bias), ops.ACT_TANH)
+    g1 = fn.act(_lin(feats, r[0], model.compute_dtype, model._derived, out_dtype=F32), ops.ACT_TANH)
     gate = fn.act(fn.linear(fn.dropout(g1, r[2].p, tr), r[3].weight, r[3].bias), ops.ACT_SIGMOID)
     if fuse:
         eo = _experts_fused(model, feats, tr)
