@@ -47,14 +47,27 @@ struct ConvLnArgs {
   const bf16* xwin;            // padded signal [nbatch, a_batch_stride]
   long long xwin_stride;       // elements per sample
   long long xwin_total;        // elements in the whole buffer
+  // fused 1x1 downsample + pair max (persistent stage-0 kernel only): pairmax[(4*m + y), 0..63] = max over the CTA's two
+  // phases of (LN/GELU row) x Wd^T + bd
+  const float* down_bias;      // [64]
+  bf16* down_out;              // [out_rows / 2, 64]
 };
 
 // ---- epilogue of one tile: bias -> LayerNorm(3*gw) -> GELU -> bf16, executed by the 8 epilogue warps ---------------
 // Sub-tiles 0 and 1 sit at TMEM columns 0 and 128; sub-tile 2 at col2 (256, or 384 in the persistent kernel's odd tiles).
-template <int NPQ>  // epilogue warps per TMEM lane quarter: the 64-column blocks of a row are dealt round-robin to them
+// DOWN (persistent stage-0 kernel): the normalised bf16 rows are not stored; they are written into a 128 x 192 K-major
+// SWIZZLE_128B tile (a2) and multiplied with the 1x1 downsample weights (wd_smem) by 12 more UMMAs per phase into the TMEM
+// columns the phase's conv-0 accumulators have just vacated; the two phases are max-ed and stored as one "pair max" row.
+struct ClDown {
+  uint32_t a2, wd;        // shared-memory addresses (1024-byte aligned)
+  uint32_t bar_d2;        // MMA-complete barrier
+  uint32_t* d2_phase;     // per-thread phase counter of bar_d2
+};
+
+template <int NPQ, bool DOWN = false>  // NPQ epilogue warps per TMEM lane quarter: 64-column blocks are dealt round-robin to them
 __device__ __forceinline__ void cl_epilogue_tile(const ConvLnArgs& p, int mt, int y, uint32_t tmem_base, uint32_t col2, const float* s_bias,
                                                  const float* s_gamma, const float* s_beta, float (*part)[NPQ][128][2], uint8_t* stg,
-                                                 int warp, int lane) {
+                                                 int warp, int lane, const ClDown* dn = nullptr) {
   const int sample0 = (mt / p.tps) * p.Bbox;
   const int l0 = (mt % p.tps) * p.Lbox;
   {
@@ -69,6 +82,7 @@ __device__ __forceinline__ void cl_epilogue_tile(const ConvLnArgs& p, int mt, in
     const int gw = 128 / p.ng;
     const float inv_n = 1.0f / (float)(3 * gw);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float d2keep[32];  // DOWN: phase-0 result of this thread's row (32 of the 64 output channels)
     for (int g = 0; g < p.ng; ++g) {
       const long long orow = m * p.row_mul + (long long)y * p.row_add_y + g;
       const bool valid = valid_row && orow < p.out_rows;
@@ -127,10 +141,22 @@ __device__ __forceinline__ void cl_epilogue_tile(const ConvLnArgs& p, int mt, in
               pk[i4 * 2 + 0] = *reinterpret_cast<uint32_t*>(&h0);
               pk[i4 * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
             }
+            if constexpr (DOWN) {
+              // K-major SWIZZLE_128B A tile: K block j (64 channels = 128 bytes per row), 16-byte chunk c of row r at c ^ (r & 7)
+#pragma unroll
+              for (int v4 = 0; v4 < 4; ++v4) {
+                const uint32_t addr = dn->a2 + (uint32_t)j * 16384u + (uint32_t)r * 128u + ((uint32_t)((hh * 4 + v4) ^ (r & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[v4 * 4 + 0]), "r"(pk[v4 * 4 + 1]), "r"(pk[v4 * 4 + 2]),
+                             "r"(pk[v4 * 4 + 3])
+                             : "memory");
+              }
+              continue;
+            }
             uint4* srow = reinterpret_cast<uint4*>(stg + lane * 144 + hh * 64);
 #pragma unroll
             for (int v4 = 0; v4 < 4; ++v4) srow[v4] = make_uint4(pk[v4 * 4 + 0], pk[v4 * 4 + 1], pk[v4 * 4 + 2], pk[v4 * 4 + 3]);
           }
+          if constexpr (DOWN) continue;
           __syncwarp();
           const int ch = j * gw + cb;  // first channel of this 64-wide block inside the concatenated row
 #pragma unroll
@@ -143,6 +169,56 @@ __device__ __forceinline__ void cl_epilogue_tile(const ConvLnArgs& p, int mt, in
             }
           }
           __syncwarp();
+        }
+      }
+      if constexpr (DOWN) {
+        // all 8 warps have written their share of the 128 x 192 tile (and are done with this phase's conv-0 columns)
+        fence_proxy_async();
+        tc_fence_before();
+        asm volatile("bar.sync 10, 256;" ::: "memory");
+        const uint32_t d2col = (uint32_t)(g * 64);  // TMEM columns [64 g, 64 g + 64): phase g of sub-tile 0, now dead
+        if (warp == 2 && elect_one_sync()) {
+          constexpr uint32_t IDESC_D = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+          tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) {
+            const uint64_t da = make_smem_desc(dn->a2 + kb * 16384u), db = make_smem_desc(dn->wd + kb * 8192u);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_base + d2col, da + 2 * k, db + 2 * k, IDESC_D, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(dn->bar_d2);
+        }
+        __syncwarp();
+        mbar_wait(dn->bar_d2, *dn->d2_phase & 1u);
+        *dn->d2_phase += 1u;
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld32(lane_base + d2col + (uint32_t)(half * 32), raw);
+        if (g == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) d2keep[i] = __uint_as_float(raw[i]);
+        } else {
+          const long long prow = 4 * m + y;  // pair index: positions 8 m + 2 y and 8 m + 2 y + 1
+          if (valid_row && 2 * prow < p.out_rows) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.down_bias + half * 32);
+            uint4* dst = reinterpret_cast<uint4*>(p.down_out + prow * 64 + half * 32);
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float4 bb = __ldg(b4 + v4 * 2 + e);
+                const int i0 = v4 * 8 + e * 4;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(d2keep[i0], __uint_as_float(raw[i0])) + bb.x,
+                                                          fmaxf(d2keep[i0 + 1], __uint_as_float(raw[i0 + 1])) + bb.y);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaxf(d2keep[i0 + 2], __uint_as_float(raw[i0 + 2])) + bb.z,
+                                                          fmaxf(d2keep[i0 + 3], __uint_as_float(raw[i0 + 3])) + bb.w);
+                w4[e * 2] = *reinterpret_cast<uint32_t*>(&h0);
+                w4[e * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+              }
+              dst[v4] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          }
         }
       }
     }
@@ -308,17 +384,20 @@ __device__ __forceinline__ void cl_mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-constexpr int CLP_NST = 2 * CL_STAGES;                       // 16 KB weight sub-tile stages
+constexpr int CLP_NST = 2 * CL_STAGES;                       // 16 KB weight sub-tile stages (8 with the fused downsample)
 constexpr int CLP_NPQ = 2;                                   // epilogue warps per TMEM lane quarter (3 was measured: no gain, and
                                                              // 2 keeps the statistics' summation order of the per-tile kernel)
 constexpr int CLP_THREADS = 64 + 128 * CLP_NPQ;
 constexpr uint32_t CLP_WIN_BYTES = (128 + 8 * 17 + 8) * 16;  // 4352 B signal window
 
+template <bool DOWN>
 __global__ void __launch_bounds__(CLP_THREADS, 1) conv_ln_hankel_persist_kernel(const __grid_constant__ CUtensorMap tmB,
+                                                                               const __grid_constant__ CUtensorMap tmD,
                                                                                const __grid_constant__ ConvLnArgs p, int MT, int NY) {
+  constexpr int NST = DOWN ? 8 : CLP_NST;
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * CLP_NST + 6];
+  __shared__ __align__(8) uint64_t bars[2 * CLP_NST + 8];
   __shared__ uint32_t tmem_holder;
   __shared__ float part[2][CLP_NPQ][128][2];
   __shared__ __align__(16) float s_bias[4][384], s_gamma[384], s_beta[384];
@@ -326,17 +405,22 @@ __global__ void __launch_bounds__(CLP_THREADS, 1) conv_ln_hankel_persist_kernel(
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = smem_u32(&bars[0]);
   const uint32_t bar_empty = smem_u32(&bars[CLP_NST]);
+  const uint32_t bar_wd = smem_u32(&bars[2 * CLP_NST + 6]);       // downsample weights landed
+  const uint32_t bar_d2 = smem_u32(&bars[2 * CLP_NST + 7]);       // downsample MMAs of one phase complete
   const uint32_t bar_acc = smem_u32(&bars[2 * CLP_NST]);           // accumulators of a tile complete (MMA -> epilogue)
   const uint32_t bar_epi = smem_u32(&bars[2 * CLP_NST + 1]);       // epilogue has drained a tile (8 warps -> MMA)
   const uint32_t bar_win_full = smem_u32(&bars[2 * CLP_NST + 2]);  // [2] signal window landed
   const uint32_t bar_win_free = smem_u32(&bars[2 * CLP_NST + 4]);  // [2] all MMAs reading the window have retired
-  const uint32_t stg_off = (uint32_t)CLP_NST * CL_SUB_BYTES;
-  const uint32_t win_off = stg_off + 4 * CLP_NPQ * CL_STG_BYTES;
+  // smem: [weight stages][transpose tiles | DOWN: 48 KB A2 tile + 24 KB downsample weights][2 signal windows]
+  const uint32_t stg_off = (uint32_t)NST * CL_SUB_BYTES;
+  const uint32_t win_off = stg_off + (DOWN ? 49152u + 24576u : 4 * CLP_NPQ * CL_STG_BYTES);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < CLP_NST; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
+    mbar_init(bar_wd, 1);
+    mbar_init(bar_d2, 1);
     mbar_init(bar_acc, 1);
     mbar_init(bar_epi, 4 * CLP_NPQ);
     for (int b = 0; b < 2; ++b) {
@@ -357,6 +441,11 @@ __global__ void __launch_bounds__(CLP_THREADS, 1) conv_ln_hankel_persist_kernel(
 
   if (warp == 0) {
     // ===================== producer: signal windows + weight sub-tiles in MMA order =====================
+    if (DOWN && elect_one_sync()) {  // the 64 x 192 downsample weights, once per CTA: three 64 x 64 K-major SWIZZLE_128B blocks
+      mbar_expect_tx(bar_wd, 24576u);
+      for (int kb = 0; kb < 3; ++kb) tma_load_2d(smem_base + stg_off + 49152u + kb * 8192u, &tmD, kb * TC_BK, 0, bar_wd);
+    }
+    __syncwarp();
     int it = 0, wi = 0;
     for (int mt = blockIdx.x; mt < MT; mt += gridDim.x, ++wi) {
       const int wb = wi & 1;
@@ -377,8 +466,8 @@ __global__ void __launch_bounds__(CLP_THREADS, 1) conv_ln_hankel_persist_kernel(
         for (int jj = 0; jj < 3; ++jj) {
           const int j = 2 - jj;  // sub-tile 2 first (it overlaps the previous tile's epilogue)
           for (int kb = p.kb_lo[j]; kb < p.kb_hi[j]; ++kb, ++it) {
-            const int s = it % CLP_NST;
-            const uint32_t ph = (uint32_t)(it / CLP_NST) & 1u;
+            const int s = it % NST;
+            const uint32_t ph = (uint32_t)(it / NST) & 1u;
             mbar_wait_sleep(bar_empty + 8 * s, ph ^ 1u);  // sleeps: a spinning warp steals issue slots from the epilogue warps
             if (elect_one_sync()) {
               mbar_expect_tx(bar_full + 8 * s, CL_SUB_BYTES);
@@ -405,8 +494,8 @@ __global__ void __launch_bounds__(CLP_THREADS, 1) conv_ln_hankel_persist_kernel(
           }
           const uint32_t acc = tmem_base + (j == 2 ? 256u + 128u * (uint32_t)(n & 1) : 128u * (uint32_t)j);
           for (int kb = p.kb_lo[j]; kb < p.kb_hi[j]; ++kb, ++it) {
-            const int s = it % CLP_NST;
-            const uint32_t ph = (uint32_t)(it / CLP_NST) & 1u;
+            const int s = it % NST;
+            const uint32_t ph = (uint32_t)(it / NST) & 1u;
             mbar_wait(bar_full + 8 * s, ph);
             tc_fence_after();
             if (elect_one_sync()) {
@@ -440,12 +529,19 @@ __global__ void __launch_bounds__(CLP_THREADS, 1) conv_ln_hankel_persist_kernel(
       asm volatile("bar.sync 9, %0;" ::"r"(128 * CLP_NPQ) : "memory");
     }
     uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + stg_off + (size_t)(warp - 2) * CL_STG_BYTES;
+    uint32_t d2_phase = 0;
+    ClDown dn;
+    dn.a2 = smem_base + stg_off;
+    dn.wd = smem_base + stg_off + 49152u;
+    dn.bar_d2 = bar_d2;
+    dn.d2_phase = &d2_phase;
+    if (DOWN) mbar_wait_sleep(bar_wd, 0);
     int n = 0;
     for (int mt = blockIdx.x; mt < MT; mt += gridDim.x) {
       for (int y = 0; y < NY; ++y, ++n) {
         mbar_wait_sleep(bar_acc, (uint32_t)n & 1u);
         tc_fence_after();
-        cl_epilogue_tile<CLP_NPQ>(p, mt, y, tmem_base, 256u + 128u * (uint32_t)(n & 1), s_bias[y], s_gamma, s_beta, part, stg, warp, lane);
+        cl_epilogue_tile<CLP_NPQ, DOWN>(p, mt, y, tmem_base, 256u + 128u * (uint32_t)(n & 1), s_bias[y], s_gamma, s_beta, part, stg, warp, lane, &dn);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) cl_mbar_arrive(bar_epi);
@@ -466,10 +562,14 @@ extern "C" int acb_spectra_conv_ln_bf16(const void* A, const void* Bw, void* out
                                         long long a_batch_stride, long long a_row_stride, int ldb, int b_rows, const int* kb_ranges_host,
                                         const int* brow_base_host, int brow_stride_y, int grid_y, int ng, long long row_mul,
                                         long long row_add_y, long long out_rows, const float* bias, const float* gamma,
-                                        const float* beta, float eps, void* stream) {
-  ACB_CHECK(A && Bw && out && bias && gamma && beta && kb_ranges_host && brow_base_host, "acb_spectra_conv_ln_bf16: null argument");
+                                        const float* beta, float eps, const void* down_w, const float* down_bias, void* down_out,
+                                        void* stream) {
+  ACB_CHECK(A && Bw && (out || down_out) && bias && gamma && beta && kb_ranges_host && brow_base_host, "acb_spectra_conv_ln_bf16: null argument");
+  ACB_CHECK((down_w == nullptr) == (down_out == nullptr) && (down_w == nullptr) == (down_bias == nullptr),
+            "acb_spectra_conv_ln_bf16: down_w / down_bias / down_out go together");
   ACB_CHECK(nbatch > 0 && L > 0 && Cin > 0 && taps > 0 && (ng == 1 || ng == 2) && grid_y >= 1, "acb_spectra_conv_ln_bf16: bad shape");
-  ACB_CHECK(((uintptr_t)A % 16 == 0) && ((uintptr_t)Bw % 16 == 0) && ((uintptr_t)out % 16 == 0) && a_row_stride % 8 == 0 && a_batch_stride % 8 == 0 && ldb % 8 == 0,
+  ACB_CHECK(((uintptr_t)A % 16 == 0) && ((uintptr_t)Bw % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)down_w % 16 == 0) &&
+                ((uintptr_t)down_out % 16 == 0) && ((uintptr_t)down_bias % 16 == 0) && a_row_stride % 8 == 0 && a_batch_stride % 8 == 0 && ldb % 8 == 0,
             "acb_spectra_conv_ln_bf16: alignment");
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
   ACB_CHECK(enc != nullptr, "acb_spectra_conv_ln_bf16: cuTensorMapEncodeTiled unavailable");
@@ -526,14 +626,36 @@ extern "C" int acb_spectra_conv_ln_bf16(const void* A, const void* Bw, void* out
     const char* e = getenv("ACB_CONVLN_PERSIST");
     persist = e ? atoi(e) : 1;
   }
-  if (hankel && persist && grid_y <= 4 && MT >= 148 && args.kb_hi[2] - args.kb_lo[2] <= 17) {
+  const bool can_persist = hankel && persist && grid_y <= 4 && MT >= 148 && args.kb_hi[2] - args.kb_lo[2] <= 17;
+  if (down_w) {
+    // fused 1x1 downsample (3*64 -> 64) + max over the CTA's two phases: only in the persistent stage-0 kernel
+    ACB_CHECK(can_persist && grid_y == 4 && ng == 2 && row_mul == 8 && row_add_y == 2,
+              "acb_spectra_conv_ln_bf16: the fused downsample needs the persistent polyphase kernel (>= 148 signal windows, 8 phases)");
+    args.down_bias = down_bias;
+    args.down_out = (bf16*)down_out;
+    CUtensorMap tmD;
+    cuuint64_t dims[2] = {192, 64};
+    cuuint64_t strides[1] = {192 * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(down_w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACB_CHECK(r == CUDA_SUCCESS, "acb_spectra_conv_ln_bf16: cuTensorMapEncodeTiled(down_w) failed with %d", (int)r);
+    constexpr size_t dsmem = (size_t)8 * CL_SUB_BYTES + 49152 + 24576 + 2 * CLP_WIN_BYTES + 1024;
+    static bool dconf = false;
+    if (!dconf) {
+      ACB_CUDA(cudaFuncSetAttribute(conv_ln_hankel_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+      dconf = true;
+    }
+    conv_ln_hankel_persist_kernel<true><<<148, CLP_THREADS, dsmem, (cudaStream_t)stream>>>(tmB, tmD, args, (int)MT, grid_y);
+  } else if (can_persist) {
     constexpr size_t psmem = (size_t)CLP_NST * CL_SUB_BYTES + 4 * CLP_NPQ * CL_STG_BYTES + 2 * CLP_WIN_BYTES + 1024;
     static bool pconf = false;
     if (!pconf) {
-      ACB_CUDA(cudaFuncSetAttribute(conv_ln_hankel_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      ACB_CUDA(cudaFuncSetAttribute(conv_ln_hankel_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
       pconf = true;
     }
-    conv_ln_hankel_persist_kernel<<<148, CLP_THREADS, psmem, (cudaStream_t)stream>>>(tmB, args, (int)MT, grid_y);
+    conv_ln_hankel_persist_kernel<false><<<148, CLP_THREADS, psmem, (cudaStream_t)stream>>>(tmB, tmB, args, (int)MT, grid_y);
   } else if (hankel)
     conv_ln_tc_kernel<true><<<dim3((unsigned)MT, (unsigned)grid_y), CL_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, args);
   else

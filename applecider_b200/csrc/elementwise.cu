@@ -517,6 +517,33 @@ int acb_maxpool4_cl(const void* x, int dtype, void* y, int B, int L, int C, void
   return ACB_OK;
 }
 
+// pair max of bf16 rows, 16 bytes per thread: y[r, :] = max(x[2r, :], x[2r+1, :])  (second half of MaxPool1d(4) after the
+// stage-0 kernel has already max-ed the two phases it owns)
+__global__ void pairmax_bf16_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long rows_out, int vec_per_row) {
+  const long long total = rows_out * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int c = (int)(i - r * vec_per_row);
+    const uint4 a = __ldcs(x + (2 * r) * vec_per_row + c), b = __ldcs(x + (2 * r + 1) * vec_per_row + c);
+    uint4 o;
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+    __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) po[k] = __hmax2(pa[k], pb[k]);
+    y[i] = o;
+  }
+}
+
+int acb_pairmax_bf16(const void* x, void* y, long long rows_out, int C, void* stream) {
+  ACB_CHECK(x && y && rows_out >= 0 && C > 0 && C % 8 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0), "acb_pairmax_bf16: bad arguments");
+  if (rows_out == 0) return ACB_OK;
+  pairmax_bf16_kernel<<<grid_for(rows_out * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, rows_out, C / 8);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
 int acb_globalmax_cl(const void* x, int dtype, float* y, int B, int L, int C, void* stream) {
   ACB_CHECK(x && y && B > 0 && L > 0 && C > 0, "acb_globalmax_cl: bad arguments");
   const long long n = (long long)B * C;

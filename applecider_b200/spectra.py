@@ -16,6 +16,7 @@ from .config import resolve_dtype
 
 FUSE_CONV_LN = True  # conv + bias + LayerNorm + GELU in one tcgen05 kernel where 3*C_out fits TMEM
 FUSE_STAGE1 = False
+FUSE_STAGE0_DOWN = True  # stage 0: also fuse the 1x1 downsample + pair max into the persistent kernel
 _PHASES = 8
 _HALO = 512  # zeros in front of every padded sample (>= max pad 510, multiple of 8)
 
@@ -144,7 +145,7 @@ class SpectraNetBlock(nn.Module):
         # separate conv + LayerNorm kernels (measured 29 ms vs 19 ms at B=4096), so it is opt-in
         return FUSE_STAGE1 and self.in_channels >= 64 and self.in_channels % 64 == 0 and self.out_channels == 128
 
-    def _conv_ln_fused_bf16(self, x, B, L, raw_signal):
+    def _conv_ln_fused_bf16(self, x, B, L, raw_signal, fuse_down=False):
         """conv x3 + bias + LayerNorm + GELU in one tcgen05 kernel. Returns ([B*Lr, 3C] bf16, Lr)."""
         cin, cout, kmax = self.in_channels, self.out_channels, self._kmax()
         dev = self.norm.weight.device
@@ -158,11 +159,22 @@ class SpectraNetBlock(nn.Module):
             for j in range(3):
                 pad = self.kernel_sizes[j] // 2
                 ranges += [(_HALO - pad) // 64, min((_HALO + pad + _PHASES + 63) // 64, kp // 64)]
+            if fuse_down:
+                # conv + LN + GELU + 1x1 downsample + max over position pairs in ONE kernel; the [B*L8, 192] activation never exists
+                wd = self._down(torch.bfloat16)
+                pm = torch.empty((B * L8 // 2, cout), dtype=torch.bfloat16, device=dev)
+                with ops.region("spectra.conv.cin1"):
+                    ops.call("acb_spectra_conv_ln_bf16", xp, w, None, B, L8 // _PHASES, kp, 1, 0, stride, _PHASES, kp, w.shape[0], ops._int_array(ranges),
+                             ops._int_array([j * _PHASES * cout for j in range(3)]), 2 * cout, _PHASES // 2, 2, _PHASES, 2, B * L8, bias,
+                             self.norm.weight, self.norm.bias, self.norm.eps, wd, self.downsample.bias, pm)
+                    z = torch.empty((B * L8 // 4, cout), dtype=torch.bfloat16, device=dev)
+                    ops.call("acb_pairmax_bf16", pm, z, B * L8 // 4, cout)
+                return z, L8
             y = torch.empty((B * L8, 3 * cout), dtype=torch.bfloat16, device=dev)
             with ops.region("spectra.conv.cin1"):
                 ops.call("acb_spectra_conv_ln_bf16", xp, w, y, B, L8 // _PHASES, kp, 1, 0, stride, _PHASES, kp, w.shape[0], ops._int_array(ranges),
                          ops._int_array([j * _PHASES * cout for j in range(3)]), 2 * cout, _PHASES // 2, 2, _PHASES, 2, B * L8, bias,
-                         self.norm.weight, self.norm.bias, self.norm.eps)
+                         self.norm.weight, self.norm.bias, self.norm.eps, None, None, None)
             return y, L8
         w, bias = self._packed(torch.bfloat16)
         cpt = cin // 64
@@ -173,7 +185,7 @@ class SpectraNetBlock(nn.Module):
         y = torch.empty((B * L, 3 * cout), dtype=torch.bfloat16, device=dev)
         with ops.region(f"spectra.conv.cin{cin}"):
             ops.call("acb_spectra_conv_ln_bf16", x, w, y, B, L, cin, kmax, kmax // 2, L * cin, cin, kmax * cin, w.shape[0], ops._int_array(ranges),
-                     ops._int_array([0, cout, 2 * cout]), 0, 1, 1, 1, 0, B * L, bias, self.norm.weight, self.norm.bias, self.norm.eps)
+                     ops._int_array([0, cout, 2 * cout]), 0, 1, 1, 1, 0, B * L, bias, self.norm.weight, self.norm.bias, self.norm.eps, None, None, None)
         return y, L
 
     def forward_cl(self, x, B, L, dtype, raw_signal=None):
@@ -184,6 +196,12 @@ class SpectraNetBlock(nn.Module):
         if dtype == torch.float32:
             y = self._convs_f32(x, B, L)
         elif FUSE_CONV_LN and self._fusable():
+            L8 = ((L + _PHASES - 1) // _PHASES) * _PHASES
+            # stage 0 with >= 148 signal windows (the persistent kernel): the 1x1 downsample and half of MaxPool(4) join the kernel
+            if (FUSE_STAGE0_DOWN and self.in_channels == 1 and self.do_pool and self.out_channels == 64 and L8 % 128 == 0
+                    and B * (L8 // _PHASES) // 128 >= 148 and L8 == L):
+                z, _ = self._conv_ln_fused_bf16(x, B, L, raw_signal, fuse_down=True)
+                return z.view(B, L // 4, cout), L // 4
             y, Lr = self._conv_ln_fused_bf16(x, B, L, raw_signal)
             fused = True
         elif self.in_channels == 1:

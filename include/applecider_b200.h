@@ -84,12 +84,16 @@ int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype, int nbatc
  * weights Bw [b_rows, ldb], per-conv K-block ranges kb_ranges_host[3][2]) + bias + LayerNorm over the concatenated
  * channels of every position + GELU -> bf16 out[out_rows, 3*(128/ng)].  Sub-tile j (= conv j, 128 accumulator columns)
  * reads weight rows brow_base_host[j] + blockIdx.y*brow_stride_y; ng = LayerNorm groups per GEMM row (stage 0 polyphase:
- * 2 phases per CTA, output row = m*row_mul + blockIdx.y*row_add_y + g).  A geometry as in acb_gemm_bf16. */
+ * 2 phases per CTA, output row = m*row_mul + blockIdx.y*row_add_y + g).  A geometry as in acb_gemm_bf16. 
+ * down_w / down_bias / down_out (optional, all or none; stage-0 polyphase form with >= 148 signal windows only): also fuse the
+ * block's 1x1 downsample Conv1d(3*64 -> 64) (down_w bf16 [64,192], down_bias f32 [64]) and the first half of MaxPool1d(4):
+ * down_out[out_rows/2, 64] bf16 = max over positions (2i, 2i+1) of conv1x1(gelu(LN(...))) + bias; `out` is then not written
+ * (may be NULL) -- the [out_rows, 192] activation never reaches HBM (spectranet.py:36-40). */
 int acb_spectra_conv_ln_bf16(const void* A, const void* Bw, void* out, int nbatch, int L, int Cin, int taps, int pad,
                              long long a_batch_stride, long long a_row_stride, int ldb, int b_rows, const int* kb_ranges_host,
                              const int* brow_base_host, int brow_stride_y, int grid_y, int ng, long long row_mul,
                              long long row_add_y, long long out_rows, const float* bias, const float* gamma,
-                             const float* beta, float eps, void* stream);
+                             const float* beta, float eps, const void* down_w, const float* down_bias, void* down_out, void* stream);
 
 /* Weight packing (derived, non-persistent buffers; refreshed after load_state_dict / optimizer step).
  * out[co*row_stride + (tap + tap_off)*Cin + ci] = w[co, ci, tap]     (w = PyTorch (Cout, Cin, k)) */
@@ -155,6 +159,9 @@ int acb_pack_conv2d_weight(const float* w, void* out, int out_dtype, int Cout, i
 /* ---- SpectraNet pooling (spectranet.py:25,38-40,163) ------------------------------------------ */
 int acb_maxpool4_cl(const void* x, int dtype, void* y, int B, int L, int C, void* stream); /* -> [B, L/4, C] */
 int acb_globalmax_cl(const void* x, int dtype, float* y, int B, int L, int C, void* stream); /* -> [B, C] f32 */
+/* y[r,:] = max(x[2r,:], x[2r+1,:]) for bf16 rows of C (C % 8 == 0) channels: finishes MaxPool1d(4) after the fused stage-0
+ * kernel (acb_spectra_conv_ln_bf16 with down_w) has max-ed the two positions each CTA owns. */
+int acb_pairmax_bf16(const void* x, void* y, long long rows_out, int C, void* stream);
 
 /* ---- metadata towers / MoE / fusion head -------------------------------------------------------- */
 /* ResidualTowerBlock (astrominn.py:44-64), eval: s = gelu(W0 x + b0); y = (W1 ln1(s) + b1) * sigmoid(W2 ln2(s) + b2)

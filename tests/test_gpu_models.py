@@ -283,3 +283,30 @@ def test_spectra_stage0_persistent_kernel_matches_per_tile_kernel():
     m32 = m32.cuda().eval()
     with torch.no_grad():
         assert_close(m((x.view(40, 1, 4096), None, None)), m32((x.view(40, 1, 4096), None, None)), 3e-2, "persistent stage 0 through the network")
+
+
+def test_spectra_stage0_fused_downsample_matches_unfused():
+    """Stage 0 with the 1x1 downsample + MaxPool fused into the persistent kernel (no [B*L,192] activation in HBM) equals the
+    conv+LN kernel followed by the pooled GEMM bit for bit: same bf16 operand rows, same K order, and max / +bias / rounding commute."""
+    import applecider_b200 as ab
+    from applecider_b200 import spectra as sp, synth
+
+    cfg = ab.default_config()
+    cfg["model"]["SpectraNet"]["compute_dtype"] = "bf16"
+    m = ab.SpectraNet(cfg)
+    m.load_state_dict(synth.det_state_dict(m, 0), strict=True)
+    m = m.cuda().eval()
+    x = synth.spectra(40, seed=78, L=4096).cuda()
+    blk = m.all_stages[0][0]
+    with torch.no_grad():
+        old = sp.FUSE_STAGE0_DOWN
+        try:
+            sp.FUSE_STAGE0_DOWN = True
+            zf, Lf = blk.forward_cl(None, 40, 4096, torch.bfloat16, raw_signal=x.view(40, 4096))
+            sp.FUSE_STAGE0_DOWN = False
+            zu, Lu = blk.forward_cl(None, 40, 4096, torch.bfloat16, raw_signal=x.view(40, 4096))
+        finally:
+            sp.FUSE_STAGE0_DOWN = old
+    assert Lf == Lu == 1024 and zf.shape == zu.shape == (40, 1024, 64)
+    assert torch.isfinite(zf.float()).all()
+    assert torch.equal(zf, zu)

@@ -37,3 +37,9 @@ if __name__ == "__main__":
     if which == "cnx":  # ConvNeXt stage-0 MLP pair (for ncu: first launch after warm-up)
         run(921600, 384, 96, act=2)
         run(921600, 96, 384, res=True)
+    if which == "down":  # SpectraNet 1x1 downsample GEMMs (stages 1-3), tile-width comparison
+        for bn in (None, 128, 64):
+            run(4194304, 128, 384, bn=bn)
+        for bn in (None, 128):
+            run(1048576, 256, 768, bn=bn)
+            run(262144, 512, 1536, bn=bn)
