@@ -17,6 +17,7 @@ namespace {
 
 constexpr int AT_DH = 16;
 constexpr int AT_THREADS = 128;
+constexpr int AT_CH = 96;  // keys per S chunk
 
 __device__ __forceinline__ unsigned attn_hash_tc(unsigned long long seed, int bh, int i, int j) {
   unsigned long long v = seed * 0x9E3779B97F4A7C15ULL + (((unsigned long long)bh << 26) | ((unsigned long long)i << 13) | (unsigned long long)j);
@@ -61,8 +62,11 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const bf16* __
   const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
   const uint32_t bar_s = smem_u32(&bars[0]), bar_p = smem_u32(&bars[1]);
 
-  uint32_t ncols = 32;
-  while (ncols < (uint32_t)(npad + 16)) ncols <<= 1;  // S (npad columns) + O (16 columns)
+  // S is produced in chunks of <= AT_CH keys (columns [0, 96)), O lives in columns [96, 112): 128 TMEM columns for EVERY
+  // sequence length, so four CTAs share an SM.  (One S tile over all keys made the 3 % longest sequences allocate all 512
+  // columns and run alone on their SM -- half of the kernel's time.)  Longer sequences recompute S in the second pass:
+  // the MMA is free, TMEM occupancy is not.
+  const uint32_t ncols = 128;
   if (tid == 0) {
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 1);
@@ -77,7 +81,7 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const bf16* __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_s = tmem_holder;
-  const uint32_t tmem_o = tmem_s + (uint32_t)npad;
+  const uint32_t tmem_o = tmem_s + (uint32_t)AT_CH;
   const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
 
   const float drop_inv = 1.0f / (1.0f - drop_p);
@@ -118,73 +122,96 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const bf16* __
       }
       fence_proxy_async();
       __syncthreads();
-      // ---- S = Q K^T : K = 16 is a single UMMA per <= 256 keys ----
-      if (warp == 0 && elect_one_sync()) {
-        tc_fence_after();
-        for (int k0 = 0; k0 < npad; k0 += 256) {
-          const int nn = min(256, npad - k0);
-          umma_bf16(tmem_s + (uint32_t)k0, desc_nosw(aQ, 128 * 16, 128), desc_nosw(aK + k0 * 16, ncap * 16, 128), idesc_bf16(nn), 0u);
-        }
-        umma_commit(bar_s);
-      }
-      mbar_wait(bar_s, ph_s);
-      ph_s ^= 1u;
-      tc_fence_after();
-      // ---- softmax over the n real keys of this thread's query row ----
+      // ---- pass 1: row maxima over all keys, S = Q K^T one chunk (one UMMA, K = 16) at a time ----
+      const bool single = npad <= AT_CH;
       const int qi = q0 + tid;
       float mx = -INFINITY;
-      for (int c0 = 0; c0 < n; c0 += 32) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, raw);
+      for (int kc = 0; kc < npad; kc += AT_CH) {
+        const int nn = min(AT_CH, npad - kc);
+        if (kc > 0) {  // every thread has read the previous chunk
+          tc_fence_before();
+          __syncthreads();
+        }
+        if (warp == 0 && elect_one_sync()) {
+          tc_fence_after();
+          umma_bf16(tmem_s, desc_nosw(aQ, 128 * 16, 128), desc_nosw(aK + kc * 16, ncap * 16, 128), idesc_bf16(nn), 0u);
+          umma_commit(bar_s);
+        }
+        mbar_wait(bar_s, ph_s);
+        ph_s ^= 1u;
+        tc_fence_after();
+        for (int c0 = 0; c0 < nn; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, raw);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < n) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          for (int i = 0; i < 32; ++i)
+            if (kc + c0 + i < n && c0 + i < nn) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        }
       }
+      // ---- pass 2: P = exp(S - max) in 64-key blocks -> smem -> O += P V ----
       float lsum = 0.0f;
       const int bh = b * n_heads + h;
       int blk = 0;
-      for (int k0 = 0; k0 < npad; k0 += 64, ++blk) {
-        const int buf = blk & 1;
-        if (p_uses[buf]) {  // the MMAs that read this P buffer must have retired
-          mbar_wait(bar_p + 8 * buf, ph_p[buf]);
-          ph_p[buf] ^= 1u;
-          p_uses[buf] = 0;
-        }
-        uint8_t* pb = sP + buf * (8 * 128 * 16);
-        const int kend = min(64, npad - k0);
-        for (int c0 = 0; c0 < kend; c0 += 32) {
-          uint32_t raw[32];
-          tmem_ld32(tmem_s + lane_addr + (uint32_t)(k0 + c0), raw);
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const int j0 = k0 + c0 + i;
-            float p0 = (j0 < n) ? __expf(__uint_as_float(raw[i]) - mx) : 0.0f;
-            float p1 = (j0 + 1 < n) ? __expf(__uint_as_float(raw[i + 1]) - mx) : 0.0f;
-            lsum += p0 + p1;
-            if (drop_p > 0.0f) {
-              p0 = attn_hash_tc(seed, bh, qi, j0) >= drop_thr ? p0 * drop_inv : 0.0f;
-              p1 = attn_hash_tc(seed, bh, qi, j0 + 1) >= drop_thr ? p1 * drop_inv : 0.0f;
-            }
-            __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
-            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+      for (int kc = 0; kc < npad; kc += AT_CH) {
+        const int nn = min(AT_CH, npad - kc);
+        if (!single) {  // S of this chunk again (the single-chunk case still holds it)
+          tc_fence_before();
+          __syncthreads();
+          if (warp == 0 && elect_one_sync()) {
+            tc_fence_after();
+            umma_bf16(tmem_s, desc_nosw(aQ, 128 * 16, 128), desc_nosw(aK + kc * 16, ncap * 16, 128), idesc_bf16(nn), 0u);
+            umma_commit(bar_s);
           }
-#pragma unroll
-          for (int c = 0; c < 4; ++c)  // 8 keys per 16-byte chunk: chunk (c0/8 + c), row tid
-            *reinterpret_cast<uint4*>(pb + (((c0 >> 3) + c) * 128 + tid) * 16) = make_uint4(pk[c * 4 + 0], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-        }
-        fence_proxy_async();
-        __syncthreads();
-        if (warp == 0 && elect_one_sync()) {
+          mbar_wait(bar_s, ph_s);
+          ph_s ^= 1u;
           tc_fence_after();
-          for (int kk = 0; kk < kend; kk += 16) {  // O += P[:, 16 keys] V[16 keys, :]
-            const uint32_t chunk = (uint32_t)(kk >> 3);
-            umma_bf16(tmem_o, desc_nosw(aP + buf * (8 * 128 * 16) + chunk * (128 * 16), 128 * 16, 128),
-                      desc_nosw(aV + (uint32_t)((k0 + kk) >> 3) * 256, 256, 128), idesc_bf16(16), (k0 + kk) > 0 ? 1u : 0u);
-          }
-          umma_commit(bar_p + 8 * buf);
         }
-        p_uses[buf] = 1;
+        for (int kl = 0; kl < nn; kl += 64, ++blk) {
+          const int k0 = kc + kl;
+          const int buf = blk & 1;
+          if (p_uses[buf]) {  // the MMAs that read this P buffer must have retired
+            mbar_wait(bar_p + 8 * buf, ph_p[buf]);
+            ph_p[buf] ^= 1u;
+            p_uses[buf] = 0;
+          }
+          uint8_t* pb = sP + buf * (8 * 128 * 16);
+          const int kend = min(64, nn - kl);
+          for (int c0 = 0; c0 < kend; c0 += 32) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_s + lane_addr + (uint32_t)(kl + c0), raw);
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const int j0 = k0 + c0 + i;
+              const bool in0 = j0 < n && kl + c0 + i < nn, in1 = j0 + 1 < n && kl + c0 + i + 1 < nn;  // inside the sequence AND this chunk
+              float p0 = in0 ? __expf(__uint_as_float(raw[i]) - mx) : 0.0f;
+              float p1 = in1 ? __expf(__uint_as_float(raw[i + 1]) - mx) : 0.0f;
+              lsum += p0 + p1;
+              if (drop_p > 0.0f) {
+                p0 = attn_hash_tc(seed, bh, qi, j0) >= drop_thr ? p0 * drop_inv : 0.0f;
+                p1 = attn_hash_tc(seed, bh, qi, j0 + 1) >= drop_thr ? p1 * drop_inv : 0.0f;
+              }
+              __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+              pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)  // 8 keys per 16-byte chunk: chunk (c0/8 + c), row tid
+              *reinterpret_cast<uint4*>(pb + (((c0 >> 3) + c) * 128 + tid) * 16) = make_uint4(pk[c * 4 + 0], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          __syncthreads();
+          if (warp == 0 && elect_one_sync()) {
+            tc_fence_after();
+            for (int kk = 0; kk < kend; kk += 16) {  // O += P[:, 16 keys] V[16 keys, :]
+              const uint32_t chunk = (uint32_t)(kk >> 3);
+              umma_bf16(tmem_o, desc_nosw(aP + buf * (8 * 128 * 16) + chunk * (128 * 16), 128 * 16, 128),
+                        desc_nosw(aV + (uint32_t)((k0 + kk) >> 3) * 256, 256, 128), idesc_bf16(16), (k0 + kk) > 0 ? 1u : 0u);
+            }
+            umma_commit(bar_p + 8 * buf);
+          }
+          p_uses[buf] = 1;
+        }
       }
       // ---- drain, normalise, store ----
       for (int buf = 0; buf < 2; ++buf) {
@@ -228,7 +255,7 @@ extern "C" int acb_attention_varlen_tc(const void* qkv, const int* cu_seqlens, i
                                        long long seed, void* out, void* stream) {
   ACB_CHECK(qkv && cu_seqlens && out && B > 0 && n_heads > 0, "acb_attention_varlen_tc: bad arguments");
   ACB_CHECK(dh == AT_DH, "acb_attention_varlen_tc: head dim %d unsupported (16 only)", dh);
-  ACB_CHECK(max_seqlen > 0 && max_seqlen <= 480, "acb_attention_varlen_tc: max_seqlen %d exceeds the TMEM budget (480 keys)", max_seqlen);
+  ACB_CHECK(max_seqlen > 0 && max_seqlen <= 1024, "acb_attention_varlen_tc: max_seqlen %d exceeds the shared-memory K/V budget (1024 keys)", max_seqlen);
   ACB_CHECK(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0) && (n_heads * dh) % 8 == 0, "acb_attention_varlen_tc: alignment");
   ACB_CHECK(drop_p >= 0.0f && drop_p < 1.0f, "acb_attention_varlen_tc: bad dropout");
   const int ncap = ((max_seqlen + 15) / 16) * 16;

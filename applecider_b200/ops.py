@@ -157,7 +157,7 @@ USE_TC_ATTENTION = True
 def attention_varlen(qkv, cu, B, n_heads, dh, max_seqlen, drop_p=0.0, seed=0):
     T = qkv.shape[0]
     out = torch.empty((T, n_heads * dh), dtype=qkv.dtype, device=qkv.device)
-    if qkv.dtype == torch.bfloat16 and USE_TC_ATTENTION and max_seqlen <= 480 and dh == 16:
+    if qkv.dtype == torch.bfloat16 and USE_TC_ATTENTION and max_seqlen <= 1024 and dh == 16:
         call("acb_attention_varlen_tc", qkv, cu, B, n_heads, dh, max_seqlen, drop_p, seed, out)
         return out
     call("acb_attention_varlen", qkv, dtype_tag(qkv), cu, B, n_heads, dh, max_seqlen, drop_p, seed, out)

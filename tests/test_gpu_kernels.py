@@ -322,7 +322,7 @@ def test_tower_moe_fusion_head():
     assert_close(out, ref, 1e-6, "moe_combine")
 
 
-@pytest.mark.parametrize("lens", [[1, 5, 16, 17, 33, 64, 100], [128, 129, 200, 257, 258], [300, 470, 3]])
+@pytest.mark.parametrize("lens", [[1, 5, 16, 17, 33, 64, 100], [128, 129, 200, 257, 258], [300, 470, 3], [96, 97, 112, 192, 193, 288], [700, 31]])
 def test_attention_tc_matches_reference(lens):
     """tcgen05 attention (bf16) vs fp32 torch on the same bf16-rounded q/k/v, incl. > 128 queries and > 256 keys."""
     ops = _ops()
