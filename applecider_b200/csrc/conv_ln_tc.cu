@@ -556,6 +556,126 @@ __global__ void __launch_bounds__(CLP_THREADS, 1) conv_ln_hankel_persist_kernel(
   }
 }
 
+// ---- persistent kernel for the tap form (stage 1: C_in = 64 -> 3 x 128, k = 3/31/251), same rotating TMEM layout ------
+// Sub-tile 2 (k = 251) is 251 of the 285 K blocks of a tile, so the whole LayerNorm + GELU epilogue of tile n hides
+// behind it; the separate LayerNorm kernel (1.4 ms, 6.4 GB of HBM traffic at B = 4096) disappears.
+__global__ void __launch_bounds__(CL_THREADS, 1) conv_ln_taps_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                             const __grid_constant__ CUtensorMap tmB,
+                                                                             const __grid_constant__ ConvLnArgs p, int MT) {
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  constexpr int NST = CL_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * NST + 2];
+  __shared__ uint32_t tmem_holder;
+  __shared__ float part[2][2][128][2];
+  __shared__ __align__(16) float s_bias[384], s_gamma[384], s_beta[384];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[NST]);
+  const uint32_t bar_acc = smem_u32(&bars[2 * NST]);
+  const uint32_t bar_epi = smem_u32(&bars[2 * NST + 1]);
+  const uint32_t stg_off = (uint32_t)NST * CL_STAGE_BYTES;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_epi, 8);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    const uint32_t a_box_bytes = (uint32_t)TC_BK * 2u * (uint32_t)p.Lbox * (uint32_t)p.Bbox;
+    int it = 0;
+    for (int mt = blockIdx.x; mt < MT; mt += gridDim.x) {
+      const int sample0 = (mt / p.tps) * p.Bbox, l0 = (mt % p.tps) * p.Lbox;
+      for (int jj = 0; jj < 3; ++jj) {
+        const int j = 2 - jj;
+        for (int kb = p.kb_lo[j]; kb < p.kb_hi[j]; ++kb, ++it) {
+          const int tap = kb / p.cpt, cc = kb - tap * p.cpt;
+          const int s = it % NST;
+          const uint32_t ph = (uint32_t)(it / NST) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          if (elect_one_sync()) {
+            const uint32_t sa = smem_base + s * CL_STAGE_BYTES;
+            mbar_expect_tx(bar_full + 8 * s, a_box_bytes + CL_SUB_BYTES);
+            tma_load_3d(sa, &tmA, cc * TC_BK, l0 + tap - p.pad, sample0, bar_full + 8 * s);
+            tma_load_2d(sa + CL_A_BYTES, &tmB, tap * p.Cin + cc * TC_BK, p.brow_base[j], bar_full + 8 * s);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int it = 0, n = 0;
+    for (int mt = blockIdx.x; mt < MT; mt += gridDim.x, ++n) {
+      for (int jj = 0; jj < 3; ++jj) {
+        const int j = 2 - jj;
+        if (jj == 1 && n > 0) {  // columns [0,256) are shared with the previous tile: wait for its epilogue
+          mbar_wait_sleep(bar_epi, ((uint32_t)(n - 1)) & 1u);
+          tc_fence_after();
+        }
+        const uint32_t acc = tmem_base + (j == 2 ? 256u + 128u * (uint32_t)(n & 1) : 128u * (uint32_t)j);
+        for (int kb = p.kb_lo[j]; kb < p.kb_hi[j]; ++kb, ++it) {
+          const int s = it % NST;
+          const uint32_t ph = (uint32_t)(it / NST) & 1u;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t sa = smem_base + s * CL_STAGE_BYTES;
+            const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + CL_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, IDESC, (kb > p.kb_lo[j] || k > 0) ? 1u : 0u);
+            umma_commit(bar_empty + 8 * s);
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one_sync()) umma_commit(bar_acc);
+      __syncwarp();
+    }
+  } else {
+    {
+      const int gw0 = 128 / p.ng;
+      for (int i = threadIdx.x - 64; i < 384; i += 256) {
+        const int j = i >> 7, c = i & 127;
+        s_bias[i] = __ldg(p.bias + p.brow_base[j] + c);
+        const int g = c / gw0, cc = c - g * gw0;
+        s_gamma[i] = __ldg(p.gamma + j * gw0 + cc);
+        s_beta[i] = __ldg(p.beta + j * gw0 + cc);
+      }
+      asm volatile("bar.sync 9, 256;" ::: "memory");
+    }
+    uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + stg_off + (size_t)(warp - 2) * CL_STG_BYTES;
+    int n = 0;
+    for (int mt = blockIdx.x; mt < MT; mt += gridDim.x, ++n) {
+      mbar_wait_sleep(bar_acc, (uint32_t)n & 1u);
+      tc_fence_after();
+      cl_epilogue_tile<2>(p, mt, 0, tmem_base, 256u + 128u * (uint32_t)(n & 1), s_bias, s_gamma, s_beta, part, stg, warp, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) cl_mbar_arrive(bar_epi);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 }  // namespace
 
 extern "C" int acb_spectra_conv_ln_bf16(const void* A, const void* Bw, void* out, int nbatch, int L, int Cin, int taps, int pad,
@@ -656,8 +776,16 @@ extern "C" int acb_spectra_conv_ln_bf16(const void* A, const void* Bw, void* out
       pconf = true;
     }
     conv_ln_hankel_persist_kernel<false><<<148, CLP_THREADS, psmem, (cudaStream_t)stream>>>(tmB, tmB, args, (int)MT, grid_y);
-  } else if (hankel)
+  } else if (hankel) {
     conv_ln_tc_kernel<true><<<dim3((unsigned)MT, (unsigned)grid_y), CL_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, args);
+  } else if (persist && grid_y == 1 && MT >= 148) {
+    static bool tconf = false;
+    if (!tconf) {
+      ACB_CUDA(cudaFuncSetAttribute(conv_ln_taps_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tconf = true;
+    }
+    conv_ln_taps_persist_kernel<<<148, CL_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, args, (int)MT);
+  }
   else
     conv_ln_tc_kernel<false><<<dim3((unsigned)MT, (unsigned)grid_y), CL_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, args);
   ACB_LAUNCH_CHECK();

@@ -310,3 +310,30 @@ def test_spectra_stage0_fused_downsample_matches_unfused():
     assert Lf == Lu == 1024 and zf.shape == zu.shape == (40, 1024, 64)
     assert torch.isfinite(zf.float()).all()
     assert torch.equal(zf, zu)
+
+
+def test_spectra_stage1_persistent_fused_conv_ln_close_to_unfused():
+    """Stage 1 (64 -> 3 x 128, k = 3/31/251): persistent fused conv + LayerNorm + GELU kernel (B = 40 -> 320 tiles) against the
+    conv GEMM followed by the LayerNorm kernel.  Statistics are one-pass from fp32 accumulators in the fused kernel and
+    two-pass from bf16-rounded conv outputs in the unfused path: agreement to bf16 rounding (2 ulp of the O(1) outputs)."""
+    import applecider_b200 as ab
+    from applecider_b200 import spectra as sp, synth
+
+    cfg = ab.default_config()
+    cfg["model"]["SpectraNet"]["compute_dtype"] = "bf16"
+    m = ab.SpectraNet(cfg)
+    m.load_state_dict(synth.det_state_dict(m, 0), strict=True)
+    m = m.cuda().eval()
+    x = (torch.randn(40, 1024, 64, device="cuda") * 0.7).to(torch.bfloat16)
+    blk = m.all_stages[1][0]
+    old = sp.FUSE_STAGE1
+    try:
+        with torch.no_grad():
+            sp.FUSE_STAGE1 = True
+            zf, _ = blk.forward_cl(x, 40, 1024, torch.bfloat16)
+            sp.FUSE_STAGE1 = False
+            zu, _ = blk.forward_cl(x, 40, 1024, torch.bfloat16)
+    finally:
+        sp.FUSE_STAGE1 = old
+    assert zf.shape == zu.shape == (40, 256, 128)
+    assert_close(zf, zu, 2e-2, "stage-1 fused vs unfused (after downsample + pool)")
