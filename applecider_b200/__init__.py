@@ -17,7 +17,7 @@ def __getattr__(name):
         "HyraxBaselineCLS": "photo", "MPTModel": "photo", "BaselineCLS": "photo", "Time2Vec": "photo", "FocalLoss": "photo",
         "SpectraNet": "spectra", "SpectraNetBlock": "spectra",
         "AstroMiNN": "astrominn", "SplitHeadConvNeXt": "astrominn", "ResidualTowerBlock": "astrominn", "ConvNeXtTiny": "astrominn",
-        "AppleCider": "fusion", "fusion_collate": "fusion",
+        "AppleCider": "fusion", "fusion_collate": "fusion", "SpectraClassificationB": "legacy",
     }
     if name in table:
         return getattr(importlib.import_module(f".{table[name]}", __name__), name)

@@ -535,6 +535,32 @@ __global__ void pairmax_bf16_kernel(const uint4* __restrict__ x, uint4* __restri
   }
 }
 
+// legacy spectra encoder (brew_cider.py:611-636): cat([MaxPool1d(4), AvgPool1d(4), -MaxPool1d(4)(-x)]) on channels-last fp32
+__global__ void tripool4_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int L, int C) {
+  const int Lo = L / 4;
+  const long long total = (long long)B * Lo * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long t = i / C;
+    const int lo = (int)(t % Lo);
+    const long long b = t / Lo;
+    const float* p = x + ((b * L + 4LL * lo) * C + c);
+    const float v0 = p[0], v1 = p[C], v2 = p[2LL * C], v3 = p[3LL * C];
+    float* o = y + (b * Lo + lo) * (3LL * C) + c;
+    o[0] = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+    o[C] = (((v0 + v1) + v2) + v3) * 0.25f;
+    o[2LL * C] = fminf(fminf(v0, v1), fminf(v2, v3));
+  }
+}
+
+int acb_tripool4_cl(const float* x, float* y, int B, int L, int C, void* stream) {
+  ACB_CHECK(x && y && B > 0 && L >= 4 && C > 0, "acb_tripool4_cl: bad arguments");
+  tripool4_kernel<<<grid_for((long long)B * (L / 4) * C), 256, 0, (cudaStream_t)stream>>>(x, y, B, L, C);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
 int acb_pairmax_bf16(const void* x, void* y, long long rows_out, int C, void* stream) {
   ACB_CHECK(x && y && rows_out >= 0 && C > 0 && C % 8 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0), "acb_pairmax_bf16: bad arguments");
   if (rows_out == 0) return ACB_OK;

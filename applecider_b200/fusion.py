@@ -16,7 +16,7 @@ from .spectra import SpectraNet
 class AppleCider(nn.Module):
     """forward(photometry, photometry_mask, metadata, images, spectra) -> (B, num_classes) logits."""
 
-    def __init__(self, config, hidden_dim=64, fusion="avg", num_classes=5, compute_dtype=None):
+    def __init__(self, config, hidden_dim=64, fusion="avg", num_classes=5, compute_dtype=None, spectra_variant="src"):
         super().__init__()
         if fusion not in ("avg", "concat"):
             raise NotImplementedError(fusion)
@@ -32,10 +32,18 @@ class AppleCider(nn.Module):
         self.fusion, self.hidden_dim, self.num_classes = fusion, hidden_dim, num_classes
         self.classification = True
         self.photometry_encoder = HyraxBaselineCLS(cfg)
-        self.spectra_encoder = SpectraNet(cfg)
+        self.spectra_variant = spectra_variant
+        if spectra_variant == "B":  # legacy checkpoints: variant-B encoder -> 256-d embedding (brew_cider.py:585-708,826)
+            from .legacy import SpectraClassificationB
+
+            self.spectra_encoder = SpectraClassificationB({"mode": "all", "classes": list(range(num_classes))})
+        elif spectra_variant == "src":
+            self.spectra_encoder = SpectraNet(cfg)
+        else:
+            raise ValueError(f"unknown spectra_variant {spectra_variant!r}")
         self.img_metadata_encoder = AstroMiNN(cfg)
         sc = cfg["model"]["SpectraNet"]
-        spec_out = 1 if sc["redshift"] else sc["class_order"]
+        spec_out = 256 if spectra_variant == "B" else (1 if sc["redshift"] else sc["class_order"])
         self.photometry_proj = nn.Linear(cfg["model"]["HyraxBaselineCLS"]["d_model"], hidden_dim)
         self.spectra_proj = nn.Linear(spec_out, hidden_dim)
         self.img_metadata_proj = nn.Linear(5, hidden_dim)
@@ -46,10 +54,10 @@ class AppleCider(nn.Module):
     CONCURRENT_ENCODERS = False
 
     def _encode(self, photometry, photometry_mask, metadata, images, spectra):
-        if self.CONCURRENT_ENCODERS and not torch.is_grad_enabled() and spectra.is_cuda:
+        if self.CONCURRENT_ENCODERS and not torch.is_grad_enabled() and spectra.is_cuda and self.spectra_variant == "src":
             return self._encode_concurrent(photometry, photometry_mask, metadata, images, spectra)
         p = self.photometry_encoder((photometry, photometry_mask, None))
-        s = self.spectra_encoder((spectra, None, None))
+        s = self.spectra_encoder(spectra) if self.spectra_variant == "B" else self.spectra_encoder((spectra, None, None))
         if s.dim() == 1:
             s = s[:, None].contiguous()
         im = self.img_metadata_encoder((metadata, images, None))

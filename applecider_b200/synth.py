@@ -38,6 +38,8 @@ def det_tensor(seed: int, key: str, shape, dtype=torch.float32) -> torch.Tensor:
         t = torch.randn(shape, generator=g)
     elif leaf in ("b0", "b"):
         t = 0.3 * torch.randn(shape, generator=g)
+    elif leaf == "running_var":  # BatchNorm statistics of the legacy spectra encoder: strictly positive
+        t = 0.5 + torch.rand(shape, generator=g)
     elif leaf == "weight":  # 1-D weight = a norm scale
         t = 1.0 + 0.1 * torch.randn(shape, generator=g)
     else:  # biases

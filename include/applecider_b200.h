@@ -162,6 +162,9 @@ int acb_globalmax_cl(const void* x, int dtype, float* y, int B, int L, int C, vo
 /* y[r,:] = max(x[2r,:], x[2r+1,:]) for bf16 rows of C (C % 8 == 0) channels: finishes MaxPool1d(4) after the fused stage-0
  * kernel (acb_spectra_conv_ln_bf16 with down_w) has max-ed the two positions each CTA owns. */
 int acb_pairmax_bf16(const void* x, void* y, long long rows_out, int C, void* stream);
+/* legacy spectra encoder ("variant B", _archive/notebooks/brew_cider.py:611-636): x[B,L,C] f32 channels-last ->
+ * y[B, L/4, 3C] = [max | mean | min] over windows of 4 positions (cat of MaxPool1d, AvgPool1d, -MaxPool1d(-x)). */
+int acb_tripool4_cl(const float* x, float* y, int B, int L, int C, void* stream);
 
 /* ---- metadata towers / MoE / fusion head -------------------------------------------------------- */
 /* ResidualTowerBlock (astrominn.py:44-64), eval: s = gelu(W0 x + b0); y = (W1 ln1(s) + b1) * sigmoid(W2 ln2(s) + b2)

@@ -488,3 +488,58 @@ class AppleCider(nn.Module):
         else:
             raise NotImplementedError
         return self.fc(emb)
+
+
+# --------------------------------------------------------------------------------------
+# legacy "variant B" spectra encoder
+# --------------------------------------------------------------------------------------
+class SpectraNetBlockB(nn.Module):
+    """_archive/notebooks/brew_cider.py:586-636 restated (BatchNorm in eval mode spelled out as an affine)."""
+
+    def __init__(self, in_channels, out_channels, kernel_sizes, use_skip=True, use_ln=True, do_pool=False):
+        super().__init__()
+        self.use_skip, self.use_ln, self.do_pool, self.k = use_skip, use_ln, do_pool, len(kernel_sizes)
+        self.convs = nn.ModuleList([nn.Conv1d(in_channels, out_channels, kernel_size=k, padding=k // 2) for k in kernel_sizes])
+        self.norm = nn.LayerNorm(out_channels * self.k) if use_ln else nn.BatchNorm1d(out_channels * self.k)
+        if use_skip:
+            self.proj = nn.Conv1d(in_channels, out_channels * self.k, kernel_size=1)
+
+    def forward(self, x):
+        residual = self.proj(x) if self.use_skip else None
+        y = torch.cat([c(x) for c in self.convs], dim=1)
+        if self.use_ln:
+            y = F.layer_norm(y.permute(0, 2, 1), (y.shape[1],), self.norm.weight, self.norm.bias, self.norm.eps).permute(0, 2, 1)
+        else:
+            n = self.norm
+            y = (y - n.running_mean[None, :, None]) / torch.sqrt(n.running_var[None, :, None] + n.eps) * n.weight[None, :, None] + n.bias[None, :, None]
+        if self.use_skip:
+            y = residual + y
+        y = F.gelu(y)
+        if self.do_pool:
+            y = torch.cat([F.max_pool1d(y, 4), F.avg_pool1d(y, 4), -F.max_pool1d(-y, 4)], dim=1)
+        return y
+
+
+class SpectraClassificationB(nn.Module):
+    """brew_cider.py:638-705: five stages (BatchNorm x4, LayerNorm x1), flatten (C-major), 12288 -> 2048 -> 256 [-> classes]."""
+
+    def __init__(self, config=None):
+        super().__init__()
+        config = config or {"mode": "all", "classes": list(range(5))}
+        ks = [[3, 61, 1021], [3, 31, 251], [3, 15, 61], [3, 11, 31], [3, 7, 13]]
+        ch, ln = [1, 16, 32, 64, 128, 256], [False, False, False, False, True]
+        cin = ch[0]
+        for i in range(5):
+            setattr(self, f"stage{i + 1}", nn.Sequential(SpectraNetBlockB(cin, ch[i + 1], ks[i], True, ln[i], do_pool=(i != 4))))
+            cin = ch[i + 1] * 3 * (3 if i != 4 else 1)
+        self.class_model = nn.Sequential(nn.Linear(ch[5] * 3 * 16, 2048), nn.LayerNorm(2048), nn.GELU(), nn.Dropout(0.5),
+                                         nn.Linear(2048, 256), nn.LayerNorm(256), nn.GELU(), nn.Dropout(0.3))
+        self.classification = config["mode"] == "spectra"
+        if self.classification:
+            self.fc = nn.Linear(256, len(config["classes"]))
+
+    def forward(self, x):
+        for i in range(5):
+            x = getattr(self, f"stage{i + 1}")(x)
+        out = self.class_model(x.reshape(x.size(0), -1))
+        return self.fc(out) if self.classification else out

@@ -6,6 +6,9 @@
    real reference on fresh inputs, including state_dict key/shape identity.
 3. The restated timm ConvNeXt-T is cross-checked against torchvision.models.convnext_tiny.
 """
+import os
+
+import numpy as np
 import pytest
 import torch
 
@@ -192,3 +195,17 @@ def test_oracle_mpt_vs_golden(golden_dir):
         if k.startswith("g_"):
             name = [n for n in grads if n.replace(".", "_") == k[2:]][0]
             assert_close(grads[name], g[k], 2e-4, "d " + name, atol=1e-6)
+
+
+def test_oracle_legacy_spectra_vs_golden(golden_dir):
+    """Variant-B spectra encoder restatement vs the real `build_spec_model` (tests/golden/make_golden_legacy.py), incl. key identity."""
+    from applecider_b200 import synth
+    from oracle import models as om
+
+    g = np.load(os.path.join(golden_dir, "legacy_spectra.npz"))
+    for mode in ("all", "spectra"):
+        m = om.SpectraClassificationB({"mode": mode, "classes": list(range(5))}).eval()
+        assert sorted(m.state_dict().keys()) == list(g[f"keys_{mode}"])
+        m.load_state_dict(synth.det_state_dict(m, 0))
+        with torch.no_grad():
+            assert_close(m(torch.from_numpy(g[f"x_{mode}"])), torch.from_numpy(g[f"y_{mode}"]), 1e-5, f"legacy spectra ({mode})")
