@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libapplecider_b200.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_SIGMOID, ACT_SOFTPLUS = 0, 1, 2, 3, 4, 5
 RES_NONE, RES_ADD, RES_MUL, RES_MUL_GELU_GRAD = 0, 1, 2, 3
 
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "applecider_b200.h")

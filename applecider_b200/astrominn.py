@@ -197,7 +197,7 @@ class AstroMiNN(nn.Module):
         self.nst2_tower = ResidualTowerBlock(2, th, fo)
         self.coord_tower = ResidualTowerBlock(2, th, fo)
         self.mega_tower = ResidualTowerBlock(19, 128, to)
-        self.image_tower = SplitHeadConvNeXt(pretrained=False, in_chans=3, outdims=to)
+        self.image_tower = SplitHeadConvNeXt(pretrained=False, in_chans=int(ac.get("in_chans", 3)), outdims=to)  # 4 = legacy XastroMiNN
         fusion_dims = 6 * to + 3 * fo
         self.fusion_dims = fusion_dims
         self.fusion_experts = nn.ModuleList([ResidualTowerBlock(fusion_dims, self.fusion_hidden_dims, 5) for _ in range(self.num_mlp_experts)])

@@ -131,6 +131,7 @@ __global__ void act_bwd_kernel(const void* dy, int dy_dt, const void* x, int x_d
       case ACB_ACT_GELU: d = (x_dt == ACB_BF16 && dx_dt == ACB_BF16) ? gelu_bf16_grad(v) : gelu_erf_grad(v); break;  // bf16 forward = tanh form
       case ACB_ACT_TANH: { const float t = tanhf(v); d = 1.0f - t * t; break; }
       case ACB_ACT_SIGMOID: { const float s = sigmoidf_(v); d = s * (1.0f - s); break; }
+      case ACB_ACT_SOFTPLUS: d = v > 20.0f ? 1.0f : sigmoidf_(v); break;
       default: d = 1.0f;
     }
     st_any(dx, i, dx_dt, g * d);

@@ -115,6 +115,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case ACB_ACT_GELU: return gelu_erf(v);
     case ACB_ACT_TANH: return tanhf(v);
     case ACB_ACT_SIGMOID: return sigmoidf_(v);
+    case ACB_ACT_SOFTPLUS: return v > 20.0f ? v : log1pf(expf(v));
     default: return v;
   }
 }

@@ -133,3 +133,27 @@ class SpectraClassificationB(nn.Module):
         if self.classification:
             z = ops.gemm(z, self.fc.weight, self.fc.bias)
         return z
+
+
+def XastroMiNN(config=None, **kw):
+    """Legacy 4-channel image+metadata classifier (_archive/notebooks/brew_cider.py:438-582): the src AstroMiNN architecture with
+    `in_chans=4` cutouts and the call signature forward(metadata, image).  Returns an AstroMiNN whose `forward` also accepts the
+    two-argument legacy form; state_dict keys are identical to the archive (`image_tower.backbone.stem.0.weight` is (96,4,4,4))."""
+    import copy
+
+    from .astrominn import AstroMiNN
+    from .config import default_config
+
+    cfg = copy.deepcopy(config) if config is not None else default_config()
+    cfg["model"]["AstroMiNN"]["in_chans"] = 4
+    cfg["model"]["AstroMiNN"].update(kw)
+    model = AstroMiNN(cfg)
+    tuple_forward = model.forward
+
+    def forward(metadata, image=None):
+        if image is None and isinstance(metadata, (tuple, list)):
+            return tuple_forward(metadata)
+        return tuple_forward((metadata, image, None))
+
+    model.forward = forward
+    return model

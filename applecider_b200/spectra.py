@@ -306,6 +306,11 @@ class SpectraNet(nn.Module):
             z = ops.gemm(ops.cast(feat, dtype), w0, head[0].bias, out_dtype=torch.float32)
         z = ops.layernorm(z, head[1].weight, head[1].bias, head[1].eps, post_act=ops.ACT_GELU)
         out = ops.gemm(z, head[4].weight, head[4].bias)
+        if self.redshift and self.config["model"]["SpectraNet"].get("redshift_softplus", False):
+            # archived redshift regressor ends in F.softplus (_archive/AppleCider/models/SpectraNetRedshift.py:112)
+            sp = torch.empty_like(out)
+            ops.call("acb_act_fwd", out, 0, sp, 0, ops.ACT_SOFTPLUS, out.numel())
+            out = sp
         return out.squeeze(1) if self.redshift else out
 
     def train_step(self, batch):

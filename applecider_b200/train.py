@@ -258,6 +258,8 @@ def spectra_forward_train(model, x):
     z = fn.layernorm(z, head[1].weight, head[1].bias, head[1].eps, post_act=ops.ACT_GELU)
     z = fn.dropout(z, head[3].p, tr)
     out = fn.linear(z, head[4].weight, head[4].bias)
+    if model.redshift and model.config["model"]["SpectraNet"].get("redshift_softplus", False):
+        out = fn.act(out, ops.ACT_SOFTPLUS)
     return out.squeeze(1) if model.redshift else out
 
 

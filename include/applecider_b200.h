@@ -33,6 +33,7 @@ extern "C" {
 #define ACB_ACT_GELU 2 /* exact erf GELU (torch F.gelu default) */
 #define ACB_ACT_TANH 3
 #define ACB_ACT_SIGMOID 4
+#define ACB_ACT_SOFTPLUS 5 /* log(1 + exp(x)), linear above 20 like torch (legacy redshift head, SpectraNetRedshift.py:112) */
 
 #define ACB_RES_NONE 0
 #define ACB_RES_ADD 1 /* C = res + gamma[n] * v   (gamma may be NULL = 1) */

@@ -422,7 +422,7 @@ class AstroMiNN(nn.Module):
         self.nst2_tower = ResidualTowerBlock(2, th, fo)
         self.coord_tower = ResidualTowerBlock(2, th, fo)
         self.mega_tower = ResidualTowerBlock(19, 128, to)
-        self.image_tower = SplitHeadConvNeXt(pretrained=False, in_chans=3, outdims=to)
+        self.image_tower = SplitHeadConvNeXt(pretrained=False, in_chans=int(ac.get("in_chans", 3)), outdims=to)  # 4 = legacy XastroMiNN
         fd = 6 * to + 3 * fo
         self.fusion_experts = nn.ModuleList([ResidualTowerBlock(fd, ac["fusion_hidden_dims"], 5) for _ in range(ac["num_mlp_experts"])])
         self.fusion_router = nn.Sequential(nn.Linear(fd, fd // 2), nn.Tanh(), nn.Dropout(0.3), nn.Linear(fd // 2, ac["num_mlp_experts"]), nn.Sigmoid())
