@@ -56,10 +56,19 @@ class AppleCider(nn.Module):
     def _encode(self, photometry, photometry_mask, metadata, images, spectra):
         if self.CONCURRENT_ENCODERS and not torch.is_grad_enabled() and spectra.is_cuda and self.spectra_variant == "src":
             return self._encode_concurrent(photometry, photometry_mask, metadata, images, spectra)
-        p = self.photometry_encoder((photometry, photometry_mask, None))
+        if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
+            p = self.photometry_encoder((photometry, photometry_mask, None))
+            packed = None
+        else:
+            # launch order matters on one stream: the packing plan needs one host read, so it goes FIRST; then the spectra encoder
+            # (20 long kernels, ~70 % of the step) is enqueued, and the ~100 short photometry / ConvNeXt / tower launches are
+            # queued while the GPU is busy with it instead of being issued one by one to an idle device
+            packed = self.photometry_encoder.pack(photometry_mask)
         s = self.spectra_encoder(spectra) if self.spectra_variant == "B" else self.spectra_encoder((spectra, None, None))
         if s.dim() == 1:
             s = s[:, None].contiguous()
+        if packed is not None:
+            p = self.photometry_encoder.encode(photometry, photometry_mask, packed=packed)
         im = self.img_metadata_encoder((metadata, images, None))
         return p, im, s
 

@@ -41,18 +41,27 @@ class _PhotoEncoderBase(nn.Module):
             return p
         return self._derived.get(("cast", id(p)), (p,), lambda: ops.cast(p.detach().contiguous(), dtype))
 
-    def encode_tokens(self, data, pad, dtype, total_tokens=None):
+    def pack(self, pad, total_tokens=None):
+        """Varlen packing plan of a key-padding mask: (cu_seqlens, src_idx, T).  Reads ONE integer back from the device (the
+        packed token count) unless total_tokens is given; callers that have other work to enqueue first (the fusion model:
+        the spectra encoder) call this early so that nothing else stalls on that read."""
+        if not pad.is_cuda:
+            raise RuntimeError("applecider_b200: inputs must be CUDA tensors (no CPU fallback)")
+        pad = pad.contiguous()
+        if pad.dtype != torch.bool:
+            pad = pad != 0
+        cu, src = ops.photo_compact(pad)
+        T = int(cu[-1].item()) if total_tokens is None else int(total_tokens)
+        return cu, src, T
+
+    def encode_tokens(self, data, pad, dtype, total_tokens=None, packed=None):
         """Returns (h [T,D] packed tokens after the last layer, cu_seqlens)."""
         if not data.is_cuda:
             raise RuntimeError("applecider_b200: inputs must be CUDA tensors (no CPU fallback)")
         B, L, F = data.shape
         assert F == 7
         data = data.contiguous().float()
-        pad = pad.contiguous()
-        if pad.dtype != torch.bool:
-            pad = pad != 0
-        cu, src = ops.photo_compact(pad)
-        T = int(cu[-1].item()) if total_tokens is None else int(total_tokens)
+        cu, src, T = packed if packed is not None else self.pack(pad, total_tokens)
         D = self.d_model
         t2v = self.time2vec
         h = ops.photo_embed(data, src, T, D, self.in_proj.weight, self.in_proj.bias, t2v.w0, t2v.b0, t2v.w, t2v.b,
@@ -104,8 +113,8 @@ class HyraxBaselineCLS(_PhotoEncoderBase):
             self.load_state_dict(torch.load(path), strict=False)
             print(f"Loaded pretrained weights from {path}")
 
-    def encode(self, data, pad, total_tokens=None):
-        h, cu = self.encode_tokens(data, pad, self.compute_dtype, total_tokens)
+    def encode(self, data, pad, total_tokens=None, packed=None):
+        h, cu = self.encode_tokens(data, pad, self.compute_dtype, total_tokens, packed)
         cls = ops.gather_cls(h, cu, data.shape[0])
         return ops.layernorm(cls, self.norm.weight, self.norm.bias, self.norm.eps)
 
