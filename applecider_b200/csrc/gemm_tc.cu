@@ -85,13 +85,30 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& p, bool have_acc,
           v[g * 4 + 0] += t.x; v[g * 4 + 1] += t.y; v[g * 4 + 2] += t.z; v[g * 4 + 3] += t.w;
         }
       }
-      uint32_t pre_pk[16];
-      if (p.pre_out) {  // warp-uniform
+      if (p.pre_out) {  // warp-uniform.  Stored right away: keeping 16 packed registers live across the activation / residual
+                        // code cost 43 registers per thread and one resident CTA per SM (ConvNeXt fc1 0.40 -> 0.54 ms)
+        uint8_t* sb = reinterpret_cast<uint8_t*>(stg);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-          pre_pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+            w4[e] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(sb + lane * 80 + j * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
+        __syncwarp();
+        const int piece = lane & 3, r8 = lane >> 2;
+        uint8_t* pbase = reinterpret_cast<uint8_t*>(p.pre_out) + ((size_t)out_col + piece * 8) * 2;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + r8;
+          const long long orow = __shfl_sync(0xffffffffu, out_row, rr);
+          if ((wmask >> rr) & 1u)
+            *reinterpret_cast<uint4*>(pbase + (size_t)orow * p.ldc * 2) = *reinterpret_cast<const uint4*>(sb + rr * 80 + piece * 16);
+        }
+        __syncwarp();
       }
       switch (p.act) {  // warp-uniform: one branch per 32-column chunk, not per element
         case ACB_ACT_RELU:
@@ -224,21 +241,6 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& p, bool have_acc,
             *reinterpret_cast<uint4*>(cbase + (size_t)orow * p.ldc * 2) = *reinterpret_cast<const uint4*>(sb + rr * 80 + piece * 16);
         }
         __syncwarp();
-        if (p.pre_out) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(sb + lane * 80 + j * 16) = make_uint4(pre_pk[4 * j], pre_pk[4 * j + 1], pre_pk[4 * j + 2], pre_pk[4 * j + 3]);
-          __syncwarp();
-          uint8_t* pbase = reinterpret_cast<uint8_t*>(p.pre_out) + ((size_t)out_col + piece * 8) * 2;
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rr = it * 8 + r8;
-            const long long orow = __shfl_sync(0xffffffffu, out_row, rr);
-            if ((wmask >> rr) & 1u)
-              *reinterpret_cast<uint4*>(pbase + (size_t)orow * p.ldc * 2) = *reinterpret_cast<const uint4*>(sb + rr * 80 + piece * 16);
-          }
-          __syncwarp();
-        }
       } else if (cvec) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = v[i];
