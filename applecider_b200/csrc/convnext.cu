@@ -21,6 +21,29 @@ __global__ void patchify_kernel(const float* __restrict__ img, int B, int Cin, i
   }
 }
 
+// p = 4, bf16 output (the ConvNeXt stem): one thread per (pixel, channel, ky) moves 4 kx values -- consecutive threads walk
+// (ci, ky) so a warp writes contiguous 8-byte pieces of the patch rows (the per-element kernel above is 6x off the HBM bound)
+__global__ void __launch_bounds__(256) patchify4_bf16_kernel(const float* __restrict__ img, int B, int Cin, int H, int W, bf16* __restrict__ out) {
+  const int Ho = H / 4, Wo = W / 4, G = Cin * 4;  // (ci, ky) groups per pixel
+  const long long total = (long long)B * Ho * Wo * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long m = i / G;
+    const int ox = (int)(m % Wo);
+    const long long t = m / Wo;
+    const int oy = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const int ci = g >> 2, ky = g & 3;
+    const float* src = img + (((long long)b * Cin + ci) * H + (oy * 4 + ky)) * W + ox * 4;
+    const float v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3);
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&h0);
+    o.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(out + m * (Cin * 16) + g * 4) = o;
+  }
+}
+
 // One CTA per (image, output row). Input rows oy-3..oy+3 are staged in shared memory (fp32, zero
 // padded), every thread produces (ox, c) outputs, then one warp per pixel applies LayerNorm over C.
 template <typename T>
@@ -351,6 +374,8 @@ int acb_patchify_nchw(const float* img, int B, int Cin, int H, int W, int p, voi
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == ACB_F32)
     patchify_kernel<float><<<grid_for(n), 256, 0, st>>>(img, B, Cin, H, W, p, (float*)out);
+  else if (p == 4 && ((uintptr_t)out % 8 == 0))
+    patchify4_bf16_kernel<<<grid_for(n / 4), 256, 0, st>>>(img, B, Cin, H, W, (bf16*)out);
   else
     patchify_kernel<bf16><<<grid_for(n), 256, 0, st>>>(img, B, Cin, H, W, p, (bf16*)out);
   ACB_LAUNCH_CHECK();

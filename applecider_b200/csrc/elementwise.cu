@@ -281,14 +281,15 @@ int launch_ln(const void* x, const void* res, const float* w, const float* b, vo
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
   const bool vec = (C % 4 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)w | (uintptr_t)b) % 16 == 0);
   if constexpr (sizeof(TX) == 2 && sizeof(TY) == 2) {
-    if (vec && !res && !pre_gelu && rows >= 65536 && (C == 128 || C == 256 || C == 384 || C == 768 || C == 1536)) {
+    if (vec && !res && !pre_gelu && rows >= 65536 && (C == 128 || C == 256 || C == 384 || C == 768 || C == 1536 || C == 3072)) {
       constexpr int RPW = 4;
       const unsigned g = (unsigned)((rows + (long long)wpb * RPW - 1) / ((long long)wpb * RPW));
       if (C == 128) layernorm_stream_kernel<1, 8><<<(unsigned)((rows + wpb * 8LL - 1) / (wpb * 8LL)), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
       else if (C == 256) layernorm_stream_kernel<2, RPW><<<g, wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
       else if (C == 384) layernorm_stream_kernel<3, RPW><<<g, wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
       else if (C == 768) layernorm_stream_kernel<6, 2><<<(unsigned)((rows + wpb * 2LL - 1) / (wpb * 2LL)), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
-      else layernorm_stream_kernel<12, 1><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
+      else if (C == 1536) layernorm_stream_kernel<12, 1><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
+      else layernorm_stream_kernel<24, 1><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
       ACB_LAUNCH_CHECK();
       acb_count_launch();
       return ACB_OK;
