@@ -322,6 +322,59 @@ __global__ void __launch_bounds__(256) ln_patch2_kernel(const T* __restrict__ x,
   for (int c = lane; c < C; c += 32) o[c] = from_f<T>((to_f<T>(v[c]) - mean) * rstd * ln_w[c] + ln_b[c]);
 }
 
+// bf16 fast path: a warp owns PPW consecutive pixels and loads all of them (C/32 values per lane each) before the first
+// reduction -- one pixel per warp left this kernel latency / CTA-launch bound at 7x the HBM time.
+template <int NPL, int PPW>
+__global__ void __launch_bounds__(256) ln_patch2_stream_kernel(const bf16* __restrict__ x, const float* __restrict__ ln_w,
+                                                               const float* __restrict__ ln_b, float eps, bf16* __restrict__ out,
+                                                               int B, int H, int W) {
+  constexpr int C = NPL * 32;
+  const int Ho = H / 2, Wo = W / 2;
+  const int lane = threadIdx.x & 31;
+  const long long pix0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PPW;
+  const long long total = (long long)B * Ho * 2 * Wo * 2;
+  if (pix0 >= total) return;
+  float v[PPW][NPL];
+  long long obase[PPW];
+#pragma unroll
+  for (int pp = 0; pp < PPW; ++pp) {
+    const long long pix = pix0 + pp < total ? pix0 + pp : total - 1;
+    const int ix = (int)(pix % (Wo * 2));
+    const long long t = pix / (Wo * 2);
+    const int iy = (int)(t % (Ho * 2));
+    const int b = (int)(t / (Ho * 2));
+    const bf16* src = x + (((long long)b * H + iy) * W + ix) * C;
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) v[pp][k] = __bfloat162float(src[lane + 32 * k]);
+    obase[pp] = (((long long)b * Ho + (iy >> 1)) * Wo + (ix >> 1)) * (4LL * C) + ((iy & 1) * 2 + (ix & 1)) * C;
+  }
+  float wv[NPL], bv[NPL];
+#pragma unroll
+  for (int k = 0; k < NPL; ++k) {
+    wv[k] = ln_w[lane + 32 * k];
+    bv[k] = ln_b[lane + 32 * k];
+  }
+#pragma unroll
+  for (int pp = 0; pp < PPW; ++pp) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) s += v[pp][k];
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+      const float d = v[pp][k] - mean;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    if (pix0 + pp < total) {
+      bf16* o = out + obase[pp];
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) o[lane + 32 * k] = __float2bfloat16_rn((v[pp][k] - mean) * rstd * wv[k] + bv[k]);
+    }
+  }
+}
+
 // CTA per image: mean over HW per channel, then LayerNorm over C
 template <typename T>
 __global__ void __launch_bounds__(256) gap_ln_kernel(const T* __restrict__ x, const float* __restrict__ ln_w,
@@ -416,6 +469,16 @@ int acb_ln_patch2(const void* x, int dtype, const float* ln_w, const float* ln_b
   const long long pix = (long long)B * (H / 2) * 2 * (W / 2) * 2;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((pix + 7) / 8);
+  if (dtype == ACB_BF16 && (C == 96 || C == 192 || C == 384)) {
+    constexpr int PPW = 4;
+    const unsigned g4 = (unsigned)((pix + 8 * PPW - 1) / (8 * PPW));
+    if (C == 96) ln_patch2_stream_kernel<3, PPW><<<g4, 256, 0, st>>>((const bf16*)x, ln_w, ln_b, eps, (bf16*)out, B, H, W);
+    else if (C == 192) ln_patch2_stream_kernel<6, PPW><<<g4, 256, 0, st>>>((const bf16*)x, ln_w, ln_b, eps, (bf16*)out, B, H, W);
+    else ln_patch2_stream_kernel<12, PPW><<<g4, 256, 0, st>>>((const bf16*)x, ln_w, ln_b, eps, (bf16*)out, B, H, W);
+    ACB_LAUNCH_CHECK();
+    acb_count_launch();
+    return ACB_OK;
+  }
   if (dtype == ACB_F32)
     ln_patch2_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ln_w, ln_b, eps, (float*)out, B, H, W, C);
   else
