@@ -337,3 +337,26 @@ def test_spectra_stage1_persistent_fused_conv_ln_close_to_unfused():
         sp.FUSE_STAGE1 = old
     assert zf.shape == zu.shape == (40, 256, 128)
     assert_close(zf, zu, 2e-2, "stage-1 fused vs unfused (after downsample + pool)")
+
+
+def test_fusion_concurrent_encoder_streams_match_single_stream():
+    """Opt-in three-stream inference (AppleCider.CONCURRENT_ENCODERS) returns the single-stream logits bit for bit."""
+    import applecider_b200 as ab
+    from applecider_b200 import synth
+
+    model = ab.AppleCider(ab.default_config(), hidden_dim=64, fusion="avg", compute_dtype="bf16")
+    model.load_state_dict(synth.det_state_dict(model, 0), strict=True)
+    model = model.cuda().eval()
+    B = 6
+    x, pad, _ = synth.photometry_batch(B, seed=61)
+    args = [t.cuda() for t in (x, pad, synth.metadata(B, seed=61), synth.cutouts(B, seed=61), synth.spectra(B, seed=61, L=4096))]
+    with torch.no_grad():
+        ref = model(*args).clone()
+        try:
+            model.CONCURRENT_ENCODERS = True
+            for _ in range(3):
+                got = model(*args)
+            torch.cuda.synchronize()
+        finally:
+            model.CONCURRENT_ENCODERS = False
+    assert torch.equal(got, ref)
