@@ -1,0 +1,119 @@
+"""Parity at BASELINE.json's headline size (fusion inference, B = 4096 alerts, bf16) through size-independent properties:
+
+* alerts are independent: the logits of an alert do not depend on which batch it is in (a chunk of 48 alerts run alone takes
+  the small-batch kernels -- per-tile conv+LN, unfused downsample, cached LayerNorm -- the full batch the persistent / fused /
+  streaming ones) and a permutation of the alerts permutes the logits;
+* a random subsample of the 4096 alerts is checked against the CPU oracle (fp32 reference arithmetic) within the bf16 bound,
+  with argmax agreement on margin-filtered rows;
+* the streaming API returns the same logits as forward().
+The oracle is only evaluated on the subsample (seconds on the host cores)."""
+import pytest
+import torch
+
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+B_FULL = 4096
+BF16_TOL = 3e-2
+
+
+@pytest.fixture(scope="module")
+def full():
+    import applecider_b200 as ab
+    from applecider_b200 import synth
+
+    model = ab.AppleCider(ab.default_config(), hidden_dim=64, fusion="avg", compute_dtype="bf16")
+    sd = synth.det_state_dict(model, 0)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    x, pad, _ = synth.photometry_batch(B_FULL, seed=1337)
+    host = (x, pad, synth.metadata(B_FULL, seed=1337), synth.cutouts(B_FULL, seed=1337), synth.spectra(B_FULL, seed=1337, L=4096))
+    dev = tuple(t.to(DEV) for t in host)
+    with torch.no_grad():
+        logits = model(*dev).float()
+    return model, sd, host, dev, logits
+
+
+def test_full_batch_is_finite_and_spread(full):
+    _, _, _, _, logits = full
+    assert logits.shape == (B_FULL, 5) and torch.isfinite(logits).all()
+    assert logits.std(0).min() > 1e-3, "logits do not depend on the input"
+
+
+def test_alerts_are_independent_of_their_batch(full):
+    model, _, _, dev, logits = full
+    idx = torch.arange(100, 148, device=DEV)
+    with torch.no_grad():
+        small = model(*[t[idx].contiguous() for t in dev]).float()
+    # different kernels (persistent vs per-tile, fused vs unfused downsample) but the same bf16 operands and accumulation order
+    assert_close(small, logits[idx], 2e-3, "chunk of 48 alerts vs the same alerts inside the batch of 4096")
+
+
+def test_permuting_alerts_permutes_logits(full):
+    model, _, _, dev, logits = full
+    g = torch.Generator(device="cpu").manual_seed(5)
+    perm = torch.randperm(B_FULL, generator=g).to(DEV)
+    with torch.no_grad():
+        out = model(*[t[perm].contiguous() for t in dev]).float()
+    assert_close(out, logits[perm], 2e-3, "permutation equivariance at B=4096")
+
+
+def test_subsample_of_the_full_batch_matches_the_cpu_oracle(full):
+    from oracle import models as om
+
+    _, sd, host, _, logits = full
+    oracle = om.AppleCider(om.default_config(), hidden_dim=64, fusion="avg").eval()
+    oracle.load_state_dict(sd)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    idx = torch.randperm(B_FULL, generator=g)[:24]
+    with torch.no_grad():
+        ref = oracle(*[t[idx] for t in host])
+    got = logits[idx.to(DEV)].cpu()
+    assert_close(got, ref, BF16_TOL, "24 random alerts of the 4096 batch vs the CPU oracle")
+    top2 = ref.topk(2, -1).values
+    keep = (top2[:, 0] - top2[:, 1]) > 2 * BF16_TOL * max(1.0, ref.abs().max().item())
+    assert (got.argmax(-1)[keep] == ref.argmax(-1)[keep]).all()
+
+
+def test_streaming_api_equals_forward_at_full_size(full):
+    model, _, host, _, logits = full
+    pinned = tuple(t.pin_memory() for t in host)
+    outs = [o.clone() for o in model.predict_batches([pinned, pinned])]
+    assert len(outs) == 2
+    for o in outs:
+        assert torch.equal(o, logits.cpu())
+
+
+def test_training_gradients_are_linear_in_the_batch_at_b512():
+    """BASELINE configs[3] size (512 alerts per GPU): with dropout off, the gradient of the mean loss over the batch equals the
+    average of the gradients over its two halves -- the invariant data-parallel training relies on.  Exercises the split-K
+    tcgen05 wgrads, tower groups and fused epilogues at full size; bf16 path: cosine >= 0.999 per large tensor."""
+    import applecider_b200 as ab
+    from applecider_b200 import fn, synth
+
+    B = 512
+    model = ab.AppleCider(ab.default_config(), hidden_dim=64, fusion="avg", compute_dtype="bf16")
+    model.load_state_dict(synth.det_state_dict(model, 0), strict=True)
+    model = model.to(DEV).eval()  # eval + autograd: deterministic (no dropout)
+    x, pad, _ = synth.photometry_batch(B, seed=3)
+    data = [t.to(DEV) for t in (x, pad, synth.metadata(B, seed=3), synth.cutouts(B, seed=3), synth.spectra(B, seed=3, L=4096))]
+    tgt = torch.nn.functional.one_hot(synth.labels(B, seed=3), 5).float().to(DEV)
+
+    def grads(sl):
+        model.zero_grad(set_to_none=True)
+        out = model(*[t[sl].contiguous() for t in data])
+        fn.soft_cross_entropy(out, tgt[sl].contiguous()).backward()
+        return {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    full = grads(slice(0, B))
+    a, b = grads(slice(0, B // 2)), grads(slice(B // 2, B))
+    checked = 0
+    for n, g in full.items():
+        if g.numel() < 4096 or g.abs().max() < 1e-7:
+            continue
+        avg = 0.5 * (a[n] + b[n])
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), avg.flatten(), dim=0).item()
+        assert cos >= 0.999, f"{n}: cosine {cos:.5f}"
+        checked += 1
+    assert checked > 60
