@@ -278,11 +278,14 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& p, bool have_acc,
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+// MSUB = 2: one CTA owns TWO 128-row sub-tiles that share every weight tile (B is fetched and read from shared memory once
+// per 256 output rows): 25 % less operand traffic per FLOP for the long-K SpectraNet convolutions.
+template <int BN, int STAGES, int MSUB = 1>
 __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ TcArgs p) {
-  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
+  constexpr uint32_t A_SUB_BYTES = TC_BM * TC_BK * 2;
+  constexpr uint32_t A_BYTES = MSUB * A_SUB_BYTES;
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   __shared__ __align__(16) float s_bias[BN], s_gamma[BN];  // staged by the epilogue warps while the main loop runs
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x, nt = blockIdx.y;
+  const int mt = blockIdx.x * MSUB, nt = blockIdx.y;  // first 128-row sub-tile of this CTA (MSUB > 1: p.tps % MSUB == 0)
   const int n0 = nt * BN;
 
   const int sample0 = (mt / p.tps) * p.Bbox;
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
-                 "r"((uint32_t)tmem_cols<BN>())
+                 "r"((uint32_t)tmem_cols<MSUB * BN>())
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -344,8 +347,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         const int tap = kb / p.cpt, cc = kb - tap * p.cpt;
         const uint32_t sa = smem_base + s * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
-        mbar_expect_tx(bar_full + 8 * s, a_box_bytes + B_BYTES);
-        tma_load_3d(sa, &tmA, cc * TC_BK, l0 + tap - p.pad, sample0, bar_full + 8 * s);
+        mbar_expect_tx(bar_full + 8 * s, MSUB * a_box_bytes + B_BYTES);
+#pragma unroll
+        for (int sub = 0; sub < MSUB; ++sub)
+          tma_load_3d(sa + sub * A_SUB_BYTES, &tmA, cc * TC_BK, l0 + sub * TC_BM + tap - p.pad, sample0, bar_full + 8 * s);
         tma_load_2d(sb, &tmB, tap * p.Cin + cc * TC_BK, n0, bar_full + 8 * s);
       }
       __syncwarp();
@@ -360,9 +365,14 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
       if (elect_one_sync()) {
         const uint32_t sa = smem_base + s * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
-        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+        const uint64_t db = make_smem_desc(sb);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+        for (int sub = 0; sub < MSUB; ++sub) {
+          const uint64_t da = make_smem_desc(sa + sub * A_SUB_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(tmem_base + (uint32_t)(sub * BN), da + 2 * k, db + 2 * k, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit(bar_empty + 8 * s);  // frees the smem stage once these MMAs retire
       }
       __syncwarp();
@@ -384,22 +394,25 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
       tc_fence_after();
     }
     float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + (warp - 2) * (32 * 33);
-    tc_epilogue_tile<BN>(p, nkb > 0, tmem_base, mt, nt, stg, s_bias, s_gamma, warp, lane);
+#pragma unroll 1
+    for (int sub = 0; sub < MSUB; ++sub)
+      tc_epilogue_tile<BN>(p, nkb > 0, tmem_base + (uint32_t)(sub * BN), mt + sub, nt, stg, s_bias, s_gamma, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols<BN>()) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols<MSUB * BN>()) : "memory");
   }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MSUB = 1>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, dim3 grid, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024;
-  auto k = gemm_tc_kernel<BN, STAGES>;
+  constexpr size_t smem = (size_t)STAGES * (MSUB * TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024;
+  auto k = gemm_tc_kernel<BN, STAGES, MSUB>;
+  if (MSUB > 1) grid.x /= MSUB;
   static bool configured = false;
   if (!configured) {
     ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -830,6 +843,23 @@ extern "C" int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype
       case 128: return launch_tc_persist<128, 2>(tmA, tmB, args, MT, NT, st);
       default: return launch_tc_persist<256, 2>(tmA, tmB, args, MT, NT, st);
     }
+  }
+  // long-K convolutions with whole 256-row blocks per sample: two M sub-tiles per CTA share the weight tiles
+  static int msub2 = -1, msub2_256 = -1;
+  if (msub2 < 0) {
+    const char* e = getenv("ACB_GEMM_MSUB2");
+    msub2 = e ? atoi(e) : 2;  // measured (stage 1, B=4096): 2 stages x 2 CTAs/SM 14.5 ms, 3 stages x 1 CTA/SM 16.7 ms, MSUB=1 16.9 ms
+    const char* e2 = getenv("ACB_GEMM_MSUB2_256");
+    msub2_256 = e2 ? atoi(e2) : 0;  // BN = 256 (stage 2) needs all 512 TMEM columns -> one CTA/SM: measured slower in the step (4.48 vs 4.14 ms)
+  }
+  const bool msub_ok = !short_k && max_kb >= 16 && args.Bbox == 1 && args.tps % 2 == 0 && L % 256 == 0 && !m_valid_dev;
+  if (msub2 && bn == 128 && msub_ok) {
+    if (msub2 == 2) return launch_tc<128, 2, 2>(tmA, tmB, args, grid, st);
+    return launch_tc<128, 3, 2>(tmA, tmB, args, grid, st);
+  }
+  if (msub2_256 && bn == 256 && msub_ok) {
+    if (msub2_256 == 2) return launch_tc<256, 2, 2>(tmA, tmB, args, grid, st);
+    return launch_tc<256, 3, 2>(tmA, tmB, args, grid, st);
   }
   switch (bn) {
     case 64: return short_k ? launch_tc<64, 2>(tmA, tmB, args, grid, st) : launch_tc<64, 4>(tmA, tmB, args, grid, st);
