@@ -261,13 +261,13 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
-                "kernel": "gemm_tc_kernel<128,3> — SpectraNet stage-1 multi-kernel Conv1d(64->3x128, k=3/31/251) implicit GEMM (tcgen05)",
+                "kernel": "gemm_tc_kernel<128,2,2> — SpectraNet stage-1 multi-kernel Conv1d(64->3x128, k=3/31/251) implicit GEMM (tcgen05, two 128-row sub-tiles per CTA)",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "kernel_ms": k_ms, "algorithmic_flops_per_launch": FLOPS_SPECTRA_STAGE1_CONV * B,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at B=4096 from one `ncu --set full` capture
-                # (profiles/r1_ncu_full_stage1_conv_gemm_tc_128_3.csv): 1.62 GB + 3.18 GB; algorithmic bytes 3.76 GB
-                "traffic": (4.797e9 if B == 4096 else None), "traffic_unit": "bytes/launch",
+                # (profiles/r1_ncu_full_stage1_conv_gemm_tc_128_2_msub2.csv): 1.62 GB + 3.18 GB; algorithmic bytes 3.76 GB
+                "traffic": (4.796e9 if B == 4096 else None), "traffic_unit": "bytes/launch",
                 "region_ms": {k: float(np.mean(v)) for k, v in regions.items()},
             },
         }
