@@ -857,6 +857,15 @@ extern "C" int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype
     if (msub2 == 2) return launch_tc<128, 2, 2>(tmA, tmB, args, grid, st);
     return launch_tc<128, 3, 2>(tmA, tmB, args, grid, st);
   }
+  static int msub2_64 = -1;
+  if (msub2_64 < 0) {
+    const char* e3 = getenv("ACB_GEMM_MSUB2_64");
+    msub2_64 = e3 ? atoi(e3) : 2;  // stage-1 dgrad (N = 64): -0.2 ms per training step
+  }
+  if (msub2_64 && bn == 64 && msub_ok) {
+    if (msub2_64 == 2) return launch_tc<64, 2, 2>(tmA, tmB, args, grid, st);
+    return launch_tc<64, 3, 2>(tmA, tmB, args, grid, st);
+  }
   if (msub2_256 && bn == 256 && msub_ok) {
     if (msub2_256 == 2) return launch_tc<256, 2, 2>(tmA, tmB, args, grid, st);
     return launch_tc<256, 3, 2>(tmA, tmB, args, grid, st);
