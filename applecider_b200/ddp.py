@@ -31,14 +31,64 @@ class FlatGradSync:
         self.flat = torch.zeros(numel, dtype=dt, device=dev)
         self.numel = numel
         self._rebind()
+        self._buckets = None  # see enable_overlap()
+
+    # ---- bucketed all-reduce overlapped with the backward pass --------------------------------------------------
+    def enable_overlap(self, bucket_elems: int = 16 * 1024 * 1024) -> "FlatGradSync":
+        """Split the flat buffer into contiguous buckets of about `bucket_elems` gradients; a bucket's all-reduce starts from
+        the post-accumulate hook of its last parameter, i.e. while autograd is still producing the other buckets
+        (NCCL orders the collective after the gradient kernels enqueued so far).  sync() then only waits / finishes the
+        buckets whose parameters received no gradient.  Buckets are contiguous slices: still no pack / unpack copies."""
+        bounds, start, acc = [], 0, 0
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            acc += p.numel()
+            last = i == len(self.params) - 1
+            if acc >= bucket_elems or last:
+                end = self.numel if last else self.offsets[i + 1]
+                bounds.append((start, end))
+                start, acc = end, 0
+        self._buckets = [dict(lo=lo, hi=hi, need=0, seen=0, work=None, done=False) for lo, hi in bounds]
+        self._bucket_of = {}
+        for p, off in zip(self.params, self.offsets):
+            b = next(i for i, bk in enumerate(self._buckets) if bk["lo"] <= off < bk["hi"])
+            self._bucket_of[id(p)] = b
+            self._buckets[b]["need"] += 1
+            p.register_post_accumulate_grad_hook(self._on_grad)
+        return self
+
+    def _launch(self, bk) -> None:
+        w = self.world_size
+        if w == 1:
+            bk["done"] = True
+            return
+        view = self.flat[bk["lo"]: bk["hi"]]
+        if self.flat.is_cuda:
+            bk["work"] = dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        else:  # gloo has no AVG
+            bk["work"] = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        bk["done"] = True
+
+    def _on_grad(self, p) -> None:
+        if self._buckets is None or not self._armed:
+            return
+        bk = self._buckets[self._bucket_of[id(p)]]
+        bk["seen"] += 1
+        if bk["seen"] == bk["need"] and not bk["done"]:
+            self._launch(bk)
 
     @property
     def world_size(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
+    _armed = False
+
     def zero(self) -> None:
         """Replaces optimizer.zero_grad(): keeps the .grad views alive."""
         self.flat.zero_()
+        if self._buckets is not None:
+            for bk in self._buckets:
+                bk.update(seen=0, work=None, done=False)
+            self._armed = True
         for p in self.params:  # an optimizer.zero_grad(set_to_none=True) elsewhere would have dropped the views
             if p.grad is None or p.grad.data_ptr() < self.flat.data_ptr() or p.grad.data_ptr() >= self.flat.data_ptr() + self.flat.numel() * self.flat.element_size():
                 self._rebind()
@@ -51,6 +101,17 @@ class FlatGradSync:
     def sync(self) -> None:
         """Average gradients over all ranks (the single exchange step of the data-parallel path)."""
         w = self.world_size
+        if self._buckets is not None:
+            self._armed = False
+            for bk in self._buckets:  # buckets with parameters that got no gradient this step were never launched
+                if not bk["done"]:
+                    self._launch(bk)
+            for bk in self._buckets:
+                if bk["work"] is not None:
+                    bk["work"].wait()
+                    if not self.flat.is_cuda:
+                        self.flat[bk["lo"]: bk["hi"]].div_(w)
+            return
         if w == 1:
             return
         if self.flat.is_cuda:

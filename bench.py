@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=32, dest="cpu_sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", dest="no_overlap", help="training workloads, N > 1: one all-reduce after the backward instead of bucketed overlap")
     ap.add_argument("--torch-optim", action="store_true", dest="torch_optim", help="training workloads: torch.optim step instead of the fused kernel")
     ap.add_argument("--workload", default="infer", choices=["infer", "train", "cnn_train", "preprocess"],
                     help="infer = headline (BASELINE configs[1]); train = fusion DP training (configs[3]); cnn_train = AstroMiNN training "

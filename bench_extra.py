@@ -65,6 +65,8 @@ def run_extra(args, peaks, ClockSampler):
 
         optimizer = fused_from_torch(topt, bf16_shadow=(args.dtype == "bf16"))
         sync = optimizer.grads
+    if world > 1 and not getattr(args, "no_overlap", False):
+        sync.enable_overlap()  # bucketed all-reduce launched from the autograd hooks, overlapped with the rest of the backward
 
     x, pad, lens = synth.photometry_batch(B, seed=1337 + rank)
     host = {"x": x, "pad": pad, "meta": synth.metadata(B, seed=1337 + rank), "img": synth.cutouts(B, seed=1337 + rank),

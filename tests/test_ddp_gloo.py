@@ -20,7 +20,7 @@ def _model():
     return torch.nn.Sequential(torch.nn.Linear(7, 16), torch.nn.Tanh(), torch.nn.Linear(16, 5))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, overlap=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from applecider_b200.ddp import FlatGradSync, ddp_train_step, shard_batch
@@ -29,6 +29,9 @@ def _worker(rank, world, port, q):
     x, y = torch.randn(12, 7), torch.randint(0, 5, (12,))
     model = _model()
     sync = FlatGradSync(model)
+    if overlap:
+        sync.enable_overlap(bucket_elems=64)  # 4 parameters -> several buckets, launched from the autograd hooks
+        assert len(sync._buckets) >= 2
     opt = torch.optim.SGD(model.parameters(), lr=0.1)
     lo, hi = shard_batch(12, rank, world)
     for _ in range(3):
@@ -39,11 +42,12 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_step_equals_single_rank_full_batch():
+@pytest.mark.parametrize("overlap", [False, True])
+def test_two_rank_step_equals_single_rank_full_batch(overlap):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, overlap)) for r in range(2)]
     for p in procs:
         p.start()
     results = dict(q.get(timeout=120) for _ in range(2))
