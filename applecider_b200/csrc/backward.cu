@@ -516,6 +516,7 @@ __global__ void __launch_bounds__(128) photo_embed_bwd_kernel(const float* x, co
   for (int t = t0; t < t1; ++t) {
     const float g = ld_any(dh, (long long)t * D + c, dh_dt);
     const int s = src[t];
+    if (s <= ACB_SRC_DEAD) continue;  // capacity row, no token
     if (s < 0) { gc += g; continue; }
     const float* xr = x + (long long)s * 7;
 #pragma unroll

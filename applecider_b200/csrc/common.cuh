@@ -35,6 +35,9 @@ void acb_set_error(const char* fmt, ...);
 
 void acb_count_launch(int n = 1);  // product-side launch counter (bench.py "gpu_launches")
 
+// src_idx entries <= ACB_SRC_DEAD mark capacity rows past the last packed token (acb_photo_compact memsets them to 0x80808080)
+#define ACB_SRC_DEAD (-0x40000000)
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------

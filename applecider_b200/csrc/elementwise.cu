@@ -38,9 +38,10 @@ template <typename TX, typename TR, typename TY, bool VEC>
 __global__ void __launch_bounds__(256) layernorm_kernel(const TX* __restrict__ x, const TR* __restrict__ res,
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         TY* __restrict__ y, long long rows, int C, float eps,
-                                                        int pre_gelu, int post_act) {
+                                                        int pre_gelu, int post_act, const int* __restrict__ rows_dev) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (rows_dev) rows = min(rows, (long long)__ldg(rows_dev));  // device-side row count: capacity rows past it are skipped
   if (row >= rows) return;
   const TX* xr = x + row * C;
   const TR* rr = res ? res + row * C : nullptr;
@@ -138,9 +139,10 @@ template <typename TX, typename TR, typename TY, int NC>
 __global__ void __launch_bounds__(256) layernorm_cached_kernel(const TX* __restrict__ x, const TR* __restrict__ res,
                                                                const float* __restrict__ w, const float* __restrict__ b,
                                                                TY* __restrict__ y, long long rows, int C, float eps,
-                                                               int pre_gelu, int post_act) {
+                                                               int pre_gelu, int post_act, const int* __restrict__ rows_dev) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (rows_dev) rows = min(rows, (long long)__ldg(rows_dev));
   if (row >= rows) return;
   const TX* xr = x + row * C;
   const TR* rr = res ? res + row * C : nullptr;
@@ -205,10 +207,11 @@ __global__ void __launch_bounds__(256) layernorm_cached_kernel(const TX* __restr
 template <int NC, int RPW>
 __global__ void __launch_bounds__(256) layernorm_stream_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ b, bf16* __restrict__ y, long long rows, float eps,
-                                                               int post_act) {
+                                                               int post_act, const int* __restrict__ rows_dev) {
   constexpr int C = NC * 128;
   const int lane = threadIdx.x & 31;
   const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (rows_dev) rows = min(rows, (long long)__ldg(rows_dev));
   if (row0 >= rows) return;
   uint2 raw[RPW][NC];
 #pragma unroll
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(256) layernorm_stream_kernel(const bf16* __res
 
 template <typename TX, typename TR, typename TY>
 int launch_ln(const void* x, const void* res, const float* w, const float* b, void* y, long long rows, int C,
-              float eps, int pre_gelu, int post_act, cudaStream_t st) {
+              float eps, int pre_gelu, int post_act, const int* rows_dev, cudaStream_t st) {
   const int wpb = 8;
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
   const bool vec = (C % 4 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)w | (uintptr_t)b) % 16 == 0);
@@ -284,25 +287,25 @@ int launch_ln(const void* x, const void* res, const float* w, const float* b, vo
     if (vec && !res && !pre_gelu && rows >= 65536 && (C == 128 || C == 256 || C == 384 || C == 768 || C == 1536 || C == 3072)) {
       constexpr int RPW = 4;
       const unsigned g = (unsigned)((rows + (long long)wpb * RPW - 1) / ((long long)wpb * RPW));
-      if (C == 128) layernorm_stream_kernel<1, 8><<<(unsigned)((rows + wpb * 8LL - 1) / (wpb * 8LL)), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
-      else if (C == 256) layernorm_stream_kernel<2, RPW><<<g, wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
-      else if (C == 384) layernorm_stream_kernel<3, RPW><<<g, wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
-      else if (C == 768) layernorm_stream_kernel<6, 2><<<(unsigned)((rows + wpb * 2LL - 1) / (wpb * 2LL)), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
-      else if (C == 1536) layernorm_stream_kernel<12, 1><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
-      else layernorm_stream_kernel<24, 1><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act);
+      if (C == 128) layernorm_stream_kernel<1, 8><<<(unsigned)((rows + wpb * 8LL - 1) / (wpb * 8LL)), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act, rows_dev);
+      else if (C == 256) layernorm_stream_kernel<2, RPW><<<g, wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act, rows_dev);
+      else if (C == 384) layernorm_stream_kernel<3, RPW><<<g, wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act, rows_dev);
+      else if (C == 768) layernorm_stream_kernel<6, 2><<<(unsigned)((rows + wpb * 2LL - 1) / (wpb * 2LL)), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act, rows_dev);
+      else if (C == 1536) layernorm_stream_kernel<12, 1><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act, rows_dev);
+      else layernorm_stream_kernel<24, 1><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act, rows_dev);
       ACB_LAUNCH_CHECK();
       acb_count_launch();
       return ACB_OK;
     }
   }
   if (vec && C <= 256)
-    layernorm_cached_kernel<TX, TR, TY, 2><<<grid, wpb * 32, 0, st>>>((const TX*)x, (const TR*)res, w, b, (TY*)y, rows, C, eps, pre_gelu, post_act);
+    layernorm_cached_kernel<TX, TR, TY, 2><<<grid, wpb * 32, 0, st>>>((const TX*)x, (const TR*)res, w, b, (TY*)y, rows, C, eps, pre_gelu, post_act, rows_dev);
   else if (vec && C <= 768)
-    layernorm_cached_kernel<TX, TR, TY, 6><<<grid, wpb * 32, 0, st>>>((const TX*)x, (const TR*)res, w, b, (TY*)y, rows, C, eps, pre_gelu, post_act);
+    layernorm_cached_kernel<TX, TR, TY, 6><<<grid, wpb * 32, 0, st>>>((const TX*)x, (const TR*)res, w, b, (TY*)y, rows, C, eps, pre_gelu, post_act, rows_dev);
   else if (vec)
-    layernorm_kernel<TX, TR, TY, true><<<grid, wpb * 32, 0, st>>>((const TX*)x, (const TR*)res, w, b, (TY*)y, rows, C, eps, pre_gelu, post_act);
+    layernorm_kernel<TX, TR, TY, true><<<grid, wpb * 32, 0, st>>>((const TX*)x, (const TR*)res, w, b, (TY*)y, rows, C, eps, pre_gelu, post_act, rows_dev);
   else
-    layernorm_kernel<TX, TR, TY, false><<<grid, wpb * 32, 0, st>>>((const TX*)x, (const TR*)res, w, b, (TY*)y, rows, C, eps, pre_gelu, post_act);
+    layernorm_kernel<TX, TR, TY, false><<<grid, wpb * 32, 0, st>>>((const TX*)x, (const TR*)res, w, b, (TY*)y, rows, C, eps, pre_gelu, post_act, rows_dev);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;
@@ -434,20 +437,25 @@ extern "C" {
 
 int acb_layernorm(const void* x, int x_dtype, const void* res, int res_dtype, const float* w, const float* b, void* y,
                   int y_dtype, long long rows, int C, float eps, int pre_gelu, int post_act, void* stream) {
+  return acb_layernorm_n(x, x_dtype, res, res_dtype, w, b, y, y_dtype, rows, C, eps, pre_gelu, post_act, nullptr, stream);
+}
+
+int acb_layernorm_n(const void* x, int x_dtype, const void* res, int res_dtype, const float* w, const float* b, void* y,
+                    int y_dtype, long long rows, int C, float eps, int pre_gelu, int post_act, const int* rows_dev, void* stream) {
   ACB_CHECK(x && y && w && b && C > 0 && rows >= 0, "acb_layernorm: bad arguments");
   if (rows == 0) return ACB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (!res) res_dtype = x_dtype;
   const int key = x_dtype * 4 + res_dtype * 2 + y_dtype;
   switch (key) {
-    case 0: return launch_ln<float, float, float>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, st);
-    case 1: return launch_ln<float, float, bf16>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, st);
-    case 2: return launch_ln<float, bf16, float>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, st);
-    case 3: return launch_ln<float, bf16, bf16>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, st);
-    case 4: return launch_ln<bf16, float, float>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, st);
-    case 5: return launch_ln<bf16, float, bf16>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, st);
-    case 6: return launch_ln<bf16, bf16, float>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, st);
-    case 7: return launch_ln<bf16, bf16, bf16>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, st);
+    case 0: return launch_ln<float, float, float>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, rows_dev, st);
+    case 1: return launch_ln<float, float, bf16>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, rows_dev, st);
+    case 2: return launch_ln<float, bf16, float>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, rows_dev, st);
+    case 3: return launch_ln<float, bf16, bf16>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, rows_dev, st);
+    case 4: return launch_ln<bf16, float, float>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, rows_dev, st);
+    case 5: return launch_ln<bf16, float, bf16>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, rows_dev, st);
+    case 6: return launch_ln<bf16, bf16, float>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, rows_dev, st);
+    case 7: return launch_ln<bf16, bf16, bf16>(x, res, w, b, y, rows, C, eps, pre_gelu, post_act, rows_dev, st);
   }
   acb_set_error("acb_layernorm: bad dtype");
   return ACB_ERR_INVALID;

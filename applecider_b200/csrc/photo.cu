@@ -17,7 +17,7 @@ __global__ void count_valid_kernel(const uint8_t* __restrict__ pad, int B, int L
 }
 
 // in-place inclusive scan of cu[1..B] by a single block
-__global__ void scan_kernel(int* cu, int B) {
+__global__ void scan_kernel(int* cu, int B, int capacity) {
   __shared__ int sh[1024];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -33,7 +33,7 @@ __global__ void scan_kernel(int* cu, int B) {
       sh[threadIdx.x] += t;
       __syncthreads();
     }
-    if (i < B) cu[i + 1] = sh[threadIdx.x] + carry;
+    if (i < B) cu[i + 1] = min(sh[threadIdx.x] + carry, capacity);  // a too-small caller bound truncates, never overruns
     __syncthreads();
     if (threadIdx.x == 1023) carry += sh[1023];
     __syncthreads();
@@ -46,13 +46,15 @@ __global__ void fill_src_kernel(const uint8_t* __restrict__ pad, int B, int L, c
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   int pos = cu[b];
-  if (lane == 0) src[pos] = -1 - b;
+  const int end = cu[b + 1];  // == pos + 1 + valid count unless the caller's capacity truncated the sequence
+  if (lane == 0 && pos < end) src[pos] = -1 - b;
   pos += 1;
   for (int l0 = 0; l0 < L; l0 += 32) {
     const int l = l0 + lane;
     const bool valid = (l < L) && (pad[(long long)b * L + l] == 0);
     const unsigned m = __ballot_sync(0xffffffffu, valid);
-    if (valid) src[pos + __popc(m & ((1u << lane) - 1u))] = b * L + l;
+    const int at = pos + __popc(m & ((1u << lane) - 1u));
+    if (valid && at < end) src[at] = b * L + l;
     pos += __popc(m);
   }
 }
@@ -74,6 +76,10 @@ __global__ void __launch_bounds__(256) photo_embed_kernel(const float* __restric
   if (t >= total) return;
   const int s = src[t];
   T* o = out + (long long)t * D;
+  if (s <= ACB_SRC_DEAD) {  // capacity row beyond the packed tokens: zeros (row-local ops keep it inert)
+    for (int c = lane; c < D; c += 32) o[c] = from_f<T>(0.0f);
+    return;
+  }
   if (s < 0) {
     for (int c = lane; c < D; c += 32) o[c] = from_f<T>(cls[c]);
     return;
@@ -189,12 +195,16 @@ __global__ void gather_cls_kernel(const T* __restrict__ x, const int* __restrict
 
 extern "C" {
 
-int acb_photo_compact(const uint8_t* pad, int B, int L, int* cu_seqlens, int* src_idx, void* stream) {
+int acb_photo_compact(const uint8_t* pad, int B, int L, int capacity, int* cu_seqlens, int* src_idx, void* stream) {
   ACB_CHECK(pad && cu_seqlens && src_idx && B > 0 && L > 0, "acb_photo_compact: bad arguments");
+  ACB_CHECK((long long)B * (L + 1) < (1LL << 30), "acb_photo_compact: B*(L+1) = %lld tokens exceed the 2^30 index range", (long long)B * (L + 1));
+  if (capacity <= 0 || capacity > B * (L + 1)) capacity = B * (L + 1);
   cudaStream_t st = (cudaStream_t)stream;
+  // every entry the fill below does not reach (rows past cu[B] of the B*(L+1) capacity) reads as "dead": 0x80808080 < ACB_SRC_DEAD
+  ACB_CUDA(cudaMemsetAsync(src_idx, 0x80, (size_t)B * (L + 1) * sizeof(int), st));
   count_valid_kernel<<<cdiv(B, 8), 256, 0, st>>>(pad, B, L, cu_seqlens);
   ACB_LAUNCH_CHECK();
-  scan_kernel<<<1, 1024, 0, st>>>(cu_seqlens, B);
+  scan_kernel<<<1, 1024, 0, st>>>(cu_seqlens, B, capacity);
   ACB_LAUNCH_CHECK();
   fill_src_kernel<<<cdiv(B, 8), 256, 0, st>>>(pad, B, L, cu_seqlens, src_idx);
   ACB_LAUNCH_CHECK();

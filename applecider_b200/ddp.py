@@ -32,13 +32,55 @@ class FlatGradSync:
         self.numel = numel
         self._rebind()
         self._buckets = None  # see enable_overlap()
+        self._hooks = []
+        self._accumulating = False
+        self.allreduce_bytes = 0  # payload of the last sync() (diagnostics for the bench)
+        self.time_sync = False    # bench: bracket the exposed wait of sync() with CUDA events (see exposed_ms())
+        self._sync_events = []
+
+    def broadcast_parameters(self, src: int = 0, flat_params=None) -> None:
+        """Make every replica start from rank `src`'s weights (DDP does this at construction).  flat_params: the flat
+        parameter buffer when the parameters are views of one (optim.FusedAdam) -- one collective instead of one per tensor."""
+        if self.world_size == 1:
+            return
+        with torch.no_grad():
+            if flat_params is not None:
+                dist.broadcast(flat_params, src=src, group=self.group)
+            else:
+                for p in self.params:
+                    dist.broadcast(p.data, src=src, group=self.group)
+
+    def no_sync(self):
+        """Context manager for gradient accumulation: backward passes inside it only accumulate into the flat buffer (the
+        bucket hooks stay disarmed); the all-reduce happens in the first sync() after the last micro-batch's backward, which
+        must run OUTSIDE the context -- call zero() once before the first micro-batch."""
+        sync = self
+
+        class _NoSync:
+            def __enter__(self_):
+                sync._accumulating = True
+                sync._armed = False
+
+            def __exit__(self_, *exc):
+                sync._accumulating = False
+                if sync._buckets is not None:  # re-arm for the final micro-batch; counters restart, buffers keep their sums
+                    for bk in sync._buckets:
+                        bk.update(seen=0, work=None, done=False)
+                    sync._armed = True
+                return False
+
+        return _NoSync()
 
     # ---- bucketed all-reduce overlapped with the backward pass --------------------------------------------------
     def enable_overlap(self, bucket_elems: int = 16 * 1024 * 1024) -> "FlatGradSync":
         """Split the flat buffer into contiguous buckets of about `bucket_elems` gradients; a bucket's all-reduce starts from
         the post-accumulate hook of its last parameter, i.e. while autograd is still producing the other buckets
         (NCCL orders the collective after the gradient kernels enqueued so far).  sync() then only waits / finishes the
-        buckets whose parameters received no gradient.  Buckets are contiguous slices: still no pack / unpack copies."""
+        buckets whose parameters received no gradient.  Buckets are contiguous slices: still no pack / unpack copies.
+        Idempotent: a second call replaces the bucket plan and its hooks instead of stacking another set."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
         bounds, start, acc = [], 0, 0
         for i, (p, off) in enumerate(zip(self.params, self.offsets)):
             acc += p.numel()
@@ -53,7 +95,7 @@ class FlatGradSync:
             b = next(i for i, bk in enumerate(self._buckets) if bk["lo"] <= off < bk["hi"])
             self._bucket_of[id(p)] = b
             self._buckets[b]["need"] += 1
-            p.register_post_accumulate_grad_hook(self._on_grad)
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
         return self
 
     def _launch(self, bk) -> None:
@@ -69,7 +111,7 @@ class FlatGradSync:
         bk["done"] = True
 
     def _on_grad(self, p) -> None:
-        if self._buckets is None or not self._armed:
+        if self._buckets is None or not self._armed or self._accumulating:
             return
         bk = self._buckets[self._bucket_of[id(p)]]
         bk["seen"] += 1
@@ -101,6 +143,31 @@ class FlatGradSync:
     def sync(self) -> None:
         """Average gradients over all ranks (the single exchange step of the data-parallel path)."""
         w = self.world_size
+        if self._accumulating:
+            raise RuntimeError("FlatGradSync.sync() called inside no_sync(): run the last micro-batch outside the context")
+        self.allreduce_bytes = self.flat.numel() * self.flat.element_size() if w > 1 else 0
+        timed = self.time_sync and self.flat.is_cuda and w > 1
+        if timed:  # e0 completes when the backward's last kernel does, e1 when the last collective has landed
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        try:
+            self._sync_impl(w)
+        finally:
+            if timed:
+                e1.record()
+                self._sync_events.append((e0, e1))
+
+    def exposed_ms(self):
+        """Mean time per step the compute stream spent waiting for the all-reduce after the backward had finished (the part
+        of the collective that the bucketed overlap did not hide).  Synchronises; clears the samples."""
+        if not self._sync_events:
+            return 0.0
+        torch.cuda.synchronize()
+        v = [a.elapsed_time(b) for a, b in self._sync_events]
+        self._sync_events = []
+        return sum(v) / len(v)
+
+    def _sync_impl(self, w) -> None:
         if self._buckets is not None:
             self._armed = False
             for bk in self._buckets:  # buckets with parameters that got no gradient this step were never launched

@@ -280,7 +280,7 @@ class Attention(Function):
     @staticmethod
     def forward(ctx, qkv, cu, B, H, dh, maxlen, drop_p, seed):
         qkv = _c(qkv)
-        out = ops.attention_varlen(qkv, cu, B, H, dh, maxlen, drop_p, seed)
+        out = ops.attention_varlen(qkv, cu, B, H, dh, maxlen, drop_p, seed, zero_tail=True)
         ctx.save_for_backward(qkv, cu)
         ctx.cfg = (B, H, dh, maxlen, drop_p, seed)
         return out
@@ -290,7 +290,7 @@ class Attention(Function):
         qkv, cu = ctx.saved_tensors
         B, H, dh, maxlen, drop_p, seed = ctx.cfg
         dout = _c(dout)
-        dqkv = torch.empty_like(qkv)
+        dqkv = torch.zeros_like(qkv)  # capacity rows past the last sequence must carry zero gradient
         call("acb_attention_varlen_bwd", qkv, dtype_tag(qkv), dout, dtype_tag(dout), cu, B, H, dh, maxlen, drop_p, seed, dqkv, dtype_tag(dqkv))
         return dqkv, None, None, None, None, None, None, None
 
@@ -648,12 +648,49 @@ def ew_scaled_sum3(a, b, c):
     return Mean3.apply(a, b, c)
 
 
-_seed_counter = [0x5EED]
+# ---- seeds of the counter-hash RNG streams (dropout, attention dropout, Time2Vec dropout, MPT masking) -----------------
+# Every stochastic op draws its 62-bit seed from torch's CUDA generator of the current device: (initial_seed, philox offset)
+# mixed with the data-parallel rank, and advances the offset -- the same bookkeeping torch's own CUDA dropout does.  So
+# torch.manual_seed / torch.cuda.manual_seed reseed these kernels, replaying a seed replays the masks, and replicas that
+# were seeded identically still draw independent masks.
+_seed_state = {"rank": None}
+_MASK62 = (1 << 62) - 1
+_M64 = (1 << 64) - 1
+
+
+def _mix64(x):
+    x &= _M64
+    x ^= x >> 33
+    x = (x * 0xFF51AFD7ED558CCD) & _M64
+    x ^= x >> 33
+    x = (x * 0xC4CEB9FE1A85EC53) & _M64
+    x ^= x >> 33
+    return x
+
+
+def _default_rank():
+    import os
+
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank()
+    return int(os.environ.get("RANK", "0"))
+
+
+def set_seed(seed=None, rank=None):
+    """Reseed the stochastic kernels: seed -> torch.cuda.manual_seed(seed) on the current device (None keeps torch's seed and
+    only rewinds nothing); rank (None -> torch.distributed rank or $RANK) decorrelates data-parallel replicas."""
+    if seed is not None:
+        torch.cuda.manual_seed(int(seed))
+    _seed_state["rank"] = _default_rank() if rank is None else int(rank)
 
 
 def next_seed():
-    _seed_counter[0] += 1
-    return _seed_counter[0]
+    if _seed_state["rank"] is None:
+        _seed_state["rank"] = _default_rank()
+    g = torch.cuda.default_generators[torch.cuda.current_device()]
+    off = g.get_offset()
+    g.set_offset(off + 4)
+    return _mix64(_mix64(g.initial_seed() * 0x9E3779B97F4A7C15 + _seed_state["rank"] + 1) + off) & _MASK62
 
 
 def dropout(x, p, training):

@@ -53,26 +53,20 @@ class AppleCider(nn.Module):
     # co-running small kernels slow the tensor-bound spectra convs by ~5 %, which muddies per-kernel timing) -> opt-in
     CONCURRENT_ENCODERS = False
 
-    def _encode(self, photometry, photometry_mask, metadata, images, spectra):
+    def _encode(self, photometry, photometry_mask, metadata, images, spectra, total_tokens=None):
         if self.CONCURRENT_ENCODERS and not torch.is_grad_enabled() and spectra.is_cuda and self.spectra_variant == "src":
-            return self._encode_concurrent(photometry, photometry_mask, metadata, images, spectra)
-        if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
-            p = self.photometry_encoder((photometry, photometry_mask, None))
-            packed = None
-        else:
-            # launch order matters on one stream: the packing plan needs one host read, so it goes FIRST; then the spectra encoder
-            # (20 long kernels, ~70 % of the step) is enqueued, and the ~100 short photometry / ConvNeXt / tower launches are
-            # queued while the GPU is busy with it instead of being issued one by one to an idle device
-            packed = self.photometry_encoder.pack(photometry_mask)
+            return self._encode_concurrent(photometry, photometry_mask, metadata, images, spectra, total_tokens)
+        # no step of the forward reads anything back from the device (the token packing works on a row capacity, see
+        # photo.pack), so the launch order is free; the spectra encoder goes first only because its ~20 long kernels keep the
+        # GPU busy while the ~100 short photometry / ConvNeXt / tower launches are queued behind them
         s = self.spectra_encoder(spectra) if self.spectra_variant == "B" else self.spectra_encoder((spectra, None, None))
         if s.dim() == 1:
             s = s[:, None].contiguous()
-        if packed is not None:
-            p = self.photometry_encoder.encode(photometry, photometry_mask, packed=packed)
+        p = self.photometry_encoder((photometry, photometry_mask, None), total_tokens=total_tokens)
         im = self.img_metadata_encoder((metadata, images, None))
         return p, im, s
 
-    def _encode_concurrent(self, photometry, photometry_mask, metadata, images, spectra):
+    def _encode_concurrent(self, photometry, photometry_mask, metadata, images, spectra, total_tokens=None):
         """Spectra on the caller's stream (it is 70 % of the work), photometry and image+metadata on two side streams."""
         dev = spectra.device
         main = torch.cuda.current_stream(dev)
@@ -87,7 +81,7 @@ class AppleCider(nn.Module):
             st.wait_event(start)
             with torch.cuda.stream(st):
                 if k == 0:
-                    outs[0] = self.photometry_encoder((photometry, photometry_mask, None))
+                    outs[0] = self.photometry_encoder((photometry, photometry_mask, None), total_tokens=total_tokens)
                 else:
                     outs[1] = self.img_metadata_encoder((metadata, images, None))
                 ev = torch.cuda.Event()
@@ -116,23 +110,27 @@ class AppleCider(nn.Module):
         )
         return logits, emb
 
-    def get_embeddings(self, photometry, photometry_mask, metadata, images, spectra):
-        p, im, s = self._encode(photometry, photometry_mask, metadata, images, spectra)
+    def get_embeddings(self, photometry, photometry_mask, metadata, images, spectra, total_tokens=None):
+        p, im, s = self._encode(photometry, photometry_mask, metadata, images, spectra, total_tokens)
         _, emb = self._head(p, im, s, True)
         return emb[0], emb[1], emb[2]
 
-    def forward(self, photometry, photometry_mask, metadata, images, spectra):
+    def forward(self, photometry, photometry_mask, metadata, images, spectra, total_tokens=None):
+        """total_tokens (optional, an extension of the reference signature): the packed token count of the batch from the
+        collate -- number of unmasked events + B -- or any upper bound of it; sizes the token matrix exactly.  Without it the
+        capacity is B*(L+1) and the kernels skip the unused rows by a device-side count; either way nothing syncs."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .train import fusion_forward_train
 
-            return fusion_forward_train(self, photometry, photometry_mask, metadata, images, spectra)
-        p, im, s = self._encode(photometry, photometry_mask, metadata, images, spectra)
+            return fusion_forward_train(self, photometry, photometry_mask, metadata, images, spectra, total_tokens)
+        p, im, s = self._encode(photometry, photometry_mask, metadata, images, spectra, total_tokens)
         return self._head(p, im, s, False)[0]
 
 
     @torch.no_grad()
     def predict_batches(self, host_batches):
-        """Streaming inference over HOST batches: yields one pinned (B, num_classes) fp32 logits tensor per batch.
+        """Streaming inference over HOST batches: yields one (B, num_classes) fp32 CPU logits tensor per batch (a fresh
+        tensor each time: the two pinned staging buffers behind it are reused, the yielded copies are the caller's).
 
         host_batches: iterable of (photometry, photometry_mask, metadata, images, spectra) CPU tensors (pinned memory
         makes the copies asynchronous).  The host->device copy of batch i+1 runs on a side stream while batch i is being
@@ -152,8 +150,12 @@ class AppleCider(nn.Module):
         outs = [None, None]
         out_done = [None, None]
 
+        ntok = [None, None]
+
         def stage(i, batch):
             k = i & 1
+            # packed token count from the HOST mask (the collate's by-product: ~1 MB of bools): sizes the token matrix exactly
+            ntok[k] = int(batch[1].numel() - int(batch[1].count_nonzero())) + batch[1].shape[0]
             with torch.cuda.stream(copy_stream):
                 if slot_free[k] is not None:
                     copy_stream.wait_event(slot_free[k])
@@ -177,7 +179,7 @@ class AppleCider(nn.Module):
                 stage(i + 1, nxt)  # overlaps with the compute of batch i
             compute.wait_event(h2d_done[k])
             d = slots[k]
-            logits = self.forward(d[0], d[1], d[2], d[3], d[4])
+            logits = self.forward(d[0], d[1], d[2], d[3], d[4], total_tokens=ntok[k])
             slot_free[k] = torch.cuda.Event()
             slot_free[k].record(compute)
             if outs[k] is None or outs[k].shape != logits.shape:
@@ -187,11 +189,11 @@ class AppleCider(nn.Module):
             out_done[k].record(compute)
             if pending is not None:
                 out_done[pending].synchronize()
-                yield outs[pending]
+                yield outs[pending].clone()
             pending = k
             i += 1
         out_done[pending].synchronize()
-        yield outs[pending]
+        yield outs[pending].clone()
 
 
 def fusion_collate(batch, mean, std, device="cuda"):

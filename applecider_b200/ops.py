@@ -68,12 +68,14 @@ def pick_bn(n: int) -> int:
 
 
 def gemm(a, w, bias=None, act=ACT_NONE, res=None, gamma=None, res_mode=RES_NONE, out=None, out_dtype=None,
-         out_col=0, conv=None, pool4=False, bn=None, tile_kb=None, colblk_off=None, a_view=None, pre_out=None):
+         out_col=0, conv=None, pool4=False, bn=None, tile_kb=None, colblk_off=None, a_view=None, pre_out=None, m_valid=None):
     """C = epilogue(A @ W^T).  a: [M,K] (or [B,L,Cin] with conv=(taps,pad)); w: [N,K'] row-major.
 
     f32 operands run the CUDA-core kernel, bf16 operands the tcgen05 kernel.
     ``out``/``out_col`` let the result land in a column slice of a wider row-major buffer.
     ``a_view`` = (nbatch, L, Cin, batch_stride, row_stride) overrides the A geometry (bf16 only).
+    ``m_valid`` = device pointer to an int32 row count (bf16 only): 128-row tiles past it exit at once, their output rows
+    stay unwritten (capacity-sized token matrices, see photo.pack).
     """
     N = w.shape[0]
     ldb = w.shape[1]
@@ -113,18 +115,18 @@ def gemm(a, w, bias=None, act=ACT_NONE, res=None, gamma=None, res_mode=RES_NONE,
         kb = _int_array(tile_kb) if tile_kb is not None else None
         co = _int_array(colblk_off) if colblk_off is not None else None
         call("acb_gemm_bf16", a, w, c_ptr, dtype_tag(out), nb, L, cin, taps, pad, bstride, rstride, N, ldb, ldc, bn, kb, co,
-             bias, act, res, (dtype_tag(res) if res is not None else 0), ldr, gamma, res_mode, int(pool4), None, pre_out)
+             bias, act, res, (dtype_tag(res) if res is not None else 0), ldr, gamma, res_mode, int(pool4), m_valid, pre_out)
     else:
         raise TypeError(f"gemm: unsupported dtype {a.dtype}")
     return out
 
 
-def layernorm(x, w, b, eps, res=None, pre_gelu=False, post_act=ACT_NONE, out_dtype=None):
+def layernorm(x, w, b, eps, res=None, pre_gelu=False, post_act=ACT_NONE, out_dtype=None, rows_dev=None):
     C = x.shape[-1]
     rows = x.numel() // C
     y = torch.empty(x.shape, dtype=(out_dtype or x.dtype), device=x.device)
-    call("acb_layernorm", x, dtype_tag(x), res, (dtype_tag(res) if res is not None else 0), w, b, y, dtype_tag(y), rows, C, eps,
-         int(pre_gelu), post_act)
+    call("acb_layernorm_n", x, dtype_tag(x), res, (dtype_tag(res) if res is not None else 0), w, b, y, dtype_tag(y), rows, C, eps,
+         int(pre_gelu), post_act, rows_dev)
     return y
 
 
@@ -136,13 +138,38 @@ def cast(x, dtype):
     return y
 
 
-def photo_compact(pad):
+def photo_compact(pad, capacity=0):
+    """-> (cu_seqlens[B+1], src_idx[B*(L+1)]); src entries past cu[B] are dead markers (acb_photo_embed writes zero rows)."""
     B, L = pad.shape
     pad_u8 = pad.view(torch.uint8) if pad.dtype == torch.bool else pad
     cu = torch.empty(B + 1, dtype=torch.int32, device=pad.device)
     src = torch.empty(B * (L + 1), dtype=torch.int32, device=pad.device)
-    call("acb_photo_compact", pad_u8, B, L, cu, src)
+    call("acb_photo_compact", pad_u8, B, L, int(capacity), cu, src)
     return cu, src
+
+
+def check_photo_inputs(data, pad):
+    """The mask must cover exactly the (B, L) rows of data: the packing indices address data by b*L+l with no bounds
+    checks on the device (the reference raises a mask-shape error in nn.MultiheadAttention for the same input)."""
+    if not data.is_cuda or not pad.is_cuda:
+        raise RuntimeError("applecider_b200: inputs must be CUDA tensors (no CPU fallback)")
+    if data.dim() != 3 or data.shape[-1] != 7:
+        raise ValueError(f"applecider_b200: photometry must be (B, L, 7), got {tuple(data.shape)}")
+    if tuple(pad.shape) != tuple(data.shape[:2]):
+        raise ValueError(f"applecider_b200: pad mask shape {tuple(pad.shape)} does not match the photometry batch {tuple(data.shape[:2])} "
+                         "(the mask covers the L events; the CLS column is added internally)")
+
+
+def token_capacity(B, L, total_tokens=None):
+    """Rows to allocate for the packed token matrix: a caller-supplied upper bound of the packed count (exact from the
+    collate is best) or the worst case B*(L+1).  Never read back from the device."""
+    cap = B * (L + 1)
+    if total_tokens is None:
+        return cap
+    T = int(total_tokens)
+    if T < B or T > cap:
+        raise ValueError(f"applecider_b200: total_tokens={T} outside [{B}, {cap}] for a ({B}, {L}) batch")
+    return T
 
 
 def photo_embed(x, src, total, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype, te_drop_p=0.0, te_seed=0):
@@ -154,9 +181,9 @@ def photo_embed(x, src, total, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype, te_d
 USE_TC_ATTENTION = True
 
 
-def attention_varlen(qkv, cu, B, n_heads, dh, max_seqlen, drop_p=0.0, seed=0):
+def attention_varlen(qkv, cu, B, n_heads, dh, max_seqlen, drop_p=0.0, seed=0, zero_tail=False):
     T = qkv.shape[0]
-    out = torch.empty((T, n_heads * dh), dtype=qkv.dtype, device=qkv.device)
+    out = (torch.zeros if zero_tail else torch.empty)((T, n_heads * dh), dtype=qkv.dtype, device=qkv.device)
     if qkv.dtype == torch.bfloat16 and USE_TC_ATTENTION and max_seqlen <= 1024 and dh == 16:
         call("acb_attention_varlen_tc", qkv, cu, B, n_heads, dh, max_seqlen, drop_p, seed, out)
         return out

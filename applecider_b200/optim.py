@@ -62,6 +62,7 @@ class FusedAdam:
                 self.flat_p[o: o + p.numel()].copy_(p.detach().reshape(-1))
                 p.data = self.flat_p[o: o + p.numel()].view(p.shape)
         self.grads = FlatGradSync(self.params, process_group, offsets=self.offsets, numel=off)
+        self.grads.broadcast_parameters(0, flat_params=self.flat_p)  # replicas start identical (no-op for one process)
         self.flat_m = torch.zeros_like(self.flat_p)
         self.flat_v = torch.zeros_like(self.flat_p)
         self._gnorm = torch.zeros(1, dtype=torch.float32, device=dev)

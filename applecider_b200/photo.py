@@ -41,40 +41,41 @@ class _PhotoEncoderBase(nn.Module):
             return p
         return self._derived.get(("cast", id(p)), (p,), lambda: ops.cast(p.detach().contiguous(), dtype))
 
-    def pack(self, pad, total_tokens=None):
-        """Varlen packing plan of a key-padding mask: (cu_seqlens, src_idx, T).  Reads ONE integer back from the device (the
-        packed token count) unless total_tokens is given; callers that have other work to enqueue first (the fusion model:
-        the spectra encoder) call this early so that nothing else stalls on that read."""
-        if not pad.is_cuda:
-            raise RuntimeError("applecider_b200: inputs must be CUDA tensors (no CPU fallback)")
+    def pack(self, data, pad, total_tokens=None):
+        """Varlen packing plan of a key-padding mask: (cu_seqlens, src_idx, T, rows_dev).  NOTHING is read back from the device:
+        T is a row capacity -- ``total_tokens`` when the collate supplies the packed count (sum of lengths + B; any upper
+        bound works) or the worst case B*(L+1).  ``rows_dev`` points at cu_seqlens[B] (the real count, on the device): the
+        GEMM / LayerNorm kernels skip the 128-row tiles past it, so the unused capacity costs no arithmetic."""
+        ops.check_photo_inputs(data, pad)
         pad = pad.contiguous()
         if pad.dtype != torch.bool:
             pad = pad != 0
-        cu, src = ops.photo_compact(pad)
-        T = int(cu[-1].item()) if total_tokens is None else int(total_tokens)
-        return cu, src, T
+        B, L = pad.shape
+        T = ops.token_capacity(B, L, total_tokens)
+        cu, src = ops.photo_compact(pad, T)
+        return cu, src, T, ops._offset_ptr(cu, B)
 
     def encode_tokens(self, data, pad, dtype, total_tokens=None, packed=None):
-        """Returns (h [T,D] packed tokens after the last layer, cu_seqlens)."""
+        """Returns (h [T,D] packed tokens after the last layer (rows past cu[B] are undefined), cu_seqlens)."""
         if not data.is_cuda:
             raise RuntimeError("applecider_b200: inputs must be CUDA tensors (no CPU fallback)")
         B, L, F = data.shape
-        assert F == 7
         data = data.contiguous().float()
-        cu, src, T = packed if packed is not None else self.pack(pad, total_tokens)
+        cu, src, T, nv = packed if packed is not None else self.pack(data, pad, total_tokens)
         D = self.d_model
         t2v = self.time2vec
         h = ops.photo_embed(data, src, T, D, self.in_proj.weight, self.in_proj.bias, t2v.w0, t2v.b0, t2v.w, t2v.b,
                             self.cls_tok, dtype)
+        mv = nv if dtype != torch.float32 else None  # the fp32 parity GEMM has no device row count: it runs all capacity rows
         for lyr in self.encoder.layers:
             sa = lyr.self_attn
-            qkv = ops.gemm(h, self._w(sa.in_proj_weight, dtype), sa.in_proj_bias)
+            qkv = ops.gemm(h, self._w(sa.in_proj_weight, dtype), sa.in_proj_bias, m_valid=mv)
             att = ops.attention_varlen(qkv, cu, B, self.n_heads, D // self.n_heads, L + 1)
-            o = ops.gemm(att, self._w(sa.out_proj.weight, dtype), sa.out_proj.bias, res=h, res_mode=ops.RES_ADD)
-            h1 = ops.layernorm(o, lyr.norm1.weight, lyr.norm1.bias, lyr.norm1.eps)
-            f = ops.gemm(h1, self._w(lyr.linear1.weight, dtype), lyr.linear1.bias, act=ops.ACT_RELU)
-            g = ops.gemm(f, self._w(lyr.linear2.weight, dtype), lyr.linear2.bias, res=h1, res_mode=ops.RES_ADD)
-            h = ops.layernorm(g, lyr.norm2.weight, lyr.norm2.bias, lyr.norm2.eps)
+            o = ops.gemm(att, self._w(sa.out_proj.weight, dtype), sa.out_proj.bias, res=h, res_mode=ops.RES_ADD, m_valid=mv)
+            h1 = ops.layernorm(o, lyr.norm1.weight, lyr.norm1.bias, lyr.norm1.eps, rows_dev=nv)
+            f = ops.gemm(h1, self._w(lyr.linear1.weight, dtype), lyr.linear1.bias, act=ops.ACT_RELU, m_valid=mv)
+            g = ops.gemm(f, self._w(lyr.linear2.weight, dtype), lyr.linear2.bias, res=h1, res_mode=ops.RES_ADD, m_valid=mv)
+            h = ops.layernorm(g, lyr.norm2.weight, lyr.norm2.bias, lyr.norm2.eps, rows_dev=nv)
         return h, cu
 
 
@@ -114,17 +115,18 @@ class HyraxBaselineCLS(_PhotoEncoderBase):
             print(f"Loaded pretrained weights from {path}")
 
     def encode(self, data, pad, total_tokens=None, packed=None):
+        """total_tokens: optional packed token count from the collate (sum of lengths + B, or any upper bound)."""
         h, cu = self.encode_tokens(data, pad, self.compute_dtype, total_tokens, packed)
         cls = ops.gather_cls(h, cu, data.shape[0])
         return ops.layernorm(cls, self.norm.weight, self.norm.bias, self.norm.eps)
 
-    def forward(self, x):
-        data, pad, _ = x
+    def forward(self, x, total_tokens=None):
+        data, pad = x[0], x[1]
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .train import photo_forward_train
 
-            return photo_forward_train(self, data, pad)
-        out = self.encode(data, pad)
+            return photo_forward_train(self, data, pad, total_tokens)
+        out = self.encode(data, pad, total_tokens)
         if self.classification:
             out = ops.gemm(out, self.fc.weight, self.fc.bias)
         if self.config["model"]["HyraxBaselineCLS"]["use_probabilities"]:
@@ -208,8 +210,8 @@ class BaselineCLS(_PhotoEncoderBase):
         self.head = nn.Linear(d_model, num_classes)
         self.compute_dtype = resolve_dtype(compute_dtype)
 
-    def forward(self, x, pad_mask):
-        h, cu = self.encode_tokens(x, pad_mask, self.compute_dtype)
+    def forward(self, x, pad_mask, total_tokens=None):
+        h, cu = self.encode_tokens(x, pad_mask, self.compute_dtype, total_tokens)
         cls = ops.gather_cls(h, cu, x.shape[0])
         z = ops.layernorm(cls, self.norm.weight, self.norm.bias, self.norm.eps)
         return ops.gemm(z, self.head.weight, self.head.bias)

@@ -34,13 +34,17 @@ def photo_encode_train(model, data, pad, total_tokens=None, tokens=False, te_dro
     tr = model.training
     mc = model.config["model"]["HyraxBaselineCLS"] if hasattr(model, "config") else {"dropout": 0.0}
     p_drop = float(mc.get("dropout", 0.0)) if tr else 0.0
+    ops.check_photo_inputs(data, pad)
     B, L, _ = data.shape
     data = data.contiguous().float()
     pad = pad.contiguous()
     if pad.dtype != torch.bool:
         pad = pad != 0
-    cu, src = ops.photo_compact(pad)
-    T = int(cu[-1].item()) if total_tokens is None else int(total_tokens)
+    # T is a row capacity (the collate's packed count, or B*(L+1)); nothing is read back from the device.  Capacity rows past
+    # cu[B] are zero after the embedding and in the attention output, every other op is row-local, and their gradient is zero
+    # (CLS scatter / loss), so the row reductions of the backward (weight gradients, bias sums) see exact zeros from them.
+    T = ops.token_capacity(B, L, total_tokens)
+    cu, src = ops.photo_compact(pad, T)
     D, H = model.d_model, model.n_heads
     t2v = model.time2vec
     te_p = float(mc.get("dropout", 0.0)) if te_dropout else 0.0  # MPTModel: F.dropout(te) is always active (:248)
@@ -67,8 +71,8 @@ def photo_encode_train(model, data, pad, total_tokens=None, tokens=False, te_dro
     return fn.layernorm(cls, model.norm.weight, model.norm.bias, model.norm.eps)
 
 
-def photo_forward_train(model, data, pad):
-    out = photo_encode_train(model, data, pad)
+def photo_forward_train(model, data, pad, total_tokens=None):
+    out = photo_encode_train(model, data, pad, total_tokens)
     if model.classification:
         out = fn.linear(out, model.fc.weight, model.fc.bias)
     if model.config["model"]["HyraxBaselineCLS"]["use_probabilities"]:
@@ -458,8 +462,8 @@ def astrominn_train_step(model, batch):
 
 
 # ---- fusion ---------------------------------------------------------------------------------------------------
-def fusion_forward_train(model, photometry, photometry_mask, metadata, images, spectra):
-    p = photo_encode_train(model.photometry_encoder, photometry, photometry_mask)
+def fusion_forward_train(model, photometry, photometry_mask, metadata, images, spectra, total_tokens=None):
+    p = photo_encode_train(model.photometry_encoder, photometry, photometry_mask, total_tokens)
     s = spectra_forward_train(model.spectra_encoder, spectra)
     if s.dim() == 1:
         s = s[:, None]

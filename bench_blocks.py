@@ -1,0 +1,403 @@
+"""The non-headline BASELINE configs, measured in the same bench.py run and printed in the same JSON line.
+
+train_block       configs[3]  fusion training, data parallel (B per GPU), NCCL all-reduce of the flat gradient, fused Adam
+cnn_train_block   configs[2]  AstroMiNN (ConvNeXt-T cutouts + metadata towers + MoE) training
+preprocess_block  configs[4]  P1-P5 over 1 M synthetic alerts streamed in HBM-resident chunks
+eager_block       the same-box library bar: the reference's modules (oracle port, plain PyTorch ops = cuDNN / cuBLAS / fused
+                  MHA) on this GPU -- bench-only use of oracle/, like the cpu_baseline leg
+
+Same timing rules as bench.py: >= 3 warm-up steps, CUDA events on the launching stream, barrier + synchronize on both sides,
+max over ranks; every working set is far larger than the 126 MB L2.
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+import time
+
+import numpy as np
+import torch
+
+
+@dataclasses.dataclass
+class Ctx:
+    args: object
+    peaks: dict
+    dist: object
+    world: int
+    rank: int
+    local_rank: int
+    ClockSampler: type
+
+
+def resolve_blocks(spec, world):
+    if spec == "none":
+        return []
+    if spec == "auto":
+        return ["train"] if world > 1 else ["train", "cnn_train", "preprocess", "eager"]
+    if spec == "all":
+        return ["train", "cnn_train", "preprocess", "eager"] if world == 1 else ["train"]
+    names = [s.strip() for s in spec.split(",") if s.strip()]
+    for n in names:
+        if n not in ("train", "cnn_train", "preprocess", "eager"):
+            raise SystemExit(f"unknown block {n!r}")
+    return [n for n in names if world == 1 or n == "train"]
+
+
+def _barrier(ctx):
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(ctx, vals):
+    t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+    if ctx.dist is not None:
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+# =========================================================================================================
+# training blocks
+# =========================================================================================================
+def _train(ctx, kind):
+    import applecider_b200 as ab
+    from applecider_b200 import _lib, fn, synth
+    from applecider_b200.ddp import FlatGradSync, ddp_train_step
+    from bench import astrominn_fwd_flops, fusion_fwd_flops
+
+    args, world, rank = ctx.args, ctx.world, ctx.rank
+    W, K = max(args.warmup, 3), args.steps
+    fusion = kind == "train"
+    B = args.train_batch if fusion else args.cnn_batch
+    if fusion:
+        model = ab.AppleCider(ab.default_config(), hidden_dim=64, fusion="avg", compute_dtype=args.dtype)
+        opt_fn = lambda ps: torch.optim.Adam(ps, lr=1e-3, weight_decay=0.01)  # noqa: E731  (brew_cider.py:1211)
+    else:
+        cfg = ab.default_config()
+        cfg["model"]["AstroMiNN"]["compute_dtype"] = args.dtype
+        model = ab.AstroMiNN(cfg)
+        opt_fn = None
+    model.load_state_dict(synth.det_state_dict(model, 0), strict=True)
+    model = model.cuda().train()
+    topt = opt_fn([p for p in model.parameters() if p.requires_grad]) if opt_fn else model.this_optimizer
+    if args.torch_optim:
+        sync = FlatGradSync(model)
+        sync.broadcast_parameters(0)
+        optimizer = topt
+    else:  # fused step: two kernels over flat buffers, bf16 weight shadow refreshed in the same pass
+        from applecider_b200.optim import fused_from_torch
+
+        optimizer = fused_from_torch(topt, bf16_shadow=(args.dtype == "bf16"))
+        sync = optimizer.grads
+    if world > 1 and not args.no_overlap:
+        sync.enable_overlap()  # bucketed all-reduce launched from the autograd hooks, overlapped with the rest of the backward
+    sync.time_sync = True
+    fn.set_seed(1234)  # torch.cuda.manual_seed + the rank: replicas draw independent dropout masks
+
+    seed = 1337 + rank
+    x, pad, lens = synth.photometry_batch(B, seed=seed)
+    host = {"x": x, "pad": pad, "meta": synth.metadata(B, seed=seed), "img": synth.cutouts(B, seed=seed),
+            "spec": synth.spectra(B, seed=seed, L=4096),
+            "tgt": torch.nn.functional.one_hot(synth.labels(B, seed=seed), 5).float()}
+    if not fusion:
+        host = {k: host[k] for k in ("meta", "img", "tgt")}
+    ntok = int(lens.sum()) + B
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    dev = {k: v.cuda() for k, v in pinned.items()}
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+
+    def fwd_loss(d):
+        if fusion:
+            out = model(d["x"], d["pad"], d["meta"], d["img"], d["spec"], total_tokens=ntok)
+        else:
+            out = model((d["meta"], d["img"], d["tgt"]))
+        return fn.soft_cross_entropy(out, d["tgt"])
+
+    def step(d):
+        return ddp_train_step(sync, lambda: fwd_loss(d), optimizer)
+
+    first_loss = None
+    for i in range(W):
+        l = step(dev)
+        if i == 0:
+            first_loss = l
+    sync.exposed_ms()
+    _barrier(ctx)
+    sampler = ctx.ClockSampler(ctx.local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    e0.record()
+    for _ in range(K):
+        loss = step(dev)
+    e1.record()
+    host_ms = (time.perf_counter() - t_host0) * 1e3  # CPU time to ENQUEUE the K steps (launch-bound check)
+    _barrier(ctx)
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count()
+    exposed = sync.exposed_ms()
+    clocks = sampler.stop() if rank == 0 else None
+    # end to end: pinned host batch -> device every step, loss read back every step
+    _barrier(ctx)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        d = {k: v.cuda(non_blocking=True) for k, v in pinned.items()}
+        lv = step(d).item()
+    _barrier(ctx)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    sync.exposed_ms()
+    ms, e2e_ms, exposed, host_ms = _max_over_ranks(ctx, [ms, e2e_ms, exposed, host_ms])
+    if rank != 0:
+        return None
+    flops_step = 3.0 * (fusion_fwd_flops(lens.numpy()) if fusion else astrominn_fwd_flops(B))  # forward + dgrad + wgrad
+    sps = world * B * K / (ms / 1e3)
+    peak = ctx.peaks["tf_sustained"] * 1e12
+    return {
+        "metric": "fusion_training_samples_per_sec" if fusion else "astrominn_training_samples_per_sec",
+        "samples_per_s": sps, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "batch_per_gpu": B, "global_batch": B * world, "dtype": args.dtype, "scaling": "weak",
+        "step": "forward + backward (C-ABI kernels) + NCCL all-reduce(avg) of the flat gradient (bucketed, launched from autograd hooks) + "
+                + ("torch optimizer step" if args.torch_optim else "fused clip/Adam kernel (acb_adam_step)") + "; dropout on",
+        "optimizer": "Adam(lr 1e-3, wd 0.01) (brew_cider.py:1211)" if fusion else "AdamW 11 groups (astrominn.py:151-218)",
+        "allreduce_ms_exposed": exposed, "allreduce_bytes": sync.allreduce_bytes, "grad_elements": sync.numel,
+        "host_enqueue_ms_per_step": host_ms / K, "gpu_launches_per_step": launches / K,
+        "algorithmic_gflop_per_sample": flops_step / B / 1e9, "tokens_per_batch": ntok if fusion else None,
+        "fraction_of_tensor_roofline": (sps / world) * (flops_step / B) / peak,
+        "e2e_samples_per_s": world * B * K / (e2e_ms / 1e3), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+        "initial_loss": float(first_loss), "final_loss": float(loss), "final_loss_e2e": float(lv), "clocks": clocks,
+    }
+
+
+def train_block(ctx):
+    return _train(ctx, "train")
+
+
+def cnn_train_block(ctx):
+    return _train(ctx, "cnn_train")
+
+
+# =========================================================================================================
+# preprocessing sweep (configs[4]): 1 M alerts
+# =========================================================================================================
+def preprocess_block(ctx):
+    """P1-P5 over `--prep-alerts` synthetic alerts.  The alerts are streamed through HBM in chunks: one chunk of every input
+    kind is generated on the host and uploaded once, then every kernel runs over ceil(N / chunk) chunk passes (the chunk
+    working sets -- 0.3-2.6 GB -- are far beyond the 126 MB L2, so re-running a chunk re-streams it from HBM).  Per kernel:
+    alerts/s over the whole sweep and achieved GB/s on its algorithmic bytes."""
+    from applecider_b200 import preprocess as pp, synth
+
+    if ctx.rank != 0:
+        return None
+    N = int(ctx.args.prep_alerts)
+    peaks = ctx.peaks
+    res = {}
+
+    def sweep(f, chunk, label, byts_per_chunk, unit="alerts"):
+        passes = max(1, (N + chunk - 1) // chunk)
+        for _ in range(3):
+            f()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(passes):
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        gbs = byts_per_chunk * passes / ms / 1e6
+        res[label] = {f"{unit}_per_s": chunk * passes / ms * 1e3, "n_" + unit: chunk * passes, "chunk": chunk, "passes": passes, "ms_total": ms,
+                      "GBps": gbs, "frac_hbm": gbs / peaks["hbm_gbs"]}
+
+    # P1 light curves: 50 k alerts per chunk (tile a 10 k-alert synthetic set)
+    raws = synth.raw_light_curves(10_000, seed=1) * 5
+    raw, off = pp.ragged(raws)
+    mean, std = torch.tensor([2.9, 0.9, 1.5, 0.08]).cuda(), torch.tensor([1.1, 0.8, 0.5, 0.04]).cuda()
+    sweep(lambda: pp.prep_lightcurves(raw, off, 100.0, mean, std), len(raws), "P1_lightcurve", raw.numel() * 4 + len(raws) * 257 * 29)
+    del raw, off
+
+    # P3 spectra: 50 k per chunk (tile 2 k synthetic ragged spectra)
+    specs = synth.raw_spectra(2000, seed=2) * 25
+    wl, offs = pp.ragged([s[:, 0] for s in specs])
+    fx, _ = pp.ragged([s[:, 1] for s in specs])
+    grid = pp.wave_grid()
+    mx = int(max(len(s) for s in specs))
+    sweep(lambda: pp.resample_spectra(wl, fx, offs, grid, mx), len(specs), "P3_spectrum_resample", wl.numel() * 16 + len(specs) * 3481 * 4)
+    del wl, fx, offs, specs
+
+    # P4 cutouts: 32 k per chunk
+    img = synth.cutouts(4096, seed=3, normalise=False).cuda().repeat(8, 1, 1, 1)
+    sweep(lambda: pp.normalize_cutouts(img, "median"), img.shape[0], "P4_cutout_median_norm", img.numel() * 8)
+    del img
+
+    # P2 event merge: 50 k objects per chunk
+    rng = np.random.default_rng(5)
+    nobj = 50_000
+    lens = rng.integers(5, 120, size=nobj)
+    tot = int(lens.sum())
+    offd = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).cuda()
+    mjd = torch.from_numpy(np.concatenate([np.sort(rng.uniform(0, 90, size=k)) for k in lens])).cuda()
+    mag = torch.from_numpy(rng.normal(19, 0.8, size=tot)).cuda()
+    magerr = torch.from_numpy(np.abs(rng.normal(0.08, 0.04, size=tot)) + 0.005).cuda()
+    fid = torch.from_numpy(rng.choice([1, 2, 3], size=tot, p=[0.45, 0.45, 0.1]).astype(np.int32)).cuda()
+    sweep(lambda: pp.prep_events(mjd, mag, magerr, fid, offd), nobj, "P2_event_merge", tot * (28 + 17))
+    del mjd, mag, magerr, fid
+
+    # P5 feature statistics over the event table of 1 M alerts (~40 events each) in 20 M-row chunks
+    ev = torch.randn(20_000_000, 14, device="cuda")
+    rows_total = N * 40
+    passes = max(1, rows_total // ev.shape[0])
+    for _ in range(3):
+        pp.feature_stats(ev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(passes):
+        pp.feature_stats(ev)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    gbs = ev.numel() * 4 * passes / ms / 1e6
+    res["P5_feature_stats"] = {"rows_per_s": ev.shape[0] * passes / ms * 1e3, "n_rows": ev.shape[0] * passes, "ms_total": ms, "GBps": gbs,
+                               "frac_hbm": gbs / peaks["hbm_gbs"]}
+    return {"metric": "preprocessing_alerts_per_sec", "unit": "alerts/s", "n_alerts": N, "kernels": res,
+            "note": "inputs resident in HBM, streamed in chunks (see chunk/passes per kernel); CUDA-event timing, 3 warm-ups; "
+                    "GBps = algorithmic bytes (SURVEY §8d) / time, frac_hbm against the measured copy bandwidth"}
+
+
+# =========================================================================================================
+# same-box library bar: the reference's modules as plain PyTorch on this GPU
+# =========================================================================================================
+def eager_block(ctx):
+    """The reference is pure PyTorch: moved to the GPU it runs on cuDNN (Conv1d/Conv2d), cuBLAS (Linear) and PyTorch's fused
+    MHA.  This leg times exactly that -- the oracle port of the reference modules (the photometry encoder calls
+    nn.TransformerEncoder with src_key_padding_mask the way HyraxBaselineCLS.py:71-78 does, so torch may take its
+    nested-tensor fast path) -- on the same synthetic batch, in two precisions: bf16 autocast (what SURVEY §8d names) and a
+    plain .bfloat16() module cast (no autocast: keeps torch's transformer fast path available); the better one is `value`.
+    Training: train mode, bf16 autocast, fwd + bwd + Adam.  A few steps only (it is a reference bar, not the product)."""
+    import torch.nn.functional as F
+
+    from applecider_b200 import synth
+    from oracle import models as om  # bench-only, like the cpu_baseline leg
+
+    if ctx.rank != 0:
+        return None
+
+    class EagerPhoto(om.HyraxBaselineCLS):
+        def encode(self, data, pad):
+            B = data.shape[0]
+            h = self.in_proj(data) + self.time2vec(data[..., 0])
+            h = torch.cat([self.cls_tok.expand(B, -1, -1).to(h.dtype), h], dim=1)
+            z = self.encoder(h, src_key_padding_mask=F.pad(pad, (1, 0), value=False))
+            return self.norm(z[:, 0])
+
+    def build():
+        m = om.AppleCider(om.default_config(), hidden_dim=64, fusion="avg")
+        m.load_state_dict(synth.det_state_dict(m, 0))
+        m.photometry_encoder.__class__ = EagerPhoto
+        return m.cuda()
+
+    def timeit(f, warm=1, reps=3):
+        for _ in range(warm):
+            f()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    out = {"what": "oracle port of the reference modules, plain PyTorch eager on the same B200 (cuDNN/cuBLAS/fused MHA), synthetic batch"}
+    torch.backends.cudnn.benchmark = True
+    B = ctx.args.batch
+    x, pad, lens = synth.photometry_batch(B, seed=1337)
+    inp = [x.cuda(), pad.cuda(), synth.metadata(B, seed=1337).cuda(), synth.cutouts(B, seed=1337).cuda(), synth.spectra(B, seed=1337, L=4096).cuda()]
+    model = build().eval()
+
+    def run_chunks(fwd, chunk):
+        for i in range(0, B, chunk):
+            fwd(*[t[i:i + chunk] for t in inp])
+
+    infer = {}
+    for mode in ("autocast_bf16", "module_bf16"):
+        chunk = B
+        while chunk >= 64:
+            try:
+                if mode == "autocast_bf16":
+                    def fwd(*a):
+                        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                            return model(*a)
+                else:
+                    m16 = build().eval().bfloat16()
+
+                    def fwd(*a, _m=m16):
+                        with torch.no_grad():
+                            return _m(a[0].bfloat16(), a[1], a[2].bfloat16(), a[3].bfloat16(), a[4].bfloat16())
+                ms = timeit(lambda: run_chunks(fwd, chunk))
+                infer[mode] = {"alerts_per_s": B / ms * 1e3, "ms_per_batch": ms, "batch": B, "chunk": chunk}
+                break
+            except torch.cuda.OutOfMemoryError:
+                torch.cuda.empty_cache()
+                chunk //= 2
+            except Exception as e:  # e.g. an op without a bf16 kernel
+                infer[mode] = {"error": f"{type(e).__name__}: {e}"[:200]}
+                break
+        torch.cuda.empty_cache()
+    ok = [v["alerts_per_s"] for v in infer.values() if "alerts_per_s" in v]
+    out["inference"] = infer
+    out["value"] = max(ok) if ok else None
+    out["unit"] = "alerts/s"
+    del model
+    torch.cuda.empty_cache()
+
+    # training: fusion B = train_batch, bf16 autocast, Adam
+    Bt = ctx.args.train_batch
+    tm = build().train()
+    opt = torch.optim.Adam(tm.parameters(), lr=1e-3, weight_decay=0.01)
+    tgt = torch.nn.functional.one_hot(synth.labels(Bt, seed=1337), 5).float().cuda()
+    ti = [t[:Bt] for t in inp]
+
+    def tstep():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = tm(*ti)
+        loss = torch.nn.functional.cross_entropy(logits.float(), tgt)
+        loss.backward()
+        opt.step()
+
+    try:
+        ms = timeit(tstep)
+        out["train"] = {"samples_per_s": Bt / ms * 1e3, "ms_per_step": ms, "batch": Bt, "mode": "autocast_bf16, torch.optim.Adam"}
+    except Exception as e:
+        out["train"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    del tm, opt
+    torch.cuda.empty_cache()
+
+    # AstroMiNN training (configs[2] bar)
+    Bc = ctx.args.cnn_batch
+    am = om.AstroMiNN(om.default_config())
+    am.load_state_dict(synth.det_state_dict(am, 0))
+    am = am.cuda().train()
+    from oracle.train_steps import astrominn_optimizer
+
+    aopt = astrominn_optimizer(am, am.config["model"]["AstroMiNN"])
+    meta, img = inp[2][:Bc], inp[3][:Bc]
+    tgt = torch.nn.functional.one_hot(synth.labels(Bc, seed=1337), 5).float().cuda()
+
+    def cstep():
+        aopt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = am((meta, img, None))
+        torch.nn.functional.cross_entropy(logits.float(), tgt).backward()
+        aopt.step()
+
+    try:
+        ms = timeit(cstep)
+        out["cnn_train"] = {"samples_per_s": Bc / ms * 1e3, "ms_per_step": ms, "batch": Bc, "mode": "autocast_bf16, torch AdamW (11 groups)"}
+    except Exception as e:
+        out["cnn_train"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    return out

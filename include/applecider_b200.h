@@ -117,12 +117,20 @@ int acb_pad_signal(const float* in, void* out, int out_dtype, int nb, int L, lon
  * timm LayerNorm/LayerNorm2d (eps 1e-6). */
 int acb_layernorm(const void* x, int x_dtype, const void* res, int res_dtype, const float* w, const float* b,
                   void* y, int y_dtype, long long rows, int C, float eps, int pre_gelu, int post_act, void* stream);
+/* the same with the row count read on the device: rows_dev (optional) caps `rows`, so a capacity-sized token matrix
+ * (acb_photo_compact) costs no work for the rows past the packed count and nothing is read back to the host. */
+int acb_layernorm_n(const void* x, int x_dtype, const void* res, int res_dtype, const float* w, const float* b,
+                    void* y, int y_dtype, long long rows, int C, float eps, int pre_gelu, int post_act, const int* rows_dev,
+                    void* stream);
 
 /* ---- photometry transformer pieces --------------------------------------------------------------- */
 /* pad[B,L] (bool bytes, nonzero = padding) -> cu_seqlens[B+1] (tokens incl. CLS) and src_idx[T]
- * (source row b*L+l of every packed token, -1-b for the CLS token of sequence b).
+ * (source row b*L+l of every packed token, -1-b for the CLS token of sequence b).  src_idx has the full capacity of
+ * B*(L+1) entries; those past cu_seqlens[B] are "dead" (0x80808080): acb_photo_embed writes zero rows for them, so a
+ * caller may size the token matrix by any upper bound of the packed count without reading it back from the device.
+ * capacity (0 = B*(L+1)) is that bound: cu_seqlens is clamped to it, so a too-small bound truncates instead of overrunning.
  * HyraxBaselineCLS.py:71-78 (CLS prepend + key-padding mask); equals PyTorch's nested-tensor packing. */
-int acb_photo_compact(const uint8_t* pad, int B, int L, int* cu_seqlens, int* src_idx, void* stream);
+int acb_photo_compact(const uint8_t* pad, int B, int L, int capacity, int* cu_seqlens, int* src_idx, void* stream);
 /* packed tokens h[t,:] = in_proj(x[src]) + Time2Vec(x[src,0]) or cls_tok  (HyraxBaselineCLS.py:60-72,
  * Time2Vec.py:63-72).  D = d_model. */
 int acb_photo_embed(const float* x, const int* src_idx, const int* total_dev, int max_tokens, int D, const float* w_in,

@@ -73,6 +73,67 @@ def test_two_rank_step_equals_single_rank_full_batch(overlap):
         assert np.array_equal(a, b), "replicas must stay bit-identical"
 
 
+def _worker_accum(rank, world, port, q):
+    """Gradient accumulation (two micro-batches, all-reduce only after the second), replicas that start from DIFFERENT
+    weights (broadcast_parameters must fix that), enable_overlap called twice (must not double-count)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from applecider_b200.ddp import FlatGradSync, shard_batch
+
+    torch.manual_seed(1)
+    x, y = torch.randn(16, 7), torch.randint(0, 5, (16,))
+    torch.manual_seed(100 + rank)  # different init per rank
+    model = torch.nn.Sequential(torch.nn.Linear(7, 16), torch.nn.Tanh(), torch.nn.Linear(16, 5))
+    sync = FlatGradSync(model)
+    sync.broadcast_parameters(0)
+    sync.enable_overlap(bucket_elems=64)
+    sync.enable_overlap(bucket_elems=64)
+    assert sum(len(p._post_accumulate_grad_hooks or {}) for p in sync.params) == len(sync.params)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    lo, hi = shard_batch(16, rank, world)
+    mid = (lo + hi) // 2
+    loss = lambda a, b: torch.nn.functional.cross_entropy(model(x[a:b]), y[a:b], reduction="sum") / 16.0 * world  # noqa: E731
+    for _ in range(2):
+        sync.zero()
+        with sync.no_sync():
+            loss(lo, mid).backward()
+        loss(mid, hi).backward()
+        sync.sync()
+        opt.step()
+    q.put((rank, [p.detach().numpy().copy() for p in model.parameters()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_accumulation_broadcast_and_idempotent_overlap():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_accum, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(1)
+    x, y = torch.randn(16, 7), torch.randint(0, 5, (16,))
+    torch.manual_seed(100)  # rank 0's init is what every replica must have used
+    model = torch.nn.Sequential(torch.nn.Linear(7, 16), torch.nn.Tanh(), torch.nn.Linear(16, 5))
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    for _ in range(2):
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(model(x), y).backward()
+        opt.step()
+    import numpy as np
+
+    for r in (0, 1):
+        for a, b in zip(results[r], model.parameters()):
+            assert np.allclose(a, b.detach().numpy(), atol=1e-6), f"rank {r}: accumulated 2-rank step != full-batch step"
+    for a, b in zip(results[0], results[1]):
+        assert np.array_equal(a, b)
+
+
 def test_shard_batch_covers_everything():
     from applecider_b200.ddp import shard_batch
 

@@ -2,7 +2,7 @@
 committed golden outputs of the REAL reference (tests/golden/*.npz).
 
 Tolerances (SURVEY.md §7 hard part 6): fp32 path |err| <= 1e-4 * max(1, |ref|_inf); bf16 path
-|err| <= 3e-2 * max(1, |ref|_inf) with 100 % argmax agreement on rows whose top-2 margin exceeds
+|err| <= 5e-3 * max(1, |ref|_inf) (measured 6e-4 .. 2e-3) with 100 % argmax agreement on rows whose top-2 margin exceeds
 the same bound."""
 import pytest
 import torch
@@ -12,7 +12,7 @@ from util import assert_close, load_golden
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 FP32_TOL = 1e-4
-BF16_TOL = 3e-2
+BF16_TOL = 5e-3
 
 
 def _pair(name, cfg_edit=None, dtype="fp32", **kw):
@@ -282,7 +282,7 @@ def test_spectra_stage0_persistent_kernel_matches_per_tile_kernel():
     m32.load_state_dict(synth.det_state_dict(m32, 0), strict=True)
     m32 = m32.cuda().eval()
     with torch.no_grad():
-        assert_close(m((x.view(40, 1, 4096), None, None)), m32((x.view(40, 1, 4096), None, None)), 3e-2, "persistent stage 0 through the network")
+        assert_close(m((x.view(40, 1, 4096), None, None)), m32((x.view(40, 1, 4096), None, None)), BF16_TOL, "persistent stage 0 through the network")
 
 
 def test_spectra_stage0_fused_downsample_matches_unfused():

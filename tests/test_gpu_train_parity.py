@@ -1,0 +1,140 @@
+"""GPU training parity, part 2 (round 2):
+
+* ``train_step`` of AstroMiNN (11-group AdamW) and SpectraNet (injected Adam + CE) against fixtures recorded from the
+  UNMODIFIED reference train_steps (tests/golden/train_steps.npz; two consecutive steps, fp32 path);
+* the bf16 tcgen05 training path of the FUSION model (the configuration bench.py's train block runs, dropout off) against
+  the CPU oracle's autograd: per tensor cosine >= 0.995 and relative L2 error <= 3 % on every large tensor;
+* the reference's own seeded random init (layer scale 1e-6, trunc-normal 0.02, randn Time2Vec) through both precisions.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from train_step_util import check_two_steps, load_steps
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _prod(name, dtype="fp32", **kw):
+    import applecider_b200 as ab
+    from applecider_b200 import synth
+
+    cfg = ab.default_config()
+    for k in cfg["model"]:
+        cfg["model"][k]["compute_dtype"] = dtype
+    m = getattr(ab, name)(cfg, **kw)
+    m.load_state_dict(synth.det_state_dict(m, 0), strict=True)
+    return m.to(DEV).eval()
+
+
+def test_astrominn_train_step_matches_reference(golden_dir):
+    """astrominn.py:308-326 with the 11 AdamW groups of :151-218 -- two steps, eval mode (dropout off)."""
+    g = load_steps(golden_dir, "astrominn")
+    m = _prod("AstroMiNN")
+    # the optimizer was built in __init__ from CPU parameters; .to() keeps the Parameter objects, so the groups still hold
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    batch = (g["meta"].to(DEV), g["img"].to(DEV), g["tgt"].to(DEV))
+    l1 = m.train_step(batch)["loss"]
+    l2 = m.train_step(batch)["loss"]
+    worst = check_two_steps(g, dict(m.named_parameters()), before, (l1, l2), loss_tol=1e-4, solid_tol=0.02)
+    print("worst solid-element update error:", worst)
+
+
+def test_spectranet_train_step_matches_reference(golden_dir):
+    """spectranet.py:172-184 with the optimizer / criterion Hyrax would inject."""
+    g = load_steps(golden_dir, "spectranet")
+    m = _prod("SpectraNet")
+    m.optimizer = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=0.01)
+    m.criterion = torch.nn.CrossEntropyLoss()
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    batch = (g["x"].to(DEV), g["labels"].to(DEV), None)
+    l1 = m.train_step(batch)["loss"]
+    l2 = m.train_step(batch)["loss"]
+    worst = check_two_steps(g, dict(m.named_parameters()), before, (l1, l2), loss_tol=1e-4, solid_tol=0.02)
+    print("worst solid-element update error:", worst)
+
+
+def _grad_report(prod, oracle, skip=(), large=4096):
+    rows = []
+    og = {n: p.grad for n, p in oracle.named_parameters()}
+    for n, p in prod.named_parameters():
+        ref = og.get(n)
+        if ref is None or any(n.startswith(s) for s in skip):
+            continue
+        assert p.grad is not None, f"no gradient for {n}"
+        got = p.grad.detach().float().cpu().flatten()
+        ref = ref.flatten()
+        assert torch.isfinite(got).all(), n
+        rn = ref.norm().item()
+        if rn < 1e-12:
+            continue
+        cos = torch.nn.functional.cosine_similarity(got, ref, dim=0).item()
+        rel = (got - ref).norm().item() / rn
+        rows.append((n, ref.numel(), cos, rel))
+    return rows
+
+
+def test_fusion_bf16_gradients_vs_oracle():
+    """The bench's training configuration (bf16 fusion, full-length spectra, Hyrax-length light curves), dropout off."""
+    import applecider_b200 as ab
+    from applecider_b200 import fn, synth
+    from oracle import models as om
+
+    torch.set_num_threads(os.cpu_count() or 8)
+    oracle = om.AppleCider(om.default_config(), hidden_dim=64, fusion="avg").eval()
+    sd = synth.det_state_dict(oracle, 0)
+    oracle.load_state_dict(sd)
+    prod = ab.AppleCider(ab.default_config(), hidden_dim=64, fusion="avg", compute_dtype="bf16")
+    prod.load_state_dict(sd, strict=True)
+    prod = prod.to(DEV).eval()
+    B = 32
+    x, pad, lens = synth.photometry_batch(B, seed=401)
+    meta, img, sp = synth.metadata(B, seed=401), synth.cutouts(B, seed=401), synth.spectra(B, seed=401, L=4096)
+    tgt = torch.nn.functional.one_hot(synth.labels(B, seed=401), 5).float()
+    out = prod(x.to(DEV), pad.to(DEV), meta.to(DEV), img.to(DEV), sp.to(DEV), total_tokens=int(lens.sum()) + B)
+    ref = oracle(x, pad, meta, img, sp)
+    assert_close(out, ref, 5e-3, "bf16 fusion train-path logits")
+    fn.soft_cross_entropy(out, tgt.to(DEV)).backward()
+    oracle.zero_grad()
+    torch.nn.functional.cross_entropy(ref, tgt).backward()
+    rows = _grad_report(prod, oracle, skip=("photometry_encoder.head.", "photometry_encoder.fc."))
+    rows.sort(key=lambda r: r[2])
+    print("lowest cosines:", [(n, k, round(c, 4), round(r, 4)) for n, k, c, r in rows[:8]])
+    print("largest rel-L2:", [(n, k, round(c, 4), round(r, 4)) for n, k, c, r in sorted(rows, key=lambda r: -r[3])[:8]])
+    bad = [(n, k, c, r) for n, k, c, r in rows if k >= 4096 and (c < 0.995 or r > 0.03)]
+    assert not bad, f"large tensors outside cosine >= 0.995 / rel-L2 <= 3 %: {bad[:10]}"
+    small_bad = [(n, k, c, r) for n, k, c, r in rows if k < 4096 and c < 0.98]
+    assert not small_bad, f"small tensors below cosine 0.98: {small_bad[:10]}"
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 5e-3)])
+def test_reference_random_init(golden_dir, dtype, tol):
+    """Weights = the reference's own seeded random init (oracle constructed under torch.manual_seed(0); the CPU suite and
+    the golden generator check that this is bit-identical to the REAL reference's init), not the trained-looking synthetic
+    state: layer scale 1e-6 and trunc-normal 0.02 make very different activation statistics."""
+    import applecider_b200 as ab
+    from oracle import models as om
+
+    z = np.load(os.path.join(golden_dir, "refinit.npz"))
+    x, pad = torch.from_numpy(z["in/x"]), torch.from_numpy(z["in/pad"])
+    meta, img, sp = torch.from_numpy(z["in/meta"]), torch.from_numpy(z["in/img"]), torch.from_numpy(z["in/spec"])
+    for name, batch in [("HyraxBaselineCLS", (x, pad, None)), ("SpectraNet", (sp, None, None)), ("AstroMiNN", (meta, img, None))]:
+        torch.manual_seed(0)
+        oracle = getattr(om, name)(om.default_config()).eval()
+        cfg = ab.default_config()
+        for k in cfg["model"]:
+            cfg["model"][k]["compute_dtype"] = dtype
+        prod = getattr(ab, name)(cfg)
+        prod.load_state_dict(oracle.state_dict(), strict=True)
+        prod = prod.to(DEV).eval()
+        with torch.no_grad():
+            got = prod(tuple(t.to(DEV) if t is not None else None for t in batch))
+            ref = oracle(batch)
+        fp = np.array([[float(v.double().sum()), float(v.double().abs().sum())] for v in oracle.state_dict().values() if v.dtype.is_floating_point])
+        if np.allclose(fp, z[f"fp/{name}"], rtol=1e-12, atol=1e-12):  # same init stream as the build container: pin on the real reference
+            assert_close(ref, torch.from_numpy(z[f"logits/{name}"]), 1e-5, f"{name}: oracle vs recorded reference logits")
+        assert_close(got, ref, tol, f"{name} {dtype} with the reference's random init")
