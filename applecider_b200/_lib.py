@@ -30,6 +30,8 @@ def _parse_header(path: str) -> dict:
     sigs = {}
     for m in re.finditer(r"\bint\s+(acb_\w+)\s*\(([^)]*)\)\s*;", text):
         name, args = m.group(1), m.group(2)
+        if name in NO_STREAM:
+            continue
         kinds = []
         for a in args.split(","):
             a = a.strip()
@@ -51,6 +53,7 @@ def _parse_header(path: str) -> dict:
     return sigs
 
 
+NO_STREAM = ("acb_version", "acb_set_seed_epoch_ptr")  # management calls without a trailing stream argument
 SIGNATURES = _parse_header(HEADER_PATH)
 
 _KIND = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float, "d": ctypes.c_double}
@@ -69,6 +72,8 @@ def lib() -> ctypes.CDLL:
         l = ctypes.CDLL(LIB_PATH)
         l.acb_last_error.restype = ctypes.c_char_p
         l.acb_launch_count.restype = ctypes.c_longlong
+        l.acb_set_seed_epoch_ptr.restype = ctypes.c_int
+        l.acb_set_seed_epoch_ptr.argtypes = [ctypes.c_void_p]
         for name, sig in SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype = ctypes.c_int
@@ -152,5 +157,10 @@ def reset_launch_count() -> None:
     lib().acb_reset_launch_count()
 
 
+def set_seed_epoch_ptr(ptr) -> None:
+    """ptr: device address of a uint64 epoch counter (a CUDA int64 tensor's data_ptr()), or None to clear."""
+    lib().acb_set_seed_epoch_ptr(ptr)
+
+
 def exported_symbols():
-    return sorted(SIGNATURES) + ["acb_last_error", "acb_version", "acb_launch_count", "acb_reset_launch_count"]
+    return sorted(SIGNATURES) + ["acb_last_error", "acb_version", "acb_launch_count", "acb_reset_launch_count", "acb_set_seed_epoch_ptr"]

@@ -46,7 +46,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 
 // shared memory (dynamic): Q [2][128] x 16 B | K [2][ncap] x 16 B | Vt [ncap/8][16] x 16 B | P [2 buffers][8][128] x 16 B
 __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const bf16* __restrict__ qkv, const int* __restrict__ cu, int n_heads,
-                                                                  int ncap, float drop_p, unsigned long long seed, bf16* __restrict__ out) {
+                                                                  int ncap, float drop_p, AcbSeed seed_s, bf16* __restrict__ out) {
+  const unsigned long long seed = seed_s.get();
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ __align__(8) uint64_t bars[3];  // [0] S ready, [1..2] P buffer consumed
   __shared__ uint32_t tmem_holder;
@@ -260,12 +261,10 @@ extern "C" int acb_attention_varlen_tc(const void* qkv, const int* cu_seqlens, i
   ACB_CHECK(drop_p >= 0.0f && drop_p < 1.0f, "acb_attention_varlen_tc: bad dropout");
   const int ncap = ((max_seqlen + 15) / 16) * 16;
   const size_t smem = (size_t)2 * 128 * 16 + (size_t)2 * ncap * 16 + (size_t)(ncap / 8) * 256 + (size_t)2 * 8 * 128 * 16;
-  static int configured = 0;
-  if (configured < (int)smem) {
-    ACB_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = (int)smem;
-  }
-  attention_tc_kernel<<<dim3(B, n_heads), AT_THREADS, smem, (cudaStream_t)stream>>>((const bf16*)qkv, cu_seqlens, n_heads, ncap, drop_p, (unsigned long long)seed,
+  // set on every call: the attribute is per device and the call is cheap (a process that touches a second GPU would otherwise
+  // launch an unconfigured kernel there)
+  ACB_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_tc_kernel<<<dim3(B, n_heads), AT_THREADS, smem, (cudaStream_t)stream>>>((const bf16*)qkv, cu_seqlens, n_heads, ncap, drop_p, acb_seed(seed),
                                                                      (bf16*)out);
   ACB_LAUNCH_CHECK();
   acb_count_launch();

@@ -407,7 +407,8 @@ __device__ __forceinline__ unsigned attn_hash(unsigned long long seed, int bh, i
 
 template <int DH>
 __global__ void __launch_bounds__(128) attention_bwd_kernel(const void* qkv, int dt, const void* dout, int do_dt, const int* cu,
-                                                            int n_heads, float drop_p, unsigned long long seed, void* dqkv, int dq_dt) {
+                                                            int n_heads, float drop_p, AcbSeed seed_s, void* dqkv, int dq_dt) {
+  const unsigned long long seed = seed_s.get();
   extern __shared__ float sm[];
   const int b = blockIdx.x, h = blockIdx.y;
   const int t0 = cu[b], n = cu[b + 1] - t0;
@@ -506,7 +507,8 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const void* qkv, int
 // | [9D+1 : 10D] db (D-1) | [10D : 11D] d cls_tok
 __global__ void __launch_bounds__(128) photo_embed_bwd_kernel(const float* x, const int* src, int T, int D, const void* dh, int dh_dt,
                                                               const float* w, const float* bb, int tok_per_block, float te_drop_p,
-                                                              unsigned long long te_seed, float* grads) {
+                                                              AcbSeed te_seed_s, float* grads) {
+  const unsigned long long te_seed = te_seed_s.get();
   const int c = threadIdx.x;  // channel
   const float drop_inv = 1.0f / (1.0f - te_drop_p);
   const unsigned drop_thr = (unsigned)(te_drop_p * 4294967296.0);
@@ -826,7 +828,8 @@ __device__ __forceinline__ unsigned hash32(unsigned long long v) {
   return (unsigned)v;
 }
 // y = keep ? x / (1-p) : 0, keep decided by a counter-based hash of (seed, index); the same call with dy gives dx
-__global__ void dropout_kernel(const void* x, int x_dt, void* y, int y_dt, float p, unsigned long long seed, long long n) {
+__global__ void dropout_kernel(const void* x, int x_dt, void* y, int y_dt, float p, AcbSeed seed_s, long long n) {
+  const unsigned long long seed = seed_s.get();
   const float inv = 1.0f / (1.0f - p);
   const unsigned thr = (unsigned)(p * 4294967296.0);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -958,7 +961,7 @@ int acb_attention_varlen_bwd(const void* qkv, int dtype, const void* dout, int d
   auto k = attention_bwd_kernel<16>;
   ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int threads = 128;  // measured: 288-thread CTAs (one round for 258-token sequences) are 25 % slower overall
-  k<<<dim3(B, n_heads), threads, smem, (cudaStream_t)stream>>>(qkv, dtype, dout, dout_dtype, cu_seqlens, n_heads, drop_p, (unsigned long long)seed, dqkv, dqkv_dtype);
+  k<<<dim3(B, n_heads), threads, smem, (cudaStream_t)stream>>>(qkv, dtype, dout, dout_dtype, cu_seqlens, n_heads, drop_p, acb_seed(seed), dqkv, dqkv_dtype);
   LAUNCHED(1);
 }
 
@@ -969,7 +972,7 @@ int acb_photo_embed_bwd(const float* x, const int* src_idx, int T, int D, const 
   ACB_CUDA(cudaMemsetAsync(grads, 0, (size_t)11 * D * 4, st));
   if (T == 0) return ACB_OK;
   const int tpb = 256;
-  photo_embed_bwd_kernel<<<cdiv(T, tpb), 128, 0, st>>>(x, src_idx, T, D, dh, dh_dtype, w, b, tpb, te_drop_p, (unsigned long long)te_seed, grads);
+  photo_embed_bwd_kernel<<<cdiv(T, tpb), 128, 0, st>>>(x, src_idx, T, D, dh, dh_dtype, w, b, tpb, te_drop_p, acb_seed(te_seed), grads);
   LAUNCHED(1);
 }
 
@@ -1056,7 +1059,7 @@ int acb_loss_fwd_bwd(const float* logits, const long long* labels, const float* 
 int acb_dropout(const void* x, int x_dtype, void* y, int y_dtype, float p, long long seed, long long n, void* stream) {
   ACB_CHECK(x && y && n >= 0 && p >= 0.0f && p < 1.0f, "acb_dropout: bad arguments");
   if (n == 0) return ACB_OK;
-  dropout_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, y, y_dtype, p, (unsigned long long)seed, n);
+  dropout_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, y, y_dtype, p, acb_seed(seed), n);
   LAUNCHED(1);
 }
 

@@ -38,6 +38,17 @@ void acb_count_launch(int n = 1);  // product-side launch counter (bench.py "gpu
 // src_idx entries <= ACB_SRC_DEAD mark capacity rows past the last packed token (acb_photo_compact memsets them to 0x80808080)
 #define ACB_SRC_DEAD (-0x40000000)
 
+// Seed of a counter-hash RNG stream as the kernels receive it: the host value plus an optional device-resident epoch
+// (acb_set_seed_epoch_ptr).  A CUDA graph bakes `base` in; bumping *epoch inside the graph gives every replay fresh masks,
+// and forward / backward kernels of one replay still agree because they read the same epoch.
+struct AcbSeed {
+  unsigned long long base;
+  const unsigned long long* epoch;
+  __device__ __forceinline__ unsigned long long get() const { return base + (epoch ? *epoch * 0xD1342543DE82EF95ULL : 0ULL); }
+};
+const unsigned long long* acb_seed_epoch_ptr();
+static inline AcbSeed acb_seed(long long s) { return AcbSeed{(unsigned long long)s, acb_seed_epoch_ptr()}; }
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------

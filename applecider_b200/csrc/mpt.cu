@@ -15,7 +15,8 @@ __device__ __forceinline__ unsigned mpt_hash(unsigned long long seed, int b, int
 // One CTA per light curve.  Every valid token gets two random keys; "take the first `take` of a random
 // permutation" == "take the `take` smallest keys", evaluated by rank counting (L <= a few hundred).
 __global__ void __launch_bounds__(128) mpt_mask_kernel(float* __restrict__ x, const uint8_t* __restrict__ pad, int L, double mask_p,
-                                                       unsigned long long seed, uint8_t* __restrict__ masked) {
+                                                       AcbSeed seed_s, uint8_t* __restrict__ masked) {
+  const unsigned long long seed = seed_s.get();
   extern __shared__ unsigned sm_u[];
   unsigned* key = sm_u;                                  // [L]
   signed char* band = reinterpret_cast<signed char*>(key + L);  // [L]  -1 = padded
@@ -166,7 +167,7 @@ int acb_mpt_mask(float* x, const uint8_t* pad, int B, int L, double mask_p, long
   ACB_CHECK(x && pad && masked && B > 0 && L > 0, "acb_mpt_mask: bad arguments");
   ACB_CHECK(mask_p >= 0.0 && mask_p <= 1.0 && L <= 8192, "acb_mpt_mask: mask_p %g / L %d out of range", mask_p, L);
   const size_t smem = (size_t)L * 4 + 2 * (size_t)L + 16;
-  mpt_mask_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(x, pad, L, mask_p, (unsigned long long)seed, masked);
+  mpt_mask_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(x, pad, L, mask_p, acb_seed(seed), masked);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;

@@ -21,7 +21,22 @@ struct AdamGroups {
 __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, bf16* __restrict__ p16, long long n4,
                                                         const __grid_constant__ AdamGroups G, const float* __restrict__ gnorm_sq,
-                                                        float max_norm, float grad_scale) {
+                                                        float max_norm, float grad_scale, const int* __restrict__ step_dev) {
+  // bias corrections: from the host step count (baked into G) or, when the step lives on the device (CUDA-graph replay: the
+  // graph increments *step_dev itself), recomputed here once per block in double precision like the host path
+  __shared__ float s_step_size[ADAM_MAX_GROUPS], s_inv_bc2[ADAM_MAX_GROUPS];
+  if (threadIdx.x < G.n) {
+    const int gi = threadIdx.x;
+    if (step_dev) {
+      const double t = (double)max(*step_dev, 1);
+      s_step_size[gi] = (float)((double)G.lr[gi] / (1.0 - pow((double)G.b1[gi], t)));
+      s_inv_bc2[gi] = (float)(1.0 / sqrt(1.0 - pow((double)G.b2[gi], t)));
+    } else {
+      s_step_size[gi] = G.step_size[gi];
+      s_inv_bc2[gi] = G.inv_bc2_sqrt[gi];
+    }
+  }
+  __syncthreads();
   float coef = grad_scale;
   if (gnorm_sq) coef *= fminf(1.0f, max_norm / (sqrtf(*gnorm_sq) * fabsf(grad_scale) + 1e-6f));  // clip_grad_norm_ arithmetic
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
@@ -45,8 +60,8 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, c
       else grad = fmaf(G.wd[gi], w, grad);                      // Adam: L2 term joins the gradient
       const float mm = fmaf(G.b1[gi], me[e], (1.0f - G.b1[gi]) * grad);
       const float vv = fmaf(G.b2[gi], ve[e], (1.0f - G.b2[gi]) * grad * grad);
-      const float denom = sqrtf(vv) * G.inv_bc2_sqrt[gi] + G.eps[gi];
-      pe[e] = w - G.step_size[gi] * (mm / denom);
+      const float denom = sqrtf(vv) * s_inv_bc2[gi] + G.eps[gi];
+      pe[e] = w - s_step_size[gi] * (mm / denom);
       me[e] = mm;
       ve[e] = vv;
     }
@@ -68,7 +83,8 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, c
 extern "C" {
 
 int acb_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, int n_groups, const long long* group_end,
-                  const float* hyper, int step, const float* gnorm_sq, float max_norm, float grad_scale, void* stream) {
+                  const float* hyper, int step, const int* step_dev, const float* gnorm_sq, float max_norm, float grad_scale,
+                  void* stream) {
   ACB_CHECK(p && g && m && v && group_end && hyper && n > 0 && step >= 1, "acb_adam_step: bad arguments");
   ACB_CHECK(n_groups >= 1 && n_groups <= ADAM_MAX_GROUPS, "acb_adam_step: %d parameter groups (max %d)", n_groups, ADAM_MAX_GROUPS);
   ACB_CHECK(n % 4 == 0 && (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && (((uintptr_t)p_bf16) & 7) == 0,
@@ -90,7 +106,7 @@ int acb_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, lo
   G.end[n_groups - 1] = n;  // trailing alignment padding belongs to the last group (its gradient is zero)
   const long long n4 = n / 4;
   const int grid = (int)std::min<long long>((n4 + 255) / 256, 148LL * 8);
-  adam_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)p_bf16, n4, G, gnorm_sq, max_norm, grad_scale);
+  adam_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)p_bf16, n4, G, gnorm_sq, max_norm, grad_scale, step_dev);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;

@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(256) photo_embed_kernel(const float* __restric
                                                           const float* __restrict__ w0, const float* __restrict__ b0,
                                                           const float* __restrict__ w, const float* __restrict__ bb,
                                                           const float* __restrict__ cls, float te_drop_p,
-                                                          unsigned long long te_seed, T* __restrict__ out) {
+                                                          AcbSeed te_seed_s, T* __restrict__ out) {
+  const unsigned long long te_seed = te_seed_s.get();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const float drop_inv = 1.0f / (1.0f - te_drop_p);
@@ -110,8 +111,9 @@ __device__ __forceinline__ unsigned attn_hash(unsigned long long seed, int bh, i
 
 template <typename T, int DH>
 __global__ void __launch_bounds__(128) attention_varlen_kernel(const T* __restrict__ qkv, const int* __restrict__ cu,
-                                                               int n_heads, float drop_p, unsigned long long seed,
+                                                               int n_heads, float drop_p, AcbSeed seed_s,
                                                                T* __restrict__ out) {
+  const unsigned long long seed = seed_s.get();
   extern __shared__ float smem[];
   const int b = blockIdx.x, h = blockIdx.y;
   const int t0 = cu[b], n = cu[b + 1] - t0;
@@ -221,9 +223,9 @@ int acb_photo_embed(const float* x, const int* src_idx, const int* total_dev, in
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = cdiv(max_tokens, 8);
   if (out_dtype == ACB_F32)
-    photo_embed_kernel<float><<<grid, 256, 0, st>>>(x, src_idx, total_dev, max_tokens, D, w_in, b_in, w0, b0, w, b, cls_tok, te_drop_p, (unsigned long long)te_seed, (float*)out);
+    photo_embed_kernel<float><<<grid, 256, 0, st>>>(x, src_idx, total_dev, max_tokens, D, w_in, b_in, w0, b0, w, b, cls_tok, te_drop_p, acb_seed(te_seed), (float*)out);
   else
-    photo_embed_kernel<bf16><<<grid, 256, 0, st>>>(x, src_idx, total_dev, max_tokens, D, w_in, b_in, w0, b0, w, b, cls_tok, te_drop_p, (unsigned long long)te_seed, (bf16*)out);
+    photo_embed_kernel<bf16><<<grid, 256, 0, st>>>(x, src_idx, total_dev, max_tokens, D, w_in, b_in, w0, b0, w, b, cls_tok, te_drop_p, acb_seed(te_seed), (bf16*)out);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;
@@ -241,11 +243,11 @@ int acb_attention_varlen(const void* qkv, int dtype, const int* cu_seqlens, int 
   if (dtype == ACB_F32) {
     auto k = attention_varlen_kernel<float, 16>;
     if (smem > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 128, smem, st>>>((const float*)qkv, cu_seqlens, n_heads, drop_p, (unsigned long long)seed, (float*)out);
+    k<<<grid, 128, smem, st>>>((const float*)qkv, cu_seqlens, n_heads, drop_p, acb_seed(seed), (float*)out);
   } else {
     auto k = attention_varlen_kernel<bf16, 16>;
     if (smem > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 128, smem, st>>>((const bf16*)qkv, cu_seqlens, n_heads, drop_p, (unsigned long long)seed, (bf16*)out);
+    k<<<grid, 128, smem, st>>>((const bf16*)qkv, cu_seqlens, n_heads, drop_p, acb_seed(seed), (bf16*)out);
   }
   ACB_LAUNCH_CHECK();
   acb_count_launch();

@@ -37,7 +37,8 @@ __device__ __forceinline__ float tw_keep(unsigned long long seed, int tower, lon
 // ---- forward (one warp per row) ------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) tower_group_fwd_kernel(const float* __restrict__ X, int ldx, int rows, const __grid_constant__ TowerGroup G,
                                                               float* __restrict__ Y, int ldy, float* __restrict__ A, int lda, float drop_p,
-                                                              unsigned long long seed) {
+                                                              AcbSeed seed_s) {
+  const unsigned long long seed = seed_s.get();
   __shared__ float xs[4][TG_MAX_IN];
   __shared__ float n1s[4][TG_MAX_HID];
   __shared__ float n2s[4][TG_MAX_HID];
@@ -109,7 +110,8 @@ __global__ void __launch_bounds__(128) tower_group_fwd_kernel(const float* __res
 __global__ void __launch_bounds__(TG_BWD_WARPS * 32) tower_group_bwd_kernel(const float* __restrict__ X, int ldx, int rows,
                                                                             const __grid_constant__ TowerGroup G, const float* __restrict__ A, int lda,
                                                                             const float* __restrict__ dY, int ldy, float* __restrict__ dA,
-                                                                            float* __restrict__ dX, float drop_p, unsigned long long seed) {
+                                                                            float* __restrict__ dX, float drop_p, AcbSeed seed_s) {
+  const unsigned long long seed = seed_s.get();
   extern __shared__ float sm[];
   const TowerT& p = G.t[blockIdx.y];
   const int in = p.in_dim, hid = p.hid, out = p.out_dim;
@@ -341,7 +343,7 @@ int acb_tower_group_fwd(const float* X, int ldx, int rows, int n_towers, const l
   const int rc = fill_group(G, n_towers, ptrs, dims, false, nullptr);
   if (rc != ACB_OK) return rc;
   if (rows == 0) return ACB_OK;
-  tower_group_fwd_kernel<<<dim3(cdiv(rows, 4), n_towers), 128, 0, (cudaStream_t)stream>>>(X, ldx, rows, G, Y, ldy, A, lda, drop_p, (unsigned long long)seed);
+  tower_group_fwd_kernel<<<dim3(cdiv(rows, 4), n_towers), 128, 0, (cudaStream_t)stream>>>(X, ldx, rows, G, Y, ldy, A, lda, drop_p, acb_seed(seed));
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;
@@ -359,7 +361,7 @@ int acb_tower_group_bwd(const float* X, int ldx, int rows, int n_towers, const l
   if (dX) ACB_CUDA(cudaMemsetAsync(dX, 0, (size_t)rows * ldx * sizeof(float), (cudaStream_t)stream));
   ACB_CUDA(cudaFuncSetAttribute(tower_group_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   tower_group_bwd_kernel<<<dim3(cdiv(rows, TG_ROWS), n_towers), TG_BWD_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      X, ldx, rows, G, A, lda, dY, ldy, dA, dX, drop_p, (unsigned long long)seed);
+      X, ldx, rows, G, A, lda, dY, ldy, dA, dX, drop_p, acb_seed(seed));
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;

@@ -687,10 +687,17 @@ def set_seed(seed=None, rank=None):
 def next_seed():
     if _seed_state["rank"] is None:
         _seed_state["rank"] = _default_rank()
+    if torch.cuda.is_current_stream_capturing():
+        # the generator may not be touched during a CUDA-graph capture: derive the seeds of the captured call sites from the
+        # last eager draw and a counter; the graph's device epoch (acb_set_seed_epoch_ptr) varies them from replay to replay
+        _seed_state["cap"] = _seed_state.get("cap", 0) + 1
+        return _mix64(_seed_state.get("last", 0x5EED) + _seed_state["cap"] * 0x9E3779B97F4A7C15) & _MASK62
     g = torch.cuda.default_generators[torch.cuda.current_device()]
     off = g.get_offset()
     g.set_offset(off + 4)
-    return _mix64(_mix64(g.initial_seed() * 0x9E3779B97F4A7C15 + _seed_state["rank"] + 1) + off) & _MASK62
+    s = _mix64(_mix64(g.initial_seed() * 0x9E3779B97F4A7C15 + _seed_state["rank"] + 1) + off) & _MASK62
+    _seed_state["last"] = s
+    return s
 
 
 def dropout(x, p, training):

@@ -67,6 +67,7 @@ class FusedAdam:
         self.flat_v = torch.zeros_like(self.flat_p)
         self._gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_count = 0
+        self.step_dev = None  # device int32 step counter (graph.GraphedTrainStep): overrides step_count inside the kernel
         self.flat_p16 = None
         if bf16_shadow:
             self.flat_p16 = torch.empty(off, dtype=torch.bfloat16, device=dev)
@@ -105,7 +106,7 @@ class FusedAdam:
         hyper = (ctypes.c_float * (6 * n))()
         for i, pg in enumerate(self.param_groups):
             hyper[6 * i: 6 * i + 6] = [pg["lr"], pg["betas"][0], pg["betas"][1], pg["eps"], pg["weight_decay"], 1.0 if pg["decoupled"] else 0.0]
-        call("acb_adam_step", self.flat_p, g, self.flat_m, self.flat_v, self.flat_p16, self.numel, n, ends, hyper, self.step_count, gn,
+        call("acb_adam_step", self.flat_p, g, self.flat_m, self.flat_v, self.flat_p16, self.numel, n, ends, hyper, self.step_count, self.step_dev, gn,
              float(self.max_grad_norm or 0.0), float(grad_scale))
         torch.autograd.graph.increment_version(self.params)  # derived-weight caches key on the version counter
         if self.flat_p16 is not None:

@@ -93,6 +93,7 @@ def _train(ctx, kind):
     if world > 1 and not args.no_overlap:
         sync.enable_overlap()  # bucketed all-reduce launched from the autograd hooks, overlapped with the rest of the backward
     sync.time_sync = True
+    graph_error = None
     fn.set_seed(1234)  # torch.cuda.manual_seed + the rank: replicas draw independent dropout masks
 
     seed = 1337 + rank
@@ -117,11 +118,39 @@ def _train(ctx, kind):
     def step(d):
         return ddp_train_step(sync, lambda: fwd_loss(d), optimizer)
 
-    first_loss = None
+    first_loss = step(dev).clone()
+    # all-reduce diagnostics measured in eager mode (CUDA events cannot be recorded inside a graph): the wait the bucketed overlap
+    # leaves exposed after the backward, and the collective on its own
+    exposed_eager = isolated = None
+    if world > 1:
+        for _ in range(3):
+            step(dev)
+        exposed_eager = sync.exposed_ms()
+        _barrier(ctx)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            ctx.dist.all_reduce(sync.flat, op=ctx.dist.ReduceOp.AVG)
+        a1.record()
+        torch.cuda.synchronize()
+        isolated = a0.elapsed_time(a1) / 5
+        sync.flat.zero_()
+    graphed = None
+    if args.graph != "off" and not args.torch_optim:
+        # replay the whole step (zero, forward, backward, all-reduce, Adam) as one CUDA graph: the eager step needs about as
+        # long on the host to enqueue its ~800 launches as the GPU needs to run them
+        from applecider_b200.graph import GraphedTrainStep
+
+        try:
+            graphed = GraphedTrainStep(sync, fwd_loss, optimizer, dev, warmup=2)
+            step = lambda d: graphed(d)  # noqa: E731
+        except Exception as e:
+            if args.graph == "on":
+                raise
+            graph_error = f"{type(e).__name__}: {e}"[:300]
+            torch.cuda.synchronize()
     for i in range(W):
-        l = step(dev)
-        if i == 0:
-            first_loss = l
+        step(dev)
     sync.exposed_ms()
     _barrier(ctx)
     sampler = ctx.ClockSampler(ctx.local_rank)
@@ -134,22 +163,26 @@ def _train(ctx, kind):
     for _ in range(K):
         loss = step(dev)
     e1.record()
+    loss = loss.clone()
     host_ms = (time.perf_counter() - t_host0) * 1e3  # CPU time to ENQUEUE the K steps (launch-bound check)
     _barrier(ctx)
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count()
+    launches = _lib.launch_count() if graphed is None else graphed.launches_per_replay * K
     exposed = sync.exposed_ms()
     clocks = sampler.stop() if rank == 0 else None
     # end to end: pinned host batch -> device every step, loss read back every step
     _barrier(ctx)
     t0 = time.perf_counter()
     for _ in range(K):
-        d = {k: v.cuda(non_blocking=True) for k, v in pinned.items()}
-        lv = step(d).item()
+        if graphed is not None:  # pinned host batch -> the graph's static input buffers -> replay -> loss read back
+            lv = graphed(pinned).item()
+        else:
+            d = {k: v.cuda(non_blocking=True) for k, v in pinned.items()}
+            lv = step(d).item()
     _barrier(ctx)
     e2e_ms = (time.perf_counter() - t0) * 1e3
     sync.exposed_ms()
-    ms, e2e_ms, exposed, host_ms = _max_over_ranks(ctx, [ms, e2e_ms, exposed, host_ms])
+    ms, e2e_ms, exposed, host_ms, exposed_eager, isolated = _max_over_ranks(ctx, [ms, e2e_ms, exposed, host_ms, exposed_eager or 0.0, isolated or 0.0])
     if rank != 0:
         return None
     flops_step = 3.0 * (fusion_fwd_flops(lens.numpy()) if fusion else astrominn_fwd_flops(B))  # forward + dgrad + wgrad
@@ -162,7 +195,10 @@ def _train(ctx, kind):
         "step": "forward + backward (C-ABI kernels) + NCCL all-reduce(avg) of the flat gradient (bucketed, launched from autograd hooks) + "
                 + ("torch optimizer step" if args.torch_optim else "fused clip/Adam kernel (acb_adam_step)") + "; dropout on",
         "optimizer": "Adam(lr 1e-3, wd 0.01) (brew_cider.py:1211)" if fusion else "AdamW 11 groups (astrominn.py:151-218)",
-        "allreduce_ms_exposed": exposed, "allreduce_bytes": sync.allreduce_bytes, "grad_elements": sync.numel,
+        "cuda_graph": (graphed is not None), "cuda_graph_error": graph_error,
+        "allreduce_ms_exposed": (exposed if graphed is None else exposed_eager), "allreduce_ms_isolated": isolated,
+        "allreduce_note": "exposed = wait left after the backward with the bucketed overlap (eager steps, CUDA events around sync()); isolated = one all-reduce(avg) of the whole flat gradient alone",
+        "allreduce_bytes": sync.numel * 4 if world > 1 else 0, "grad_elements": sync.numel,
         "host_enqueue_ms_per_step": host_ms / K, "gpu_launches_per_step": launches / K,
         "algorithmic_gflop_per_sample": flops_step / B / 1e9, "tokens_per_batch": ntok if fusion else None,
         "fraction_of_tensor_roofline": (sps / world) * (flops_step / B) / peak,

@@ -50,6 +50,12 @@ const char* acb_last_error(void);
 int acb_version(void);
 long long acb_launch_count(void); /* kernels launched by this library since the last reset */
 void acb_reset_launch_count(void);
+/* Device-resident epoch of the stochastic kernels (dropout, attention dropout, Time2Vec dropout, MPT masking): when set
+ * (NULL clears it), every such kernel uses seed + f(*dev_ptr) instead of the bare host seed.  A captured CUDA graph bakes
+ * host seeds in; incrementing *dev_ptr inside the graph gives each replay fresh masks while the forward and backward
+ * kernels of one replay still regenerate the same ones.  Dropout sites: nn.TransformerEncoderLayer (HyraxBaselineCLS.py:26-33),
+ * astrominn.py:48-54,268, spectranet.py:148. */
+int acb_set_seed_epoch_ptr(const unsigned long long* dev_ptr);
 
 /* ---- GEMM / implicit-GEMM conv1d ---------------------------------------------------------------
  * v[m,n] = sum_k A(m,k) * Bw[n*ldb + k] (+ bias[n]); C = epilogue(act(v)).
@@ -311,11 +317,14 @@ int acb_mpt_loss_fwd_bwd(const void* pred, int pred_dtype, const int* src_idx, i
  * clip (gnorm_sq = device scalar holding sum(g^2), e.g. from acb_sumsq; coef = min(1, max_norm/(norm+1e-6))),
  * gradient scaling, then Adam (L2 weight decay joins the gradient) or AdamW (decoupled) with per-group
  * hyper-parameters; group i covers [group_end[i-1], group_end[i]) and hyper[6*i..] = {lr, beta1, beta2, eps,
- * weight_decay, decoupled}; both arrays live on the HOST.  step >= 1 is the 1-based step count (bias correction).
+ * weight_decay, decoupled}; both arrays live on the HOST.  step >= 1 is the 1-based step count (bias correction);
+ * step_dev (optional, device int) overrides it with a count the device owns, so a captured CUDA graph that increments
+ * it replays with the right bias correction.
  * p_bf16 (optional) receives the bf16 copy of the updated weights.  Replaces clip_grad_norm_ + optimizer.step at
  * HyraxBaselineCLS.py:108-120,228,279-280, astrominn.py:151-218,311-326, brew_cider.py:1211. */
 int acb_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, int n_groups, const long long* group_end,
-                  const float* hyper, int step, const float* gnorm_sq, float max_norm, float grad_scale, void* stream);
+                  const float* hyper, int step, const int* step_dev, const float* gnorm_sq, float max_norm, float grad_scale,
+                  void* stream);
 
 /* ---- tower groups, training path (ResidualTowerBlock x N in one launch; astrominn.py:44-64,264-300) ---- */
 /* ptrs: HOST array, 25 device addresses per tower = {cols (int*, or 0 = columns 0..in-1 of X),

@@ -111,7 +111,7 @@ def test_fusion_bf16_gradients_vs_oracle():
     assert not small_bad, f"small tensors below cosine 0.98: {small_bad[:10]}"
 
 
-@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 5e-3)])
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
 def test_reference_random_init(golden_dir, dtype, tol):
     """Weights = the reference's own seeded random init (oracle constructed under torch.manual_seed(0); the CPU suite and
     the golden generator check that this is bit-identical to the REAL reference's init), not the trained-looking synthetic
