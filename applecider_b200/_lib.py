@@ -157,9 +157,21 @@ def reset_launch_count() -> None:
     lib().acb_reset_launch_count()
 
 
-def set_seed_epoch_ptr(ptr) -> None:
-    """ptr: device address of a uint64 epoch counter (a CUDA int64 tensor's data_ptr()), or None to clear."""
-    lib().acb_set_seed_epoch_ptr(ptr)
+_seed_epoch_tensor = None
+
+
+def set_seed_epoch(tensor) -> None:
+    """tensor: a 1-element CUDA int64 tensor the stochastic kernels add to their seeds (see acb_set_seed_epoch_ptr), or None to
+    clear.  The module keeps a reference, so the device pointer the library holds can never dangle."""
+    global _seed_epoch_tensor
+    if tensor is None:
+        lib().acb_set_seed_epoch_ptr(None)
+        _seed_epoch_tensor = None
+        return
+    if not (tensor.is_cuda and tensor.dtype == torch.int64 and tensor.numel() == 1):
+        raise TypeError("seed epoch must be a 1-element CUDA int64 tensor")
+    lib().acb_set_seed_epoch_ptr(tensor.data_ptr())
+    _seed_epoch_tensor = tensor
 
 
 def exported_symbols():

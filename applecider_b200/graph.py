@@ -31,7 +31,8 @@ class GraphedTrainStep:
     def __init__(self, sync: FlatGradSync, forward_loss, optimizer, example_inputs: dict, clip_norm=None, warmup: int = 2):
         """forward_loss(inputs: dict of CUDA tensors) -> scalar loss tensor; optimizer: optim.FusedAdam (its `grads` is `sync`).
 
-        Runs `warmup` eager steps on a side stream (they are real training steps), then captures one more."""
+        Runs `warmup` eager steps on a side stream (they are REAL training steps on the example inputs), then captures the
+        step (capturing executes nothing)."""
         if not hasattr(optimizer, "flat_p"):
             raise TypeError("GraphedTrainStep needs optim.FusedAdam (torch optimizers read their step count on the host)")
         self.sync, self.optimizer, self.forward_loss = sync, optimizer, forward_loss
@@ -41,7 +42,7 @@ class GraphedTrainStep:
         self.static = {k: v.clone() for k, v in example_inputs.items()}
         self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
         optimizer.step_dev = torch.full((1,), optimizer.step_count, dtype=torch.int32, device=dev)
-        _lib.set_seed_epoch_ptr(self.epoch.data_ptr())
+        _lib.set_seed_epoch(self.epoch)
         self._timed = sync.time_sync
         sync.time_sync = False  # CUDA events with timing cannot be recorded inside a capture
         side = torch.cuda.Stream(dev)
@@ -53,8 +54,10 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
+        count0 = optimizer.step_count
         with torch.cuda.graph(self.graph):
             self.loss = self._one_step()
+        optimizer.step_count = count0  # a capture records the step, it does not run it
         self.launches_per_replay = _lib.launch_count() - n0
         self.replays = 0
 
@@ -83,6 +86,14 @@ class GraphedTrainStep:
         return self.loss
 
     def close(self):
-        _lib.set_seed_epoch_ptr(None)
+        """Back to eager stepping: clears the device seed epoch and the device step counter."""
+        if _lib._seed_epoch_tensor is self.epoch:
+            _lib.set_seed_epoch(None)
         self.optimizer.step_dev = None
         self.sync.time_sync = self._timed
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

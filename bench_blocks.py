@@ -182,6 +182,8 @@ def _train(ctx, kind):
     _barrier(ctx)
     e2e_ms = (time.perf_counter() - t0) * 1e3
     sync.exposed_ms()
+    if graphed is not None:
+        graphed.close()
     ms, e2e_ms, exposed, host_ms, exposed_eager, isolated = _max_over_ranks(ctx, [ms, e2e_ms, exposed, host_ms, exposed_eager or 0.0, isolated or 0.0])
     if rank != 0:
         return None

@@ -15,7 +15,7 @@ from util import assert_close
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 B_FULL = 4096
-BF16_TOL = 5e-3
+BF16_TOL = 5e-3  # fusion logits (measured 6e-4); stand-alone encoders use 1.5e-2, see tests/test_gpu_models.py
 
 
 @pytest.fixture(scope="module")

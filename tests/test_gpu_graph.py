@@ -30,24 +30,27 @@ def _setup(dropout, dtype="fp32", seed=0):
 
 
 def test_graph_replay_equals_eager_steps():
-    """Dropout off: warm-up (2 eager steps) + capture (1) + 3 replays == 6 eager steps; Adam's bias correction must follow the
-    device step counter, and a new batch copied into the static buffers must be the one the replay trains on."""
+    """Dropout off: warm-up (2 eager steps; the capture itself executes nothing) + 3 replays == 5 eager steps; Adam's bias
+    correction must follow the device step counter, and a new batch copied into the static buffers must be the one the replay
+    trains on."""
     from applecider_b200.ddp import ddp_train_step
     from applecider_b200.graph import GraphedTrainStep
 
     m1, o1, inp, f1 = _setup(0.0)
     m2, o2, _, f2 = _setup(0.0)
     inp_b = {k: (v.flip(0).contiguous() if k != "pad" else v.flip(0).contiguous()) for k, v in inp.items()}
-    seq = [inp, inp, inp, inp_b, inp, inp_b]
+    seq = [inp, inp, inp_b, inp, inp_b]
     for d in seq:
         ddp_train_step(o1.grads, lambda d=d: f1(d), o1)
-    g = GraphedTrainStep(o2.grads, f2, o2, inp, warmup=2)  # consumes seq[0:3]
-    losses = [g(d).item() for d in seq[3:]]
+    g = GraphedTrainStep(o2.grads, f2, o2, inp, warmup=2)  # consumes seq[0:2]
+    losses = [g(d).item() for d in seq[2:]]
     g.close()
-    assert o2.step_count == o1.step_count == 6
+    assert o2.step_count == o1.step_count == 5
     assert all(l == l for l in losses)
     for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
-        assert torch.allclose(a, b, rtol=1e-4, atol=2e-6), f"{n}: graph replay diverged from eager ({(a - b).abs().max().item():.3e})"
+        # 5 Adam steps of lr 1e-3 move a weight by <= 5e-3; Adam divides by |g|, so the fp32-atomic ordering noise of the gradient
+        # kernels shows up at the 1e-5 level -- a wrong bias correction or a stale batch would show at 1e-3
+        assert torch.allclose(a, b, rtol=0, atol=1e-4), f"{n}: graph replay diverged from eager ({(a - b).abs().max().item():.3e})"
 
 
 def test_graph_dropout_changes_every_replay_and_trains():

@@ -22,9 +22,12 @@ def load_steps(golden_dir, prefix):
 def check_two_steps(g, params, before, losses, loss_tol, solid_tol, grad_floor=1e-6):
     """losses: the two values train_step returned; params/before: name -> tensor after / before the two steps.
 
-    Adam's first update is lr * g / (|g| + eps): an element whose gradient sits at the noise floor is sign-like, so element
-    -wise comparison of the recorded update head is restricted to 'solid' elements (|g1| > grad_floor * max|g1| of that tensor);
-    the L2 norm of the whole update is compared for every tensor (sign flips of noise-floor elements leave it unchanged)."""
+    Adam's first update is lr * g / (|g| + eps): it divides every element by its own magnitude, so an absolute gradient error e
+    (the kernels meet 5e-4 * max|g| per tensor, tests/test_gpu_train.py) becomes a relative update error e / |g_i| -- sign-like
+    at the noise floor.  Element-wise comparison of the recorded update head is therefore restricted to 'solid' elements
+    (|g1| > grad_floor * max|g1| of that tensor; grad_floor 1e-6 for the bit-faithful CPU oracle, 0.05 on the GPU so that
+    5e-4 / 0.05 = 1 % stays inside solid_tol); the L2 norm of the whole update is compared for every tensor (sign flips of
+    noise-floor elements leave it unchanged)."""
     for got, key in zip(losses, ("loss1", "loss2")):
         ref = float(g[key])
         assert abs(got - ref) <= loss_tol * max(1.0, abs(ref)), f"{key}: {got} vs reference {ref}"
