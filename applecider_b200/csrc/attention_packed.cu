@@ -1,0 +1,309 @@
+// Packed multi-sequence varlen attention on tcgen05 (bf16 in, fp32 softmax, bf16 out), head_dim 16.
+//
+// ZTF light curves are short (median ~40 tokens, max 258): one CTA per (sequence, head) -- the round-1 kernel -- spends its time
+// on CTA set-up and fills 58 of the 128 rows of a UMMA tile.  Here
+//   * a PLAN kernel (once per batch, reused by every layer) greedily packs CONSECUTIVE whole sequences into tiles of <= 128
+//     packed token rows (queries and keys of a tile are the same rows; the mask is block-diagonal);
+//   * one CTA owns (tile, group of 4 heads).  TMA brings the Q / K / V columns of its heads for the 128 rows into shared
+//     memory as boxes of {8 elements x 128 rows}: each lands as [128 rows][16 B], a column of UMMA core matrices, so the 8
+//     boxes of an operand form [chunk][row][16 B] -- exactly the canonical no-swizzle layout (K-major for Q and K with
+//     LBO = 2048 B between the two k-chunks of a head and SBO = 128 B between 8-row groups; MN-major for V, so P V needs no
+//     transpose).  No thread touches global memory for the operands.
+//   * per head: S = Q K^T is one UMMA (M 128, N = padded rows, K 16) into TMEM; thread r owns query row r: masked max and
+//     exp/sum over ITS sequence's key range only (single pass over <= 128 keys, straight from TMEM), P (bf16) goes to shared
+//     memory as the K-major A operand, O_h += P V_h by N = 16 UMMAs into its own 16 TMEM columns; the next head's S is issued
+//     behind them, so the tensor pipe never waits for the softmax of another head.
+//   * the four heads' O sit side by side in TMEM: one 128-byte contiguous store per row at the end.
+// Sequences longer than 128 tokens (3 % of a ZTF batch) keep the per-(sequence, head) kernel of attention_tc.cu, driven by the
+// plan's list.  Dropout (training) uses the same counter hash as every other attention kernel here, so any backward matches.
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int AP_DH = 16;
+constexpr int AP_ROWS = 128;   // packed rows per tile = UMMA M
+constexpr int AP_HG = 4;       // heads per CTA
+constexpr int AP_THREADS = 128;
+constexpr uint32_t AP_OPER_BYTES = AP_HG * 2 * AP_ROWS * 16;  // 16 KB: [8 chunks][128 rows][16 B]
+constexpr uint32_t AP_P_BYTES = 16 * AP_ROWS * 16;            // 32 KB: [16 key chunks][128 rows][16 B]
+constexpr uint32_t AP_SMEM = 3 * AP_OPER_BYTES + AP_P_BYTES + 1024;
+
+__device__ __forceinline__ unsigned ap_hash(unsigned long long seed, int bh, int i, int j) {
+  unsigned long long v = seed * 0x9E3779B97F4A7C15ULL + (((unsigned long long)bh << 26) | ((unsigned long long)i << 13) | (unsigned long long)j);
+  v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
+  return (unsigned)v;
+}
+// canonical no-swizzle descriptors (cute/atom/mma_traits_sm100.hpp):
+//   K-major  ((8,m),(T,2)):((1T,SBO),(1,LBO))      -- 8-row groups SBO apart, the two 16-byte K chunks LBO apart
+//   MN-major ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO))  -- 8-element MN blocks SBO apart, 8-row K groups LBO apart
+__device__ __forceinline__ uint64_t ap_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t ap_idesc(int n, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major ? (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ---- plan: plan[0] = n_tiles, plan[1] = n_long, plan[2 + 2t] = first sequence of tile t, plan[3 + 2t] = sequences in it,
+//            plan[2 + 2*max_tiles + i] = i-th long sequence --------------------------------------------------------------
+__global__ void __launch_bounds__(1024) attn_plan_kernel(const int* __restrict__ cu, int B, int max_tiles, int* __restrict__ plan) {
+  extern __shared__ int s_len[];
+  for (int b = threadIdx.x; b < B; b += blockDim.x) s_len[b] = cu[b + 1] - cu[b];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  int nt = 0, nl = 0, first = 0, cnt = 0, rows = 0;
+  int* tiles = plan + 2;
+  int* longs = plan + 2 + 2 * max_tiles;
+#pragma unroll 8
+  for (int b = 0; b < B; ++b) {
+    const int n = s_len[b];
+    const bool flush = n <= 0 || n > AP_ROWS || rows + n > AP_ROWS;  // empty (cu clamped by a too-small capacity) or long or full
+    if (flush && cnt > 0) {
+      if (nt < max_tiles) { tiles[2 * nt] = first; tiles[2 * nt + 1] = cnt; }
+      ++nt;
+      cnt = 0; rows = 0;
+    }
+    if (n > AP_ROWS) longs[nl++] = b;  // nl <= B: the list has room for every sequence
+    else if (n > 0) {
+      if (cnt == 0) first = b;
+      ++cnt; rows += n;
+    }
+  }
+  if (cnt > 0) {
+    if (nt < max_tiles) { tiles[2 * nt] = first; tiles[2 * nt + 1] = cnt; }
+    ++nt;
+  }
+  nt = min(nt, max_tiles);  // cannot happen with the host-side bound (acb_attention_plan_size); never overrun the table
+  plan[0] = nt;
+  plan[1] = nl;
+}
+
+__global__ void __launch_bounds__(AP_THREADS) attention_packed_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict__ cu,
+                                                                      const int* __restrict__ plan, int n_heads, float drop_p,
+                                                                      AcbSeed seed_s, bf16* __restrict__ out) {
+  const int tile = blockIdx.x;
+  if (tile >= plan[0]) return;  // uniform: the grid is a host-side upper bound of the tile count
+  const unsigned long long seed = seed_s.get();
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2];  // [0] operands landed, [1] MMA batch retired
+  __shared__ uint32_t tmem_holder;
+  __shared__ int s_cu[AP_ROWS + 2];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int hg = blockIdx.y;  // heads hg*4 .. hg*4+3
+  const int seq0 = plan[2 + 2 * tile], nseq = plan[3 + 2 * tile];
+  const int row0 = cu[seq0];
+  const int nrows = cu[seq0 + nseq] - row0;  // <= 128
+  const int npad = max(16, (nrows + 15) & ~15);
+  const int D = n_heads * AP_DH;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t aQ = base, aK = base + AP_OPER_BYTES, aV = base + 2 * AP_OPER_BYTES, aP = base + 3 * AP_OPER_BYTES;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* sV = gen_base + 2 * AP_OPER_BYTES;
+  uint8_t* sP = gen_base + 3 * AP_OPER_BYTES;
+  const uint32_t bar_load = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+
+  if (tid == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i <= nseq && i <= AP_ROWS; i += AP_THREADS) s_cu[i] = cu[seq0 + i] - row0;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = tmem_holder;          // columns [0, 128): S
+  const uint32_t tmem_o = tmem_holder + 128u;   // columns [128, 192): O of the 4 heads
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+
+  if (warp == 0 && elect_one_sync()) {
+    mbar_expect_tx(bar_load, 3 * AP_OPER_BYTES);
+    // one {8 elements x 128 rows} box per 16-byte column chunk: it lands as [128 rows][16 B] = a column of core matrices
+#pragma unroll
+    for (int op = 0; op < 3; ++op)
+#pragma unroll
+      for (int c = 0; c < AP_HG * 2; ++c)
+        tma_load_2d(base + (uint32_t)op * AP_OPER_BYTES + (uint32_t)c * (AP_ROWS * 16), &tmQKV, op * D + hg * (AP_HG * AP_DH) + c * 8, row0, bar_load);
+  }
+  // this thread's query row: its sequence and key range (tile-relative)
+  int lo = 0, hi = 0, b_seq = seq0;
+  if (tid < nrows) {
+    int j = 0;
+    while (j + 1 < nseq && s_cu[j + 1] <= tid) ++j;
+    lo = s_cu[j];
+    hi = s_cu[j + 1];
+    b_seq = seq0 + j;
+  }
+  const int wlo = __reduce_min_sync(0xffffffffu, tid < nrows ? lo : 1 << 30);
+  const int whi = __reduce_max_sync(0xffffffffu, tid < nrows ? hi : 0);
+  const float drop_inv = 1.0f / (1.0f - drop_p);
+  const unsigned drop_thr = (unsigned)(drop_p * 4294967296.0);
+
+  mbar_wait(bar_load, 0);
+  // V rows in [nrows, npad) belong to the next tile or to unwritten capacity rows: P is zero there, but 0 * NaN is not
+  for (int i = tid; i < (npad - nrows) * (AP_HG * 2); i += AP_THREADS) {
+    const int r = nrows + i / (AP_HG * 2), c = i % (AP_HG * 2);
+    *reinterpret_cast<uint4*>(sV + ((size_t)c * AP_ROWS + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async();
+  __syncthreads();
+  uint32_t ph = 0;
+  if (warp == 0 && elect_one_sync()) {
+    tc_fence_after();
+    umma_bf16(tmem_s, ap_desc(aQ, AP_ROWS * 16, 128), ap_desc(aK, AP_ROWS * 16, 128), ap_idesc(npad, false), 0u);
+    umma_commit(bar_mma);
+  }
+  float inv_sum[AP_HG];
+#pragma unroll
+  for (int h = 0; h < AP_HG; ++h) {
+    mbar_wait(bar_mma, ph);
+    ph ^= 1u;
+    tc_fence_after();
+    // ---- softmax of row `tid` over its own sequence's keys [lo, hi); S carries no 1/sqrt(dh) yet (0.25, exact) ----
+    float mx = -INFINITY;
+    for (int c0 = wlo & ~31; c0 < whi; c0 += 32) {  // warp-uniform chunk range: union of the lanes' key ranges
+      uint32_t raw[32];
+      tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, raw);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c0 + i >= lo && c0 + i < hi) mx = fmaxf(mx, __uint_as_float(raw[i]));
+    }
+    mx *= 0.25f;
+    float lsum = 0.0f;
+    const int bh = b_seq * n_heads + hg * AP_HG + h;
+    const int qi = tid - lo;
+    for (int c0 = 0; c0 < npad; c0 += 32) {
+      uint32_t pk[16];
+      if (c0 + 32 > wlo && c0 < whi) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, raw);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const int j0 = c0 + i;
+          float p0 = (j0 >= lo && j0 < hi) ? __expf(fmaf(__uint_as_float(raw[i]), 0.25f, -mx)) : 0.0f;
+          float p1 = (j0 + 1 >= lo && j0 + 1 < hi) ? __expf(fmaf(__uint_as_float(raw[i + 1]), 0.25f, -mx)) : 0.0f;
+          lsum += p0 + p1;
+          if (drop_p > 0.0f) {
+            p0 = ap_hash(seed, bh, qi, j0 - lo) >= drop_thr ? p0 * drop_inv : 0.0f;
+            p1 = ap_hash(seed, bh, qi, j0 + 1 - lo) >= drop_thr ? p1 * drop_inv : 0.0f;
+          }
+          __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)  // 8 keys per 16-byte chunk: chunk (c0/8 + c), row tid
+        if (c0 + 8 * c < npad)
+          *reinterpret_cast<uint4*>(sP + (((c0 >> 3) + c) * AP_ROWS + tid) * 16) = make_uint4(pk[c * 4 + 0], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+    }
+    inv_sum[h] = lsum > 0.0f ? 1.0f / lsum : 0.0f;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();  // P complete, every thread is done with S
+    if (warp == 0 && elect_one_sync()) {
+      tc_fence_after();
+      const uint32_t vh = aV + (uint32_t)h * (2 * AP_ROWS * 16);
+      for (int ks = 0; ks < npad; ks += 16)  // O_h += P[:, 16 keys] V_h[16 keys, :]
+        umma_bf16(tmem_o + (uint32_t)(h * AP_DH), ap_desc(aP + (uint32_t)(ks >> 3) * (AP_ROWS * 16), AP_ROWS * 16, 128),
+                  ap_desc(vh + (uint32_t)ks * 16, 128, AP_ROWS * 16), ap_idesc(AP_DH, true), ks > 0 ? 1u : 0u);
+      if (h + 1 < AP_HG) {
+        const uint32_t off = (uint32_t)(h + 1) * (2 * AP_ROWS * 16);
+        umma_bf16(tmem_s, ap_desc(aQ + off, AP_ROWS * 16, 128), ap_desc(aK + off, AP_ROWS * 16, 128), ap_idesc(npad, false), 0u);
+      }
+      umma_commit(bar_mma);
+    }
+  }
+  mbar_wait(bar_mma, ph);
+  tc_fence_after();
+  // ---- O / sum -> bf16, 128 contiguous bytes per row ----
+  {
+    uint32_t o0[32], o1[32];
+    tmem_ld32(tmem_o + lane_addr, o0);
+    tmem_ld32(tmem_o + lane_addr + 32u, o1);
+    if (tid < nrows) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (long long)(row0 + tid) * D + hg * (AP_HG * AP_DH));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t* src = q < 4 ? o0 + q * 8 : o1 + (q - 4) * 8;
+        const float s = inv_sum[q >> 1];
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(src[2 * e]) * s, __uint_as_float(src[2 * e + 1]) * s);
+          w[e] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        dst[q] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_s), "r"(256u) : "memory");
+  }
+}
+
+}  // namespace
+
+int acb_attention_tc_long(const void* qkv, const int* cu_seqlens, const int* long_list, const int* n_long_dev, int grid_x, int n_heads,
+                          int max_seqlen, float drop_p, long long seed, void* out, cudaStream_t st);  // attention_tc.cu
+
+extern "C" {
+
+int acb_attention_plan(const int* cu_seqlens, int B, int max_tiles, int* plan, void* stream) {
+  ACB_CHECK(cu_seqlens && plan && B > 0 && max_tiles > 0, "acb_attention_plan: bad arguments");
+  ACB_CHECK(B <= 48 * 1024, "acb_attention_plan: B = %d sequences exceed the 48 K shared-memory length table", B);
+  const size_t smem = (size_t)B * sizeof(int);
+  if (smem > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(attn_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attn_plan_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(cu_seqlens, B, max_tiles, plan);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+int acb_attention_packed(const void* qkv, const int* cu_seqlens, const int* plan, int B, int max_tiles, long long total_rows, int n_heads,
+                         int dh, int max_seqlen, float drop_p, long long seed, void* out, void* stream) {
+  ACB_CHECK(qkv && cu_seqlens && plan && out && B > 0 && max_tiles > 0 && total_rows > 0, "acb_attention_packed: bad arguments");
+  ACB_CHECK(dh == AP_DH && n_heads % AP_HG == 0, "acb_attention_packed: needs head_dim 16 and a head count that is a multiple of 4");
+  ACB_CHECK(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0), "acb_attention_packed: alignment");
+  ACB_CHECK(drop_p >= 0.0f && drop_p < 1.0f, "acb_attention_packed: bad dropout");
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
+  ACB_CHECK(enc != nullptr, "acb_attention_packed: cuTensorMapEncodeTiled unavailable");
+  const int D = n_heads * dh;
+  CUtensorMap tm;
+  {
+    // qkv[T, 3D] row-major; box = {8 elements (one 16-byte chunk), 128 rows}; rows past T are zero-filled
+    cuuint64_t dims[2] = {(cuuint64_t)(3 * D), (cuuint64_t)total_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)(3 * D) * 2};
+    cuuint32_t box[2] = {8, (cuuint32_t)AP_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACB_CHECK(r == CUDA_SUCCESS, "acb_attention_packed: cuTensorMapEncodeTiled failed with %d", (int)r);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  ACB_CUDA(cudaFuncSetAttribute(attention_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AP_SMEM));
+  attention_packed_kernel<<<dim3(max_tiles, n_heads / AP_HG), AP_THREADS, AP_SMEM, st>>>(tm, cu_seqlens, plan, n_heads, drop_p, acb_seed(seed),
+                                                                                      (bf16*)out);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  // sequences longer than one tile: the per-(sequence, head) kernel over the plan's list (grid = host-side upper bound)
+  const int max_long = (int)std::min<long long>((long long)B, total_rows / (AP_ROWS + 1));
+  if (max_long > 0 && max_seqlen > AP_ROWS) {
+    const int rc = acb_attention_tc_long(qkv, cu_seqlens, plan + 2 + 2 * max_tiles, plan + 1, max_long, n_heads, max_seqlen, drop_p, seed, out, st);
+    if (rc != ACB_OK) return rc;
+  }
+  return ACB_OK;
+}
+
+}  // extern "C"

@@ -46,12 +46,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 
 // shared memory (dynamic): Q [2][128] x 16 B | K [2][ncap] x 16 B | Vt [ncap/8][16] x 16 B | P [2 buffers][8][128] x 16 B
 __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const bf16* __restrict__ qkv, const int* __restrict__ cu, int n_heads,
-                                                                  int ncap, float drop_p, AcbSeed seed_s, bf16* __restrict__ out) {
+                                                                  int ncap, float drop_p, AcbSeed seed_s, bf16* __restrict__ out,
+                                                                  const int* __restrict__ seq_list, const int* __restrict__ n_list) {
+  // seq_list (optional): blockIdx.x indexes a device-side list of sequences (the long sequences of attention_packed.cu's plan);
+  // the grid is then a host-side upper bound and the blocks past *n_list leave at once
+  if (seq_list && (int)blockIdx.x >= *n_list) return;
   const unsigned long long seed = seed_s.get();
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ __align__(8) uint64_t bars[3];  // [0] S ready, [1..2] P buffer consumed
   __shared__ uint32_t tmem_holder;
-  const int b = blockIdx.x;
+  const int b = seq_list ? seq_list[blockIdx.x] : (int)blockIdx.x;
   const int t0 = cu[b], n = cu[b + 1] - t0;
   const int D = n_heads * AT_DH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -265,7 +269,21 @@ extern "C" int acb_attention_varlen_tc(const void* qkv, const int* cu_seqlens, i
   // launch an unconfigured kernel there)
   ACB_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attention_tc_kernel<<<dim3(B, n_heads), AT_THREADS, smem, (cudaStream_t)stream>>>((const bf16*)qkv, cu_seqlens, n_heads, ncap, drop_p, acb_seed(seed),
-                                                                     (bf16*)out);
+                                                                     (bf16*)out, nullptr, nullptr);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+// the per-(sequence, head) kernel over a device-side list of sequences (attention_packed.cu: sequences longer than one tile)
+int acb_attention_tc_long(const void* qkv, const int* cu_seqlens, const int* long_list, const int* n_long_dev, int grid_x, int n_heads,
+                          int max_seqlen, float drop_p, long long seed, void* out, cudaStream_t st) {
+  ACB_CHECK(max_seqlen > 0 && max_seqlen <= 1024, "acb_attention_packed: max_seqlen %d exceeds the shared-memory K/V budget (1024 keys)", max_seqlen);
+  const int ncap = ((max_seqlen + 15) / 16) * 16;
+  const size_t smem = (size_t)2 * 128 * 16 + (size_t)2 * ncap * 16 + (size_t)(ncap / 8) * 256 + (size_t)2 * 8 * 128 * 16;
+  ACB_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_tc_kernel<<<dim3(grid_x, n_heads), AT_THREADS, smem, st>>>((const bf16*)qkv, cu_seqlens, n_heads, ncap, drop_p, acb_seed(seed), (bf16*)out,
+                                                                    long_list, n_long_dev);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;

@@ -278,9 +278,9 @@ class MlpBlock(Function):
 
 class Attention(Function):
     @staticmethod
-    def forward(ctx, qkv, cu, B, H, dh, maxlen, drop_p, seed):
+    def forward(ctx, qkv, cu, B, H, dh, maxlen, drop_p, seed, plan=None):
         qkv = _c(qkv)
-        out = ops.attention_varlen(qkv, cu, B, H, dh, maxlen, drop_p, seed, zero_tail=True)
+        out = ops.attention_varlen(qkv, cu, B, H, dh, maxlen, drop_p, seed, zero_tail=True, plan=plan)
         ctx.save_for_backward(qkv, cu)
         ctx.cfg = (B, H, dh, maxlen, drop_p, seed)
         return out
@@ -292,11 +292,11 @@ class Attention(Function):
         dout = _c(dout)
         dqkv = torch.zeros_like(qkv)  # capacity rows past the last sequence must carry zero gradient
         call("acb_attention_varlen_bwd", qkv, dtype_tag(qkv), dout, dtype_tag(dout), cu, B, H, dh, maxlen, drop_p, seed, dqkv, dtype_tag(dqkv))
-        return dqkv, None, None, None, None, None, None, None
+        return dqkv, None, None, None, None, None, None, None, None
 
 
-def attention(qkv, cu, B, H, dh, maxlen, drop_p=0.0, seed=0):
-    return Attention.apply(qkv, cu, B, H, dh, maxlen, drop_p, seed)
+def attention(qkv, cu, B, H, dh, maxlen, drop_p=0.0, seed=0, plan=None):
+    return Attention.apply(qkv, cu, B, H, dh, maxlen, drop_p, seed, plan)
 
 
 class PhotoEmbed(Function):

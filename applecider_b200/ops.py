@@ -179,11 +179,25 @@ def photo_embed(x, src, total, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype, te_d
 
 
 USE_TC_ATTENTION = True
+USE_PACKED_ATTENTION = True  # several whole sequences per 128-row tile, 4 heads per CTA, TMA-fed (attention_packed.cu)
 
 
-def attention_varlen(qkv, cu, B, n_heads, dh, max_seqlen, drop_p=0.0, seed=0, zero_tail=False):
+def attention_plan(cu, B, total_rows):
+    """Tile plan of the packed attention kernel for one batch (acb_attention_plan): (plan int32 tensor, max_tiles).
+    Built once per forward and shared by every layer; sized from host-side bounds only."""
+    max_tiles = max(1, min(B, 2 * (total_rows // 128) + total_rows // 129 + 2))
+    plan = torch.empty(2 + 2 * max_tiles + B, dtype=torch.int32, device=cu.device)
+    call("acb_attention_plan", cu, B, max_tiles, plan)
+    return plan, max_tiles
+
+
+def attention_varlen(qkv, cu, B, n_heads, dh, max_seqlen, drop_p=0.0, seed=0, zero_tail=False, plan=None):
     T = qkv.shape[0]
     out = (torch.zeros if zero_tail else torch.empty)((T, n_heads * dh), dtype=qkv.dtype, device=qkv.device)
+    if (qkv.dtype == torch.bfloat16 and USE_TC_ATTENTION and USE_PACKED_ATTENTION and plan is not None and max_seqlen <= 1024
+            and dh == 16 and n_heads % 4 == 0):
+        call("acb_attention_packed", qkv, cu, plan[0], B, plan[1], T, n_heads, dh, max_seqlen, drop_p, seed, out)
+        return out
     if qkv.dtype == torch.bfloat16 and USE_TC_ATTENTION and max_seqlen <= 1024 and dh == 16:
         call("acb_attention_varlen_tc", qkv, cu, B, n_heads, dh, max_seqlen, drop_p, seed, out)
         return out

@@ -67,10 +67,11 @@ class _PhotoEncoderBase(nn.Module):
         h = ops.photo_embed(data, src, T, D, self.in_proj.weight, self.in_proj.bias, t2v.w0, t2v.b0, t2v.w, t2v.b,
                             self.cls_tok, dtype)
         mv = nv if dtype != torch.float32 else None  # the fp32 parity GEMM has no device row count: it runs all capacity rows
+        plan = ops.attention_plan(cu, B, T) if dtype == torch.bfloat16 and ops.USE_PACKED_ATTENTION else None
         for lyr in self.encoder.layers:
             sa = lyr.self_attn
             qkv = ops.gemm(h, self._w(sa.in_proj_weight, dtype), sa.in_proj_bias, m_valid=mv)
-            att = ops.attention_varlen(qkv, cu, B, self.n_heads, D // self.n_heads, L + 1)
+            att = ops.attention_varlen(qkv, cu, B, self.n_heads, D // self.n_heads, L + 1, plan=plan)
             o = ops.gemm(att, self._w(sa.out_proj.weight, dtype), sa.out_proj.bias, res=h, res_mode=ops.RES_ADD, m_valid=mv)
             h1 = ops.layernorm(o, lyr.norm1.weight, lyr.norm1.bias, lyr.norm1.eps, rows_dev=nv)
             f = ops.gemm(h1, self._w(lyr.linear1.weight, dtype), lyr.linear1.bias, act=ops.ACT_RELU, m_valid=mv)

@@ -52,10 +52,11 @@ def photo_encode_train(model, data, pad, total_tokens=None, tokens=False, te_dro
                             te_p, fn.next_seed() if te_p > 0 else 0)
     dc = model._derived
     n_layers = len(model.encoder.layers)
+    plan = ops.attention_plan(cu, B, T) if dtype == torch.bfloat16 and ops.USE_PACKED_ATTENTION else None
     for li, lyr in enumerate(model.encoder.layers):
         sa = lyr.self_attn
         qkv = fn.linear(h, sa.in_proj_weight, sa.in_proj_bias, _wc(dc, sa.in_proj_weight, dtype))
-        att = fn.attention(qkv, cu, B, H, D // H, L + 1, p_drop, fn.next_seed() if p_drop > 0 else 0)
+        att = fn.attention(qkv, cu, B, H, D // H, L + 1, p_drop, fn.next_seed() if p_drop > 0 else 0, plan)
         o = fn.linear(att, sa.out_proj.weight, sa.out_proj.bias, _wc(dc, sa.out_proj.weight, dtype))
         o = fn.dropout(o, p_drop, tr)
         h1 = fn.layernorm(fn.add(h, o), lyr.norm1.weight, lyr.norm1.bias, lyr.norm1.eps)

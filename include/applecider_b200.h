@@ -152,6 +152,18 @@ int acb_attention_varlen(const void* qkv, int dtype, const int* cu_seqlens, int 
  * per accumulator row, P V accumulated in TMEM; operands are no-swizzle K-major core matrices written by the CTA. */
 int acb_attention_varlen_tc(const void* qkv, const int* cu_seqlens, int B, int n_heads, int dh, int max_seqlen, float drop_p,
                             long long seed, void* out, void* stream);
+/* Packed multi-sequence attention (the default bf16 path): same arithmetic as acb_attention_varlen_tc, but
+ *  - acb_attention_plan (once per batch, reused by every layer and by the backward) packs consecutive whole sequences into
+ *    tiles of <= 128 token rows: plan[0] = tiles, plan[1] = long sequences (> 128 tokens), plan[2+2t], plan[3+2t] = first
+ *    sequence / sequence count of tile t, plan[2+2*max_tiles+i] = i-th long sequence.  plan holds 2 + 2*max_tiles + B ints;
+ *    max_tiles >= min(B, 2*(total_rows/128) + total_rows/129 + 2) is a host-side bound, nothing is read back;
+ *  - acb_attention_packed: one CTA per (tile, 4 heads); Q/K/V of the tile arrive by TMA in the canonical UMMA layout, S and
+ *    the per-head O live in TMEM, the block-diagonal mask is each row's own key range; long sequences run the
+ *    per-(sequence, head) kernel over the plan's list.  total_rows = rows of the qkv / out matrices (capacity).
+ * nn.MultiheadAttention inside nn.TransformerEncoderLayer with src_key_padding_mask (HyraxBaselineCLS.py:26-33,78). */
+int acb_attention_plan(const int* cu_seqlens, int B, int max_tiles, int* plan, void* stream);
+int acb_attention_packed(const void* qkv, const int* cu_seqlens, const int* plan, int B, int max_tiles, long long total_rows,
+                         int n_heads, int dh, int max_seqlen, float drop_p, long long seed, void* out, void* stream);
 /* out[b,:] = x[cu_seqlens[b],:]  (CLS read-out z[:,0], HyraxBaselineCLS.py:79) */
 int acb_gather_cls(const void* x, int dtype, const int* cu_seqlens, int B, int D, float* out, void* stream);
 
