@@ -16,6 +16,8 @@
 //   * the four heads' O sit side by side in TMEM: one 128-byte contiguous store per row at the end.
 // Sequences longer than 128 tokens (3 % of a ZTF batch) keep the per-(sequence, head) kernel of attention_tc.cu, driven by the
 // plan's list.  Dropout (training) uses the same counter hash as every other attention kernel here, so any backward matches.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -25,7 +27,7 @@ namespace {
 constexpr int AP_DH = 16;
 constexpr int AP_ROWS = 128;   // packed rows per tile = UMMA M
 constexpr int AP_HG = 4;       // heads per CTA
-constexpr int AP_THREADS = 128;
+constexpr int AP_THREADS = 256;  // two warpgroups: each owns one half of the key columns of S
 constexpr uint32_t AP_OPER_BYTES = AP_HG * 2 * AP_ROWS * 16;  // 16 KB: [8 chunks][128 rows][16 B]
 constexpr uint32_t AP_P_BYTES = 16 * AP_ROWS * 16;            // 32 KB: [16 key chunks][128 rows][16 B]
 constexpr uint32_t AP_SMEM = 3 * AP_OPER_BYTES + AP_P_BYTES + 1024;
@@ -46,26 +48,120 @@ __device__ __forceinline__ uint32_t ap_idesc(int n, bool b_mn_major) {
 }
 
 // ---- plan: plan[0] = n_tiles, plan[1] = n_long, plan[2 + 2t] = first sequence of tile t, plan[3 + 2t] = sequences in it,
-//            plan[2 + 2*max_tiles + i] = i-th long sequence --------------------------------------------------------------
-__global__ void __launch_bounds__(1024) attn_plan_kernel(const int* __restrict__ cu, int B, int max_tiles, int* __restrict__ plan) {
-  extern __shared__ int s_len[];
-  for (int b = threadIdx.x; b < B; b += blockDim.x) s_len[b] = cu[b + 1] - cu[b];
+//            plan[2 + 2*max_tiles + i] = i-th long sequence.
+// A tile is a maximal run of consecutive sequences with <= 128 rows in total, each <= 128 rows, at most 128 sequences (greedy,
+// left to right).  Greedy packing is a chain (the next tile starts where this one ends), so instead of walking it serially
+// (230 us for 4096 sequences) every sequence b computes where a tile starting AT b would end -- nxt[b], a binary search in the
+// prefix sums -- and the chain from sequence 0 is marked by pointer doubling in log2(B) parallel rounds. ------------------------
+constexpr int AP_PLAN_THREADS = 1024;
+constexpr int AP_PLAN_MAX_B = 8192;  // sequences per batch the parallel planner holds in shared memory
+
+__device__ __forceinline__ int ap_tile_end(const int* pre, int B, int b) {
+  // largest e in (b, B] with pre[e] - pre[b] <= 128 rows and e - b <= 128 sequences; b itself is known to fit
+  int lo = b + 1, hi = min(B, b + AP_ROWS);
+  const int lim = pre[b] + AP_ROWS;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (pre[mid] <= lim) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(AP_PLAN_THREADS) attn_plan_kernel(const int* __restrict__ cu, int B, int max_tiles, int* __restrict__ plan) {
+  extern __shared__ int sm_plan[];
+  int* pre = sm_plan;                 // [B + 1] prefix rows
+  int* ja = pre + (B + 1);            // [B + 1] jump pointers (double buffered)
+  int* jb = ja + (B + 1);
+  int* nxt = jb + (B + 1);            // [B]
+  unsigned char* mark = reinterpret_cast<unsigned char*>(nxt + B);  // [B + 1]
+  __shared__ int s_warp[2][32];
+  __shared__ int s_tot[2];
+  const int tid = threadIdx.x;
+  for (int b = tid; b <= B; b += AP_PLAN_THREADS) { pre[b] = cu[b]; mark[b] = 0; }
   __syncthreads();
-  if (threadIdx.x != 0) return;
+  for (int b = tid; b < B; b += AP_PLAN_THREADS) {
+    const int n = pre[b + 1] - pre[b];
+    const int e = (n > AP_ROWS) ? b + 1 : ap_tile_end(pre, B, b);  // a long sequence is a chain node of its own
+    nxt[b] = e;
+    ja[b] = e;
+  }
+  if (tid == 0) { ja[B] = B; jb[B] = B; mark[0] = 1; }
+  __syncthreads();
+  int* jc = ja;
+  int* jn = jb;
+  for (int span = 1; span < B; span <<= 1) {  // after the round with jump length `span`, nodes < 2*span steps from 0 are marked
+    for (int b = tid; b < B; b += AP_PLAN_THREADS)
+      if (mark[b] && jc[b] < B) mark[jc[b]] = 1;
+    for (int b = tid; b < B; b += AP_PLAN_THREADS) jn[b] = jc[jc[b]];
+    __syncthreads();
+    int* t = jc; jc = jn; jn = t;
+  }
+  // ---- compact the marked chain nodes: tiles (<= 128 rows) and long sequences, both in sequence order ----
+  constexpr int PER = AP_PLAN_MAX_B / AP_PLAN_THREADS;
+  int ct = 0, cl = 0;
+  const int b0 = tid * PER;
+  for (int i = 0; i < PER; ++i) {
+    const int b = b0 + i;
+    if (b < B && mark[b]) {
+      if (pre[b + 1] - pre[b] > AP_ROWS) ++cl;
+      else ++ct;
+    }
+  }
+  const int lane = tid & 31, w = tid >> 5;
+  int it = ct, il = cl;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, it, o), c = __shfl_up_sync(0xffffffffu, il, o);
+    if (lane >= o) { it += a; il += c; }
+  }
+  if (lane == 31) { s_warp[0][w] = it; s_warp[1][w] = il; }
+  __syncthreads();
+  if (w == 0) {
+    int a = s_warp[0][lane], c = s_warp[1][lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a2 = __shfl_up_sync(0xffffffffu, a, o), c2 = __shfl_up_sync(0xffffffffu, c, o);
+      if (lane >= o) { a += a2; c += c2; }
+    }
+    s_warp[0][lane] = a; s_warp[1][lane] = c;
+    if (lane == 31) { s_tot[0] = a; s_tot[1] = c; }
+  }
+  __syncthreads();
+  int ot = it - ct + (w > 0 ? s_warp[0][w - 1] : 0), ol = il - cl + (w > 0 ? s_warp[1][w - 1] : 0);
+  int* tiles = plan + 2;
+  int* longs = plan + 2 + 2 * max_tiles;
+  for (int i = 0; i < PER; ++i) {
+    const int b = b0 + i;
+    if (b < B && mark[b]) {
+      if (pre[b + 1] - pre[b] > AP_ROWS) longs[ol++] = b;
+      else {
+        if (ot < max_tiles) { tiles[2 * ot] = b; tiles[2 * ot + 1] = nxt[b] - b; }
+        ++ot;
+      }
+    }
+  }
+  if (tid == 0) {
+    plan[0] = min(s_tot[0], max_tiles);  // cannot exceed the host-side bound; never overrun the table
+    plan[1] = s_tot[1];
+  }
+}
+
+// serial fallback for batches of more than AP_PLAN_MAX_B sequences (same packing rule)
+__global__ void attn_plan_serial_kernel(const int* __restrict__ cu, int B, int max_tiles, int* __restrict__ plan) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int nt = 0, nl = 0, first = 0, cnt = 0, rows = 0;
   int* tiles = plan + 2;
   int* longs = plan + 2 + 2 * max_tiles;
-#pragma unroll 8
   for (int b = 0; b < B; ++b) {
-    const int n = s_len[b];
-    const bool flush = n <= 0 || n > AP_ROWS || rows + n > AP_ROWS;  // empty (cu clamped by a too-small capacity) or long or full
-    if (flush && cnt > 0) {
+    const int n = cu[b + 1] - cu[b];
+    if ((n > AP_ROWS || rows + n > AP_ROWS || cnt >= AP_ROWS) && cnt > 0) {
       if (nt < max_tiles) { tiles[2 * nt] = first; tiles[2 * nt + 1] = cnt; }
       ++nt;
       cnt = 0; rows = 0;
     }
-    if (n > AP_ROWS) longs[nl++] = b;  // nl <= B: the list has room for every sequence
-    else if (n > 0) {
+    if (n > AP_ROWS) longs[nl++] = b;
+    else {
       if (cnt == 0) first = b;
       ++cnt; rows += n;
     }
@@ -74,14 +170,17 @@ __global__ void __launch_bounds__(1024) attn_plan_kernel(const int* __restrict__
     if (nt < max_tiles) { tiles[2 * nt] = first; tiles[2 * nt + 1] = cnt; }
     ++nt;
   }
-  nt = min(nt, max_tiles);  // cannot happen with the host-side bound (acb_attention_plan_size); never overrun the table
-  plan[0] = nt;
+  plan[0] = min(nt, max_tiles);
   plan[1] = nl;
 }
 
-__global__ void __launch_bounds__(AP_THREADS) attention_packed_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict__ cu,
-                                                                      const int* __restrict__ plan, int n_heads, float drop_p,
-                                                                      AcbSeed seed_s, bf16* __restrict__ out) {
+// 256 threads = two warpgroups.  Both see all 128 query rows (TMEM lane = tid & 127); warpgroup g owns the key columns
+// [64 g, 64 g + 64) of S: it reduces / exponentiates / writes P for its half, the halves meet through 1 KB of shared memory.
+// That doubles the threads working on the softmax (the issue-bound part) without more TMEM or shared memory per CTA, so two
+// CTAs still share an SM (2 x 256 TMEM columns, 2 x 81 KB).
+__global__ void __launch_bounds__(AP_THREADS, 2) attention_packed_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict__ cu,
+                                                                         const int* __restrict__ plan, int n_heads, float drop_p,
+                                                                         AcbSeed seed_s, bf16* __restrict__ out) {
   const int tile = blockIdx.x;
   if (tile >= plan[0]) return;  // uniform: the grid is a host-side upper bound of the tile count
   const unsigned long long seed = seed_s.get();
@@ -89,7 +188,10 @@ __global__ void __launch_bounds__(AP_THREADS) attention_packed_kernel(const __gr
   __shared__ __align__(8) uint64_t bars[2];  // [0] operands landed, [1] MMA batch retired
   __shared__ uint32_t tmem_holder;
   __shared__ int s_cu[AP_ROWS + 2];
+  __shared__ float s_red[2][AP_ROWS];        // per-row partial max of the two key halves
+  __shared__ float s_sum[AP_HG][AP_ROWS];    // per-row partial exp-sums of warpgroup 1
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & (AP_ROWS - 1), wg = tid >> 7;
   const int hg = blockIdx.y;  // heads hg*4 .. hg*4+3
   const int seq0 = plan[2 + 2 * tile], nseq = plan[3 + 2 * tile];
   const int row0 = cu[seq0];
@@ -120,7 +222,7 @@ __global__ void __launch_bounds__(AP_THREADS) attention_packed_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_s = tmem_holder;          // columns [0, 128): S
   const uint32_t tmem_o = tmem_holder + 128u;   // columns [128, 192): O of the 4 heads
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
 
   if (warp == 0 && elect_one_sync()) {
     mbar_expect_tx(bar_load, 3 * AP_OPER_BYTES);
@@ -133,17 +235,20 @@ __global__ void __launch_bounds__(AP_THREADS) attention_packed_kernel(const __gr
   }
   // this thread's query row: its sequence and key range (tile-relative)
   int lo = 0, hi = 0, b_seq = seq0;
-  if (tid < nrows) {
+  if (row < nrows) {
     int j = 0;
-    while (j + 1 < nseq && s_cu[j + 1] <= tid) ++j;
+    while (j + 1 < nseq && s_cu[j + 1] <= row) ++j;
     lo = s_cu[j];
     hi = s_cu[j + 1];
     b_seq = seq0 + j;
   }
-  const int wlo = __reduce_min_sync(0xffffffffu, tid < nrows ? lo : 1 << 30);
-  const int whi = __reduce_max_sync(0xffffffffu, tid < nrows ? hi : 0);
+  const unsigned len = (unsigned)(hi - lo);
+  const int wlo = __reduce_min_sync(0xffffffffu, row < nrows ? lo : 1 << 30);
+  const int whi = __reduce_max_sync(0xffffffffu, row < nrows ? hi : 0);
   const float drop_inv = 1.0f / (1.0f - drop_p);
   const unsigned drop_thr = (unsigned)(drop_p * 4294967296.0);
+  const int kbeg = wg * 64, kend = min(npad, kbeg + 64);  // this warpgroup's key columns
+  constexpr float SC = 0.25f * 1.4426950408889634f;       // 1/sqrt(dh) * log2(e): p = 2^(s*SC - max*SC)
 
   mbar_wait(bar_load, 0);
   // V rows in [nrows, npad) belong to the next tile or to unwritten capacity rows: P is zero there, but 0 * NaN is not
@@ -159,39 +264,46 @@ __global__ void __launch_bounds__(AP_THREADS) attention_packed_kernel(const __gr
     umma_bf16(tmem_s, ap_desc(aQ, AP_ROWS * 16, 128), ap_desc(aK, AP_ROWS * 16, 128), ap_idesc(npad, false), 0u);
     umma_commit(bar_mma);
   }
-  float inv_sum[AP_HG];
+  float psum[AP_HG];
 #pragma unroll
   for (int h = 0; h < AP_HG; ++h) {
     mbar_wait(bar_mma, ph);
     ph ^= 1u;
     tc_fence_after();
-    // ---- softmax of row `tid` over its own sequence's keys [lo, hi); S carries no 1/sqrt(dh) yet (0.25, exact) ----
+    // ---- pass 1: max of row `row` over its own sequence's keys inside this warpgroup's half ----
     float mx = -INFINITY;
-    for (int c0 = wlo & ~31; c0 < whi; c0 += 32) {  // warp-uniform chunk range: union of the lanes' key ranges
+    for (int c0 = max(kbeg, wlo & ~31); c0 < min(kend, whi); c0 += 32) {  // warp-uniform: union of the lanes' key ranges
       uint32_t raw[32];
       tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, raw);
+      const unsigned off = (unsigned)(c0 - lo);
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (c0 + i >= lo && c0 + i < hi) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        if (off + (unsigned)i < len) mx = fmaxf(mx, __uint_as_float(raw[i]));
     }
-    mx *= 0.25f;
+    s_red[wg][row] = mx;
+    __syncthreads();
+    const float mxs = fmaxf(s_red[0][row], s_red[1][row]) * SC;
+    // ---- pass 2: p = exp(s/4 - max), partial sum, P (bf16) into the K-major A-operand layout ----
     float lsum = 0.0f;
     const int bh = b_seq * n_heads + hg * AP_HG + h;
-    const int qi = tid - lo;
-    for (int c0 = 0; c0 < npad; c0 += 32) {
+    const int qi = row - lo;
+    for (int c0 = kbeg; c0 < kend; c0 += 32) {
       uint32_t pk[16];
       if (c0 + 32 > wlo && c0 < whi) {
         uint32_t raw[32];
         tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, raw);
+        const unsigned off = (unsigned)(c0 - lo);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const int j0 = c0 + i;
-          float p0 = (j0 >= lo && j0 < hi) ? __expf(fmaf(__uint_as_float(raw[i]), 0.25f, -mx)) : 0.0f;
-          float p1 = (j0 + 1 >= lo && j0 + 1 < hi) ? __expf(fmaf(__uint_as_float(raw[i + 1]), 0.25f, -mx)) : 0.0f;
+          float p0, p1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(raw[i]), SC, -mxs)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(raw[i + 1]), SC, -mxs)));
+          p0 = off + (unsigned)i < len ? p0 : 0.0f;
+          p1 = off + (unsigned)(i + 1) < len ? p1 : 0.0f;
           lsum += p0 + p1;
           if (drop_p > 0.0f) {
-            p0 = ap_hash(seed, bh, qi, j0 - lo) >= drop_thr ? p0 * drop_inv : 0.0f;
-            p1 = ap_hash(seed, bh, qi, j0 + 1 - lo) >= drop_thr ? p1 * drop_inv : 0.0f;
+            p0 = ap_hash(seed, bh, qi, (int)off + i) >= drop_thr ? p0 * drop_inv : 0.0f;
+            p1 = ap_hash(seed, bh, qi, (int)off + i + 1) >= drop_thr ? p1 * drop_inv : 0.0f;
           }
           __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
@@ -201,14 +313,15 @@ __global__ void __launch_bounds__(AP_THREADS) attention_packed_kernel(const __gr
         for (int i = 0; i < 16; ++i) pk[i] = 0u;
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c)  // 8 keys per 16-byte chunk: chunk (c0/8 + c), row tid
-        if (c0 + 8 * c < npad)
-          *reinterpret_cast<uint4*>(sP + (((c0 >> 3) + c) * AP_ROWS + tid) * 16) = make_uint4(pk[c * 4 + 0], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+      for (int c = 0; c < 4; ++c)  // 8 keys per 16-byte chunk: chunk (c0/8 + c), row `row`
+        if (c0 + 8 * c < kend)
+          *reinterpret_cast<uint4*>(sP + (((c0 >> 3) + c) * AP_ROWS + row) * 16) = make_uint4(pk[c * 4 + 0], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
     }
-    inv_sum[h] = lsum > 0.0f ? 1.0f / lsum : 0.0f;
+    psum[h] = lsum;
+    if (wg == 1) s_sum[h][row] = lsum;
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();  // P complete, every thread is done with S
+    __syncthreads();  // P complete, every thread is done with S and with s_red
     if (warp == 0 && elect_one_sync()) {
       tc_fence_after();
       const uint32_t vh = aV + (uint32_t)h * (2 * AP_ROWS * 16);
@@ -224,21 +337,25 @@ __global__ void __launch_bounds__(AP_THREADS) attention_packed_kernel(const __gr
   }
   mbar_wait(bar_mma, ph);
   tc_fence_after();
-  // ---- O / sum -> bf16, 128 contiguous bytes per row ----
-  {
-    uint32_t o0[32], o1[32];
-    tmem_ld32(tmem_o + lane_addr, o0);
-    tmem_ld32(tmem_o + lane_addr + 32u, o1);
-    if (tid < nrows) {
-      uint4* dst = reinterpret_cast<uint4*>(out + (long long)(row0 + tid) * D + hg * (AP_HG * AP_DH));
+  // ---- O / sum -> bf16: warpgroup g stores heads 2g, 2g+1 (64 contiguous bytes per row) ----
+  if (wg == 0) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint32_t* src = q < 4 ? o0 + q * 8 : o1 + (q - 4) * 8;
-        const float s = inv_sum[q >> 1];
+    for (int h = 0; h < AP_HG; ++h) s_sum[h][row] += psum[h];  // this row's entries were written by the other warpgroup only
+  }
+  __syncthreads();
+  {
+    uint32_t o[32];
+    tmem_ld32(tmem_o + lane_addr + (uint32_t)(wg * 32), o);
+    if (row < nrows) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (long long)(row0 + row) * D + hg * (AP_HG * AP_DH) + wg * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float tot = s_sum[wg * 2 + (q >> 1)][row];
+        const float s = tot > 0.0f ? 1.0f / tot : 0.0f;
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(src[2 * e]) * s, __uint_as_float(src[2 * e + 1]) * s);
+          __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(o[q * 8 + 2 * e]) * s, __uint_as_float(o[q * 8 + 2 * e + 1]) * s);
           w[e] = *reinterpret_cast<uint32_t*>(&hh);
         }
         dst[q] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -262,10 +379,13 @@ extern "C" {
 
 int acb_attention_plan(const int* cu_seqlens, int B, int max_tiles, int* plan, void* stream) {
   ACB_CHECK(cu_seqlens && plan && B > 0 && max_tiles > 0, "acb_attention_plan: bad arguments");
-  ACB_CHECK(B <= 48 * 1024, "acb_attention_plan: B = %d sequences exceed the 48 K shared-memory length table", B);
-  const size_t smem = (size_t)B * sizeof(int);
-  if (smem > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(attn_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attn_plan_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(cu_seqlens, B, max_tiles, plan);
+  if (B > AP_PLAN_MAX_B) {
+    attn_plan_serial_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(cu_seqlens, B, max_tiles, plan);
+  } else {
+    const size_t smem = (size_t)(4 * (B + 1)) * sizeof(int) + (size_t)(B + 1) + 16;
+    ACB_CUDA(cudaFuncSetAttribute(attn_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_plan_kernel<<<1, AP_PLAN_THREADS, smem, (cudaStream_t)stream>>>(cu_seqlens, B, max_tiles, plan);
+  }
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;
@@ -293,16 +413,38 @@ int acb_attention_packed(const void* qkv, const int* cu_seqlens, const int* plan
   }
   cudaStream_t st = (cudaStream_t)stream;
   ACB_CUDA(cudaFuncSetAttribute(attention_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AP_SMEM));
-  attention_packed_kernel<<<dim3(max_tiles, n_heads / AP_HG), AP_THREADS, AP_SMEM, st>>>(tm, cu_seqlens, plan, n_heads, drop_p, acb_seed(seed),
-                                                                                      (bf16*)out);
-  ACB_LAUNCH_CHECK();
-  acb_count_launch();
-  // sequences longer than one tile: the per-(sequence, head) kernel over the plan's list (grid = host-side upper bound)
+  static int dbg = -1;  // ACB_ATTN_DEBUG: 1 = packed tiles only, 2 = long sequences only (timing probes; results incomplete)
+  if (dbg < 0) { const char* e = getenv("ACB_ATTN_DEBUG"); dbg = e ? atoi(e) : 0; }
+  // Sequences longer than one tile run the per-(sequence, head) kernel over the plan's list (grid = host-side upper bound).
+  // Both kernels are latency-chain bound and touch disjoint rows, so the long list is FORKED onto a side stream (event
+  // fork / join, capturable in a CUDA graph) and the two kernels share the SMs instead of running back to back.
   const int max_long = (int)std::min<long long>((long long)B, total_rows / (AP_ROWS + 1));
-  if (max_long > 0 && max_seqlen > AP_ROWS) {
-    const int rc = acb_attention_tc_long(qkv, cu_seqlens, plan + 2 + 2 * max_tiles, plan + 1, max_long, n_heads, max_seqlen, drop_p, seed, out, st);
+  const bool has_long = max_long > 0 && max_seqlen > AP_ROWS && dbg != 1;
+  int dev = 0;
+  ACB_CUDA(cudaGetDevice(&dev));
+  ACB_CHECK(dev >= 0 && dev < 64, "acb_attention_packed: device index %d out of range", dev);
+  static cudaStream_t side[64];
+  static cudaEvent_t ev_fork[64], ev_join[64];
+  if (has_long) {
+    if (!side[dev]) {
+      ACB_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+      ACB_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
+      ACB_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
+    }
+    ACB_CUDA(cudaEventRecord(ev_fork[dev], st));
+    ACB_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
+    const int rc = acb_attention_tc_long(qkv, cu_seqlens, plan + 2 + 2 * max_tiles, plan + 1, max_long, n_heads, max_seqlen, drop_p, seed, out,
+                                         side[dev]);
     if (rc != ACB_OK) return rc;
+    ACB_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
   }
+  if (dbg != 2) {
+    attention_packed_kernel<<<dim3(max_tiles, n_heads / AP_HG), AP_THREADS, AP_SMEM, st>>>(tm, cu_seqlens, plan, n_heads, drop_p, acb_seed(seed),
+                                                                                        (bf16*)out);
+    ACB_LAUNCH_CHECK();
+    acb_count_launch();
+  }
+  if (has_long) ACB_CUDA(cudaStreamWaitEvent(st, ev_join[dev], 0));
   return ACB_OK;
 }
 

@@ -30,15 +30,15 @@ def _ref(qkv, cu):
 
 
 def _greedy(lens):
+    """A tile = maximal run of consecutive sequences with <= 128 rows in total, each <= 128 rows, at most 128 sequences."""
     tiles, longs, first, cnt, rows = [], [], 0, 0, 0
     for b, n in enumerate(lens):
-        if n <= 0 or n > 128 or rows + n > 128:
-            if cnt:
-                tiles.append((first, cnt))
+        if (n > 128 or rows + n > 128 or cnt >= 128) and cnt:
+            tiles.append((first, cnt))
             cnt = rows = 0
         if n > 128:
             longs.append(b)
-        elif n > 0:
+        else:
             if cnt == 0:
                 first = b
             cnt += 1
