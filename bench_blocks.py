@@ -337,7 +337,7 @@ def eager_block(ctx):
         m.photometry_encoder.__class__ = EagerPhoto
         return m.cuda()
 
-    def timeit(f, warm=1, reps=3):
+    def timeit(f, warm=3, reps=3):  # cudnn.benchmark autotunes during the first calls
         for _ in range(warm):
             f()
         torch.cuda.synchronize()
