@@ -416,6 +416,70 @@ class MaxPool(Function):
         return dx, None, None, None, None
 
 
+class BatchNormResAct(Function):
+    """out = act(res + BatchNorm1d(y)) over channels-last rows (legacy variant-B block, brew_cider.py:618-627).
+
+    training: batch statistics, running statistics blended in place (momentum); eval: running statistics.  Backward
+    recomputes the pre-activation, so only y and res are kept."""
+
+    @staticmethod
+    def forward(ctx, y, res, w, b, bn, training, act, out_dtype):
+        y = _c(y)
+        res = _c(res) if res is not None else None
+        rows, C = y.shape
+        dev = y.device
+        if bn.momentum is None:
+            raise NotImplementedError("BatchNorm with cumulative moving average (momentum=None) is not implemented")
+        stats = torch.empty(6 * C, dtype=F32, device=dev)
+        sums, scale, shift, mean, rstd = stats[:2 * C], stats[2 * C:3 * C], stats[3 * C:4 * C], stats[4 * C:5 * C], stats[5 * C:]
+        if training:
+            call("acb_bn_stats", y, dtype_tag(y), rows, C, sums)
+            bn.num_batches_tracked.add_(1)
+        call("acb_bn_finalize", sums if training else None, rows, C, w, b, bn.eps, float(bn.momentum), int(training), bn.running_mean,
+             bn.running_var, scale, shift, mean, rstd)
+        out = torch.empty((rows, C), dtype=out_dtype, device=dev)
+        call("acb_affine_res_act", y, dtype_tag(y), scale, shift, res, (dtype_tag(res) if res is not None else 0), act, out, dtype_tag(out), rows, C)
+        ctx.save_for_backward(y, res, scale, shift, mean, rstd)
+        ctx.cfg = (training, act)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, res, scale, shift, mean, rstd = ctx.saved_tensors
+        training, act = ctx.cfg
+        dout = _c(dout)
+        rows, C = y.shape
+        dpre = torch.empty((rows, C), dtype=(res.dtype if res is not None else y.dtype), device=y.device)
+        sums = torch.empty(2 * C, dtype=F32, device=y.device)
+        call("acb_affine_res_act_bwd", y, dtype_tag(y), scale, shift, res, (dtype_tag(res) if res is not None else 0), act, dout, dtype_tag(dout),
+             mean, rstd, dpre, dtype_tag(dpre), sums, rows, C)
+        dy = torch.empty_like(y)
+        call("acb_bn_bwd_apply", y, dtype_tag(y), dpre, dtype_tag(dpre), scale, mean, rstd, sums, int(training), dy, dtype_tag(dy), rows, C)
+        return dy, (dpre if res is not None else None), sums[C:], sums[:C], None, None, None, None
+
+
+class TriPool(Function):
+    """[B, L, C] -> [B, L//4, 3C] = [max | mean | min] over windows of 4 (brew_cider.py:629-634)."""
+
+    @staticmethod
+    def forward(ctx, x, B, L, C):
+        x = _c(x)
+        y = torch.empty((B, L // 4, 3 * C), dtype=x.dtype, device=x.device)
+        call("acb_tripool4", x, dtype_tag(x), y, dtype_tag(y), B, L, C)
+        ctx.save_for_backward(x)
+        ctx.dims = (B, L, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        B, L, C = ctx.dims
+        dy = _c(dy)
+        dx = torch.empty_like(x)
+        call("acb_tripool4_bwd", x, dtype_tag(x), dy, dtype_tag(dy), dx, dtype_tag(dx), B, L, C)
+        return dx, None, None, None
+
+
 class ConcatCols(Function):
     @staticmethod
     def forward(ctx, *parts):

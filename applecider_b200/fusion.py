@@ -36,7 +36,7 @@ class AppleCider(nn.Module):
         if spectra_variant == "B":  # legacy checkpoints: variant-B encoder -> 256-d embedding (brew_cider.py:585-708,826)
             from .legacy import SpectraClassificationB
 
-            self.spectra_encoder = SpectraClassificationB({"mode": "all", "classes": list(range(num_classes))})
+            self.spectra_encoder = SpectraClassificationB({"mode": "all", "classes": list(range(num_classes))}, compute_dtype=compute_dtype)
         elif spectra_variant == "src":
             self.spectra_encoder = SpectraNet(cfg)
         else:

@@ -1,7 +1,12 @@
 """Legacy fusion-checkpoint compatibility: the "variant B" spectra encoder of
 _archive/notebooks/brew_cider.py:585-708 (BatchNorm stages, 1x1 skip projection, max/avg/min tri-pool, flatten
-12288 -> 2048 -> 256), inference only, fp32, on the same kernel families as the src SpectraNet (CUDA-core implicit-GEMM
-multi-kernel Conv1d, LayerNorm, elementwise) plus one tri-pool kernel.  State-dict keys are the reference's
+12288 -> 2048 -> 256) on the same kernel families as the src SpectraNet.  Three paths:
+  * eval + no_grad + fp32: BatchNorm folded into the conv GEMM epilogue (CUDA-core implicit GEMM; the round-1 parity path);
+  * differentiable (autograd on, or train()): convs through train.SpectraConvs (forward AND backward on the C-ABI kernels),
+    BatchNorm1d with batch statistics + running-statistics update (csrc/legacy_train.cu) fused with the skip add and the GELU,
+    tri-pool with its backward -- so the archived fusion model can be fine-tuned;
+  * bf16: stages 2-5 (144 .. 1152 input channels) on the tcgen05 implicit GEMM, stage 1 (one input channel, 16 outputs) on the
+    fp32 conv, activations bf16, statistics fp32.  State-dict keys are the reference's
 (`stage{1..5}.0.convs.{j}`, `.norm` incl. BatchNorm running statistics, `.proj`, `class_model.{0,1,4,5}`, `fc`), so the
 archived `cider_weights/*.pth` spectra sub-dicts load with strict=True.  Activations are channels-last [B, L, C]."""
 from __future__ import annotations
@@ -10,6 +15,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .config import resolve_dtype
+from .spectra import SpectraNetBlock
 
 KERNEL_SIZES = [[3, 61, 1021], [3, 31, 251], [3, 15, 61], [3, 11, 31], [3, 7, 13]]
 USE_LN = [False, False, False, False, True]
@@ -30,7 +37,16 @@ class SpectraNetBlockB(nn.Module):
             self.proj = nn.Conv1d(in_channels, nc, kernel_size=1)
         self._derived = ops.DerivedCache()
 
-    def _packed(self):
+    # the multi-kernel conv machinery of the src block (packed tap-major weights, fp32 / tcgen05 implicit GEMMs)
+    _kmax = SpectraNetBlock._kmax
+    _packed_dt = SpectraNetBlock._packed
+    _convs_f32 = SpectraNetBlock._convs_f32
+    _convs_bf16 = SpectraNetBlock._convs_bf16
+
+    def _packed(self, dtype=None):
+        if dtype is not None:
+            return self._packed_dt(dtype)
+
         def build():
             kmax, cin, cout = max(self.kernel_sizes), self.in_channels, self.out_channels
             w = torch.zeros((self.k * cout, kmax * cin), dtype=torch.float32, device=self.convs[0].weight.device)
@@ -50,6 +66,34 @@ class SpectraNetBlockB(nn.Module):
             return scale.contiguous(), (n.bias.detach() - n.running_mean * scale).contiguous()
 
         return self._derived.get("bn", [n.weight, n.bias, n.running_mean, n.running_var], build)
+
+    def forward_diff(self, h, B, L, dtype, training):
+        """Differentiable path.  h: [B, L, Cin] channels-last (fp32 for the 1-channel first stage, else `dtype`).
+        Returns (activation [B, L', C'], L', C')."""
+        from . import fn
+        from .train import SpectraConvs
+
+        cin, nc = self.in_channels, self.out_channels * self.k
+        params = [c.weight for c in self.convs] + [c.bias for c in self.convs]
+        y = SpectraConvs.apply(h, None, self, B, L, dtype, *params)  # [B*L, nc] in `dtype`
+        res = None
+        if self.use_skip:
+            hp = h.reshape(B * L, cin)
+            wp = self.proj.weight.view(nc, cin)
+            if hp.dtype != torch.float32 and cin % 8 == 0:
+                res = fn.linear(hp, wp, self.proj.bias)
+            else:  # first stage: K = 1
+                res = fn.linear(hp.float(), wp, self.proj.bias)
+        if self.use_ln:
+            z = fn.layernorm(y, self.norm.weight, self.norm.bias, self.norm.eps)
+            if res is not None:
+                z = fn.add(fn.cast(res, z.dtype), z)
+            g = fn.act(z, ops.ACT_GELU)
+        else:
+            g = fn.BatchNormResAct.apply(y, res, self.norm.weight, self.norm.bias, self.norm, bool(training), ops.ACT_GELU, dtype)
+        if not self.do_pool:
+            return g.view(B, L, nc), L, nc
+        return fn.TriPool.apply(g.view(B, L, nc), B, L, nc), L // 4, 3 * nc
 
     def forward_cl(self, x, B, L):
         from .fn import ew  # thin acb_ew wrapper (no autograd involved here)
@@ -88,9 +132,10 @@ class SpectraNetBlockB(nn.Module):
 class SpectraClassificationB(nn.Module):
     """forward(x[B,1,4096]) -> (B,256) embedding, or (B,num_classes) when config['mode'] == 'spectra' (brew_cider.py:638-705)."""
 
-    def __init__(self, config=None, depths=(1, 1, 1, 1, 1), length=4096):
+    def __init__(self, config=None, depths=(1, 1, 1, 1, 1), length=4096, compute_dtype=None):
         super().__init__()
         config = config or {"mode": "all", "classes": list(range(5))}
+        self.compute_dtype = resolve_dtype(compute_dtype if compute_dtype is not None else config.get("compute_dtype"))
         if list(depths) != [1, 1, 1, 1, 1]:
             raise NotImplementedError("applecider_b200: the archived checkpoints use depths [1,1,1,1,1]")
         self.classification = config["mode"] == "spectra"
@@ -113,14 +158,46 @@ class SpectraClassificationB(nn.Module):
         C, L = CHANNELS[5] * 3, self.length
         return self._derived.get("w0", [lin.weight], lambda: lin.weight.detach().view(-1, C, L).permute(0, 2, 1).reshape(-1, L * C).contiguous())
 
-    @torch.no_grad()
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("applecider_b200: inputs must be CUDA tensors (no CPU fallback)")
-        if self.training:
-            raise NotImplementedError("applecider_b200: the legacy spectra encoder is inference-only (BatchNorm in eval mode)")
         B, c, L = x.shape
         assert c == 1 and L // 256 == self.length, "the legacy encoder expects (B, 1, 4096) spectra"
+        grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if self.training or grad or self.compute_dtype != torch.float32:
+            return self._forward_diff(x)
+        with torch.no_grad():
+            return self._forward_eval_f32(x)
+
+    def _forward_diff(self, x):
+        """BatchNorm with batch statistics in train(), running statistics in eval(); every op has a C-ABI backward."""
+        from . import fn
+
+        dtype = self.compute_dtype
+        B, _, L = x.shape
+        h = x.contiguous().float().view(B, L, 1)
+        for i in range(5):
+            h, L, C = getattr(self, f"stage{i + 1}")[0].forward_diff(h, B, L, dtype, self.training)
+        z = h.reshape(B, L * C)
+        cm = self.class_model
+        Cc, Ll = CHANNELS[5] * 3, self.length
+        # class_model.0 consumes x.reshape(B, C*L) (C-major); our rows are [L, C]: a differentiable re-layout of the weight columns
+        w0 = cm[0].weight.view(-1, Cc, Ll).permute(0, 2, 1).reshape(-1, Ll * Cc)
+        if dtype != torch.float32 and B >= 64:
+            z = fn.linear(z, w0, cm[0].bias, out_dtype=torch.float32)
+        else:
+            z = fn.linear(fn.cast(z, torch.float32), w0, cm[0].bias)
+        z = fn.layernorm(z, cm[1].weight, cm[1].bias, cm[1].eps, post_act=ops.ACT_GELU)
+        z = fn.dropout(z, cm[3].p, self.training)
+        z = fn.linear(z, cm[4].weight, cm[4].bias)
+        z = fn.layernorm(z, cm[5].weight, cm[5].bias, cm[5].eps, post_act=ops.ACT_GELU)
+        z = fn.dropout(z, cm[7].p, self.training)
+        if self.classification:
+            z = fn.linear(z, self.fc.weight, self.fc.bias)
+        return z
+
+    def _forward_eval_f32(self, x):
+        B, c, L = x.shape
         h = x.contiguous().float().view(B, L, 1)
         for i in range(5):
             h, L, C = getattr(self, f"stage{i + 1}")[0].forward_cl(h, B, L)

@@ -96,12 +96,15 @@ class SpectraNetBlock(nn.Module):
         w, bias = self._packed(torch.bfloat16)
         N = self.k * cout
         bn = 256 if cout % 256 == 0 else (128 if cout % 128 == 0 else 64)
-        if cout % bn:
-            raise RuntimeError("applecider_b200: bf16 SpectraNet needs out_channels to be a multiple of 64")
+        if cin % 8 or N % 8:
+            raise RuntimeError("applecider_b200: the bf16 conv path needs channel counts that are multiples of 8")
         cpt = (cin + 63) // 64
         ranges = []
-        for nt in range(N // bn):
-            kj = self.kernel_sizes[(nt * bn) // cout]
+        for nt in range((N + bn - 1) // bn):
+            # an N tile normally holds channels of ONE conv; narrow convs (legacy variant B: 16 / 32 channels) share a tile, which
+            # then runs the union of their tap ranges (the packed weights are zero outside a conv's own taps)
+            js = range((nt * bn) // cout, min(self.k - 1, (min(N, (nt + 1) * bn) - 1) // cout) + 1)
+            kj = max(self.kernel_sizes[j] for j in js)
             t_lo, t_hi = kmax // 2 - kj // 2, kmax // 2 + kj // 2 + 1
             ranges += [t_lo * cpt, t_hi * cpt]
         with ops.region(f"spectra.conv.cin{cin}"):

@@ -138,6 +138,12 @@ class SpectraConvs(torch.autograd.Function):
         ctx.blk, ctx.dims, ctx.dtype = blk, (B, L), dtype
         if dtype == F32:
             y, Lr = blk._convs_f32(x, B, L), L
+        elif blk.in_channels == 1 and blk.out_channels % 64:
+            # one input channel and a narrow output (legacy variant B stage 1: 16 channels): the polyphase tcgen05 view needs 64-channel
+            # column blocks, and 0.14 GFLOP per spectrum is nothing -- fp32 CUDA-core conv, result handed on in the compute dtype
+            xf = x if x is not None else sig.view(B, L, 1)
+            y, Lr = ops.cast(blk._convs_f32(xf.float().contiguous(), B, L), dtype), L
+            x = xf
         elif blk.in_channels == 1:
             y, Lr = blk._convs_bf16_polyphase(sig, B, L)
             if Lr != L:
@@ -465,7 +471,7 @@ def astrominn_train_step(model, batch):
 # ---- fusion ---------------------------------------------------------------------------------------------------
 def fusion_forward_train(model, photometry, photometry_mask, metadata, images, spectra, total_tokens=None):
     p = photo_encode_train(model.photometry_encoder, photometry, photometry_mask, total_tokens)
-    s = spectra_forward_train(model.spectra_encoder, spectra)
+    s = model.spectra_encoder(spectra) if getattr(model, "spectra_variant", "src") == "B" else spectra_forward_train(model.spectra_encoder, spectra)
     if s.dim() == 1:
         s = s[:, None]
     im = astrominn_forward_train(model.img_metadata_encoder, metadata, images)

@@ -192,6 +192,30 @@ int acb_pairmax_bf16(const void* x, void* y, long long rows_out, int C, void* st
 /* legacy spectra encoder ("variant B", _archive/notebooks/brew_cider.py:611-636): x[B,L,C] f32 channels-last ->
  * y[B, L/4, 3C] = [max | mean | min] over windows of 4 positions (cat of MaxPool1d, AvgPool1d, -MaxPool1d(-x)). */
 int acb_tripool4_cl(const float* x, float* y, int B, int L, int C, void* stream);
+/* the same for fp32 or bf16 tensors, and its backward: dx[l] = dmax*[l is the first argmax] + davg/4 + dmin*[l is the first
+ * argmin] (torch's MaxPool1d routing); positions past 4*(L/4) get zero. */
+int acb_tripool4(const void* x, int x_dtype, void* y, int y_dtype, int B, int L, int C, void* stream);
+int acb_tripool4_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, void* dx, int dx_dtype, int B, int L, int C,
+                     void* stream);
+/* ---- BatchNorm1d over channels-last [rows, C] (legacy variant-B stages, brew_cider.py:601-604) ------------------------
+ * acb_bn_stats      sums[0:C] = sum_r y[r,c], sums[C:2C] = sum_r y[r,c]^2 (fp32).
+ * acb_bn_finalize   training: mean / biased var from sums -> scale = w*rstd, shift = b - mean*scale (and mean, rstd), and
+ *                   running_mean / running_var blended with `momentum` (unbiased var), as nn.BatchNorm1d.train();
+ *                   eval (training = 0): the same from the running statistics (sums unused).
+ * acb_affine_res_act      out = act(res + scale[c]*y + shift[c])   (BN + skip projection + GELU of the block in one pass)
+ * acb_affine_res_act_bwd  dpre = dout * act'(pre) with pre recomputed; sums[0:C] = sum dpre, sums[C:2C] = sum dpre*xhat
+ *                         (= d bias, d weight of the BatchNorm); dpre is also the gradient of `res`.
+ * acb_bn_bwd_apply  dy = scale * (dpre - sums[c]/rows - xhat*sums[C+c]/rows) in training, scale*dpre in eval. */
+int acb_bn_stats(const void* y, int y_dtype, long long rows, int C, float* sums, void* stream);
+int acb_bn_finalize(const float* sums, long long rows, int C, const float* w, const float* b, float eps, float momentum, int training,
+                    float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* rstd, void* stream);
+int acb_affine_res_act(const void* y, int y_dtype, const float* scale, const float* shift, const void* res, int res_dtype, int act,
+                       void* out, int out_dtype, long long rows, int C, void* stream);
+int acb_affine_res_act_bwd(const void* y, int y_dtype, const float* scale, const float* shift, const void* res, int res_dtype, int act,
+                           const void* dout, int dout_dtype, const float* mean, const float* rstd, void* dpre, int dpre_dtype,
+                           float* sums, long long rows, int C, void* stream);
+int acb_bn_bwd_apply(const void* y, int y_dtype, const void* dpre, int dpre_dtype, const float* scale, const float* mean,
+                     const float* rstd, const float* sums, int training, void* dy, int dy_dtype, long long rows, int C, void* stream);
 
 /* ---- metadata towers / MoE / fusion head -------------------------------------------------------- */
 /* ResidualTowerBlock (astrominn.py:44-64), eval: s = gelu(W0 x + b0); y = (W1 ln1(s) + b1) * sigmoid(W2 ln2(s) + b2)

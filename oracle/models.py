@@ -509,6 +509,8 @@ class SpectraNetBlockB(nn.Module):
         y = torch.cat([c(x) for c in self.convs], dim=1)
         if self.use_ln:
             y = F.layer_norm(y.permute(0, 2, 1), (y.shape[1],), self.norm.weight, self.norm.bias, self.norm.eps).permute(0, 2, 1)
+        elif self.training:
+            y = self.norm(y)  # nn.BatchNorm1d in train mode: batch statistics, running statistics blended in place
         else:
             n = self.norm
             y = (y - n.running_mean[None, :, None]) / torch.sqrt(n.running_var[None, :, None] + n.eps) * n.weight[None, :, None] + n.bias[None, :, None]

@@ -53,6 +53,40 @@ def main():
     path = os.path.join(HERE, "legacy_spectra.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path} ({os.path.getsize(path)/1024:.1f} KiB)")
+    train_record(build)
+
+
+def train_record(build):
+    """legacy_train.npz: ONE training-mode forward + backward of the real `build_spec_model` (BatchNorm on batch statistics,
+    running statistics updated in place; the two Dropout layers set to p = 0 so that the step is deterministic):
+    loss, a selection of gradients, and the BatchNorm running statistics after the step."""
+    cfg = {"mode": "spectra", "classes": list(range(5))}
+    ref = build(cfg).train()
+    ref.load_state_dict(synth.det_state_dict(ref, 0))
+    for m in ref.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = 0.0
+    x = synth.spectra(4, seed=33, L=4096)
+    y = torch.tensor([0, 3, 1, 4])
+    logits = ref(x)
+    loss = F.cross_entropy(logits, y)
+    loss.backward()
+    out = {"x": x.numpy(), "y": y.numpy(), "logits": logits.detach().numpy(), "loss": np.float32(loss.item())}
+    sd = ref.state_dict()
+    for i in range(1, 5):
+        out[f"rm{i}"] = sd[f"stage{i}.0.norm.running_mean"].numpy()
+        out[f"rv{i}"] = sd[f"stage{i}.0.norm.running_var"].numpy()
+    grads = {n: p.grad for n, p in ref.named_parameters()}
+    for n in ["stage1.0.convs.2.weight", "stage1.0.norm.weight", "stage1.0.norm.bias", "stage1.0.proj.weight", "stage2.0.convs.1.weight",
+              "stage3.0.convs.0.bias", "stage3.0.norm.weight", "stage4.0.proj.weight", "stage5.0.convs.2.weight", "stage5.0.norm.weight",
+              "class_model.4.weight", "fc.weight"]:
+        g = grads[n]
+        out["g_" + n] = g.reshape(g.shape[0], -1)[:, :256].numpy() if g.dim() > 1 else g.numpy()
+    w0 = grads["class_model.0.weight"]
+    out["g_class_model.0.weight_rows"] = w0[:4].numpy()
+    path = os.path.join(HERE, "legacy_train.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path} ({os.path.getsize(path)/1024:.1f} KiB) loss={loss.item():.6f}")
 
 
 if __name__ == "__main__":

@@ -125,3 +125,89 @@ def test_redshift_head_softplus_forward_and_gradient():
     yt.sum().backward()
     g = soft.regressor[4].weight.grad
     assert g is not None and torch.isfinite(g).all() and g.abs().max() > 0
+
+
+def _legacy_train_pair(golden_dir, dtype):
+    from applecider_b200 import synth
+    from applecider_b200.legacy import SpectraClassificationB
+
+    g = np.load(os.path.join(golden_dir, "legacy_train.npz"))
+    m = SpectraClassificationB({"mode": "spectra", "classes": list(range(5))}, compute_dtype=dtype)
+    m.load_state_dict(synth.det_state_dict(m, 0), strict=True)
+    m = m.to(DEV).train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    return g, m
+
+
+def test_legacy_variant_b_training_matches_reference(golden_dir):
+    """ONE training-mode forward + backward (BatchNorm on batch statistics, running statistics updated in place) against the
+    record of the REAL `build_spec_model` in train() mode (brew_cider.py:585-708; tests/golden/make_golden_legacy.py)."""
+    from applecider_b200 import fn
+
+    g, m = _legacy_train_pair(golden_dir, "fp32")
+    logits = m(torch.from_numpy(g["x"]).to(DEV))
+    assert_close(logits, torch.from_numpy(g["logits"]), 1e-4, "variant-B train-mode logits")
+    tgt = torch.nn.functional.one_hot(torch.from_numpy(g["y"]), 5).float().to(DEV)
+    loss = fn.soft_cross_entropy(logits, tgt)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-4
+    sd = m.state_dict()
+    for i in range(1, 5):
+        assert_close(sd[f"stage{i}.0.norm.running_mean"], torch.from_numpy(g[f"rm{i}"]), 1e-5, f"running_mean stage {i}", atol=1e-6)
+        assert_close(sd[f"stage{i}.0.norm.running_var"], torch.from_numpy(g[f"rv{i}"]), 1e-5, f"running_var stage {i}", atol=1e-6)
+        assert int(sd[f"stage{i}.0.norm.num_batches_tracked"]) == 1
+    grads = {n: p.grad for n, p in m.named_parameters()}
+    for k in g.files:
+        if k.startswith("g_") and not k.endswith("_rows"):
+            gr = grads[k[2:]].detach().cpu()
+            got = gr.reshape(gr.shape[0], -1)[:, :256] if gr.dim() > 1 else gr
+            ref = torch.from_numpy(g[k])
+            s = ref.abs().max().clamp_min(1e-12)
+            assert_close(got / s, ref / s, 1e-3, f"variant-B gradient {k[2:]}")
+    ref = torch.from_numpy(g["g_class_model.0.weight_rows"])
+    s = ref.abs().max().clamp_min(1e-12)
+    assert_close(grads["class_model.0.weight"][:4].cpu() / s, ref / s, 1e-3, "class_model.0.weight gradient (C-major flatten re-layout)")
+
+
+def test_legacy_variant_b_bf16_path(golden_dir):
+    """bf16 path (stages 2-5 on the tcgen05 implicit GEMM, stage 1 fp32): logits within 1.5e-2, gradients aligned with the reference."""
+    from applecider_b200 import fn
+
+    g, m = _legacy_train_pair(golden_dir, "bf16")
+    logits = m(torch.from_numpy(g["x"]).to(DEV))
+    assert_close(logits, torch.from_numpy(g["logits"]), 1.5e-2, "variant-B bf16 train-mode logits")
+    tgt = torch.nn.functional.one_hot(torch.from_numpy(g["y"]), 5).float().to(DEV)
+    fn.soft_cross_entropy(logits, tgt).backward()
+    grads = {n: p.grad for n, p in m.named_parameters()}
+    for k in g.files:
+        if k.startswith("g_") and not k.endswith("_rows"):
+            gr = grads[k[2:]].detach().float().cpu()
+            got = (gr.reshape(gr.shape[0], -1)[:, :256] if gr.dim() > 1 else gr).flatten()
+            ref = torch.from_numpy(g[k]).flatten()
+            cos = torch.nn.functional.cosine_similarity(got, ref, dim=0).item()
+            assert cos > 0.97, f"{k[2:]}: cosine {cos:.4f}"
+    m.eval()
+    with torch.no_grad():
+        e = m(torch.from_numpy(g["x"]).to(DEV))
+    assert torch.isfinite(e).all()
+
+
+def test_fusion_with_legacy_encoder_trains():
+    """AppleCider(spectra_variant='B') through the whole-step training path: loss decreases over a few fused-Adam steps."""
+    import applecider_b200 as ab
+    from applecider_b200 import fn, synth
+    from applecider_b200.ddp import ddp_train_step
+    from applecider_b200.optim import FusedAdam
+
+    model = ab.AppleCider(ab.default_config(), hidden_dim=64, fusion="avg", spectra_variant="B", compute_dtype="fp32")
+    model.load_state_dict(synth.det_state_dict(model, 0), strict=True)
+    model = model.to(DEV).train()
+    B = 8
+    x, pad, lens = synth.photometry_batch(B, seed=9, L=64)
+    args = [t.to(DEV) for t in (x, pad, synth.metadata(B, seed=9, missing_frac=0.0), synth.cutouts(B, seed=9), synth.spectra(B, seed=9, L=4096))]
+    tgt = torch.nn.functional.one_hot(synth.labels(B, seed=9), 5).float().to(DEV)
+    opt = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=2e-4)
+    losses = [ddp_train_step(opt.grads, lambda: fn.soft_cross_entropy(model(*args), tgt), opt).item() for _ in range(8)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0], losses

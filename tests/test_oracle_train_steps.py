@@ -58,3 +58,31 @@ def test_oracle_seeded_init_matches_reference_fingerprint(golden_dir):
             out = m(batch)
         ref = torch.from_numpy(z[f"logits/{name}"])
         assert (out - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()), name
+
+
+def test_oracle_legacy_variant_b_training_vs_reference(golden_dir):
+    """Train-mode forward + backward of the variant-B spectra encoder (BatchNorm on batch statistics) vs the record of the REAL
+    `build_spec_model` (tests/golden/make_golden_legacy.py::train_record)."""
+    from applecider_b200 import synth
+    from oracle import models as om
+
+    g = np.load(os.path.join(golden_dir, "legacy_train.npz"))
+    m = om.SpectraClassificationB({"mode": "spectra", "classes": list(range(5))}).train()
+    m.load_state_dict(synth.det_state_dict(m, 0))
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    logits = m(torch.from_numpy(g["x"]))
+    loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(g["y"]))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5
+    sd = m.state_dict()
+    for i in range(1, 5):
+        assert np.allclose(sd[f"stage{i}.0.norm.running_mean"].numpy(), g[f"rm{i}"], rtol=1e-5, atol=1e-6)
+        assert np.allclose(sd[f"stage{i}.0.norm.running_var"].numpy(), g[f"rv{i}"], rtol=1e-5, atol=1e-6)
+    grads = {n: p.grad for n, p in m.named_parameters()}
+    for k in g.files:
+        if k.startswith("g_") and not k.endswith("_rows"):
+            gr = grads[k[2:]]
+            got = gr.reshape(gr.shape[0], -1)[:, :256].numpy() if gr.dim() > 1 else gr.numpy()
+            assert np.abs(got - g[k]).max() <= 1e-4 * max(np.abs(g[k]).max(), 1e-8) + 1e-8, k
