@@ -127,6 +127,11 @@ def test_redshift_head_softplus_forward_and_gradient():
     assert g is not None and torch.isfinite(g).all() and g.abs().max() > 0
 
 
+def _ZERO_GRAD(name):
+    """conv biases of the BatchNorm stages (1-4) in training mode"""
+    return name.startswith(("stage1.", "stage2.", "stage3.", "stage4.")) and ".convs." in name and name.endswith(".bias")
+
+
 def _legacy_train_pair(golden_dir, dtype):
     from applecider_b200 import synth
     from applecider_b200.legacy import SpectraClassificationB
@@ -164,6 +169,12 @@ def test_legacy_variant_b_training_matches_reference(golden_dir):
             gr = grads[k[2:]].detach().cpu()
             got = gr.reshape(gr.shape[0], -1)[:, :256] if gr.dim() > 1 else gr
             ref = torch.from_numpy(g[k])
+            if _ZERO_GRAD(k[2:]):
+                # a bias in front of a train-mode BatchNorm has an exactly zero gradient (the batch mean removes it): the reference
+                # holds rounding noise there; ours must be noise too, not a value
+                wmax = grads[k[2:].replace(".bias", ".weight")].abs().max().item()
+                assert got.abs().max().item() <= 1e-4 * wmax, f"{k[2:]}: gradient of a pre-BatchNorm bias must vanish"
+                continue
             s = ref.abs().max().clamp_min(1e-12)
             assert_close(got / s, ref / s, 1e-3, f"variant-B gradient {k[2:]}")
     ref = torch.from_numpy(g["g_class_model.0.weight_rows"])
@@ -182,7 +193,7 @@ def test_legacy_variant_b_bf16_path(golden_dir):
     fn.soft_cross_entropy(logits, tgt).backward()
     grads = {n: p.grad for n, p in m.named_parameters()}
     for k in g.files:
-        if k.startswith("g_") and not k.endswith("_rows"):
+        if k.startswith("g_") and not k.endswith("_rows") and not _ZERO_GRAD(k[2:]):
             gr = grads[k[2:]].detach().float().cpu()
             got = (gr.reshape(gr.shape[0], -1)[:, :256] if gr.dim() > 1 else gr).flatten()
             ref = torch.from_numpy(g[k]).flatten()
