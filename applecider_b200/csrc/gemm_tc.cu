@@ -33,6 +33,8 @@ struct TcArgs {
   int res_mode, pool4;
   const int* m_valid_dev;
   void* pre_out;  // optional second bf16 output: the value after the bias, before activation / residual (same ldc, columns)
+  float* row_stats;  // optional [rows][gridDim.y][2]: per-row sum and sum of squares of this CTA's output columns (LayerNorm
+                     // statistics for the consumer GEMM, acb_gemm_ln_bf16, which then never needs its own pass over the activation)
   int has_ranges, has_coloff;
   int kb_lo[TC_MAX_NT], kb_hi[TC_MAX_NT];
   int col_off[TC_MAX_CB];
@@ -62,6 +64,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& p, bool have_acc,
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
     const int esz = p.c_dtype == ACB_BF16 ? 2 : 4;
     const int rsz = p.res_dtype == ACB_BF16 ? 2 : 4;
+    float st_sum = 0.0f, st_sq = 0.0f;
     for (int c0 = 0; c0 < BN; c0 += 32) {
       const int n_first = n0 + c0;
       if (n_first >= p.N) break;  // warp-uniform
@@ -216,6 +219,11 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& p, bool have_acc,
           v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 2));
         }
       }
+      if (p.row_stats) {  // warp-uniform
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) { st_sum += v[i]; st_sq = fmaf(v[i], v[i], st_sq); }
+      }
       const bool cvec = ncols == 32 && ((((uintptr_t)p.C + (size_t)out_col * esz) & 15) == 0) && ((((size_t)p.ldc * esz) & 15) == 0);
       if (cvec && esz == 2) {
         // bf16 output: pack in registers, 4 x 16-byte smem stores per lane (80-byte row pitch: conflict-free), then 8 rows x
@@ -274,6 +282,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& p, bool have_acc,
           if (i < ncols) st_any(p.C, off + i, p.c_dtype, v[i]);
       }
     }
+    if (p.row_stats && valid)
+      *reinterpret_cast<float2*>(p.row_stats + ((size_t)m * gridDim.y + nt) * 2) = make_float2(st_sum, st_sq);
   }
 }
 
@@ -424,6 +434,174 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args
   return ACB_OK;
 }
 
+
+// ---- GEMM whose A operand is LayerNorm + GELU of the stored activation (SpectraNet: norm -> GELU -> 1x1 downsample) -------
+// y = gelu(LN(x)) W^T: x tiles arrive by TMA exactly as in gemm_tc_kernel; before the MMA warp may read a stage, the four
+// epilogue warps (idle during a main loop anyway) normalise it IN PLACE in shared memory: thread r owns row r of the tile, its
+// mean / rstd come from the per-row partial sums that the PRODUCER GEMM's epilogue left behind (TcArgs::row_stats), so the
+// activation is read from HBM exactly once and the normalised copy never exists in global memory.  In-place keeps the
+// SWIZZLE_128B layout TMA wrote: row r's 16-byte chunk c sits at r*128 + ((c ^ (r & 7)) << 4).
+struct TcLnArgs {
+  const float* stats;  // [rows][parts][2] partial (sum, sum of squares)
+  int parts;
+  const float* w;      // LayerNorm weight / bias over the K = Cin columns
+  const float* b;
+  float eps;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) gemm_ln_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ TcArgs p, const __grid_constant__ TcLnArgs q) {
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
+  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * STAGES + 1];  // full | transformed | empty | accumulator
+  __shared__ uint32_t tmem_holder;
+  __shared__ __align__(16) float s_bias[BN], s_gamma[BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x, nt = blockIdx.y;
+  const int n0 = nt * BN;
+  const int l0 = mt * TC_BM;  // plain GEMM: one "sample" of L = M rows
+  const int nkb = p.cpt;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* s_lnw = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES);
+  float* s_lnb = s_lnw + p.Cin;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_xf = smem_u32(&bars[STAGES]);
+  const uint32_t bar_empty = smem_u32(&bars[2 * STAGES]);
+  const uint32_t bar_acc = smem_u32(&bars[3 * STAGES]);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_xf + 8 * s, 4);  // one arrival per transform warp
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"((uint32_t)tmem_cols<BN>())
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+      if (elect_one_sync()) {
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        mbar_expect_tx(bar_full + 8 * s, A_BYTES + B_BYTES);
+        tma_load_3d(sa, &tmA, it * TC_BK, l0, 0, bar_full + 8 * s);
+        tma_load_2d(sa + A_BYTES, &tmB, it * TC_BK, n0, bar_full + 8 * s);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(bar_xf + 8 * s, ph);  // TMA landed AND the tile has been normalised
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar_empty + 8 * s);
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) umma_commit(bar_acc);
+    __syncwarp();
+  } else {
+    const int tq = threadIdx.x - 64;
+    for (int i = tq; i < BN; i += 128) {
+      const int n = n0 + i;
+      s_bias[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
+      s_gamma[i] = 1.0f;
+    }
+    for (int i = tq; i < p.Cin; i += 128) {
+      s_lnw[i] = __ldg(q.w + i);
+      s_lnb[i] = __ldg(q.b + i);
+    }
+    // this thread's row and its LayerNorm statistics from the producer's partial sums
+    const int r = (warp & 3) * 32 + lane;
+    const long long m = (long long)l0 + r;
+    float mean = 0.0f, rstd = 0.0f;
+    if (m < (long long)p.L) {
+      float s1 = 0.0f, s2 = 0.0f;
+      for (int j = 0; j < q.parts; ++j) {
+        const float2 t = *reinterpret_cast<const float2*>(q.stats + ((size_t)m * q.parts + j) * 2);
+        s1 += t.x;
+        s2 += t.y;
+      }
+      mean = s1 / (float)p.Cin;
+      rstd = rsqrtf(fmaxf(s2 / (float)p.Cin - mean * mean, 0.0f) + q.eps);
+    }
+    asm volatile("bar.sync 9, 128;" ::: "memory");
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(bar_full + 8 * s, ph);
+      uint8_t* row = gen_base + s * STAGE_BYTES + r * 128;
+      const float* gw = s_lnw + it * TC_BK;
+      const float* gb = s_lnb + it * TC_BK;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4* ptr = reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4));
+        const uint4 pk = *ptr;
+        const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+        uint32_t o4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = c * 8 + 2 * e;
+          const float a0 = rstd * gw[k], a1 = rstd * gw[k + 1];
+          const float x0 = __uint_as_float(w4[e] << 16), x1 = __uint_as_float(w4[e] & 0xffff0000u);
+          const float y0 = gelu_bf16(fmaf(x0, a0, fmaf(-mean, a0, gb[k])));
+          const float y1 = gelu_bf16(fmaf(x1, a1, fmaf(-mean, a1, gb[k + 1])));
+          __nv_bfloat162 hh = __floats2bfloat162_rn(y0, y1);
+          o4[e] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        *ptr = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_xf + 8 * s) : "memory");
+    }
+    mbar_wait_sleep(bar_acc, 0);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(gen_base) + (warp - 2) * (32 * 33);
+    tc_epilogue_tile<BN>(p, true, tmem_base, mt, nt, stg, s_bias, s_gamma, warp, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols<BN>()) : "memory");
+  }
+}
+
+template <int BN, int STAGES>
+int launch_ln_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, const TcLnArgs& ln, dim3 grid, cudaStream_t st) {
+  const size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024 + (size_t)2 * args.Cin * sizeof(float);
+  auto k = gemm_ln_tc_kernel<BN, STAGES>;
+  ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, args, ln);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
 
 // ---- persistent variant for short-K problems ---------------------------------------------------------------
 // A tile with <= a few K blocks is over before its epilogue has started, so the non-persistent kernel is bound by
@@ -749,11 +927,47 @@ int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcWgradAr
 
 }  // namespace
 
+static int gemm_bf16_impl(const void* A, const void* Bw, void* C, int c_dtype, int nbatch, int L, int Cin, int taps,
+                         int pad, long long a_batch_stride, long long a_row_stride, int N, int ldb, int ldc, int bn,
+                         const int* tile_kb_host, const int* colblk_off_host, const float* bias, int act,
+                         const void* res, int res_dtype, int ldr, const float* gamma, int res_mode, int pool4,
+                         const int* m_valid_dev, void* pre_out, float* row_stats, const TcLnArgs* ln, void* stream);
+
 extern "C" int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype, int nbatch, int L, int Cin, int taps,
                              int pad, long long a_batch_stride, long long a_row_stride, int N, int ldb, int ldc, int bn,
                              const int* tile_kb_host, const int* colblk_off_host, const float* bias, int act,
                              const void* res, int res_dtype, int ldr, const float* gamma, int res_mode, int pool4,
                              const int* m_valid_dev, void* pre_out, void* stream) {
+  return gemm_bf16_impl(A, Bw, C, c_dtype, nbatch, L, Cin, taps, pad, a_batch_stride, a_row_stride, N, ldb, ldc, bn, tile_kb_host,
+                        colblk_off_host, bias, act, res, res_dtype, ldr, gamma, res_mode, pool4, m_valid_dev, pre_out, nullptr, nullptr, stream);
+}
+
+// the same GEMM that also leaves per-row (sum, sum of squares) of every N tile's columns in row_stats[rows][ceil(N/bn)][2]
+extern "C" int acb_gemm_bf16_stats(const void* A, const void* Bw, void* C, int c_dtype, int nbatch, int L, int Cin, int taps,
+                                   int pad, long long a_batch_stride, long long a_row_stride, int N, int ldb, int ldc, int bn,
+                                   const int* tile_kb_host, const float* bias, float* row_stats, void* stream) {
+  ACB_CHECK(row_stats != nullptr, "acb_gemm_bf16_stats: row_stats is null");
+  return gemm_bf16_impl(A, Bw, C, c_dtype, nbatch, L, Cin, taps, pad, a_batch_stride, a_row_stride, N, ldb, ldc, bn, tile_kb_host, nullptr, bias,
+                        ACB_ACT_NONE, nullptr, 0, 0, nullptr, ACB_RES_NONE, 0, nullptr, nullptr, row_stats, nullptr, stream);
+}
+
+// C = [maxpool4]( gelu(LayerNorm(A)) W^T + bias ), LayerNorm statistics from the producer's row_stats (parts partial sums per row)
+extern "C" int acb_gemm_ln_bf16(const void* A, const void* Bw, void* C, int c_dtype, long long M, int K, int N, int ldc, const float* bias,
+                                int pool4, const float* row_stats, int parts, const float* ln_w, const float* ln_b, float ln_eps,
+                                void* stream) {
+  ACB_CHECK(row_stats && ln_w && ln_b && parts > 0 && parts <= 64, "acb_gemm_ln_bf16: bad LayerNorm arguments");
+  ACB_CHECK(K % 64 == 0 && K <= 4096 && M < (1LL << 31), "acb_gemm_ln_bf16: K must be a multiple of 64 (<= 4096)");
+  ACB_CHECK(N % 128 == 0, "acb_gemm_ln_bf16: N must be a multiple of 128");
+  TcLnArgs ln{row_stats, parts, ln_w, ln_b, ln_eps};
+  return gemm_bf16_impl(A, Bw, C, c_dtype, 1, (int)M, K, 1, 0, (long long)M * K, K, N, K, ldc, N % 256 == 0 ? 256 : 128, nullptr, nullptr, bias,
+                        ACB_ACT_NONE, nullptr, 0, 0, nullptr, ACB_RES_NONE, pool4, nullptr, nullptr, nullptr, &ln, stream);
+}
+
+static int gemm_bf16_impl(const void* A, const void* Bw, void* C, int c_dtype, int nbatch, int L, int Cin, int taps,
+                         int pad, long long a_batch_stride, long long a_row_stride, int N, int ldb, int ldc, int bn,
+                         const int* tile_kb_host, const int* colblk_off_host, const float* bias, int act,
+                         const void* res, int res_dtype, int ldr, const float* gamma, int res_mode, int pool4,
+                         const int* m_valid_dev, void* pre_out, float* row_stats, const TcLnArgs* ln, void* stream) {
   ACB_CHECK(A && Bw && C, "acb_gemm_bf16: null operand");
   ACB_CHECK(nbatch > 0 && L > 0 && Cin > 0 && taps > 0 && N > 0, "acb_gemm_bf16: bad shape");
   ACB_CHECK(bn == 64 || bn == 128 || bn == 256, "acb_gemm_bf16: bn must be 64, 128 or 256 (got %d)", bn);
@@ -783,6 +997,7 @@ extern "C" int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype
   args.N = N; args.ldc = ldc; args.c_dtype = c_dtype; args.C = C;
   args.bias = bias; args.act = act; args.res = res; args.res_dtype = res_dtype; args.ldr = ldr; args.gamma = gamma;
   args.res_mode = res_mode; args.pool4 = pool4; args.m_valid_dev = m_valid_dev; args.pre_out = pre_out;
+  args.row_stats = row_stats;
   const int kb_total = taps * cpt;
   if (tile_kb_host) {
     args.has_ranges = 1;
@@ -832,12 +1047,17 @@ extern "C" int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype
     for (int i = 0; i < NT; ++i) max_kb = args.kb_hi[i] - args.kb_lo[i] > max_kb ? args.kb_hi[i] - args.kb_lo[i] : max_kb;
   }
   const bool short_k = max_kb <= 4;
+  if (ln) {
+    ACB_CHECK(args.Bbox == 1 && !tile_kb_host && !colblk_off_host, "acb_gemm_ln_bf16: plain GEMM with M >= 128 only");
+    if (bn == 256) return launch_ln_tc<256, 2>(tmA, tmB, args, *ln, grid, st);
+    return launch_ln_tc<128, 3>(tmA, tmB, args, *ln, grid, st);
+  }
   static int persist_kb = -1;  // K blocks per tile up to which the persistent (overlapped-epilogue) kernel is used
   if (persist_kb < 0) {
     const char* e = getenv("ACB_PERSIST_KB");
     persist_kb = e ? atoi(e) : 0;  // measured on B200: no gain over 2-3 co-resident non-persistent CTAs, opt-in
   }
-  if (max_kb <= persist_kb && MT * NT < (1LL << 31) && MT * NT > 148) {
+  if (max_kb <= persist_kb && MT * NT < (1LL << 31) && MT * NT > 148 && !row_stats) {
     switch (bn) {
       case 64: return launch_tc_persist<64, 2>(tmA, tmB, args, MT, NT, st);
       case 128: return launch_tc_persist<128, 2>(tmA, tmB, args, MT, NT, st);

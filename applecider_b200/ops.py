@@ -68,7 +68,8 @@ def pick_bn(n: int) -> int:
 
 
 def gemm(a, w, bias=None, act=ACT_NONE, res=None, gamma=None, res_mode=RES_NONE, out=None, out_dtype=None,
-         out_col=0, conv=None, pool4=False, bn=None, tile_kb=None, colblk_off=None, a_view=None, pre_out=None, m_valid=None):
+         out_col=0, conv=None, pool4=False, bn=None, tile_kb=None, colblk_off=None, a_view=None, pre_out=None, m_valid=None,
+         row_stats=None):
     """C = epilogue(A @ W^T).  a: [M,K] (or [B,L,Cin] with conv=(taps,pad)); w: [N,K'] row-major.
 
     f32 operands run the CUDA-core kernel, bf16 operands the tcgen05 kernel.
@@ -114,10 +115,23 @@ def gemm(a, w, bias=None, act=ACT_NONE, res=None, gamma=None, res_mode=RES_NONE,
             bn = pick_bn(N)
         kb = _int_array(tile_kb) if tile_kb is not None else None
         co = _int_array(colblk_off) if colblk_off is not None else None
+        if row_stats is not None:  # conv / GEMM that also leaves per-row LayerNorm partial sums (one pair per N tile)
+            assert co is None and res is None and act == ACT_NONE and not pool4 and pre_out is None and m_valid is None and out_col == 0
+            call("acb_gemm_bf16_stats", a, w, c_ptr, dtype_tag(out), nb, L, cin, taps, pad, bstride, rstride, N, ldb, ldc, bn, kb, bias, row_stats)
+            return out
         call("acb_gemm_bf16", a, w, c_ptr, dtype_tag(out), nb, L, cin, taps, pad, bstride, rstride, N, ldb, ldc, bn, kb, co,
              bias, act, res, (dtype_tag(res) if res is not None else 0), ldr, gamma, res_mode, int(pool4), m_valid, pre_out)
     else:
         raise TypeError(f"gemm: unsupported dtype {a.dtype}")
+    return out
+
+
+def gemm_ln(a, w, bias, row_stats, parts, ln_w, ln_b, ln_eps, pool4=False, out_dtype=None):
+    """[maxpool4]( gelu(LayerNorm(a)) @ w^T + bias ) with the LayerNorm statistics taken from `row_stats` (acb_gemm_ln_bf16)."""
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M // 4 if pool4 else M, N), dtype=(out_dtype or a.dtype), device=a.device)
+    call("acb_gemm_ln_bf16", a, w, out, dtype_tag(out), M, K, N, N, bias, int(pool4), row_stats, parts, ln_w, ln_b, float(ln_eps))
     return out
 
 

@@ -17,6 +17,7 @@ from .config import resolve_dtype
 FUSE_CONV_LN = True  # conv + bias + LayerNorm + GELU in one tcgen05 kernel where 3*C_out fits TMEM
 FUSE_STAGE1 = False
 FUSE_STAGE0_DOWN = True  # stage 0: also fuse the 1x1 downsample + pair max into the persistent kernel
+FUSE_LN_DOWN = True  # stages 1-3: LayerNorm + GELU applied to the A operand of the 1x1 downsample GEMM (statistics from the conv epilogue)
 _PHASES = 8
 _HALO = 512  # zeros in front of every padded sample (>= max pad 510, multiple of 8)
 
@@ -91,7 +92,7 @@ class SpectraNetBlock(nn.Module):
                      kj // 2, ops._offset_ptr(bias, j * cout), ops.ACT_NONE, None, 0, None, ops.RES_NONE)
         return y
 
-    def _convs_bf16(self, x, B, L):
+    def _convs_bf16(self, x, B, L, want_stats=False):
         cin, cout, kmax = self.in_channels, self.out_channels, self._kmax()
         w, bias = self._packed(torch.bfloat16)
         N = self.k * cout
@@ -108,6 +109,10 @@ class SpectraNetBlock(nn.Module):
             t_lo, t_hi = kmax // 2 - kj // 2, kmax // 2 + kj // 2 + 1
             ranges += [t_lo * cpt, t_hi * cpt]
         with ops.region(f"spectra.conv.cin{cin}"):
+            if want_stats:  # per-row (sum, sum^2) of every N tile from the epilogue's fp32 accumulators: LayerNorm statistics for free
+                parts = (N + bn - 1) // bn
+                stats = torch.empty((B * L, parts, 2), dtype=torch.float32, device=x.device)
+                return ops.gemm(x.view(B, L, cin), w, bias, conv=(kmax, kmax // 2), bn=bn, tile_kb=ranges, row_stats=stats), stats, parts
             return ops.gemm(x.view(B, L, cin), w, bias, conv=(kmax, kmax // 2), bn=bn, tile_kb=ranges)
 
     def _convs_bf16_polyphase(self, x_f32, B, L):
@@ -212,6 +217,13 @@ class SpectraNetBlock(nn.Module):
             if cout % 64:
                 raise RuntimeError("applecider_b200: bf16 SpectraNet needs out_channels to be a multiple of 64")
             y, Lr = self._convs_bf16_polyphase(raw_signal, B, L)
+        elif (FUSE_LN_DOWN and self.do_pool and nc % 64 == 0 and cout % 128 == 0 and L % 4 == 0 and B * L >= 128):
+            # conv (+ LayerNorm statistics from its epilogue) -> ONE GEMM that normalises + GELUs its A tiles in shared memory,
+            # multiplies by the 1x1 downsample weights and max-pools: the normalised [B*L, 3C] activation never exists in HBM
+            y, stats, parts = self._convs_bf16(x, B, L, want_stats=True)
+            with ops.region(f"spectra.ln_down.cin{self.in_channels}"):
+                z = ops.gemm_ln(y, self._down(dtype), self.downsample.bias, stats, parts, self.norm.weight, self.norm.bias, self.norm.eps, pool4=True)
+            return z.view(B, L // 4, cout), L // 4
         else:
             y = self._convs_bf16(x, B, L)
         if not fused:

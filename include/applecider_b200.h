@@ -86,6 +86,20 @@ int acb_gemm_bf16(const void* A, const void* Bw, void* C, int c_dtype, int nbatc
                   const int* tile_kb_host, const int* colblk_off_host, const float* bias, int act, const void* res,
                   int res_dtype, int ldr, const float* gamma, int res_mode, int pool4, const int* m_valid_dev,
                   void* pre_out, void* stream);
+/* SpectraNet block tail without the normalised activation ever reaching HBM (spectranet.py:36-40: norm -> GELU -> downsample
+ * -> MaxPool1d(4)):
+ *  - acb_gemm_bf16_stats: the conv GEMM above that ALSO writes, per output row and per N tile (ceil(N/bn) tiles), the sum and
+ *    the sum of squares of that tile's columns: row_stats[rows][tiles][2] fp32 -- the LayerNorm statistics, for free, from
+ *    the fp32 accumulators in the epilogue.
+ *  - acb_gemm_ln_bf16: C = [maxpool4 over row quadruples]( gelu(LayerNorm_K(A)) Bw^T + bias ).  A[M,K] is the stored conv
+ *    output; each TMA-loaded 128 x 64 tile is normalised in place in shared memory (mean / rstd from row_stats, weight /
+ *    bias ln_w / ln_b over the K columns, erf-GELU via the bf16-accurate tanh form) before the tcgen05 MMA reads it.
+ *    K % 64 == 0, N % 128 == 0. */
+int acb_gemm_bf16_stats(const void* A, const void* Bw, void* C, int c_dtype, int nbatch, int L, int Cin, int taps, int pad,
+                        long long a_batch_stride, long long a_row_stride, int N, int ldb, int ldc, int bn,
+                        const int* tile_kb_host, const float* bias, float* row_stats, void* stream);
+int acb_gemm_ln_bf16(const void* A, const void* Bw, void* C, int c_dtype, long long M, int K, int N, int ldc, const float* bias,
+                     int pool4, const float* row_stats, int parts, const float* ln_w, const float* ln_b, float ln_eps, void* stream);
 
 /* SpectraNet block front half fused on tcgen05 (spectranet.py:29-35): three same-padded Conv1d (implicit GEMM, packed
  * weights Bw [b_rows, ldb], per-conv K-block ranges kb_ranges_host[3][2]) + bias + LayerNorm over the concatenated

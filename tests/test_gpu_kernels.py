@@ -377,3 +377,36 @@ def test_gemm_bf16_pre_out_and_gelu_grad_epilogue():
     pf = pre.float().requires_grad_(True)
     torch.nn.functional.gelu(pf, approximate="tanh").sum().backward()
     assert_close(du, (x.float() @ wt.float().t()) * pf.grad, 1.5e-2, "(A W^T) * gelu'(res)")
+
+
+@pytest.mark.parametrize("M,K,N,bn", [(1024, 384, 128, 128), (640, 768, 256, 256), (520, 1536, 512, 256)])
+def test_gemm_row_stats_and_ln_fused_downsample(M, K, N, bn):
+    """(a) acb_gemm_bf16_stats: per-row (sum, sum of squares) of every N tile from the epilogue's fp32 accumulators;
+    (b) acb_gemm_ln_bf16: maxpool4(gelu(LayerNorm(y)) Wd^T + b) with those statistics, the normalised activation staying in
+    shared memory (SpectraNet block tail, spectranet.py:36-40).  Reference: torch fp32 on the bf16-rounded operands."""
+    from applecider_b200 import ops
+
+    torch.manual_seed(M + K)
+    K0 = 192
+    x = torch.randn(M, K0, device=DEV).to(torch.bfloat16)
+    w0 = (torch.randn(K, K0, device=DEV) * K0 ** -0.5).to(torch.bfloat16)
+    b0 = torch.randn(K, device=DEV) * 0.5
+    parts = (K + bn - 1) // bn
+    stats = torch.full((M, parts, 2), float("nan"), device=DEV)
+    y = ops.gemm(x, w0, b0, bn=bn, row_stats=stats)
+    y_ref = x.float() @ w0.float().t() + b0
+    assert_close(y, y_ref, 1e-2, "producer GEMM output")
+    assert_close(stats[:, :, 0].sum(1), y_ref.sum(1), 2e-3, "row sums from the epilogue")
+    assert_close(stats[:, :, 1].sum(1), (y_ref * y_ref).sum(1), 2e-3, "row sums of squares from the epilogue")
+    for j in range(parts):
+        assert_close(stats[:, j, 0], y_ref[:, j * bn:(j + 1) * bn].sum(1), 2e-3, f"partial sums of N tile {j}")
+    g, be = 1.0 + 0.1 * torch.randn(K, device=DEV), 0.1 * torch.randn(K, device=DEV)
+    wd = (torch.randn(N, K, device=DEV) * K ** -0.5).to(torch.bfloat16)
+    bd = torch.randn(N, device=DEV) * 0.1
+    mean, var = y_ref.mean(1, keepdim=True), y_ref.var(1, unbiased=False, keepdim=True)
+    yn = torch.nn.functional.gelu((y.float() - mean) * torch.rsqrt(var + 1e-5) * g + be).to(torch.bfloat16).float()
+    full = yn @ wd.float().t() + bd
+    for pool in (False, True):
+        got = ops.gemm_ln(y, wd, bd, stats, parts, g, be, 1e-5, pool4=pool)
+        ref = full.view(M // 4, 4, N).amax(1) if pool else full
+        assert_close(got, ref, 2e-2, f"gelu(LN(y)) Wd^T (pool4={pool})")
