@@ -45,7 +45,8 @@ struct TcArgs {
 // per warp) -> row-contiguous 16-byte global stores.
 template <int BN>
 __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& p, bool have_acc, uint32_t tmem_acc, int mt, int nt, float* stg,
-                                                 const float* s_bias, const float* s_gamma, int warp, int lane) {
+                                                 const float* s_bias, const float* s_gamma, int warp, int lane, int c_lo = 0,
+                                                 int c_hi = BN) {
   const int n0 = nt * BN;
   const int sample0 = (mt / p.tps) * p.Bbox;
   const int l0 = (mt % p.tps) * p.Lbox;
@@ -65,7 +66,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& p, bool have_acc,
     const int esz = p.c_dtype == ACB_BF16 ? 2 : 4;
     const int rsz = p.res_dtype == ACB_BF16 ? 2 : 4;
     float st_sum = 0.0f, st_sq = 0.0f;
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {  // [c_lo, c_hi): the column range of this call (several warps may share a lane quarter)
       const int n_first = n0 + c0;
       if (n_first >= p.N) break;  // warp-uniform
       uint32_t raw[32];
@@ -449,8 +450,10 @@ struct TcLnArgs {
   float eps;
 };
 
+constexpr int TC_LN_THREADS = 64 + 256;  // TMA warp, MMA warp, 8 transform warps (the first 4 of them also run the epilogue)
+
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS) gemm_ln_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(TC_LN_THREADS, 2) gemm_ln_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ TcArgs p, const __grid_constant__ TcLnArgs q) {
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
@@ -477,7 +480,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_ln_tc_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_xf + 8 * s, 4);  // one arrival per transform warp
+      mbar_init(bar_xf + 8 * s, 8);  // one arrival per transform warp
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_acc, 1);
@@ -525,18 +528,21 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_ln_tc_kernel(const __grid_con
     if (elect_one_sync()) umma_commit(bar_acc);
     __syncwarp();
   } else {
+    // 8 transform warps: thread = (row r, half of the row's eight 16-byte chunks); twice the warps of one-thread-per-row,
+    // because the in-place LayerNorm + GELU (about 11 instructions per element, MUFU.TANH latency) is what bounds this kernel
     const int tq = threadIdx.x - 64;
-    for (int i = tq; i < BN; i += 128) {
+    for (int i = tq; i < BN; i += 256) {
       const int n = n0 + i;
       s_bias[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
       s_gamma[i] = 1.0f;
     }
-    for (int i = tq; i < p.Cin; i += 128) {
+    for (int i = tq; i < p.Cin; i += 256) {
       s_lnw[i] = __ldg(q.w + i);
       s_lnb[i] = __ldg(q.b + i);
     }
     // this thread's row and its LayerNorm statistics from the producer's partial sums
     const int r = (warp & 3) * 32 + lane;
+    const int half = (warp - 2) >> 2;  // warps 2-5: chunks 0-3, warps 6-9: chunks 4-7
     const long long m = (long long)l0 + r;
     float mean = 0.0f, rstd = 0.0f;
     if (m < (long long)p.L) {
@@ -549,40 +555,44 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_ln_tc_kernel(const __grid_con
       mean = s1 / (float)p.Cin;
       rstd = rsqrtf(fmaxf(s2 / (float)p.Cin - mean * mean, 0.0f) + q.eps);
     }
-    asm volatile("bar.sync 9, 128;" ::: "memory");
+    const float nmr = -mean * rstd;
+    asm volatile("bar.sync 9, 256;" ::: "memory");
     for (int it = 0; it < nkb; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(bar_full + 8 * s, ph);
       uint8_t* row = gen_base + s * STAGE_BYTES + r * 128;
-      const float* gw = s_lnw + it * TC_BK;
-      const float* gb = s_lnb + it * TC_BK;
+      const float* gw = s_lnw + it * TC_BK + half * 32;
+      const float* gb = s_lnb + it * TC_BK + half * 32;
+      uint4 pk[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4* ptr = reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4));
-        const uint4 pk = *ptr;
-        const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+      for (int c = 0; c < 4; ++c) pk[c] = *reinterpret_cast<const uint4*>(row + (((half * 4 + c) ^ (r & 7)) << 4));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t w4[4] = {pk[c].x, pk[c].y, pk[c].z, pk[c].w};
         uint32_t o4[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int k = c * 8 + 2 * e;
-          const float a0 = rstd * gw[k], a1 = rstd * gw[k + 1];
-          const float x0 = __uint_as_float(w4[e] << 16), x1 = __uint_as_float(w4[e] & 0xffff0000u);
-          const float y0 = gelu_bf16(fmaf(x0, a0, fmaf(-mean, a0, gb[k])));
-          const float y1 = gelu_bf16(fmaf(x1, a1, fmaf(-mean, a1, gb[k + 1])));
+          const float2 g2 = *reinterpret_cast<const float2*>(gw + k), b2 = *reinterpret_cast<const float2*>(gb + k);
+          const float x0 = fmaf(__uint_as_float(w4[e] << 16), rstd, nmr), x1 = fmaf(__uint_as_float(w4[e] & 0xffff0000u), rstd, nmr);
+          const float y0 = gelu_bf16(fmaf(x0, g2.x, b2.x));
+          const float y1 = gelu_bf16(fmaf(x1, g2.y, b2.y));
           __nv_bfloat162 hh = __floats2bfloat162_rn(y0, y1);
           o4[e] = *reinterpret_cast<uint32_t*>(&hh);
         }
-        *ptr = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        *reinterpret_cast<uint4*>(row + (((half * 4 + c) ^ (r & 7)) << 4)) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_xf + 8 * s) : "memory");
     }
-    mbar_wait_sleep(bar_acc, 0);
-    tc_fence_after();
-    float* stg = reinterpret_cast<float*>(gen_base) + (warp - 2) * (32 * 33);
-    tc_epilogue_tile<BN>(p, true, tmem_base, mt, nt, stg, s_bias, s_gamma, warp, lane);
+    {  // all 8 warps run the epilogue: warps w and w + 4 share a TMEM lane quarter and split the BN columns
+      mbar_wait_sleep(bar_acc, 0);
+      tc_fence_after();
+      float* stg = reinterpret_cast<float*>(gen_base) + (warp - 2) * (32 * 33);
+      tc_epilogue_tile<BN>(p, true, tmem_base, mt, nt, stg, s_bias, s_gamma, warp, lane, half * (BN / 2), (half + 1) * (BN / 2));
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -597,7 +607,7 @@ int launch_ln_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a
   const size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024 + (size_t)2 * args.Cin * sizeof(float);
   auto k = gemm_ln_tc_kernel<BN, STAGES>;
   ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, args, ln);
+  k<<<grid, TC_LN_THREADS, smem, st>>>(tmA, tmB, args, ln);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;
