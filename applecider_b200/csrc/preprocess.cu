@@ -147,33 +147,73 @@ __global__ void __launch_bounds__(128) prep_events_kernel(const double* __restri
 
 // ================================ selection helper ===================================================
 // k-th smallest (0-based) of `n` keys produced by key(i), radix select over NB-bit unsigned keys, 8 bits/pass.
+// k-th smallest key among key(0..n-1) by MSB-first radix selection with 8-bit digits, for blocks of exactly 256 threads:
+//   * the 256-bin histogram is scanned by all threads (one bin each: warp scan + cross-warp offsets), not by thread 0;
+//   * as soon as the bin that holds rank k has <= 256 members the pass loop stops: the members are gathered into shared memory
+//     and ranked against each other (one candidate per thread) -- smooth spectra / sky-dominated cutouts share their sign,
+//     exponent and leading mantissa bits, so this happens after 2-3 of the 4 (fp32) or 8 (fp64) passes.
+// hist: 256 counters; sh_k: 8 words of scratch; cand: 257 keys (slot 256 receives the result).
+constexpr int SEL_THREADS = 256;
 template <typename KeyT, typename KeyFn>
-__device__ KeyT block_select(int n, int k, KeyFn key, unsigned* hist /* 256 */, unsigned* sh_k /* 2 */) {
+__device__ KeyT block_select(int n, int k, KeyFn key, unsigned* hist /* 256 */, unsigned* sh_k /* 8 */, KeyT* cand /* 257 */) {
   constexpr int NBITS = sizeof(KeyT) * 8;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   KeyT prefix = 0, pmask = 0;
   for (int shift = NBITS - 8; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    hist[tid] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = tid; i < n; i += SEL_THREADS) {
       const KeyT kk = key(i);
       if ((kk & pmask) == prefix) atomicAdd(&hist[(unsigned)((kk >> shift) & 0xff)], 1u);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned acc = 0;
-      int bin = 0;
-      for (; bin < 256; ++bin) {
-        if (acc + hist[bin] > (unsigned)k) break;
-        acc += hist[bin];
-      }
-      sh_k[0] = (unsigned)bin;
-      sh_k[1] = (unsigned)k - acc;
+    // inclusive scan of the 256 bins, one per thread
+    const unsigned v = hist[tid];
+    unsigned inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) sh_k[wid] = inc;  // 8 warp totals
+    __syncthreads();
+    unsigned base = 0;
+    for (int w = 0; w < wid; ++w) base += sh_k[w];
+    const unsigned excl = base + inc - v;
+    __syncthreads();
+    if (excl <= (unsigned)k && (unsigned)k < excl + v) {  // exactly one thread: the bin holding rank k
+      sh_k[0] = (unsigned)tid;
+      sh_k[1] = (unsigned)k - excl;
+      sh_k[2] = v;
     }
     __syncthreads();
     prefix |= (KeyT)sh_k[0] << shift;
     pmask |= (KeyT)0xff << shift;
     k = (int)sh_k[1];
+    const unsigned members = sh_k[2];
     __syncthreads();
+    if (shift > 0 && members <= (unsigned)SEL_THREADS) {
+      if (tid == 0) sh_k[3] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += SEL_THREADS) {
+        const KeyT kk = key(i);
+        if ((kk & pmask) == prefix) cand[atomicAdd(&sh_k[3], 1u)] = kk;
+      }
+      __syncthreads();
+      if (tid < (int)members) {
+        const KeyT c = cand[tid];
+        int rank = 0;
+        for (int j = 0; j < (int)members; ++j) {
+          const KeyT o = cand[j];
+          rank += (o < c) || (o == c && j < tid);
+        }
+        if (rank == k) cand[SEL_THREADS] = c;  // slot 256: the result (exactly one thread has this rank)
+      }
+      __syncthreads();
+      const KeyT res = cand[SEL_THREADS];
+      __syncthreads();
+      return res;
+    }
   }
   return prefix;
 }
@@ -218,15 +258,17 @@ __device__ double block_sum_d(double v, double* sh /* 33 */) {
 // operations), mean, MAD by radix selection, (y - mean) / scale -> float32.
 __global__ void __launch_bounds__(256) prep_spectrum_kernel(const double* __restrict__ wl, const double* __restrict__ fx,
                                                             const long long* __restrict__ offsets, int cap,
-                                                            const float* __restrict__ grid, int n_grid, float* __restrict__ out) {
+                                                            const float* __restrict__ grid, int n_grid, float* __restrict__ out,
+                                                            int* __restrict__ idx_out) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   double* xs = reinterpret_cast<double*>(sm_raw);
   double* ys = xs + cap;
   double* yg = ys + cap;
   double* red = yg + n_grid;                                  // 33 doubles
   unsigned* hist = reinterpret_cast<unsigned*>(red + 34);     // 256
-  unsigned* shk = hist + 256;                                  // 2
-  int* shi = reinterpret_cast<int*>(shk + 2);                  // counters
+  unsigned* shk = hist + 256;                                  // 8
+  int* shi = reinterpret_cast<int*>(shk + 8);                  // 16 counters
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(shi + 16);  // 257 keys (8-byte aligned: 34*8 + 280*4 bytes before)
   const int b = blockIdx.x;
   const long long r0 = offsets[b];
   const int n_in = (int)(offsets[b + 1] - r0);
@@ -266,7 +308,10 @@ __global__ void __launch_bounds__(256) prep_spectrum_kernel(const double* __rest
   }
   const int n = shi[0];
   if (n < 2) {
-    for (int g = tid; g < n_grid; g += nthr) ob[g] = CUDART_NAN_F;
+    for (int g = tid; g < n_grid; g += nthr) {
+      ob[g] = CUDART_NAN_F;
+      if (idx_out) idx_out[(long long)b * n_grid + g] = -1;
+    }
     return;
   }
   // ---- sort by wavelength if needed ----
@@ -296,14 +341,25 @@ __global__ void __launch_bounds__(256) prep_spectrum_kernel(const double* __rest
     }
   }
   // ---- interpolation ----
+  // every thread owns a CONTIGUOUS run of grid points: the wavelength grid ascends, so the searchsorted position of a point
+  // is found by an exponential + binary search that starts at the previous point's position (a few steps instead of log2(n))
   double s_loc = 0.0;
-  for (int g = tid; g < n_grid; g += nthr) {
+  const int per = (n_grid + nthr - 1) / nthr;
+  int prev_lo = 0;
+  double prev_x = -CUDART_INF;
+  for (int g = tid * per; g < min(n_grid, (tid + 1) * per); ++g) {
     const double xn = (double)grid[g];
-    int lo = 0, hi = n;  // first index with xs[idx] >= xn
+    int lo = xn >= prev_x ? prev_lo : 0;  // first index with xs[idx] >= xn  (numpy searchsorted side='left')
+    int hi = lo, step = 1;
+    while (hi < n && xs[hi] < xn) { lo = hi + 1; hi += step; step <<= 1; }
+    hi = min(hi, n);
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       if (xs[mid] < xn) lo = mid + 1; else hi = mid;
     }
+    prev_lo = lo;
+    prev_x = xn;
+    if (idx_out) idx_out[(long long)b * n_grid + g] = lo;
     int ih = min(max(lo, 1), n - 1);
     const int il = ih - 1;
     const double slope = __ddiv_rn(__dsub_rn(ys[ih], ys[il]), __dsub_rn(xs[ih], xs[il]));
@@ -320,11 +376,11 @@ __global__ void __launch_bounds__(256) prep_spectrum_kernel(const double* __rest
   double scale = 1.0;
   if (nfin > 0) {
     auto key_y = [&](int i) { const double v = yg[i]; return isnan(v) ? ~0ull : dkey(v); };
-    double med = dkey_inv(block_select<unsigned long long>(n_grid, (nfin - 1) / 2, key_y, hist, shk));
-    if ((nfin & 1) == 0) med = 0.5 * (med + dkey_inv(block_select<unsigned long long>(n_grid, nfin / 2, key_y, hist, shk)));
+    double med = dkey_inv(block_select<unsigned long long>(n_grid, (nfin - 1) / 2, key_y, hist, shk, cand));
+    if ((nfin & 1) == 0) med = 0.5 * (med + dkey_inv(block_select<unsigned long long>(n_grid, nfin / 2, key_y, hist, shk, cand)));
     auto key_d = [&](int i) { const double v = yg[i]; return isnan(v) ? ~0ull : dkey(fabs(v - med)); };
-    double mad = dkey_inv(block_select<unsigned long long>(n_grid, (nfin - 1) / 2, key_d, hist, shk));
-    if ((nfin & 1) == 0) mad = 0.5 * (mad + dkey_inv(block_select<unsigned long long>(n_grid, nfin / 2, key_d, hist, shk)));
+    double mad = dkey_inv(block_select<unsigned long long>(n_grid, (nfin - 1) / 2, key_d, hist, shk, cand));
+    if ((nfin & 1) == 0) mad = 0.5 * (mad + dkey_inv(block_select<unsigned long long>(n_grid, nfin / 2, key_d, hist, shk, cand)));
     if (!isfinite(mad) || mad == 0.0) {
       double q = 0.0;
       for (int g = tid; g < n_grid; g += nthr) {
@@ -350,7 +406,8 @@ __global__ void __launch_bounds__(256) cutout_median_kernel(const float* __restr
   float* pl = reinterpret_cast<float*>(sm_raw);
   double* red = reinterpret_cast<double*>(pl + ((S * S + 3) & ~3));
   unsigned* hist = reinterpret_cast<unsigned*>(red + 34);
-  unsigned* shk = hist + 256;
+  unsigned* shk = hist + 256;   // 8
+  unsigned* cand = shk + 8;     // 257
   const int bc = blockIdx.x;  // b*C + c
   const float* src = img + (long long)bc * H * W;
   const int n = S * S;
@@ -360,8 +417,8 @@ __global__ void __launch_bounds__(256) cutout_median_kernel(const float* __restr
   }
   __syncthreads();
   auto key = [&](int i) { return fkey(pl[i]); };
-  float med = fkey_inv(block_select<unsigned>(n, (n - 1) / 2, key, hist, shk));
-  if (mode == 2 && (n & 1) == 0) med = 0.5f * (med + fkey_inv(block_select<unsigned>(n, n / 2, key, hist, shk)));
+  float med = fkey_inv(block_select<unsigned>(n, (n - 1) / 2, key, hist, shk, cand));
+  if (mode == 2 && (n & 1) == 0) med = 0.5f * (med + fkey_inv(block_select<unsigned>(n, n / 2, key, hist, shk, cand)));
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float p = pl[i] - med;
@@ -491,14 +548,19 @@ int acb_prep_events(const double* mjd, const double* mag, const double* magerr, 
 
 int acb_prep_spectrum_resample(const double* wl, const double* fx, const long long* offsets, int B, int max_n, const float* grid,
                                int n_grid, float* out, void* stream) {
+  return acb_prep_spectrum_resample_idx(wl, fx, offsets, B, max_n, grid, n_grid, out, nullptr, stream);
+}
+
+int acb_prep_spectrum_resample_idx(const double* wl, const double* fx, const long long* offsets, int B, int max_n, const float* grid,
+                                   int n_grid, float* out, int* idx_out, void* stream) {
   ACB_CHECK(wl && fx && offsets && grid && out && B > 0 && n_grid > 0 && max_n > 0, "acb_prep_spectrum_resample: bad arguments");
   int cap = 64;
   while (cap < max_n) cap <<= 1;
-  const size_t smem = (size_t)(2 * cap + n_grid + 34) * 8 + (256 + 2 + 16) * 4;
+  const size_t smem = (size_t)(2 * cap + n_grid + 34) * 8 + (256 + 8 + 16) * 4 + 258 * 8;
   ACB_CHECK(smem <= 220 * 1024, "acb_prep_spectrum_resample: spectrum too long for shared memory (max_n=%d, n_grid=%d)", max_n, n_grid);
   auto k = prep_spectrum_kernel;
   ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<B, 256, smem, (cudaStream_t)stream>>>(wl, fx, offsets, cap, grid, n_grid, out);
+  k<<<B, 256, smem, (cudaStream_t)stream>>>(wl, fx, offsets, cap, grid, n_grid, out, idx_out);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;
@@ -518,7 +580,7 @@ int acb_prep_cutout_norm(const float* img, int B, int C, int H, int W, int cutou
   if (mode == 1) {
     cutout_l2_kernel<<<B, 256, 0, st>>>(img, C, H, W, i1, S, out);
   } else {
-    const size_t smem = (size_t)((S * S + 3) & ~3) * 4 + 34 * 8 + 258 * 4;
+    const size_t smem = (size_t)((S * S + 3) & ~3) * 4 + 34 * 8 + (256 + 8 + 258) * 4;
     auto k = cutout_median_kernel;
     if (smem > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<B * C, 256, smem, st>>>(img, C, H, W, i1, S, mode, out);

@@ -60,15 +60,17 @@ def wave_grid(lo=4500.0, hi=7980.0, step=1.0, device="cuda"):
     return torch.from_numpy(np.linspace(lo, hi, n, dtype=np.float32)).to(device)
 
 
-def resample_spectra(wl, fx, offsets, grid, max_n=None):
-    """P3 (preprocess_multimodal.py:146-170,598-609) -> out[B, n_grid] f32 (mean 0, MAD 1)."""
+def resample_spectra(wl, fx, offsets, grid, max_n=None, return_index=False):
+    """P3 (preprocess_multimodal.py:146-170,598-609) -> out[B, n_grid] f32 (mean 0, MAD 1)
+    [, idx[B, n_grid] int32 = searchsorted(side='left') position of every grid point among the finite, sorted wavelengths]."""
     B = offsets.numel() - 1
     if max_n is None:
         max_n = int((offsets[1:] - offsets[:-1]).max().item())
     out = torch.empty((B, grid.numel()), dtype=torch.float32, device=wl.device)
-    call("acb_prep_spectrum_resample", wl.double().contiguous(), fx.double().contiguous(), offsets, B, max_n, grid.float().contiguous(),
-         grid.numel(), out)
-    return out
+    idx = torch.empty((B, grid.numel()), dtype=torch.int32, device=wl.device) if return_index else None
+    call("acb_prep_spectrum_resample_idx", wl.double().contiguous(), fx.double().contiguous(), offsets, B, max_n, grid.float().contiguous(),
+         grid.numel(), out, idx)
+    return (out, idx) if return_index else out
 
 
 _MODES = {"median": 0, "L2": 1, "l2": 1, "median_notebook": 2}

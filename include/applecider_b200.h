@@ -274,6 +274,11 @@ int acb_prep_events(const double* mjd, const double* mag, const double* magerr, 
  * -> out[B,n_grid] f32.  max_n = longest input spectrum. */
 int acb_prep_spectrum_resample(const double* wl, const double* fx, const long long* offsets, int B, int max_n,
                                const float* grid, int n_grid, float* out, void* stream);
+/* the same, also returning the searchsorted(side='left') position of every grid point among the spectrum's finite, sorted
+ * wavelengths (idx_out[B, n_grid], -1 for spectra with < 2 finite samples): the integer part of the interpolation, which must
+ * equal numpy's bit for bit (scipy interp1d picks the interval [idx-1, idx] clipped to [1, n-1], preprocess_multimodal.py:146-170). */
+int acb_prep_spectrum_resample_idx(const double* wl, const double* fx, const long long* offsets, int B, int max_n,
+                                   const float* grid, int n_grid, float* out, int* idx_out, void* stream);
 /* P4  datasets/image_and_metadata_dataset.py:78-99; Fusion_Dataset.ipynb cell 0.
  * img[B,C,H,W] f32 -> centre crop [i1:i2] (i1 = int((H-cutout_size)/2), i2 = H-i1) -> mode 0: per-channel
  * lower-median subtraction and division by (unbiased std + 1e-8); mode 1: division by the L2 norm over all

@@ -120,6 +120,19 @@ def interp_with_extrap(x, y, xnew):
     return slope * (xnew - x[lo]) + y[lo]
 
 
+def searchsorted_index(x, y, xnew):
+    """The integer part of interp_with_extrap: np.searchsorted(side='left') of every new point among the finite samples sorted
+    by wavelength (scipy interp1d then uses the interval [idx-1, idx] clipped to [1, n-1]; preprocess_multimodal.py:146-170).
+    -1 everywhere when fewer than two finite samples remain."""
+    x, y, xnew = np.asarray(x, np.float64), np.asarray(y, np.float64), np.asarray(xnew, np.float64)
+    order = np.argsort(x)
+    x, y = x[order], y[order]
+    x = x[np.isfinite(x) & np.isfinite(y)]
+    if len(x) < 2:
+        return np.full(xnew.shape, -1, np.int32)
+    return np.searchsorted(x, xnew).astype(np.int32)
+
+
 def resample_spectrum(wl, fx, grid):
     yg = interp_with_extrap(wl, fx, np.asarray(grid, np.float64))
     mean = float(np.nanmean(yg))

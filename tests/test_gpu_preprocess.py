@@ -86,6 +86,41 @@ def test_p3_spectra(g):
     assert exact > 0.999, f"only {exact*100:.3f}% of the resampled samples are bit-identical"
 
 
+def test_p3_interval_index_is_exact():
+    """The searchsorted interval index of EVERY grid point (the integer/indexing part of P3, SURVEY §8a: bit-exact) against
+    numpy: sorted and unsorted inputs, duplicated wavelengths (side='left' must pick the first), non-finite samples dropped,
+    grid points outside the sampled range (extrapolation: index 0 / n), a grid point exactly on a sample."""
+    from applecider_b200 import preprocess as pp, synth
+    from oracle import preprocess as op
+
+    rng = np.random.default_rng(7)
+    specs = synth.raw_spectra(60, seed=79)
+    grid_np = pp.wave_grid().cpu().numpy()
+    # edge cases
+    s = specs[0].copy(); s[::7, 0] = s[1::7, 0][: len(s[::7])]  # duplicated wavelengths
+    specs.append(s[np.argsort(s[:, 0])])
+    s = specs[1].copy(); rng.shuffle(s)                            # unsorted input
+    specs.append(s)
+    s = specs[2].copy(); s[5, 1] = np.nan; s[9, 0] = np.inf; s[11, 1] = -np.inf   # non-finite samples
+    specs.append(s)
+    s = specs[3].copy(); s = s[(s[:, 0] > 5000) & (s[:, 0] < 7000)]               # grid extends past both ends
+    specs.append(s)
+    s = specs[4].copy(); s[40:60, 0] = grid_np[1000:1020].astype(np.float64)       # samples exactly on grid points
+    specs.append(s[np.argsort(s[:, 0])])
+    specs.append(np.array([[5000.0, 1.0], [np.nan, 2.0]]))                         # < 2 finite samples
+    wl, off = pp.ragged([s[:, 0] for s in specs])
+    fx, _ = pp.ragged([s[:, 1] for s in specs])
+    out, idx = pp.resample_spectra(wl, fx, off, pp.wave_grid(), return_index=True)
+    idx = idx.cpu().numpy()
+    for i, s in enumerate(specs):
+        ref = op.searchsorted_index(s[:, 0], s[:, 1], grid_np)
+        assert np.array_equal(idx[i], ref), f"spectrum {i}: {(idx[i] != ref).sum()} interval indices differ from numpy searchsorted"
+    keep = [i for i in range(len(specs) - 1) if i != 60]  # 60 = duplicated wavelengths: the order of ties (and so 0/0 slopes) is not defined
+    ref_vals = np.stack([op.resample_spectrum(specs[i][:, 0], specs[i][:, 1], grid_np) for i in keep])
+    _ulp_close(out[keep].cpu().numpy(), ref_vals, 1, "resampled values of the edge-case spectra")
+    assert torch.isnan(out[-1]).all()
+
+
 def test_p3_properties_large():
     from applecider_b200 import preprocess as pp, synth
     from oracle import preprocess as op
