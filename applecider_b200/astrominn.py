@@ -100,6 +100,11 @@ class ConvNeXtTiny(nn.Module):
                 x = ops.gemm(a, self._wds(st.downsample[1], dtype), st.downsample[1].bias)
             for blk in st.blocks:
                 y = ops.dwconv7_ln(x, B, h, w, C, blk.conv_dw.weight, blk.conv_dw.bias, blk.norm.weight, blk.norm.bias, blk.norm.eps)
+                if ops.FUSE_CONVNEXT_MLP and dtype == torch.bfloat16 and C in (96, 192) and x.shape[0] >= 128:
+                    # one kernel for fc1 + GELU + fc2 + layer scale + residual: the [rows, 4C] hidden activation never reaches HBM
+                    x = ops.convnext_mlp(y, x, self._w(blk.mlp.fc1.weight, dtype), blk.mlp.fc1.bias, self._w(blk.mlp.fc2.weight, dtype),
+                                         blk.mlp.fc2.bias, blk.gamma)
+                    continue
                 hid = ops.gemm(y, self._w(blk.mlp.fc1.weight, dtype), blk.mlp.fc1.bias, act=ops.ACT_GELU)
                 x = ops.gemm(hid, self._w(blk.mlp.fc2.weight, dtype), blk.mlp.fc2.bias, res=x, gamma=blk.gamma, res_mode=ops.RES_ADD)
         return ops.gap_ln(x, B, h * w, self.dims[-1], self.head.norm.weight, self.head.norm.bias, self.head.norm.eps)

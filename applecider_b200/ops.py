@@ -233,6 +233,17 @@ def patchify(img, p, dtype):
     return out
 
 
+FUSE_CONVNEXT_MLP = True  # fc1 -> GELU -> fc2 -> layer scale -> residual in one tcgen05 kernel (C = 96 / 192), hidden never in HBM
+
+
+def convnext_mlp(y, res, w1, b1, w2, b2, gamma):
+    """out = res + gamma * (fc2(gelu(fc1(y) + b1)) + b2); y, res [M, C] bf16; w1 [4C, C], w2 [C, 4C] bf16 (acb_convnext_mlp_bf16)."""
+    M, C = y.shape
+    out = torch.empty_like(res)
+    call("acb_convnext_mlp_bf16", y, res, w1, b1, w2, b2, gamma, out, M, C)
+    return out
+
+
 def dwconv7_ln(x, B, H, W, C, w, b, ln_w, ln_b, eps):
     y = torch.empty_like(x)
     call("acb_dwconv7_ln", x, dtype_tag(x), w, b, ln_w, ln_b, eps, y, B, H, W, C)

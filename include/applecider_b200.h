@@ -182,6 +182,12 @@ int acb_attention_packed(const void* qkv, const int* cu_seqlens, const int* plan
 int acb_gather_cls(const void* x, int dtype, const int* cu_seqlens, int B, int D, float* out, void* stream);
 
 /* ---- ConvNeXt-T pieces (timm convnext_tiny via astrominn.py:12-17; channels-last activations) ---- */
+/* Fused MLP tail of a ConvNeXt block (inference, bf16):  out = res + gamma * (fc2(gelu(fc1(y) + b1)) + b2)  with y[M,C] the
+ * LayerNorm-ed depthwise-conv output, w1[4C,C], w2[C,4C] bf16 row-major, res/out[M,C] bf16.  The [M,4C] hidden activation
+ * stays in shared memory / TMEM (one 64- or 128-column chunk at a time).  C = 96 or 192 (stages 0 and 1, 98 % of the rows);
+ * other widths return ACB_ERR_UNSUPPORTED and the caller keeps the two-GEMM path. */
+int acb_convnext_mlp_bf16(const void* y, const void* res, const void* w1, const float* b1, const void* w2, const float* b2,
+                          const float* gamma, void* out, long long M, int C, void* stream);
 /* NCHW f32 image -> patch matrix [B*Ho*Wo, Cin*p*p] (k = ci*p*p + ky*p + kx), Ho = H/p (floor). */
 int acb_patchify_nchw(const float* img, int B, int Cin, int H, int W, int p, void* out, int out_dtype, void* stream);
 /* depthwise 7x7 (pad 3) + LayerNorm over C (eps) : x,y = [B,H,W,C]; w = (C,1,7,7), b = (C). */

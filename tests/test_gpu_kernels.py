@@ -410,3 +410,24 @@ def test_gemm_row_stats_and_ln_fused_downsample(M, K, N, bn):
         got = ops.gemm_ln(y, wd, bd, stats, parts, g, be, 1e-5, pool4=pool)
         ref = full.view(M // 4, 4, N).amax(1) if pool else full
         assert_close(got, ref, 2e-2, f"gelu(LN(y)) Wd^T (pool4={pool})")
+
+
+@pytest.mark.parametrize("C,M", [(96, 1000), (96, 128 * 37 + 5), (192, 640), (192, 49 * 64)])
+def test_convnext_mlp_fused(C, M):
+    """acb_convnext_mlp_bf16 (fc1 + GELU + fc2 + layer scale + residual, hidden activation on chip) vs torch fp32 on the
+    bf16-rounded operands and vs the two-GEMM path it replaces."""
+    from applecider_b200 import ops
+
+    torch.manual_seed(C + M)
+    y = torch.randn(M, C, device=DEV).to(torch.bfloat16)
+    res = torch.randn(M, C, device=DEV).to(torch.bfloat16)
+    w1 = (torch.randn(4 * C, C, device=DEV) * C ** -0.5).to(torch.bfloat16)
+    w2 = (torch.randn(C, 4 * C, device=DEV) * (4 * C) ** -0.5).to(torch.bfloat16)
+    b1, b2 = torch.randn(4 * C, device=DEV) * 0.3, torch.randn(C, device=DEV) * 0.3
+    gamma = 0.2 + 0.05 * torch.randn(C, device=DEV)
+    got = ops.convnext_mlp(y, res, w1, b1, w2, b2, gamma)
+    hid = torch.nn.functional.gelu(y.float() @ w1.float().t() + b1).to(torch.bfloat16).float()
+    ref = res.float() + gamma * (hid @ w2.float().t() + b2)
+    assert_close(got, ref, 1.5e-2, f"fused ConvNeXt MLP C={C} M={M}")
+    two = ops.gemm(ops.gemm(y, w1, b1, act=ops.ACT_GELU), w2, b2, res=res, gamma=gamma, res_mode=ops.RES_ADD)
+    assert_close(got, two.float(), 1.5e-2, "fused vs two-GEMM path")
