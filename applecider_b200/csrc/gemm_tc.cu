@@ -803,6 +803,8 @@ struct TcWgradArgs {
   int chunks_per_split;
   float* C;
   int ldc;
+  float* db;  // optional bias gradient db[m] = sum_rows dY[row, a_col0 + m]: computed by one extra N tile (blockIdx.y == gridDim.y - 1)
+              // whose B operand is a constant tile of ones -- the column sums fall out of the tensor core instead of a second pass over dY
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr) {
@@ -824,6 +826,9 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
   __shared__ uint32_t tmem_holder;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  const bool bias_tile = p.db != nullptr && blockIdx.y == gridDim.y - 1;
+  constexpr uint32_t IDESC_ONES = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(16 >> 3) << 17) |
+                                  ((uint32_t)(TC_BM >> 4) << 24);
   const int total_chunks = p.nb * p.cps;
   const int c_begin = blockIdx.z * p.chunks_per_split;
   const int c_end = min(total_chunks, c_begin + p.chunks_per_split);
@@ -849,6 +854,11 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (bias_tile) {  // the B slot of stage 0 becomes the constant ones tile (the producer never loads B in this mode)
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_raw + (smem_base - smem_u32(smem_raw)) + A_BYTES);
+    for (int i = threadIdx.x; i < 8192 / 4; i += TC_THREADS) ones[i] = 0x3F803F80u;  // two bf16 1.0
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -864,9 +874,10 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
         const int b = ch / p.cps, l0 = (ch - b * p.cps) * 64;
         const uint32_t sa = smem_base + s * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
-        mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+        mbar_expect_tx(bar_full + 8 * s, bias_tile ? A_BYTES : STAGE_BYTES);
         tma_load_3d(sa, &tmA, p.a_col0 + m0, l0, b, bar_full + 8 * s);
         tma_load_3d(sa + 8192, &tmA, p.a_col0 + m0 + 64, l0, b, bar_full + 8 * s);
+        if (!bias_tile)
 #pragma unroll
         for (int qn = 0; qn < BN / 64; ++qn) {
           const int n = n0 + qn * 64;
@@ -885,10 +896,10 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
       if (elect_one_sync()) {
         const uint32_t sa = smem_base + s * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
-        const uint64_t da = make_smem_desc_mn(sa), db = make_smem_desc_mn(sb);
+        const uint64_t da = make_smem_desc_mn(sa), db = make_smem_desc_mn(bias_tile ? smem_base + A_BYTES : sb);
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // 64 rows = 4 x UMMA_K(16); 16 rows = 2 KB = 128 descriptor units
-          umma_bf16(tmem_base, da + 128 * k, db + 128 * k, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, da + 128 * k, db + 128 * k, bias_tile ? IDESC_ONES : IDESC, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(bar_empty + 8 * s);
       }
       __syncwarp();
@@ -900,6 +911,11 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
     const int m = m0 + q * 32 + lane;
     mbar_wait_sleep(bar_acc, 0);
     tc_fence_after();
+    if (bias_tile) {  // every column of the 16-wide accumulator holds the same column sum of dY
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), raw);
+      if (m < p.M_out) atomicAdd(p.db + m, __uint_as_float(raw[0]));
+    } else
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= p.n_total) break;
       uint32_t raw[32];
@@ -1108,8 +1124,16 @@ static int gemm_bf16_impl(const void* A, const void* Bw, void* C, int c_dtype, i
 }
 
 
+extern "C" int acb_wgrad_bias_bf16(const void* dY, int ldy, int a_col0, int M_out, const void* X, int nb, int L, int Cin, int taps, int pad,
+                                   long long x_batch_stride, long long x_row_stride, float* dW, int ldc, int accumulate, float* db, void* stream);
+
 extern "C" int acb_wgrad_bf16(const void* dY, int ldy, int a_col0, int M_out, const void* X, int nb, int L, int Cin, int taps, int pad,
                               long long x_batch_stride, long long x_row_stride, float* dW, int ldc, int accumulate, void* stream) {
+  return acb_wgrad_bias_bf16(dY, ldy, a_col0, M_out, X, nb, L, Cin, taps, pad, x_batch_stride, x_row_stride, dW, ldc, accumulate, nullptr, stream);
+}
+
+extern "C" int acb_wgrad_bias_bf16(const void* dY, int ldy, int a_col0, int M_out, const void* X, int nb, int L, int Cin, int taps, int pad,
+                                   long long x_batch_stride, long long x_row_stride, float* dW, int ldc, int accumulate, float* db, void* stream) {
   ACB_CHECK(dY && X && dW && nb > 0 && L > 0 && Cin > 0 && taps > 0 && M_out > 0, "acb_wgrad_bf16: bad arguments");
   ACB_CHECK(taps == 1 || Cin % 64 == 0, "acb_wgrad_bf16: convolution weight gradients need Cin %% 64 == 0 (got %d)", Cin);
   ACB_CHECK(((uintptr_t)dY % 16 == 0) && ((uintptr_t)X % 16 == 0) && ldy % 8 == 0 && x_row_stride % 8 == 0 && x_batch_stride % 8 == 0,
@@ -1142,6 +1166,7 @@ extern "C" int acb_wgrad_bf16(const void* dY, int ldy, int a_col0, int M_out, co
   args.Cin = Cin; args.pad = pad; args.n_total = n_total;
   args.a_col0 = a_col0; args.M_out = M_out;
   args.C = dW; args.ldc = ldc;
+  args.db = db;
   const int bn = n_total >= 256 ? 256 : (n_total > 64 ? 128 : 64);
   const int mt = cdiv(M_out, TC_BM), ntl = cdiv(n_total, bn);
   const long long total_chunks = (long long)nb * args.cps;
@@ -1165,8 +1190,9 @@ extern "C" int acb_wgrad_bf16(const void* dY, int ldy, int a_col0, int M_out, co
   args.chunks_per_split = (int)((total_chunks + splits - 1) / splits);
   splits = (int)((total_chunks + args.chunks_per_split - 1) / args.chunks_per_split);
   if (!accumulate) ACB_CUDA(cudaMemset2DAsync(dW, (size_t)ldc * 4, 0, (size_t)n_total * 4, M_out, st));
-  dim3 grid(mt, ntl, splits);
-  ACB_CHECK(ntl <= 65535, "acb_wgrad_bf16: too many column tiles");
+  if (db && !accumulate) ACB_CUDA(cudaMemsetAsync(db, 0, (size_t)M_out * 4, st));
+  dim3 grid(mt, ntl + (db ? 1 : 0), splits);  // + one N tile of ones for the bias gradient
+  ACB_CHECK(ntl < 65535, "acb_wgrad_bf16: too many column tiles");
   switch (bn) {
     case 64: return launch_wgrad<64, 4>(tmA, tmB, args, grid, st);
     case 128: return launch_wgrad<128, 4>(tmA, tmB, args, grid, st);

@@ -79,9 +79,14 @@ def transpose(x, dtype):
     return y
 
 
-def wgrad_tc(dy, ldy, a_col0, M_out, x, nb, L, Cin, taps, pad, x_bstride, x_rstride, dev):
-    """tcgen05 weight gradient (bf16 operands, fp32 result [M_out, taps*Cin])."""
+def wgrad_tc(dy, ldy, a_col0, M_out, x, nb, L, Cin, taps, pad, x_bstride, x_rstride, dev, want_db=False):
+    """tcgen05 weight gradient (bf16 operands, fp32 result [M_out, taps*Cin]); want_db: also the bias gradient (column sums of
+    the dY slice) from the same launch -> (dW, db)."""
     out = torch.empty((M_out, taps * Cin), dtype=F32, device=dev)
+    if want_db:
+        db = torch.empty(M_out, dtype=F32, device=dev)
+        call("acb_wgrad_bias_bf16", dy, ldy, a_col0, M_out, x, nb, L, Cin, taps, pad, x_bstride, x_rstride, out, taps * Cin, 0, db)
+        return out, db
     call("acb_wgrad_bf16", dy, ldy, a_col0, M_out, x, nb, L, Cin, taps, pad, x_bstride, x_rstride, out, taps * Cin, 0)
     return out
 
@@ -118,12 +123,15 @@ class Linear(Function):
                 dx = ops.gemm(dy, transpose(W.detach(), BF16), None)
             else:
                 dx = cast_to(gemm_ex(dy, dtype_tag(dy), W, 0, M, K, N, N, 1, 1, K, x.device), x.dtype)
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            if tc:  # tcgen05 wgrad with MN-major operands (no activation transposes)
+            if tc and want_db:  # tcgen05 wgrad with MN-major operands (no activation transposes); bias gradient from the same launch
+                dW, db = wgrad_tc(dy, N, 0, N, x, 1, M, K, 1, 0, M * K, K, x.device, want_db=True)
+            elif tc:
                 dW = wgrad_tc(dy, N, 0, N, x, 1, M, K, 1, 0, M * K, K, x.device)
             else:
                 dW = gemm_ex(dy, dtype_tag(dy), x, dtype_tag(x), N, K, M, 1, N, 1, K, x.device, splits=_splits(M))
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if want_db and db is None:
             db = colsum(dy)
         return dx, dW, db, None, None
 
@@ -267,11 +275,9 @@ class MlpBlock(Function):
         H, C = W1.shape[0], W2.shape[0]
         dgamma = colsum(dy.view(-1, C), v.view(-1, C))
         dv = ew(dy, None, 3, g=gamma, C=C, out_dtype=BF16)
-        db2 = colsum(dv)
-        dW2 = wgrad_tc(dv, C, 0, C, h, 1, M, H, 1, 0, M * H, H, y.device)
+        dW2, db2 = wgrad_tc(dv, C, 0, C, h, 1, M, H, 1, 0, M * H, H, y.device, want_db=True)
         du = ops.gemm(dv, transpose(W2.detach(), BF16), None, res=u, res_mode=ops.RES_MUL_GELU_GRAD)  # [M,H] = (dv W2) * gelu'(u)
-        db1 = colsum(du)
-        dW1 = wgrad_tc(du, H, 0, H, y, 1, M, C, 1, 0, M * C, C, y.device)
+        dW1, db1 = wgrad_tc(du, H, 0, H, y, 1, M, C, 1, 0, M * C, C, y.device, want_db=True)
         dyin = ops.gemm(du, transpose(W1.detach(), BF16), None)
         return dy, dyin, dW1, db1, dW2, db2, dgamma, None, None
 

@@ -196,14 +196,14 @@ class SpectraConvs(torch.autograd.Function):
             dW = torch.empty(conv.weight.shape, dtype=F32, device=dev)
             if tc:
                 # tcgen05 wgrad (MN-major operands): G[co, tap*Cin+ci]; unpack = pack with (Cin <-> k) exchanged
-                G = fn.wgrad_tc(dy, ldy, j * cout, cout, x, B, L, cin, kj, kj // 2, L * cin, cin, dev)
+                G, db = fn.wgrad_tc(dy, ldy, j * cout, cout, x, B, L, cin, kj, kj // 2, L * cin, cin, dev, want_db=True)
                 fn.call("acb_pack_conv_weight", G, dW, 0, cout, kj, cin, cin * kj, 0)
             else:
                 # G[(tap,ci), co] = sum_(b,l) X[b, l+tap-pad, ci] * dY[(b,l), j*cout+co]
                 G = fn.gemm_ex(x, fn.dtype_tag(x), ops._offset_ptr(dy, j * cout), fn.dtype_tag(dy), kj * cin, cout, B * L, 0, 0, 1, ldy, dev,
                                convT=(L, cin, kj // 2), splits=fn._splits(B * L))
                 fn.call("acb_unpack_conv_wgrad", G, dW, cout, cin, kj)
-            db = fn.colsum(ops._offset_ptr(dy, j * cout), None, M=B * L, N=cout, ld=ldy, a_dt=fn.dtype_tag(dy), dev=dev)
+                db = fn.colsum(ops._offset_ptr(dy, j * cout), None, M=B * L, N=cout, ld=ldy, a_dt=fn.dtype_tag(dy), dev=dev)
             grads.append((dW, db))
             if need_dx and tc:
                 # tcgen05 dgrad: conv of the dY_j column slice with the flipped/transposed kernel, accumulated over j

@@ -306,6 +306,11 @@ int acb_gemm_ex(const void* A, int a_dtype, const void* B, int b_dtype, float* C
  * Linear layers: nb=1, L=rows, taps=1, pad=0.  Convolutions need Cin % 64 == 0. */
 int acb_wgrad_bf16(const void* dY, int ldy, int a_col0, int M_out, const void* X, int nb, int L, int Cin, int taps, int pad,
                    long long x_batch_stride, long long x_row_stride, float* dW, int ldc, int accumulate, void* stream);
+/* the same launch also producing the bias gradient db[m] (+)= sum_rows dY[row, a_col0 + m]: one extra N tile multiplies the dY
+ * tiles with a constant tile of ones, so the column sums cost no second pass over dY (replaces acb_colsum after a Linear /
+ * Conv1d backward: nn.Linear / nn.Conv1d bias gradients, e.g. spectranet.py:18-22, timm Mlp fc1/fc2). */
+int acb_wgrad_bias_bf16(const void* dY, int ldy, int a_col0, int M_out, const void* X, int nb, int L, int Cin, int taps, int pad,
+                        long long x_batch_stride, long long x_row_stride, float* dW, int ldc, int accumulate, float* db, void* stream);
 /* out[n] (+)= sum_m a[m*ld+n] * (b ? b[m*ld+n] : 1)   (bias / layer-scale gradients; ld <= 0 means N) */
 int acb_colsum(const void* a, int a_dtype, const void* b, int b_dtype, long long M, int N, long long ld, float* out,
                int accumulate, void* stream);
