@@ -79,10 +79,20 @@ def transpose(x, dtype):
     return y
 
 
+import os as _os
+
+FOLD_BIAS_GRAD = _os.environ.get("ACB_FOLD_BIAS_GRAD", "1") != "0"  # bias gradient from the wgrad launch (ones tile) vs a colsum pass
+
+
 def wgrad_tc(dy, ldy, a_col0, M_out, x, nb, L, Cin, taps, pad, x_bstride, x_rstride, dev, want_db=False):
     """tcgen05 weight gradient (bf16 operands, fp32 result [M_out, taps*Cin]); want_db: also the bias gradient (column sums of
     the dY slice) from the same launch -> (dW, db)."""
     out = torch.empty((M_out, taps * Cin), dtype=F32, device=dev)
+    # the ones tile is one more N tile of the same K loop: next to >= 8 real N tiles (convolutions: taps * Cin columns) it is free and
+    # saves a pass over dY; next to 1-2 (Linear layers) it would cost more than the HBM-speed column sum (measured: +0.25 ms per step)
+    if want_db and not (FOLD_BIAS_GRAD and taps * Cin >= 2048):
+        call("acb_wgrad_bf16", dy, ldy, a_col0, M_out, x, nb, L, Cin, taps, pad, x_bstride, x_rstride, out, taps * Cin, 0)
+        return out, colsum(ops._offset_ptr(dy, a_col0), None, M=nb * L, N=M_out, ld=ldy, a_dt=dtype_tag(dy), dev=dev)
     if want_db:
         db = torch.empty(M_out, dtype=F32, device=dev)
         call("acb_wgrad_bias_bf16", dy, ldy, a_col0, M_out, x, nb, L, Cin, taps, pad, x_bstride, x_rstride, out, taps * Cin, 0, db)
