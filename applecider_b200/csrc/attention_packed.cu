@@ -370,10 +370,252 @@ __global__ void __launch_bounds__(AP_THREADS, 2) attention_packed_kernel(const _
   }
 }
 
+// ======================================================================================================================
+// Backward of the packed attention on tcgen05.  Same tiles, same plan, same canonical TMA layouts; per (tile, 4 heads) CTA:
+//   S  = Q K^T            dP = dO V^T                      (two K = 16 UMMAs into TMEM, recomputed: nothing was saved)
+//   threads: row r, 32-key slice: P = softmax(S/4) recomputed (max and sum meet across the 4 slices through shared memory),
+//            D = sum_j P_j dP_j, dS = P (dP - D) / 4; P (with the forward's dropout mask) and dS go to shared memory as bf16
+//   dV = P^T dO           dQ = dS K           dK = dS^T Q  (N = 16 UMMAs; P^T / dS^T are the SAME buffers read MN-major)
+// 512 threads: 16 warps = 4 TMEM lane quarters x 4 key slices, so a thread keeps its 32 scores and 32 dP values in registers
+// across the three softmax passes (one TMEM read each).  TMEM: S | dP | dQ[4 heads] | dK | dV = 448 columns.
+constexpr int AB_THREADS = 512;
+constexpr uint32_t AB_SMEM = 4 * AP_OPER_BYTES + 2 * AP_P_BYTES + 1024;
+
+__device__ __forceinline__ uint32_t ab_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1) attention_packed_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                             const __grid_constant__ CUtensorMap tmDO, const int* __restrict__ cu,
+                                                                             const int* __restrict__ plan, int n_heads, float drop_p,
+                                                                             AcbSeed seed_s, bf16* __restrict__ dqkv) {
+  const int tile = blockIdx.x;
+  if (tile >= plan[0]) return;
+  const unsigned long long seed = seed_s.get();
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_holder;
+  __shared__ int s_cu[AP_ROWS + 2];
+  __shared__ float s_red[3][4][AP_ROWS];  // per-row partial max / sum / sum(p dP) of the four key slices
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, sl = warp >> 2;   // TMEM lane quarter, key slice
+  const int row = q * 32 + lane;
+  const int hg = blockIdx.y;
+  const int seq0 = plan[2 + 2 * tile], nseq = plan[3 + 2 * tile];
+  const int row0 = cu[seq0];
+  const int nrows = cu[seq0 + nseq] - row0;
+  const int npad = max(16, (nrows + 15) & ~15);
+  const int D = n_heads * AP_DH;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t aQ = base, aK = base + AP_OPER_BYTES, aV = base + 2 * AP_OPER_BYTES, aO = base + 3 * AP_OPER_BYTES;
+  const uint32_t aP = base + 4 * AP_OPER_BYTES, aS = aP + AP_P_BYTES;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* sP = gen + 4 * AP_OPER_BYTES;
+  uint8_t* sS = sP + AP_P_BYTES;
+  const uint32_t bar_load = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+  if (tid == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i <= nseq && i <= AP_ROWS; i += AB_THREADS) s_cu[i] = cu[seq0 + i] - row0;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_holder;
+  const uint32_t tm_s = tm, tm_dp = tm + 128u, tm_dq = tm + 256u, tm_dk = tm + 320u, tm_dv = tm + 384u;
+  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+
+  if (warp == 0 && elect_one_sync()) {
+    mbar_expect_tx(bar_load, 4 * AP_OPER_BYTES);
+#pragma unroll
+    for (int op = 0; op < 3; ++op)
+#pragma unroll
+      for (int c = 0; c < AP_HG * 2; ++c)
+        tma_load_2d(base + (uint32_t)op * AP_OPER_BYTES + (uint32_t)c * (AP_ROWS * 16), &tmQKV, op * D + hg * (AP_HG * AP_DH) + c * 8, row0, bar_load);
+#pragma unroll
+    for (int c = 0; c < AP_HG * 2; ++c) tma_load_2d(aO + (uint32_t)c * (AP_ROWS * 16), &tmDO, hg * (AP_HG * AP_DH) + c * 8, row0, bar_load);
+  }
+  int lo = 0, hi = 0, b_seq = seq0;
+  if (row < nrows) {
+    int j = 0;
+    while (j + 1 < nseq && s_cu[j + 1] <= row) ++j;
+    lo = s_cu[j];
+    hi = s_cu[j + 1];
+    b_seq = seq0 + j;
+  }
+  const unsigned len = (unsigned)(hi - lo);
+  const int c0 = sl * 32;                       // this thread's key columns [c0, c0 + 32)
+  const bool slice_live = c0 < npad;            // warp-uniform
+  const unsigned off = (unsigned)(c0 - lo);
+  const float drop_inv = 1.0f / (1.0f - drop_p);
+  const unsigned drop_thr = (unsigned)(drop_p * 4294967296.0);
+  constexpr float SC = 0.25f * 1.4426950408889634f;
+
+  mbar_wait(bar_load, 0);
+  // rows in [nrows, npad) belong to the next tile or to capacity rows: keep them out of the MMAs (0 * NaN)
+  for (int i = tid; i < (npad - nrows) * (4 * AP_HG * 2); i += AB_THREADS) {
+    const int r = nrows + i / (4 * AP_HG * 2), c = i % (4 * AP_HG * 2);  // c over the 32 chunk columns of Q | K | V | dO
+    *reinterpret_cast<uint4*>(gen + ((size_t)c * AP_ROWS + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async();
+  __syncthreads();
+  uint32_t ph = 0;
+  if (warp == 0 && elect_one_sync()) {
+    tc_fence_after();
+    umma_bf16(tm_s, ap_desc(aQ, AP_ROWS * 16, 128), ap_desc(aK, AP_ROWS * 16, 128), ab_idesc(npad, false, false), 0u);
+    umma_bf16(tm_dp, ap_desc(aO, AP_ROWS * 16, 128), ap_desc(aV, AP_ROWS * 16, 128), ab_idesc(npad, false, false), 0u);
+    umma_commit(bar_mma);
+  }
+#pragma unroll 1
+  for (int h = 0; h < AP_HG; ++h) {
+    mbar_wait(bar_mma, ph);
+    ph ^= 1u;
+    tc_fence_after();
+    float sv[32], dv[32];
+    float mx = -INFINITY;
+    if (slice_live) {
+      uint32_t raw[32];
+      tmem_ld32(tm_s + lane_addr + (uint32_t)c0, raw);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        sv[i] = __uint_as_float(raw[i]);
+        if (off + (unsigned)i < len) mx = fmaxf(mx, sv[i]);
+      }
+      tmem_ld32(tm_dp + lane_addr + (uint32_t)c0, raw);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dv[i] = __uint_as_float(raw[i]);
+    }
+    s_red[0][sl][row] = mx;
+    __syncthreads();
+    const float mxs = fmaxf(fmaxf(s_red[0][0][row], s_red[0][1][row]), fmaxf(s_red[0][2][row], s_red[0][3][row])) * SC;
+    const int bh = b_seq * n_heads + hg * AP_HG + h;
+    const int qi = row - lo;
+    float l_part = 0.0f, d_part = 0.0f;
+    if (slice_live) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float p;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(sv[i], SC, -mxs)));
+        p = off + (unsigned)i < len ? p : 0.0f;
+        l_part += p;
+        float g = dv[i];
+        if (drop_p > 0.0f) {  // forward: P_drop = P * keep / (1 - p)  ->  dP = dP_drop * keep / (1 - p)
+          const bool keep = ap_hash(seed, bh, qi, (int)off + i) >= drop_thr;
+          g = keep ? g * drop_inv : 0.0f;
+          dv[i] = g;
+        }
+        d_part = fmaf(p, g, d_part);
+        sv[i] = p;  // unnormalised probability
+      }
+    }
+    s_red[1][sl][row] = l_part;
+    s_red[2][sl][row] = d_part;
+    __syncthreads();
+    const float lsum = (s_red[1][0][row] + s_red[1][1][row]) + (s_red[1][2][row] + s_red[1][3][row]);
+    const float dsum = (s_red[2][0][row] + s_red[2][1][row]) + (s_red[2][2][row] + s_red[2][3][row]);
+    const float inv_l = lsum > 0.0f ? 1.0f / lsum : 0.0f;
+    const float Dr = dsum * inv_l;
+    if (slice_live) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c0 + 8 * c < npad) {
+          uint32_t pw[4], sw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = c * 8 + 2 * e;
+            const float p0 = sv[i] * inv_l, p1 = sv[i + 1] * inv_l;
+            const float s0 = p0 * (dv[i] - Dr) * 0.25f, s1 = p1 * (dv[i + 1] - Dr) * 0.25f;
+            float pd0 = p0, pd1 = p1;
+            if (drop_p > 0.0f) {
+              pd0 = ap_hash(seed, bh, qi, (int)off + i) >= drop_thr ? p0 * drop_inv : 0.0f;
+              pd1 = ap_hash(seed, bh, qi, (int)off + i + 1) >= drop_thr ? p1 * drop_inv : 0.0f;
+            }
+            __nv_bfloat162 hp = __floats2bfloat162_rn(pd0, pd1), hs = __floats2bfloat162_rn(s0, s1);
+            pw[e] = *reinterpret_cast<uint32_t*>(&hp);
+            sw[e] = *reinterpret_cast<uint32_t*>(&hs);
+          }
+          const size_t o = ((size_t)((c0 >> 3) + c) * AP_ROWS + row) * 16;
+          *reinterpret_cast<uint4*>(sP + o) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+          *reinterpret_cast<uint4*>(sS + o) = make_uint4(sw[0], sw[1], sw[2], sw[3]);
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0 && elect_one_sync()) {
+      tc_fence_after();
+      const uint32_t ho = (uint32_t)h * (2 * AP_ROWS * 16);  // this head's two 16-byte chunks inside an operand
+      for (int ks = 0; ks < npad; ks += 16) {
+        const uint32_t acc = ks > 0 ? 1u : 0u;
+        // dV[key, d] += sum_q P[q, key] dO[q, d]   A = P^T (MN-major view, K = queries), B = dO (MN-major)
+        umma_bf16(tm_dv + (uint32_t)(h * AP_DH), ap_desc(aP + (uint32_t)ks * 16, 128, AP_ROWS * 16), ap_desc(aO + ho + (uint32_t)ks * 16, 128, AP_ROWS * 16),
+                  ab_idesc(AP_DH, true, true), acc);
+        // dQ[q, d] += sum_key dS[q, key] K[key, d]  A = dS (K-major, K = keys), B = K (MN-major)
+        umma_bf16(tm_dq + (uint32_t)(h * AP_DH), ap_desc(aS + (uint32_t)(ks >> 3) * (AP_ROWS * 16), AP_ROWS * 16, 128),
+                  ap_desc(aK + ho + (uint32_t)ks * 16, 128, AP_ROWS * 16), ab_idesc(AP_DH, false, true), acc);
+        // dK[key, d] += sum_q dS[q, key] Q[q, d]    A = dS^T (MN-major view), B = Q (MN-major)
+        umma_bf16(tm_dk + (uint32_t)(h * AP_DH), ap_desc(aS + (uint32_t)ks * 16, 128, AP_ROWS * 16), ap_desc(aQ + ho + (uint32_t)ks * 16, 128, AP_ROWS * 16),
+                  ab_idesc(AP_DH, true, true), acc);
+      }
+      if (h + 1 < AP_HG) {
+        const uint32_t no = (uint32_t)(h + 1) * (2 * AP_ROWS * 16);
+        umma_bf16(tm_s, ap_desc(aQ + no, AP_ROWS * 16, 128), ap_desc(aK + no, AP_ROWS * 16, 128), ab_idesc(npad, false, false), 0u);
+        umma_bf16(tm_dp, ap_desc(aO + no, AP_ROWS * 16, 128), ap_desc(aV + no, AP_ROWS * 16, 128), ab_idesc(npad, false, false), 0u);
+      }
+      umma_commit(bar_mma);
+    }
+  }
+  mbar_wait(bar_mma, ph);
+  tc_fence_after();
+  // ---- dQ | dK | dV (192 contiguous TMEM columns) -> bf16 rows of dqkv: slice sl stores the 16-column groups 3 sl .. 3 sl + 2 ----
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int g = sl * 3 + t;  // 0..11: array g / 4 (dQ, dK, dV), head g % 4
+    uint32_t o[16];
+    {
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]), "=r"(o[9]), "=r"(o[10]),
+            "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15])
+          : "r"(tm_dq + lane_addr + (uint32_t)(g * 16))
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    }
+    if (row < nrows) {
+      uint32_t w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(o[2 * e]), __uint_as_float(o[2 * e + 1]));
+        w[e] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(dqkv + (long long)(row0 + row) * 3 * D + (g >> 2) * D + hg * (AP_HG * AP_DH) + (g & 3) * AP_DH);
+      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u) : "memory");
+  }
+}
+
 }  // namespace
 
 int acb_attention_tc_long(const void* qkv, const int* cu_seqlens, const int* long_list, const int* n_long_dev, int grid_x, int n_heads,
                           int max_seqlen, float drop_p, long long seed, void* out, cudaStream_t st);  // attention_tc.cu
+int acb_attention_bwd_long(const void* qkv, const void* dout, const int* cu_seqlens, const int* long_list, const int* n_long_dev, int grid_x,
+                           int n_heads, int max_seqlen, float drop_p, long long seed, void* dqkv, cudaStream_t st);  // backward.cu
 
 extern "C" {
 
@@ -445,6 +687,37 @@ int acb_attention_packed(const void* qkv, const int* cu_seqlens, const int* plan
     acb_count_launch();
   }
   if (has_long) ACB_CUDA(cudaStreamWaitEvent(st, ev_join[dev], 0));
+  return ACB_OK;
+}
+
+int acb_attention_packed_bwd(const void* qkv, const void* dout, const int* cu_seqlens, const int* plan, int B, int max_tiles,
+                             long long total_rows, int n_heads, int dh, int max_seqlen, float drop_p, long long seed, void* dqkv, void* stream) {
+  ACB_CHECK(qkv && dout && cu_seqlens && plan && dqkv && B > 0 && max_tiles > 0 && total_rows > 0, "acb_attention_packed_bwd: bad arguments");
+  ACB_CHECK(dh == AP_DH && n_heads % AP_HG == 0, "acb_attention_packed_bwd: needs head_dim 16 and a head count that is a multiple of 4");
+  ACB_CHECK((((uintptr_t)qkv | (uintptr_t)dout | (uintptr_t)dqkv) % 16) == 0, "acb_attention_packed_bwd: alignment");
+  ACB_CHECK(drop_p >= 0.0f && drop_p < 1.0f, "acb_attention_packed_bwd: bad dropout");
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
+  ACB_CHECK(enc != nullptr, "acb_attention_packed_bwd: cuTensorMapEncodeTiled unavailable");
+  const int D = n_heads * dh;
+  CUtensorMap tmQ, tmO;
+  auto mk = [&](CUtensorMap* tm, const void* ptr, int cols) -> CUresult {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)total_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {8, (cuuint32_t)AP_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  ACB_CHECK(mk(&tmQ, qkv, 3 * D) == CUDA_SUCCESS && mk(&tmO, dout, D) == CUDA_SUCCESS, "acb_attention_packed_bwd: cuTensorMapEncodeTiled failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  ACB_CUDA(cudaFuncSetAttribute(attention_packed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AB_SMEM));
+  attention_packed_bwd_kernel<<<dim3(max_tiles, n_heads / AP_HG), AB_THREADS, AB_SMEM, st>>>(tmQ, tmO, cu_seqlens, plan, n_heads, drop_p, acb_seed(seed),
+                                                                                         (bf16*)dqkv);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  const int max_long = (int)std::min<long long>((long long)B, total_rows / (AP_ROWS + 1));
+  if (max_long > 0 && max_seqlen > AP_ROWS)
+    return acb_attention_bwd_long(qkv, dout, cu_seqlens, plan + 2 + 2 * max_tiles, plan + 1, max_long, n_heads, max_seqlen, drop_p, seed, dqkv, st);
   return ACB_OK;
 }
 

@@ -407,10 +407,12 @@ __device__ __forceinline__ unsigned attn_hash(unsigned long long seed, int bh, i
 
 template <int DH>
 __global__ void __launch_bounds__(128) attention_bwd_kernel(const void* qkv, int dt, const void* dout, int do_dt, const int* cu,
-                                                            int n_heads, float drop_p, AcbSeed seed_s, void* dqkv, int dq_dt) {
+                                                            int n_heads, float drop_p, AcbSeed seed_s, void* dqkv, int dq_dt,
+                                                            const int* __restrict__ seq_list, const int* __restrict__ n_list) {
+  if (seq_list && (int)blockIdx.x >= *n_list) return;  // list mode (long sequences of the packed plan): grid = host-side upper bound
   const unsigned long long seed = seed_s.get();
   extern __shared__ float sm[];
-  const int b = blockIdx.x, h = blockIdx.y;
+  const int b = seq_list ? seq_list[blockIdx.x] : (int)blockIdx.x, h = blockIdx.y;
   const int t0 = cu[b], n = cu[b + 1] - t0;
   const int D = n_heads * DH;
   float* Qs = sm;
@@ -961,9 +963,25 @@ int acb_attention_varlen_bwd(const void* qkv, int dtype, const void* dout, int d
   auto k = attention_bwd_kernel<16>;
   ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int threads = 128;  // measured: 288-thread CTAs (one round for 258-token sequences) are 25 % slower overall
-  k<<<dim3(B, n_heads), threads, smem, (cudaStream_t)stream>>>(qkv, dtype, dout, dout_dtype, cu_seqlens, n_heads, drop_p, acb_seed(seed), dqkv, dqkv_dtype);
+  k<<<dim3(B, n_heads), threads, smem, (cudaStream_t)stream>>>(qkv, dtype, dout, dout_dtype, cu_seqlens, n_heads, drop_p, acb_seed(seed), dqkv, dqkv_dtype,
+                                                                nullptr, nullptr);
   LAUNCHED(1);
 }
+
+}  // extern "C"
+
+// the same kernel over a device-side list of sequences (attention_packed.cu: sequences longer than one tile)
+int acb_attention_bwd_long(const void* qkv, const void* dout, const int* cu_seqlens, const int* long_list, const int* n_long_dev, int grid_x,
+                           int n_heads, int max_seqlen, float drop_p, long long seed, void* dqkv, cudaStream_t st) {
+  const size_t smem = ((size_t)max_seqlen * 16 * 4 + 2 * (size_t)max_seqlen) * 4;
+  ACB_CHECK(smem <= 200 * 1024, "acb_attention_packed_bwd: max_seqlen %d too long", max_seqlen);
+  auto k = attention_bwd_kernel<16>;
+  ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  k<<<dim3(grid_x, n_heads), 128, smem, st>>>(qkv, ACB_BF16, dout, ACB_BF16, cu_seqlens, n_heads, drop_p, acb_seed(seed), dqkv, ACB_BF16, long_list, n_long_dev);
+  LAUNCHED(1);
+}
+
+extern "C" {
 
 int acb_photo_embed_bwd(const float* x, const int* src_idx, int T, int D, const void* dh, int dh_dtype, const float* w, const float* b,
                         float te_drop_p, long long te_seed, float* grads, void* stream) {

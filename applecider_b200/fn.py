@@ -299,6 +299,7 @@ class Attention(Function):
         out = ops.attention_varlen(qkv, cu, B, H, dh, maxlen, drop_p, seed, zero_tail=True, plan=plan)
         ctx.save_for_backward(qkv, cu)
         ctx.cfg = (B, H, dh, maxlen, drop_p, seed)
+        ctx.plan = plan
         return out
 
     @staticmethod
@@ -307,6 +308,11 @@ class Attention(Function):
         B, H, dh, maxlen, drop_p, seed = ctx.cfg
         dout = _c(dout)
         dqkv = torch.zeros_like(qkv)  # capacity rows past the last sequence must carry zero gradient
+        plan = ctx.plan
+        if (plan is not None and ops.USE_PACKED_ATTENTION and ops.USE_TC_ATTENTION_BWD and qkv.dtype == BF16 and dout.dtype == BF16 and dh == 16
+                and H % 4 == 0 and maxlen <= 1024):
+            call("acb_attention_packed_bwd", qkv, dout, cu, plan[0], B, plan[1], qkv.shape[0], H, dh, maxlen, drop_p, seed, dqkv)
+            return dqkv, None, None, None, None, None, None, None, None
         call("acb_attention_varlen_bwd", qkv, dtype_tag(qkv), dout, dtype_tag(dout), cu, B, H, dh, maxlen, drop_p, seed, dqkv, dtype_tag(dqkv))
         return dqkv, None, None, None, None, None, None, None, None
 

@@ -194,6 +194,7 @@ def photo_embed(x, src, total, D, w_in, b_in, w0, b0, w, b, cls_tok, dtype, te_d
 
 USE_TC_ATTENTION = True
 USE_PACKED_ATTENTION = True  # several whole sequences per 128-row tile, 4 heads per CTA, TMA-fed (attention_packed.cu)
+USE_TC_ATTENTION_BWD = True  # backward of the packed attention on tcgen05 (attention_packed_bwd_kernel)
 
 
 def attention_plan(cu, B, total_rows):

@@ -178,6 +178,13 @@ int acb_attention_varlen_tc(const void* qkv, const int* cu_seqlens, int B, int n
 int acb_attention_plan(const int* cu_seqlens, int B, int max_tiles, int* plan, void* stream);
 int acb_attention_packed(const void* qkv, const int* cu_seqlens, const int* plan, int B, int max_tiles, long long total_rows,
                          int n_heads, int dh, int max_seqlen, float drop_p, long long seed, void* out, void* stream);
+/* backward of acb_attention_packed on tcgen05 (bf16 qkv / dout / dqkv): S and dP = dO V^T recomputed into TMEM, softmax and
+ * dS = P (dP - sum P dP) / sqrt(dh) in registers, dV = P^T dO, dQ = dS K, dK = dS^T Q by N = 16 UMMAs (P^T / dS^T are the
+ * shared-memory P / dS tiles read MN-major); the same plan and dropout hash as the forward; long sequences use the
+ * per-(sequence, head) CUDA-core backward over the plan's list.  dqkv rows outside every sequence are left untouched. */
+int acb_attention_packed_bwd(const void* qkv, const void* dout, const int* cu_seqlens, const int* plan, int B, int max_tiles,
+                             long long total_rows, int n_heads, int dh, int max_seqlen, float drop_p, long long seed, void* dqkv,
+                             void* stream);
 /* out[b,:] = x[cu_seqlens[b],:]  (CLS read-out z[:,0], HyraxBaselineCLS.py:79) */
 int acb_gather_cls(const void* x, int dtype, const int* cu_seqlens, int B, int D, float* out, void* stream);
 
