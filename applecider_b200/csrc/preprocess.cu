@@ -64,84 +64,174 @@ __global__ void __launch_bounds__(256) prep_lightcurve_kernel(const float* __res
 }
 
 // ================================ P2: merge + event features ======================================
-// One thread per object.  Per band (reference group order g, i, r) a greedy anchored window merge in
-// fp64 with un-fused multiply/add (same rounding sequence as the reference loop), then a stable 3-way
-// merge by time and the float32 feature columns.
-__global__ void __launch_bounds__(128) prep_events_kernel(const double* __restrict__ mjd, const double* __restrict__ mag,
+// Per object: per band (reference group order g, i, r) a greedy anchored window merge in fp64 with un-fused multiply/add
+// (same rounding sequence as the reference loop), then a stable 3-way merge by time and the float32 feature columns.
+// One WARP per object:
+//   lanes 0-2  walk "their" band and emit the windows [first, last] (integer / compare work only -- the greedy chain),
+//   all lanes  then take windows round-robin and do the fp64 weighted means (the pow() per detection is what costs),
+//   all lanes  rank the merged events of the three bands against each other by binary search (stable: ties go to the earlier band),
+//   all lanes  write the float32 feature columns.
+// Objects with more than P2_MAX_N detections are handled serially by lane 0 (same arithmetic, same results).
+constexpr int P2_MAX_N = 512;
+constexpr int P2_WARPS = 4;
+
+struct P2Sum { double t, f, e; };
+
+__device__ __forceinline__ P2Sum p2_window(const double* __restrict__ mjd, const double* __restrict__ mag, const double* __restrict__ magerr,
+                                           const int* __restrict__ fid, long long i, long long j, int band) {
+  const double eps = 1e-8;
+  const double c_err = 2.5 / 2.302585092994046;  // 2.5 / ln(10)
+  double totw = 0.0;
+  for (long long k = i; k <= j; ++k) {
+    if (fid[k] != band) continue;
+    const double flux = pow(10.0, -0.4 * (mag[k] - 23.9));
+    const double err = __dmul_rn(magerr[k] / c_err, flux);
+    totw = __dadd_rn(totw, 1.0 / __dadd_rn(err, eps));
+  }
+  P2Sum s{0.0, 0.0, 0.0};
+  for (long long k = i; k <= j; ++k) {
+    if (fid[k] != band) continue;
+    const double flux = pow(10.0, -0.4 * (mag[k] - 23.9));
+    const double err = __dmul_rn(magerr[k] / c_err, flux);
+    const double w = (1.0 / __dadd_rn(err, eps)) / totw;
+    s.t = __dadd_rn(s.t, __dmul_rn(w, mjd[k]));
+    s.f = __dadd_rn(s.f, __dmul_rn(w, flux));
+    s.e = __dadd_rn(s.e, __dmul_rn(w, err));
+  }
+  return s;
+}
+
+__device__ __forceinline__ void p2_emit(long long dst, double t, double t_first, double t_prev, double f, double e, signed char band,
+                                        float* __restrict__ o_dt, float* __restrict__ o_dtp, signed char* __restrict__ o_band,
+                                        float* __restrict__ o_lf, float* __restrict__ o_lfe) {
+  const float f32 = fmaxf((float)f, 1e-6f);
+  o_dt[dst] = (float)(t - t_first);
+  o_dtp[dst] = (float)(t - t_prev);
+  o_band[dst] = band;
+  o_lf[dst] = log10f(f32);
+  o_lfe[dst] = (float)(__dmul_rn((double)(float)e, 0.43429448190325176) / (double)f32);
+}
+
+// next window of `band` starting the search at detection i: returns false when the band has no detection left
+__device__ __forceinline__ bool p2_next_window(const double* __restrict__ mjd, const int* __restrict__ fid, long long r1, int band, double dt_days,
+                                               long long& i, long long& j, long long& next) {
+  while (i < r1 && fid[i] != band) ++i;
+  if (i >= r1) return false;
+  const double t0 = mjd[i];
+  j = i;
+  long long scan = i + 1;
+  for (; scan < r1; ++scan) {
+    if (fid[scan] != band) continue;
+    if (mjd[scan] - t0 <= dt_days) j = scan; else break;
+  }
+  next = scan;  // first detection of this band beyond the window (or r1)
+  return true;
+}
+
+__global__ void __launch_bounds__(32 * P2_WARPS) prep_events_kernel(const double* __restrict__ mjd, const double* __restrict__ mag,
                                                           const double* __restrict__ magerr, const int* __restrict__ fid,
                                                           const long long* __restrict__ offsets, int B, double dt_days,
                                                           double* __restrict__ tmp /* [3][total] t,f,e */, signed char* __restrict__ tmp_b,
                                                           long long total, float* __restrict__ o_dt, float* __restrict__ o_dtp,
                                                           signed char* __restrict__ o_band, float* __restrict__ o_lf,
                                                           float* __restrict__ o_lfe, int* __restrict__ n_events) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ unsigned short s_first[P2_WARPS][3][P2_MAX_N];   // window bounds per band (n <= 512), later reused as the merged order
+  __shared__ unsigned short s_last[P2_WARPS][3][P2_MAX_N];
+  __shared__ int s_cnt[P2_WARPS][4];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int b = blockIdx.x * P2_WARPS + wib;
   if (b >= B) return;
   const long long r0 = offsets[b], r1 = offsets[b + 1];
+  const int n = (int)(r1 - r0);
   double* tt = tmp + r0;
   double* tf = tmp + total + r0;
   double* te = tmp + 2 * total + r0;
   signed char* tb = tmp_b + r0;
-  const double eps = 1e-8;
-  const double c_err = 2.5 / 2.302585092994046;  // 2.5 / ln(10)
   const int order[3] = {1, 3, 2};
-  int seg_start[4];
-  int cnt = 0;
-  for (int g = 0; g < 3; ++g) {
-    seg_start[g] = cnt;
-    const int band = order[g];
-    long long i = r0;
-    while (i < r1) {
-      while (i < r1 && fid[i] != band) ++i;
-      if (i >= r1) break;
-      // window [i .. j] over detections of this band (time ordered)
-      const double t0 = mjd[i];
-      long long j = i, scan = i + 1;
-      for (; scan < r1; ++scan) {
-        if (fid[scan] != band) continue;
-        if (mjd[scan] - t0 <= dt_days) j = scan; else break;
-      }
-      double totw = 0.0;
-      for (long long k = i; k <= j; ++k) {
-        if (fid[k] != band) continue;
-        const double flux = pow(10.0, -0.4 * (mag[k] - 23.9));
-        const double err = __dmul_rn(magerr[k] / c_err, flux);
-        totw = __dadd_rn(totw, 1.0 / __dadd_rn(err, eps));
-      }
-      double tw = 0.0, fw = 0.0, ew = 0.0;
-      for (long long k = i; k <= j; ++k) {
-        if (fid[k] != band) continue;
-        const double flux = pow(10.0, -0.4 * (mag[k] - 23.9));
-        const double err = __dmul_rn(magerr[k] / c_err, flux);
-        const double w = (1.0 / __dadd_rn(err, eps)) / totw;
-        tw = __dadd_rn(tw, __dmul_rn(w, mjd[k]));
-        fw = __dadd_rn(fw, __dmul_rn(w, flux));
-        ew = __dadd_rn(ew, __dmul_rn(w, err));
-      }
-      tt[cnt] = tw; tf[cnt] = fw; te[cnt] = ew; tb[cnt] = (signed char)(band - 1);
-      ++cnt;
-      i = scan;  // first detection of this band beyond the window (or r1)
-    }
-  }
-  seg_start[3] = cnt;
-  n_events[b] = cnt;
-  // stable 3-way merge by merged time
-  int p[3] = {seg_start[0], seg_start[1], seg_start[2]};
-  double t_first = 0.0, t_prev = 0.0;
-  for (int o = 0; o < cnt; ++o) {
-    int best = -1;
+  if (n > P2_MAX_N) {  // rare: serial path on lane 0
+    if (lane != 0) return;
+    int seg_start[4];
+    int cnt = 0;
     for (int g = 0; g < 3; ++g) {
-      if (p[g] < seg_start[g + 1] && (best < 0 || tt[p[g]] < tt[p[best]])) best = g;
+      seg_start[g] = cnt;
+      long long i = r0, j = 0, nx = 0;
+      while (p2_next_window(mjd, fid, r1, order[g], dt_days, i, j, nx)) {
+        const P2Sum w = p2_window(mjd, mag, magerr, fid, i, j, order[g]);
+        tt[cnt] = w.t; tf[cnt] = w.f; te[cnt] = w.e; tb[cnt] = (signed char)(order[g] - 1);
+        ++cnt;
+        i = nx;
+      }
     }
-    const int s = p[best]++;
-    const double t = tt[s];
-    if (o == 0) { t_first = t; t_prev = t; }
-    const float f32 = fmaxf((float)tf[s], 1e-6f);
-    o_dt[r0 + o] = (float)(t - t_first);
-    o_dtp[r0 + o] = (float)(t - t_prev);
-    o_band[r0 + o] = tb[s];
-    o_lf[r0 + o] = log10f(f32);
-    o_lfe[r0 + o] = (float)(__dmul_rn((double)(float)te[s], 0.43429448190325176) / (double)f32);
-    t_prev = t;
+    seg_start[3] = cnt;
+    n_events[b] = cnt;
+    int p[3] = {seg_start[0], seg_start[1], seg_start[2]};
+    double t_first = 0.0, t_prev = 0.0;
+    for (int o = 0; o < cnt; ++o) {
+      int best = -1;
+      for (int g = 0; g < 3; ++g)
+        if (p[g] < seg_start[g + 1] && (best < 0 || tt[p[g]] < tt[p[best]])) best = g;
+      const int sidx = p[best]++;
+      const double t = tt[sidx];
+      if (o == 0) { t_first = t; t_prev = t; }
+      p2_emit(r0 + o, t, t_first, t_prev, tf[sidx], te[sidx], tb[sidx], o_dt, o_dtp, o_band, o_lf, o_lfe);
+      t_prev = t;
+    }
+    return;
+  }
+  // ---- A: the three greedy window chains, one lane per band ----
+  if (lane < 3) {
+    int c = 0;
+    long long i = r0, j = 0, nx = 0;
+    while (p2_next_window(mjd, fid, r1, order[lane], dt_days, i, j, nx)) {
+      s_first[wib][lane][c] = (unsigned short)(i - r0);
+      s_last[wib][lane][c] = (unsigned short)(j - r0);
+      ++c;
+      i = nx;
+    }
+    s_cnt[wib][lane] = c;
+  }
+  __syncwarp();
+  const int c0 = s_cnt[wib][0], c1 = s_cnt[wib][1], c2 = s_cnt[wib][2];
+  const int seg[4] = {0, c0, c0 + c1, c0 + c1 + c2};
+  const int cnt = seg[3];
+  if (lane == 0) n_events[b] = cnt;
+  // ---- B: weighted means of the windows (fp64, the reference's summation order inside a window) ----
+  for (int sidx = lane; sidx < cnt; sidx += 32) {
+    const int g = sidx < seg[1] ? 0 : (sidx < seg[2] ? 1 : 2);
+    const int k = sidx - seg[g];
+    const P2Sum w = p2_window(mjd, mag, magerr, fid, r0 + s_first[wib][g][k], r0 + s_last[wib][g][k], order[g]);
+    tt[sidx] = w.t; tf[sidx] = w.f; te[sidx] = w.e; tb[sidx] = (signed char)(order[g] - 1);
+  }
+  __syncwarp();
+  // ---- C: stable 3-way merge by rank: position = index in own band + events of the other bands that come first ----
+  unsigned short* ord = &s_first[wib][0][0];  // 3 * P2_MAX_N entries >= cnt
+  __syncwarp();
+  for (int sidx = lane; sidx < cnt; sidx += 32) {
+    const int g = sidx < seg[1] ? 0 : (sidx < seg[2] ? 1 : 2);
+    const double t = tt[sidx];
+    int pos = sidx - seg[g];
+    for (int g2 = 0; g2 < 3; ++g2) {
+      if (g2 == g) continue;
+      // events of band g2 placed before this one: time < t, or time == t when g2 is the earlier band (the serial merge is stable)
+      int lo = seg[g2], hi = seg[g2 + 1];
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const double tm = tt[mid];
+        if (tm < t || (tm == t && g2 < g)) lo = mid + 1; else hi = mid;
+      }
+      pos += lo - seg[g2];
+    }
+    // ord is written after every lane has finished reading s_first / s_last in phase B (the __syncwarp above)
+    ord[pos] = (unsigned short)sidx;
+  }
+  __syncwarp();
+  // ---- D: feature columns ----
+  const double t_first = cnt > 0 ? tt[ord[0]] : 0.0;
+  for (int o = lane; o < cnt; o += 32) {
+    const int sidx = ord[o];
+    const double t = tt[sidx];
+    const double t_prev = o > 0 ? tt[ord[o - 1]] : t;
+    p2_emit(r0 + o, t, t_first, t_prev, tf[sidx], te[sidx], tb[sidx], o_dt, o_dtp, o_band, o_lf, o_lfe);
   }
 }
 
@@ -539,7 +629,7 @@ int acb_prep_events(const double* mjd, const double* mag, const double* magerr, 
                     signed char* band_id, float* logflux, float* logflux_err, int* n_events, void* stream) {
   ACB_CHECK(mjd && mag && magerr && fid && offsets && tmp && tmp_b && dt && dt_prev && band_id && logflux && logflux_err && n_events && B > 0,
             "acb_prep_events: bad arguments");
-  prep_events_kernel<<<cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(mjd, mag, magerr, fid, offsets, B, dt_days, tmp, tmp_b, total, dt,
+  prep_events_kernel<<<cdiv(B, P2_WARPS), 32 * P2_WARPS, 0, (cudaStream_t)stream>>>(mjd, mag, magerr, fid, offsets, B, dt_days, tmp, tmp_b, total, dt,
                                                                       dt_prev, band_id, logflux, logflux_err, n_events);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
