@@ -239,11 +239,12 @@ __global__ void __launch_bounds__(32 * P2_WARPS) prep_events_kernel(const double
 // k-th smallest (0-based) of `n` keys produced by key(i), radix select over NB-bit unsigned keys, 8 bits/pass.
 // k-th smallest key among key(0..n-1) by MSB-first radix selection with 8-bit digits, for blocks of exactly 256 threads:
 //   * the 256-bin histogram is scanned by all threads (one bin each: warp scan + cross-warp offsets), not by thread 0;
-//   * as soon as the bin that holds rank k has <= 256 members the pass loop stops: the members are gathered into shared memory
+//   * as soon as the bin that holds rank k has <= 64 members the pass loop stops: the members are gathered into shared memory
 //     and ranked against each other (one candidate per thread) -- smooth spectra / sky-dominated cutouts share their sign,
 //     exponent and leading mantissa bits, so this happens after 2-3 of the 4 (fp32) or 8 (fp64) passes.
 // hist: 256 counters; sh_k: 8 words of scratch; cand: 257 keys (slot 256 receives the result).
 constexpr int SEL_THREADS = 256;
+constexpr int SEL_CAND = 64;  // candidates ranked against each other: 64 x 64 compares cost less than one more histogram pass
 template <typename KeyT, typename KeyFn>
 __device__ KeyT block_select(int n, int k, KeyFn key, unsigned* hist /* 256 */, unsigned* sh_k /* 8 */, KeyT* cand /* 257 */) {
   constexpr int NBITS = sizeof(KeyT) * 8;
@@ -252,7 +253,7 @@ __device__ KeyT block_select(int n, int k, KeyFn key, unsigned* hist /* 256 */, 
   for (int shift = NBITS - 8; shift >= 0; shift -= 8) {
     hist[tid] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += SEL_THREADS) {
+    for (int i = tid; i < n; i += SEL_THREADS) {  // (warp-aggregating these atomics with match.any was measured 25 % SLOWER)
       const KeyT kk = key(i);
       if ((kk & pmask) == prefix) atomicAdd(&hist[(unsigned)((kk >> shift) & 0xff)], 1u);
     }
@@ -282,7 +283,7 @@ __device__ KeyT block_select(int n, int k, KeyFn key, unsigned* hist /* 256 */, 
     k = (int)sh_k[1];
     const unsigned members = sh_k[2];
     __syncthreads();
-    if (shift > 0 && members <= (unsigned)SEL_THREADS) {
+    if (shift > 0 && members <= (unsigned)SEL_CAND) {
       if (tid == 0) sh_k[3] = 0;
       __syncthreads();
       for (int i = tid; i < n; i += SEL_THREADS) {
