@@ -128,6 +128,7 @@ def call(name: str, *args):
     if len(args) != len(sig):
         raise TypeError(f"{name}: expected {len(sig)} arguments, got {len(args)}")
     conv = []
+    dev = None
     for k, a in zip(sig, args):
         if k == "p":
             if a is None or type(a) is int:
@@ -137,6 +138,10 @@ def call(name: str, *args):
                     raise RuntimeError("applecider_b200: tensors must live on a CUDA device (no CPU fallback)")
                 if not a.is_contiguous():
                     raise RuntimeError("applecider_b200: tensors must be contiguous")
+                if dev is None:
+                    dev = a.device.index
+                elif a.device.index != dev:
+                    raise RuntimeError(f"applecider_b200: {name}: tensors live on different devices (cuda:{dev} and cuda:{a.device.index})")
                 conv.append(a.data_ptr())
             else:
                 conv.append(_ptr(a))
@@ -144,6 +149,9 @@ def call(name: str, *args):
             conv.append(int(a))
         else:
             conv.append(float(a))
+    if dev is not None and dev != torch.cuda.current_device():
+        # the launch goes to the CURRENT device's stream: run under torch.cuda.device(tensor.device) (one process per GPU is the norm)
+        raise RuntimeError(f"applecider_b200: {name}: tensors live on cuda:{dev} but the current device is cuda:{torch.cuda.current_device()}")
     rc = fn(*conv, _current_stream())
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error().decode()}")
