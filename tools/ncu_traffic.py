@@ -1,6 +1,8 @@
 """Distil `ncu --set full --page raw --csv` pages under profiles/ into profiles/ncu_traffic.json.
 
-    python tools/ncu_traffic.py [--dominant profiles/<page>.csv]
+    python tools/ncu_traffic.py [--dominant profiles/<page>.csv[::kernel-name-substring]]
+
+(a page may hold many launches: the LONGEST launch whose name contains the substring is taken)
 
 For every kernel row of every `profiles/*ncu_full*.csv`: DRAM bytes read / written per launch, duration, achieved DRAM
 bandwidth and the tensor-pipe / issue utilisation when the page has them.  bench.py reads the entry marked "dominant" for
@@ -47,6 +49,8 @@ def parse(path):
             return v * UNIT.get(units[i], 1.0) if scale else v
 
         rd, wr, ms = get("dram__bytes_read.sum"), get("dram__bytes_write.sum"), get("gpu__time_duration.sum")
+        if rd is None and wr is None and ms is None:
+            continue
         ent = {"file": os.path.relpath(path, ROOT), "kernel": r[col["Kernel Name"]].replace("void <unnamed>::", "")[:120],
                "grid": r[col["Grid Size"]], "block": r[col["Block Size"]], "dram_read_bytes": rd, "dram_write_bytes": wr, "time_ms": ms}
         if rd is not None and wr is not None and ms:
@@ -58,25 +62,30 @@ def parse(path):
                           ("l2_hit_pct", "lts__t_sector_hit_rate.pct")]:
             v = get(name, scale=False)
             if v is not None and key not in ent:
+                if key == "sm_clock_mhz" and units[col[name]].lower() == "ghz":
+                    v *= 1000.0
                 ent[key] = v
         out.append(ent)
     return out
 
 
 def main():
-    dominant = None
+    dominant, dom_sub = None, ""
     if "--dominant" in sys.argv:
-        dominant = os.path.relpath(os.path.abspath(sys.argv[sys.argv.index("--dominant") + 1]), ROOT)
+        spec = sys.argv[sys.argv.index("--dominant") + 1]
+        spec, _, dom_sub = spec.partition("::")
+        dominant = os.path.relpath(os.path.abspath(spec), ROOT)
     dst = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     prev = json.load(open(dst)) if os.path.exists(dst) else {}
     if dominant is None:
-        dominant = prev.get("dominant_file")
+        dominant, dom_sub = prev.get("dominant_file"), prev.get("dominant_kernel_substring", "")
     entries = []
     for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_full*.csv"))):
         entries += parse(p)
-    dom = next((e for e in entries if e["file"] == dominant), None)
+    cands = [e for e in entries if e["file"] == dominant and dom_sub in e["kernel"] and e.get("time_ms")]
+    dom = max(cands, key=lambda e: e["time_ms"]) if cands else None
     json.dump({"how": "tools/ncu_traffic.py over profiles/*ncu_full*.csv (ncu --set full --clock-control none, --page raw --csv)",
-               "dominant_file": dominant, "dominant": dom, "kernels": entries}, open(dst, "w"), indent=1)
+               "dominant_file": dominant, "dominant_kernel_substring": dom_sub, "dominant": dom, "kernels": entries}, open(dst, "w"), indent=1)
     print(f"{len(entries)} kernel pages -> {dst}; dominant = {dom['kernel'] if dom else None}")
 
 
