@@ -33,7 +33,10 @@ struct TcArgs {
   int res_mode, pool4;
   const int* m_valid_dev;
   void* pre_out;  // optional second bf16 output: the value after the bias, before activation / residual (same ldc, columns)
-  float* row_stats;  // optional [rows][gridDim.y][2]: per-row sum and sum of squares of this CTA's output columns (LayerNorm
+  int nt_fast;       // 1: blockIdx.x walks the N tiles (the CTAs that share an A tile are scheduled together, so A comes from DRAM
+                     // once and from L2 for the other N tiles); 0: blockIdx.x walks the M tiles (grid.y would exceed 65535)
+  int n_tiles_n;     // number of N tiles (row_stats layout)
+  float* row_stats;  // optional [rows][n_tiles_n][2]: per-row sum and sum of squares of this CTA's output columns (LayerNorm
                      // statistics for the consumer GEMM, acb_gemm_ln_bf16, which then never needs its own pass over the activation)
   int has_ranges, has_coloff;
   int kb_lo[TC_MAX_NT], kb_hi[TC_MAX_NT];
@@ -284,7 +287,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& p, bool have_acc,
       }
     }
     if (p.row_stats && valid)
-      *reinterpret_cast<float2*>(p.row_stats + ((size_t)m * gridDim.y + nt) * 2) = make_float2(st_sum, st_sq);
+      *reinterpret_cast<float2*>(p.row_stats + ((size_t)m * p.n_tiles_n + nt) * 2) = make_float2(st_sum, st_sq);
   }
 }
 
@@ -307,7 +310,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   __shared__ __align__(16) float s_bias[BN], s_gamma[BN];  // staged by the epilogue warps while the main loop runs
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x * MSUB, nt = blockIdx.y;  // first 128-row sub-tile of this CTA (MSUB > 1: p.tps % MSUB == 0)
+  const int mt = (p.nt_fast ? blockIdx.y : blockIdx.x) * MSUB;  // first 128-row sub-tile of this CTA (MSUB > 1: p.tps % MSUB == 0)
+  const int nt = p.nt_fast ? blockIdx.x : blockIdx.y;
   const int n0 = nt * BN;
 
   const int sample0 = (mt / p.tps) * p.Bbox;
@@ -424,6 +428,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args
   constexpr size_t smem = (size_t)STAGES * (MSUB * TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024;
   auto k = gemm_tc_kernel<BN, STAGES, MSUB>;
   if (MSUB > 1) grid.x /= MSUB;
+  if (args.nt_fast) grid = dim3(grid.y, grid.x);
   static bool configured = false;
   if (!configured) {
     ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -465,7 +470,7 @@ __global__ void __launch_bounds__(TC_LN_THREADS, 2) gemm_ln_tc_kernel(const __gr
   __shared__ __align__(16) float s_bias[BN], s_gamma[BN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x, nt = blockIdx.y;
+  const int mt = p.nt_fast ? blockIdx.y : blockIdx.x, nt = p.nt_fast ? blockIdx.x : blockIdx.y;
   const int n0 = nt * BN;
   const int l0 = mt * TC_BM;  // plain GEMM: one "sample" of L = M rows
   const int nkb = p.cpt;
@@ -607,6 +612,7 @@ int launch_ln_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a
   const size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024 + (size_t)2 * args.Cin * sizeof(float);
   auto k = gemm_ln_tc_kernel<BN, STAGES>;
   ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (args.nt_fast) grid = dim3(grid.y, grid.x);
   k<<<grid, TC_LN_THREADS, smem, st>>>(tmA, tmB, args, ln);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
@@ -1064,6 +1070,10 @@ static int gemm_bf16_impl(const void* A, const void* Bw, void* C, int c_dtype, i
 
   const long long MT = (long long)cdiv(nbatch, args.Bbox) * args.tps;
   ACB_CHECK(MT < (1LL << 31) && NT <= 65535, "acb_gemm_bf16: grid too large");
+  static int nt_fast_env = -1;
+  if (nt_fast_env < 0) { const char* e = getenv("ACB_GEMM_NT_FAST"); nt_fast_env = e ? atoi(e) : 1; }
+  args.n_tiles_n = NT;
+  args.nt_fast = (nt_fast_env && NT > 1 && MT <= 65535) ? 1 : 0;
   dim3 grid((unsigned)MT, (unsigned)NT);
   cudaStream_t st = (cudaStream_t)stream;
   // short-K problems (<= 4 K blocks per tile) are epilogue/latency bound: shallow pipeline, more CTAs per SM
