@@ -608,6 +608,23 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const void* x, int x
   atomicAdd(db + c, sb);
 }
 
+// 1x1 maps (ConvNeXt stage 3 at 63x63 cutouts): only the centre tap ever sees data: dw[c, 3, 3] = sum_b x[b,c] dy[b,c], db[c] = sum_b dy[b,c].
+// thread = channel (coalesced), blockIdx.y strides over image chunks; two atomics per thread instead of 50.
+__global__ void __launch_bounds__(256) dwconv7_wgrad_1x1_kernel(const void* __restrict__ x, int x_dt, const void* __restrict__ dy, int dy_dt, int B,
+                                                                int C, int img_per_block, float* __restrict__ dw, float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int b0 = blockIdx.y * img_per_block, b1 = min(B, b0 + img_per_block);
+  float acc = 0.0f, sb = 0.0f;
+  for (int b = b0; b < b1; ++b) {
+    const float g = ld_any(dy, (long long)b * C + c, dy_dt);
+    sb += g;
+    acc = fmaf(g, ld_any(x, (long long)b * C + c, x_dt), acc);
+  }
+  atomicAdd(dw + c * 49 + 24, acc);
+  atomicAdd(db + c, sb);
+}
+
 // Row-register variant for the square ConvNeXt maps (W = H in {15, 7, 3}): thread = (channel, row phase); the dy row
 // and one x row live in registers, so every x value loaded feeds up to 7 taps (loads : FMAs = 1 : 7 instead of 1 : 1);
 // partial sums are merged in shared memory before the global atomics.
@@ -1020,6 +1037,11 @@ int acb_dwconv7_wgrad(const void* x, int x_dtype, const void* dy, int dy_dtype, 
   if (!accumulate) {
     ACB_CUDA(cudaMemsetAsync(dw, 0, (size_t)C * 49 * 4, st));
     ACB_CUDA(cudaMemsetAsync(db, 0, (size_t)C * 4, st));
+  }
+  if (H == 1 && W == 1) {
+    const int ipb = 32;
+    dwconv7_wgrad_1x1_kernel<<<dim3(cdiv(C, 256), cdiv(B, ipb)), 256, 0, st>>>(x, x_dtype, dy, dy_dtype, B, C, ipb, dw, db);
+    LAUNCHED(1);
   }
   if (x_dtype == dy_dtype) {
     const bool done = x_dtype == ACB_F32 ? launch_dwconv7_wgrad_w<float>(x, dy, B, H, W, C, dw, db, st) : launch_dwconv7_wgrad_w<bf16>(x, dy, B, H, W, C, dw, db, st);
