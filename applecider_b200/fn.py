@@ -32,7 +32,11 @@ def gemm_ex(A, a_dt, B, b_dt, M, N, K, sam, sak, sbn, sbk, dev, convT=None, spli
     return out
 
 
-def _splits(k):
+def _splits(k, tiles=None):
+    """Split-K factor of the CUDA-core GEMM for a reduction of length k.  With few output tiles (64 x 64 each) a single CTA would
+    walk the whole reduction serially (router 144 -> 4 at 1024 rows: 195 us): split until ~2 CTAs per SM are busy."""
+    if tiles is not None and tiles < 64:
+        return max(1, min(128, k // 128, 296 // max(1, tiles)))
     return max(1, min(128, k // 2048))
 
 
@@ -140,7 +144,7 @@ class Linear(Function):
             elif tc:
                 dW = wgrad_tc(dy, N, 0, N, x, 1, M, K, 1, 0, M * K, K, x.device)
             else:
-                dW = gemm_ex(dy, dtype_tag(dy), x, dtype_tag(x), N, K, M, 1, N, 1, K, x.device, splits=_splits(M))
+                dW = gemm_ex(dy, dtype_tag(dy), x, dtype_tag(x), N, K, M, 1, N, 1, K, x.device, splits=_splits(M, ((N + 63) // 64) * ((K + 63) // 64)))
         if want_db and db is None:
             db = colsum(dy)
         return dx, dW, db, None, None
