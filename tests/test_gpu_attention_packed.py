@@ -156,3 +156,26 @@ def test_attention_autograd_uses_packed_backward():
         parts.append((p @ v).transpose(0, 1).reshape(e - s, D))
     (torch.cat(parts) * w.to(torch.bfloat16).float()).sum().backward()
     assert_close(qkv.grad, q32.grad, 3e-2, "d qkv through the packed attention")
+
+
+def test_plan_serial_fallback_for_huge_batches():
+    """More than 8192 sequences: the planner's serial kernel must produce the same greedy packing, and the attention must match."""
+    from applecider_b200 import ops
+
+    rng = np.random.default_rng(9)
+    lens = [int(x) for x in rng.integers(2, 40, size=9000)]
+    lens[100], lens[5000] = 200, 131
+    B = len(lens)
+    cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device=DEV)
+    T = int(cu[-1])
+    plan, max_tiles = ops.attention_plan(cu, B, T)
+    tiles, longs = _greedy(lens)
+    p = plan.cpu().numpy()
+    assert p[0] == len(tiles) and p[1] == len(longs)
+    assert [(int(p[2 + 2 * t]), int(p[3 + 2 * t])) for t in range(len(tiles))] == tiles
+    assert list(p[2 + 2 * max_tiles: 2 + 2 * max_tiles + len(longs)]) == longs
+    torch.manual_seed(1)
+    qkv = torch.randn(T, 3 * D, device=DEV).to(torch.bfloat16)
+    got = ops.attention_varlen(qkv, cu, B, H, 16, max(lens), plan=(plan, max_tiles))
+    old = ops.attention_varlen(qkv, cu, B, H, 16, max(lens))
+    assert_close(got, old.float(), 1.2e-2, "packed attention over 9000 sequences vs the per-sequence kernel")
