@@ -21,6 +21,7 @@ namespace {
 
 struct MlpArgs {
   long long M;
+  const int* rows_dev;  // optional device-side row count (capacity-sized token matrices): tiles past it exit at once
   const float* b1;
   const float* b2;
   const float* gamma;
@@ -37,7 +38,7 @@ struct MlpCfg {
   static constexpr int NEW = HC / 32;                // epilogue warps per TMEM lane quarter
   static constexpr int NE_WARPS = 4 * NEW;
   static constexpr int THREADS = 64 + 32 * NE_WARPS;
-  static constexpr int NW2 = (C <= 96) ? 1 : 2;      // W2 ring depth
+  static constexpr int NW2 = (C == 192) ? 2 : 1;     // W2 ring depth (what fits next to the other tiles)
   static constexpr uint32_t Y_BYTES = KB1 * 16384;
   static constexpr uint32_t W1_BYTES = KB1 * HC * 128;
   static constexpr uint32_t W2_BYTES = KB2 * C * 128;
@@ -60,7 +61,7 @@ __device__ __forceinline__ void tmem_ld16b(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int C, int HC>
+template <int C, int HC, int ACT>
 __global__ void __launch_bounds__(MlpCfg<C, HC>::THREADS, 1) mlp_block_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                              const __grid_constant__ CUtensorMap tmW1,
                                                                              const __grid_constant__ CUtensorMap tmW2,
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(MlpCfg<C, HC>::THREADS, 1) mlp_block_kernel(co
   __shared__ uint32_t tmem_holder;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m0 = (long long)blockIdx.x * 128;
+  if (p.rows_dev && m0 >= (long long)(*p.rows_dev)) return;  // uniform, before any barrier / TMEM allocation
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t aY = base, aW1 = aY + G::Y_BYTES, aW2 = aW1 + 2 * G::W1_BYTES, aH = aW2 + G::NW2 * G::W2_BYTES;
@@ -184,7 +186,8 @@ __global__ void __launch_bounds__(MlpCfg<C, HC>::THREADS, 1) mlp_block_kernel(co
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const float2 b2v = *reinterpret_cast<const float2*>(bb + i);
-        __nv_bfloat162 hh = __floats2bfloat162_rn(gelu_bf16(__uint_as_float(raw[i]) + b2v.x), gelu_bf16(__uint_as_float(raw[i + 1]) + b2v.y));
+        const float u0 = __uint_as_float(raw[i]) + b2v.x, u1 = __uint_as_float(raw[i + 1]) + b2v.y;
+        __nv_bfloat162 hh = ACT == ACB_ACT_RELU ? __floats2bfloat162_rn(fmaxf(u0, 0.0f), fmaxf(u1, 0.0f)) : __floats2bfloat162_rn(gelu_bf16(u0), gelu_bf16(u1));
         pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
       }
       // H tile: K block (cg*32)/64, 16-byte chunks c0..c0+3 of row r, SWIZZLE_128B
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(MlpCfg<C, HC>::THREADS, 1) mlp_block_kernel(co
   }
 }
 
-template <int C, int HC>
+template <int C, int HC, int ACT>
 int launch_mlp(const void* y, const void* w1, const void* w2, const MlpArgs& args, cudaStream_t st) {
   using G = MlpCfg<C, HC>;
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
@@ -252,7 +255,7 @@ int launch_mlp(const void* y, const void* w1, const void* w2, const MlpArgs& arg
   ACB_CHECK(mk(&tmY, y, args.M, C, 128) == CUDA_SUCCESS, "acb_convnext_mlp_bf16: tensor map (y) failed");
   ACB_CHECK(mk(&tmW1, w1, 4 * C, C, HC) == CUDA_SUCCESS, "acb_convnext_mlp_bf16: tensor map (fc1 weight) failed");
   ACB_CHECK(mk(&tmW2, w2, C, 4 * C, C) == CUDA_SUCCESS, "acb_convnext_mlp_bf16: tensor map (fc2 weight) failed");
-  auto k = mlp_block_kernel<C, HC>;
+  auto k = mlp_block_kernel<C, HC, ACT>;
   ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
   k<<<(unsigned)((args.M + 127) / 128), G::THREADS, G::SMEM, st>>>(tmY, tmW1, tmW2, args);
   ACB_LAUNCH_CHECK();
@@ -266,10 +269,21 @@ extern "C" int acb_convnext_mlp_bf16(const void* y, const void* res, const void*
                                      const float* gamma, void* out, long long M, int C, void* stream) {
   ACB_CHECK(y && res && w1 && b1 && w2 && b2 && gamma && out && M > 0, "acb_convnext_mlp_bf16: bad arguments");
   ACB_CHECK((((uintptr_t)y | (uintptr_t)res | (uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)out) & 15) == 0, "acb_convnext_mlp_bf16: 16-byte alignment");
-  MlpArgs args{M, b1, b2, gamma, (const bf16*)res, (bf16*)out};
+  MlpArgs args{M, nullptr, b1, b2, gamma, (const bf16*)res, (bf16*)out};
   cudaStream_t st = (cudaStream_t)stream;
-  if (C == 96) return launch_mlp<96, 128>(y, w1, w2, args, st);
-  if (C == 192) return launch_mlp<192, 64>(y, w1, w2, args, st);
+  if (C == 96) return launch_mlp<96, 128, ACB_ACT_GELU>(y, w1, w2, args, st);
+  if (C == 192) return launch_mlp<192, 64, ACB_ACT_GELU>(y, w1, w2, args, st);
   acb_set_error("acb_convnext_mlp_bf16: C = %d is not fused (96 and 192 are; wider stages hold too few rows to matter)", C);
   return ACB_ERR_UNSUPPORTED;
+}
+
+// Transformer feed-forward block (nn.TransformerEncoderLayer, HyraxBaselineCLS.py:26-33: linear1 128 -> 512, ReLU, linear2 512 -> 128,
+// residual add) on the same kernel: out = x + linear2(relu(linear1(x) + b1)) + b2; `ones` = a vector of C ones (the layer-scale slot).
+extern "C" int acb_ffn_relu_bf16(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* ones, void* out,
+                                 long long M, int C, const int* rows_dev, void* stream) {
+  ACB_CHECK(x && w1 && b1 && w2 && b2 && ones && out && M > 0, "acb_ffn_relu_bf16: bad arguments");
+  ACB_CHECK((((uintptr_t)x | (uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)out) & 15) == 0, "acb_ffn_relu_bf16: 16-byte alignment");
+  ACB_CHECK(C == 128, "acb_ffn_relu_bf16: d_model = %d is not supported (128 with a 4x feed-forward width is)", C);
+  MlpArgs args{M, rows_dev, b1, b2, ones, (const bf16*)x, (bf16*)out};
+  return launch_mlp<128, 128, ACB_ACT_RELU>(x, w1, w2, args, (cudaStream_t)stream);
 }

@@ -245,6 +245,22 @@ def convnext_mlp(y, res, w1, b1, w2, b2, gamma):
     return out
 
 
+FUSE_FFN = True  # transformer feed-forward block (linear1 + ReLU + linear2 + residual) in one tcgen05 kernel, hidden on chip
+
+_ones_cache = {}
+
+
+def ffn_relu(x, w1, b1, w2, b2, rows_dev=None):
+    """out = x + linear2(relu(linear1(x) + b1)) + b2 for bf16 tokens x [T, 128], w1 [512, 128], w2 [128, 512] (acb_ffn_relu_bf16)."""
+    T, C = x.shape
+    ones = _ones_cache.get((x.device, C))
+    if ones is None:
+        ones = _ones_cache[(x.device, C)] = torch.ones(C, dtype=torch.float32, device=x.device)
+    out = torch.empty_like(x)
+    call("acb_ffn_relu_bf16", x, w1, b1, w2, b2, ones, out, T, C, rows_dev)
+    return out
+
+
 def dwconv7_ln(x, B, H, W, C, w, b, ln_w, ln_b, eps):
     y = torch.empty_like(x)
     call("acb_dwconv7_ln", x, dtype_tag(x), w, b, ln_w, ln_b, eps, y, B, H, W, C)

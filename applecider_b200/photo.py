@@ -74,8 +74,12 @@ class _PhotoEncoderBase(nn.Module):
             att = ops.attention_varlen(qkv, cu, B, self.n_heads, D // self.n_heads, L + 1, plan=plan)
             o = ops.gemm(att, self._w(sa.out_proj.weight, dtype), sa.out_proj.bias, res=h, res_mode=ops.RES_ADD, m_valid=mv)
             h1 = ops.layernorm(o, lyr.norm1.weight, lyr.norm1.bias, lyr.norm1.eps, rows_dev=nv)
-            f = ops.gemm(h1, self._w(lyr.linear1.weight, dtype), lyr.linear1.bias, act=ops.ACT_RELU, m_valid=mv)
-            g = ops.gemm(f, self._w(lyr.linear2.weight, dtype), lyr.linear2.bias, res=h1, res_mode=ops.RES_ADD, m_valid=mv)
+            if ops.FUSE_FFN and dtype == torch.bfloat16 and D == 128 and lyr.linear1.out_features == 4 * D and T >= 128:
+                # linear1 + ReLU + linear2 + residual in one kernel: the [T, 512] hidden activation never reaches HBM
+                g = ops.ffn_relu(h1, self._w(lyr.linear1.weight, dtype), lyr.linear1.bias, self._w(lyr.linear2.weight, dtype), lyr.linear2.bias, nv)
+            else:
+                f = ops.gemm(h1, self._w(lyr.linear1.weight, dtype), lyr.linear1.bias, act=ops.ACT_RELU, m_valid=mv)
+                g = ops.gemm(f, self._w(lyr.linear2.weight, dtype), lyr.linear2.bias, res=h1, res_mode=ops.RES_ADD, m_valid=mv)
             h = ops.layernorm(g, lyr.norm2.weight, lyr.norm2.bias, lyr.norm2.eps, rows_dev=nv)
         return h, cu
 

@@ -195,6 +195,11 @@ int acb_gather_cls(const void* x, int dtype, const int* cu_seqlens, int B, int D
  * other widths return ACB_ERR_UNSUPPORTED and the caller keeps the two-GEMM path. */
 int acb_convnext_mlp_bf16(const void* y, const void* res, const void* w1, const float* b1, const void* w2, const float* b2,
                           const float* gamma, void* out, long long M, int C, void* stream);
+/* The same kernel as the transformer feed-forward block of nn.TransformerEncoderLayer (HyraxBaselineCLS.py:26-33):
+ * out = x + linear2(relu(linear1(x) + b1)) + b2, d_model C = 128, width 4C; `ones` = C ones; rows_dev (optional) = device row
+ * count of a capacity-sized token matrix (128-row tiles past it exit). */
+int acb_ffn_relu_bf16(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* ones, void* out,
+                      long long M, int C, const int* rows_dev, void* stream);
 /* NCHW f32 image -> patch matrix [B*Ho*Wo, Cin*p*p] (k = ci*p*p + ky*p + kx), Ho = H/p (floor). */
 int acb_patchify_nchw(const float* img, int B, int Cin, int H, int W, int p, void* out, int out_dtype, void* stream);
 /* depthwise 7x7 (pad 3) + LayerNorm over C (eps) : x,y = [B,H,W,C]; w = (C,1,7,7), b = (C). */

@@ -431,3 +431,25 @@ def test_convnext_mlp_fused(C, M):
     assert_close(got, ref, 1.5e-2, f"fused ConvNeXt MLP C={C} M={M}")
     two = ops.gemm(ops.gemm(y, w1, b1, act=ops.ACT_GELU), w2, b2, res=res, gamma=gamma, res_mode=ops.RES_ADD)
     assert_close(got, two.float(), 1.5e-2, "fused vs two-GEMM path")
+
+
+@pytest.mark.parametrize("T,valid", [(1000, None), (128 * 9 + 17, 700)])
+def test_ffn_relu_fused(T, valid):
+    """acb_ffn_relu_bf16 (transformer feed-forward block in one kernel) vs the two-GEMM path; with a device row count the tiles
+    past it are skipped (their rows stay untouched)."""
+    from applecider_b200 import ops
+
+    torch.manual_seed(T)
+    C = 128
+    x = torch.randn(T, C, device=DEV).to(torch.bfloat16)
+    w1 = (torch.randn(4 * C, C, device=DEV) * C ** -0.5).to(torch.bfloat16)
+    w2 = (torch.randn(C, 4 * C, device=DEV) * (4 * C) ** -0.5).to(torch.bfloat16)
+    b1, b2 = torch.randn(4 * C, device=DEV) * 0.3, torch.randn(C, device=DEV) * 0.3
+    nv = torch.tensor([valid], dtype=torch.int32, device=DEV) if valid is not None else None
+    got = ops.ffn_relu(x, w1, b1, w2, b2, nv.data_ptr() if nv is not None else None)
+    hid = torch.relu(x.float() @ w1.float().t() + b1).to(torch.bfloat16).float()
+    ref = x.float() + hid @ w2.float().t() + b2
+    n = T if valid is None else valid
+    assert_close(got[:n], ref[:n], 1.5e-2, "fused transformer FFN")
+    two = ops.gemm(ops.gemm(x, w1, b1, act=ops.ACT_RELU), w2, b2, res=x, res_mode=ops.RES_ADD)
+    assert_close(got[:n], two[:n].float(), 1.5e-2, "fused vs two-GEMM path")
