@@ -148,9 +148,14 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const bf16* __
         for (int c0 = 0; c0 < nn; c0 += 32) {
           uint32_t raw[32];
           tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, raw);
+          if (kc + c0 + 32 <= n && c0 + 32 <= nn) {  // interior chunk (every key real): no per-element predicates
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kc + c0 + i < n && c0 + i < nn) mx = fmaxf(mx, __uint_as_float(raw[i]));
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kc + c0 + i < n && c0 + i < nn) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          }
         }
       }
       // ---- pass 2: P = exp(S - max) in 64-key blocks -> smem -> O += P V ----
@@ -185,19 +190,39 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const bf16* __
             uint32_t raw[32];
             tmem_ld32(tmem_s + lane_addr + (uint32_t)(kl + c0), raw);
             uint32_t pk[16];
+            const bool interior = k0 + c0 + 32 <= n && kl + c0 + 32 <= nn;  // warp-uniform: every key of the chunk is real
+            constexpr float LOG2E = 1.4426950408889634f;
+            const float mx2 = mx * LOG2E;
+            if (interior) {  // no per-element range predicates (all chunks of a long sequence but its last one)
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const int j0 = k0 + c0 + i;
-              const bool in0 = j0 < n && kl + c0 + i < nn, in1 = j0 + 1 < n && kl + c0 + i + 1 < nn;  // inside the sequence AND this chunk
-              float p0 = in0 ? __expf(__uint_as_float(raw[i]) - mx) : 0.0f;
-              float p1 = in1 ? __expf(__uint_as_float(raw[i + 1]) - mx) : 0.0f;
-              lsum += p0 + p1;
-              if (drop_p > 0.0f) {
-                p0 = attn_hash_tc(seed, bh, qi, j0) >= drop_thr ? p0 * drop_inv : 0.0f;
-                p1 = attn_hash_tc(seed, bh, qi, j0 + 1) >= drop_thr ? p1 * drop_inv : 0.0f;
+              for (int i = 0; i < 32; i += 2) {
+                const int j0 = k0 + c0 + i;
+                float p0, p1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(raw[i]), LOG2E, -mx2)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(raw[i + 1]), LOG2E, -mx2)));
+                lsum += p0 + p1;
+                if (drop_p > 0.0f) {
+                  p0 = attn_hash_tc(seed, bh, qi, j0) >= drop_thr ? p0 * drop_inv : 0.0f;
+                  p1 = attn_hash_tc(seed, bh, qi, j0 + 1) >= drop_thr ? p1 * drop_inv : 0.0f;
+                }
+                __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+                pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
               }
-              __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
-              pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const int j0 = k0 + c0 + i;
+                const bool in0 = j0 < n && kl + c0 + i < nn, in1 = j0 + 1 < n && kl + c0 + i + 1 < nn;  // inside the sequence AND this chunk
+                float p0 = in0 ? __expf(__uint_as_float(raw[i]) - mx) : 0.0f;
+                float p1 = in1 ? __expf(__uint_as_float(raw[i + 1]) - mx) : 0.0f;
+                lsum += p0 + p1;
+                if (drop_p > 0.0f) {
+                  p0 = attn_hash_tc(seed, bh, qi, j0) >= drop_thr ? p0 * drop_inv : 0.0f;
+                  p1 = attn_hash_tc(seed, bh, qi, j0 + 1) >= drop_thr ? p1 * drop_inv : 0.0f;
+                }
+                __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+                pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+              }
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c)  // 8 keys per 16-byte chunk: chunk (c0/8 + c), row tid
