@@ -245,6 +245,10 @@ __global__ void __launch_bounds__(AP_THREADS, 2) attention_packed_kernel(const _
   const unsigned len = (unsigned)(hi - lo);
   const int wlo = __reduce_min_sync(0xffffffffu, row < nrows ? lo : 1 << 30);
   const int whi = __reduce_max_sync(0xffffffffu, row < nrows ? hi : 0);
+  // keys that are inside the range of EVERY lane of the warp (empty when the warp straddles sequences or has idle rows):
+  // chunks inside need no per-element range predicates
+  const int ilo = __reduce_max_sync(0xffffffffu, lo);
+  const int ihi = __reduce_min_sync(0xffffffffu, hi);
   const float drop_inv = 1.0f / (1.0f - drop_p);
   const unsigned drop_thr = (unsigned)(drop_p * 4294967296.0);
   const int kbeg = wg * 64, kend = min(npad, kbeg + 64);  // this warpgroup's key columns
@@ -276,9 +280,14 @@ __global__ void __launch_bounds__(AP_THREADS, 2) attention_packed_kernel(const _
       uint32_t raw[32];
       tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, raw);
       const unsigned off = (unsigned)(c0 - lo);
+      if (c0 >= ilo && c0 + 32 <= ihi) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (off + (unsigned)i < len) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (off + (unsigned)i < len) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      }
     }
     s_red[wg][row] = mx;
     __syncthreads();
@@ -293,13 +302,16 @@ __global__ void __launch_bounds__(AP_THREADS, 2) attention_packed_kernel(const _
         uint32_t raw[32];
         tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, raw);
         const unsigned off = (unsigned)(c0 - lo);
+        const bool interior = c0 >= ilo && c0 + 32 <= ihi;  // warp-uniform
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float p0, p1;
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(raw[i]), SC, -mxs)));
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(raw[i + 1]), SC, -mxs)));
-          p0 = off + (unsigned)i < len ? p0 : 0.0f;
-          p1 = off + (unsigned)(i + 1) < len ? p1 : 0.0f;
+          if (!interior) {
+            p0 = off + (unsigned)i < len ? p0 : 0.0f;
+            p1 = off + (unsigned)(i + 1) < len ? p1 : 0.0f;
+          }
           lsum += p0 + p1;
           if (drop_p > 0.0f) {
             p0 = ap_hash(seed, bh, qi, (int)off + i) >= drop_thr ? p0 * drop_inv : 0.0f;
