@@ -534,6 +534,201 @@ __global__ void __launch_bounds__(256) cutout_median_kernel(const float* __restr
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = pl[i] / denom;
 }
 
+// Register-resident variant for planes of <= 16 x 256 pixels (the 63 x 63 ZTF cutout and every crop of it): each thread keeps its
+// 16 order-preserving keys in registers, so a radix pass is 4 instructions per pixel with no shared-memory reads, the statistics
+// are ONE fp64 pass (sum and sum of squares of the median-centred pixels) and the only shared memory is the 256-bin histogram.
+// Pixels past n carry the key 0xffffffff, which sorts after every real value and therefore never changes a rank below n.
+constexpr int CUT_EPT = 16;
+
+// hist: 4 x 256 counters (one set per radix pass) and sh_k[3], all ZERO on entry (the caller zeroes them before a barrier): a pass
+// then costs two barriers -- histogram complete / owner bin published -- and warp 0 alone scans the 256 bins (8 per lane).
+__device__ __forceinline__ unsigned cutout_select_reg(const unsigned (&key)[CUT_EPT], int k, unsigned* hist, unsigned* sh_k, unsigned* cand) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  unsigned prefix = 0, pmask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8, hist += 256) {
+    if (shift == 24) {
+      // sign + leading exponent bits: a sky-dominated plane puts nearly every pixel into ONE bin -- a warp whose 512 digits are
+      // all equal adds them with one atomic
+      const unsigned d0 = __shfl_sync(0xffffffffu, key[0] >> 24, 0);
+      bool same = true;
+#pragma unroll
+      for (int e = 0; e < CUT_EPT; ++e) same &= (key[e] >> 24) == d0;
+      if (__all_sync(0xffffffffu, same)) {
+        if (lane == 0) atomicAdd(&hist[d0], 32u * CUT_EPT);
+      } else {
+#pragma unroll
+        for (int e = 0; e < CUT_EPT; ++e) atomicAdd(&hist[key[e] >> 24], 1u);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < CUT_EPT; ++e)
+        if ((key[e] & pmask) == prefix) atomicAdd(&hist[(key[e] >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    if (wid == 0) {
+      const uint4 lo = reinterpret_cast<const uint4*>(hist)[2 * lane], hi = reinterpret_cast<const uint4*>(hist)[2 * lane + 1];
+      const unsigned c[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      const unsigned tot = c[0] + c[1] + c[2] + c[3] + c[4] + c[5] + c[6] + c[7];
+      unsigned inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      unsigned kk = (unsigned)k - (inc - tot);  // rank inside this lane's 8 bins (wraps when the rank is in an earlier lane)
+      if (kk < tot) {                           // exactly one lane
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (kk < c[j]) {
+            sh_k[0] = (unsigned)(8 * lane + j);
+            sh_k[1] = kk;
+            sh_k[2] = c[j];
+            kk = 0xffffffffu;
+          } else {
+            kk -= c[j];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= sh_k[0] << shift;
+    pmask |= 0xffu << shift;
+    k = (int)sh_k[1];
+    const unsigned members = sh_k[2];  // (the next pass rewrites sh_k only after its histogram barrier)
+    if (shift > 0 && members <= (unsigned)SEL_CAND) {
+#pragma unroll
+      for (int e = 0; e < CUT_EPT; ++e)
+        if ((key[e] & pmask) == prefix) cand[atomicAdd(&sh_k[3], 1u)] = key[e];
+      __syncthreads();
+      if (tid < (int)members) {
+        const unsigned c = cand[tid];
+        int rank = 0;
+        for (int j = 0; j < (int)members; ++j) {
+          const unsigned o = cand[j];
+          rank += (o < c) || (o == c && j < tid);
+        }
+        if (rank == k) cand[SEL_THREADS] = c;
+      }
+      __syncthreads();
+      return cand[SEL_THREADS];
+    }
+  }
+  return prefix;
+}
+
+// Persistent CTAs (5 per SM): while a plane is being processed its successor is already in flight -- each thread copies ITS 16 pixels
+// of the next plane into a 16 KB staging buffer with 4-byte cp.async (the plane start is only 4-byte aligned) as soon as it has
+// moved the current ones into registers, so no barrier is involved and the DRAM latency hides behind a whole plane of work.
+__device__ __forceinline__ void cutout_cp_async4(const float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 5) cutout_median_reg_kernel(const float* __restrict__ img, int planes, int H, int W, int i1, int S,
+                                                                int mode, float* __restrict__ out) {
+  __shared__ __align__(16) unsigned hist[4 * 256];
+  __shared__ unsigned shk[8];
+  __shared__ unsigned cand[SEL_THREADS + 1];
+  __shared__ double red[2][9];
+  __shared__ float stage[CUT_EPT * 256];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = S * S;
+  const double inv_n = 1.0 / (double)n, inv_nm1 = 1.0 / (double)(n - 1);
+  const bool crop = S != W;
+  auto prefetch = [&](int plane) {
+    const float* src = img + (long long)plane * H * W;
+    if (!crop) {
+#pragma unroll
+      for (int e = 0; e < CUT_EPT; ++e)
+        if (tid + e * 256 < n) cutout_cp_async4(&stage[tid + e * 256], src + tid + e * 256);
+    } else {
+      // pixel tid + 256 e of the cropped plane: (row, column) advance by (256 / S, 256 % S) per step -- no division per pixel
+      const int qs = 256 / S, rs = 256 - qs * S;
+      int yy = tid / S, xx = tid - yy * S;
+#pragma unroll
+      for (int e = 0; e < CUT_EPT; ++e) {
+        if (tid + e * 256 < n) cutout_cp_async4(&stage[tid + e * 256], src + (yy + i1) * W + (xx + i1));
+        xx += rs;
+        yy += qs;
+        if (xx >= S) {
+          xx -= S;
+          ++yy;
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int plane = blockIdx.x;
+  if (plane < planes) prefetch(plane);
+  for (; plane < planes; plane += gridDim.x) {
+    // (the barriers of the previous plane's statistics stand between its last readers of hist / shk / cand / red and these writes)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hist[tid + 256 * j] = 0;
+    if (tid < 8) shk[tid] = 0;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    unsigned key[CUT_EPT];
+#pragma unroll
+    for (int e = 0; e < CUT_EPT; ++e) key[e] = tid + e * 256 < n ? fkey(stage[tid + e * 256]) : 0xffffffffu;
+    if (plane + (int)gridDim.x < planes) prefetch(plane + (int)gridDim.x);  // a thread refills only the slots it has just read
+    __syncthreads();
+    float med = fkey_inv(cutout_select_reg(key, (n - 1) / 2, hist, shk, cand));
+    if (mode == 2 && (n & 1) == 0) {  // np.median of an even count: mean of the two middle values
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hist[tid + 256 * j] = 0;
+      if (tid < 8) shk[tid] = 0;
+      __syncthreads();
+      med = 0.5f * (med + fkey_inv(cutout_select_reg(key, n / 2, hist, shk, cand)));
+    }
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int e = 0; e < CUT_EPT; ++e) {
+      if (tid + e * 256 < n) {
+        const double d = (double)(fkey_inv(key[e]) - med);
+        s += d;
+        q = fma(d, d, q);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+      red[0][wid] = s;
+      red[1][wid] = q;
+    }
+    __syncthreads();
+    s = 0.0, q = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {  // every thread adds the 8 warp partials in the same order
+      s += red[0][w];
+      q += red[1][w];
+    }
+    // sum of squares about the mean; the pixels are already centred on the median, so the subtraction loses nothing in fp64
+    const double ss = fmax(q - s * s * inv_n, 0.0);
+    float denom;
+    if (mode == 0) {
+      denom = (float)sqrt(ss * inv_nm1) + 1e-8f;
+    } else {
+      const double sd = sqrt(ss * inv_n);
+      denom = (isfinite(sd) && sd > 1e-8) ? (float)sd : 1.0f;
+    }
+    // p / denom, correctly rounded without the 20-instruction division sequence: with r = RN(1 / denom), q0 = RN(p r) and the
+    // exact remainder p - q0 denom (one fma), RN(q0 + rem r) is the correctly rounded quotient (Markstein); denom >= 1e-8 is normal
+    const float r = __frcp_rn(denom);
+    float* dst = out + (long long)plane * n;
+#pragma unroll
+    for (int e = 0; e < CUT_EPT; ++e) {
+      const int i = tid + e * 256;
+      if (i < n) {
+        const float pe = fkey_inv(key[e]) - med;
+        const float q0 = pe * r;
+        dst[i] = fmaf(fmaf(-q0, denom, pe), r, q0);
+      }
+    }
+  }
+}
+
 // mode 1: x / ||x||_2 over all channels of the (cropped) cutout.  CTA per image.
 __global__ void __launch_bounds__(256) cutout_l2_kernel(const float* __restrict__ img, int C, int H, int W, int i1, int S,
                                                         float* __restrict__ out) {
@@ -671,6 +866,13 @@ int acb_prep_cutout_norm(const float* img, int B, int C, int H, int W, int cutou
   if (mode == 1) {
     cutout_l2_kernel<<<B, 256, 0, st>>>(img, C, H, W, i1, S, out);
   } else {
+    if (S * S <= CUT_EPT * 256) {
+      const int planes = B * C;
+      cutout_median_reg_kernel<<<planes < 148 * 5 ? planes : 148 * 5, 256, 0, st>>>(img, planes, H, W, i1, S, mode, out);
+      ACB_LAUNCH_CHECK();
+      acb_count_launch();
+      return ACB_OK;
+    }
     const size_t smem = (size_t)((S * S + 3) & ~3) * 4 + 34 * 8 + (256 + 8 + 258) * 4;
     auto k = cutout_median_kernel;
     if (smem > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

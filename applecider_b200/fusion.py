@@ -4,6 +4,8 @@ from __future__ import annotations
 
 import copy
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -51,7 +53,7 @@ class AppleCider(nn.Module):
 
     # inference: the three encoders are independent and can run on three streams (measured +1.8 % throughput at B=4096, but the
     # co-running small kernels slow the tensor-bound spectra convs by ~5 %, which muddies per-kernel timing) -> opt-in
-    CONCURRENT_ENCODERS = False
+    CONCURRENT_ENCODERS = int(os.environ.get("ACB_CONCURRENT_ENCODERS", "0"))  # 1 = side streams, 2 = high-priority side streams
 
     def _encode(self, photometry, photometry_mask, metadata, images, spectra, total_tokens=None):
         if self.CONCURRENT_ENCODERS and not torch.is_grad_enabled() and spectra.is_cuda and self.spectra_variant == "src":
@@ -72,7 +74,8 @@ class AppleCider(nn.Module):
         main = torch.cuda.current_stream(dev)
         side = getattr(self, "_side_streams", None)
         if side is None:
-            side = self._side_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            pr = -1 if int(self.CONCURRENT_ENCODERS) >= 2 else 0
+            side = self._side_streams = (torch.cuda.Stream(dev, priority=pr), torch.cuda.Stream(dev, priority=pr))
         start = torch.cuda.Event()
         start.record(main)
         outs = [None, None]

@@ -155,6 +155,17 @@ def test_p4_cutouts(g):
     _ulp_close(nb, ref, 2, "notebook median/std")
     # even crop geometry follows the reference's int((63-cs)/2) rule: 32 -> 33x33
     assert pp.normalize_cutouts(img, "L2", 32).shape == (4, 3, 33, 33)
+    # other plane sizes: 64x64 (even pixel count: the notebook median averages the two middle values; exactly fills the
+    # register-resident kernel) and 80x80 (the shared-memory kernel), constant planes, planes with ties
+    rng = np.random.default_rng(5)
+    for hw in (64, 80, 9):
+        big = (rng.standard_normal((3, 3, hw, hw)) * 20 + 300).astype(np.float32)
+        big[1, 0] = np.round(big[1, 0] / 8) * 8     # many ties
+        big[2, 1] = 7.0                             # constant plane: std 0
+        for name, variant in (("median", "dataset"), ("median_notebook", "notebook")):
+            got = pp.normalize_cutouts(torch.from_numpy(big).to(DEV), name).cpu().numpy()
+            want = np.stack([op.normalize_cutout(i, "median", hw, variant=variant) for i in big])
+            _ulp_close(got, want, 2, f"{name} {hw}x{hw}")
 
 
 def test_p5_feature_stats(g):
