@@ -679,11 +679,14 @@ __global__ void __launch_bounds__(256, 5) cutout_median_reg_kernel(const float* 
       __syncthreads();
       med = 0.5f * (med + fkey_inv(cutout_select_reg(key, n / 2, hist, shk, cand)));
     }
+    // n > 15 x 256 (the 63 x 63 plane and its neighbours): only a thread's LAST pixel can lie past the plane
+    const bool full = n > (CUT_EPT - 1) * 256;
     double s = 0.0, q = 0.0;
 #pragma unroll
     for (int e = 0; e < CUT_EPT; ++e) {
-      if (tid + e * 256 < n) {
-        const double d = (double)(fkey_inv(key[e]) - med);
+      key[e] = __float_as_uint(fkey_inv(key[e]) - med);  // the registers now hold the median-centred pixels
+      if ((full && e < CUT_EPT - 1) || tid + e * 256 < n) {
+        const double d = (double)__uint_as_float(key[e]);
         s += d;
         q = fma(d, d, q);
       }
@@ -720,8 +723,8 @@ __global__ void __launch_bounds__(256, 5) cutout_median_reg_kernel(const float* 
 #pragma unroll
     for (int e = 0; e < CUT_EPT; ++e) {
       const int i = tid + e * 256;
-      if (i < n) {
-        const float pe = fkey_inv(key[e]) - med;
+      if ((full && e < CUT_EPT - 1) || i < n) {
+        const float pe = __uint_as_float(key[e]);
         const float q0 = pe * r;
         dst[i] = fmaf(fmaf(-q0, denom, pe), r, q0);
       }
