@@ -1,6 +1,8 @@
 // Backward / training kernels: generic strided fp32 GEMM with split-K (dgrad / wgrad / conv wgrad),
 // column reductions, activation / LayerNorm / attention / depthwise-conv / pooling backward, embedding and
 // MoE backward, losses, dropout.  Elementwise kernels are dtype-tagged (f32 | bf16 IO, fp32 math).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -154,6 +156,29 @@ __global__ void ew_kernel(const void* a, int a_dt, const void* b, int b_dt, cons
       default: r = av * s0 + bv * s1;
     }
     st_any(y, i, y_dt, r);
+  }
+}
+
+// a, b, y bf16, n % 8 == 0, ops 0 / 1 / 4: 16 bytes per thread and step
+__global__ void __launch_bounds__(256) ew_bf16x8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y, int op,
+                                                        float s0, float s1, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    uint4 av = a[i];
+    const uint4 bv = b[i];
+    uint32_t* aw = reinterpret_cast<uint32_t*>(&av);
+    const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[j]));
+      const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
+      float2 r;
+      if (op == 0) r = make_float2(fa.x + fb.x, fa.y + fb.y);
+      else if (op == 1) r = make_float2(fa.x * fb.x, fa.y * fb.y);
+      else r = make_float2(fa.x * s0 + fb.x * s1, fa.y * s0 + fb.y * s1);
+      const __nv_bfloat162 o = __floats2bfloat162_rn(r.x, r.y);
+      aw[j] = *reinterpret_cast<const uint32_t*>(&o);
+    }
+    y[i] = av;
   }
 }
 
@@ -372,6 +397,133 @@ __global__ void __launch_bounds__(256) layernorm_bwd_reg_kernel(const T* __restr
   }
 }
 
+// Wide rows (C = NPT x 512 >= 1024: the last SpectraNet blocks): a CTA walks rows_per_cta rows, thread t owns the column pairs
+// (k 256 + t) of every row, so x / dy / dx move as coalesced 4-byte accesses, the d(weight) / d(bias) partial sums live in registers
+// for the whole walk and the next row is in flight while the current one is reduced (three block reductions per row).
+template <int NPT>
+__global__ void __launch_bounds__(256) layernorm_bwd_wide_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                                 const float* __restrict__ w, const float* __restrict__ bias, int gelu,
+                                                                 bf16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
+                                                                 long long rows, float eps, int rows_per_cta) {
+  constexpr int C = NPT * 512, NE = NPT * 2;
+  __shared__ float red[2][2][8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int phase = 0;
+  auto block_sum2 = [&](float& a, float& b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      red[phase][0][wid] = a;
+      red[phase][1][wid] = b;
+    }
+    __syncthreads();
+    a = 0.0f, b = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a += red[phase][0][i];
+      b += red[phase][1][i];
+    }
+    phase ^= 1;  // the buffer written two reductions ago is free again: every thread has passed the barrier in between
+  };
+  float wv[NE], bv[NE], aw[NE], ab[NE];
+#pragma unroll
+  for (int k = 0; k < NPT; ++k)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = (k * 256 + tid) * 2 + e;
+      wv[k * 2 + e] = w[c];
+      bv[k * 2 + e] = gelu ? bias[c] : 0.0f;
+      aw[k * 2 + e] = 0.0f;
+      ab[k * 2 + e] = 0.0f;
+    }
+  const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(rows, row0 + rows_per_cta);
+  uint32_t px[NPT], pg[NPT];
+  if (row0 < row1) {
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+      px[k] = __ldcs(reinterpret_cast<const uint32_t*>(x + row0 * C) + k * 256 + tid);
+      pg[k] = __ldcs(reinterpret_cast<const uint32_t*>(dy + row0 * C) + k * 256 + tid);
+    }
+  }
+  for (long long row = row0; row < row1; ++row) {
+    float xv[NE], gv[NE];
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&px[k]));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pg[k]));
+      xv[k * 2] = a.x; xv[k * 2 + 1] = a.y; gv[k * 2] = b.x; gv[k * 2 + 1] = b.y;
+    }
+    if (row + 1 < row1) {
+#pragma unroll
+      for (int k = 0; k < NPT; ++k) {
+        px[k] = __ldcs(reinterpret_cast<const uint32_t*>(x + (row + 1) * C) + k * 256 + tid);
+        pg[k] = __ldcs(reinterpret_cast<const uint32_t*>(dy + (row + 1) * C) + k * 256 + tid);
+      }
+    }
+    float s = 0.0f, dummy = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) s += xv[i];
+    block_sum2(s, dummy);
+    const float mean = s / (float)C;
+    float q = 0.0f;
+    dummy = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) { xv[i] -= mean; q += xv[i] * xv[i]; }
+    block_sum2(q, dummy);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    float sg = 0.0f, sgx = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      xv[i] *= rstd;  // xhat
+      if (gelu) gv[i] *= gelu_bf16_grad(fmaf(xv[i], wv[i], bv[i]));
+      const float g = gv[i] * wv[i];
+      sg += g;
+      sgx += g * xv[i];
+      aw[i] = fmaf(gv[i], xv[i], aw[i]);
+      ab[i] += gv[i];
+    }
+    block_sum2(sg, sgx);
+    sg /= (float)C;
+    sgx /= (float)C;
+    uint32_t* dr = reinterpret_cast<uint32_t*>(dx + row * C);
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+      const float o0 = rstd * (gv[k * 2] * wv[k * 2] - sg - xv[k * 2] * sgx);
+      const float o1 = rstd * (gv[k * 2 + 1] * wv[k * 2 + 1] - sg - xv[k * 2 + 1] * sgx);
+      const __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+      dr[k * 256 + tid] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NPT; ++k)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = (k * 256 + tid) * 2 + e;
+      atomicAdd(dw + c, aw[k * 2 + e]);
+      atomicAdd(db + c, ab[k * 2 + e]);
+    }
+}
+
+static bool launch_ln_bwd_wide(const void* x, const void* dy, const float* w, const float* bias, int gelu, void* dx, float* dw, float* db,
+                               long long rows, int C, float eps, cudaStream_t st) {
+  const int rpc = (int)std::max<long long>(1, std::min<long long>(64, rows / (148 * 8 * 2)));
+  const unsigned grid = (unsigned)((rows + rpc - 1) / rpc);
+#define LNW(NPT)                                                                                                                  \
+  layernorm_bwd_wide_kernel<NPT><<<grid, 256, 0, st>>>((const bf16*)x, (const bf16*)dy, w, bias, gelu, (bf16*)dx, dw, db, rows, eps, rpc); \
+  return true
+  switch (C) {
+    case 1024: LNW(2);
+    case 1536: LNW(3);
+    case 2048: LNW(4);
+    case 3072: LNW(6);
+    default: return false;
+  }
+#undef LNW
+}
+
 template <typename T>
 static bool launch_ln_bwd_reg(const void* x, const void* dy, const float* w, const float* bias, int gelu, void* dx, float* dw, float* db,
                               long long rows, int C, float eps, cudaStream_t st) {
@@ -406,7 +558,7 @@ __device__ __forceinline__ unsigned attn_hash(unsigned long long seed, int bh, i
 }
 
 template <int DH>
-__global__ void __launch_bounds__(128) attention_bwd_kernel(const void* qkv, int dt, const void* dout, int do_dt, const int* cu,
+__global__ void __launch_bounds__(512) attention_bwd_kernel(const void* qkv, int dt, const void* dout, int do_dt, const int* cu,
                                                             int n_heads, float drop_p, AcbSeed seed_s, void* dqkv, int dq_dt,
                                                             const int* __restrict__ seq_list, const int* __restrict__ n_list) {
   if (seq_list && (int)blockIdx.x >= *n_list) return;  // list mode (long sequences of the packed plan): grid = host-side upper bound
@@ -763,6 +915,46 @@ __global__ void maxpool_bwd_kernel(const void* x, int x_dt, const void* dy, int 
   }
 }
 
+// bf16, window 4, C % 8 == 0: a thread owns 8 channels of one window -- four 16-byte loads of x, one of dy, four 16-byte stores
+__global__ void __launch_bounds__(256) maxpool4_bwd_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx,
+                                                                  long long B, int L, int C8) {
+  const int Lo = L / 4;
+  const long long tot = B * Lo * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    const long long t = i / C8;
+    const int lo = (int)(t % Lo);
+    const long long b = t / Lo;
+    const long long base = (b * L + (long long)lo * 4) * C8 + c;
+    uint4 xv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xv[k] = __ldcs(x + base + (long long)k * C8);
+    const uint4 g = __ldcs(dy + i);
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(&g);
+    uint4 o[4];
+    uint32_t* ow[4] = {reinterpret_cast<uint32_t*>(&o[0]), reinterpret_cast<uint32_t*>(&o[1]), reinterpret_cast<uint32_t*>(&o[2]),
+                       reinterpret_cast<uint32_t*>(&o[3])};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // two channels per 32-bit word
+      float m0 = -INFINITY, m1 = -INFINITY;
+      int a0 = 0, a1 = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const uint32_t*>(&xv[k]) + j));
+        if (v.x > m0) { m0 = v.x; a0 = k; }
+        if (v.y > m1) { m1 = v.y; a1 = k; }
+      }
+      const uint32_t glo = gw[j] & 0xffffu, ghi = gw[j] & 0xffff0000u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ow[k][j] = (a0 == k ? glo : 0u) | (a1 == k ? ghi : 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dx[base + (long long)k * C8] = o[k];
+    if (lo == Lo - 1)
+      for (int l = Lo * 4; l < L; ++l) dx[(b * L + l) * C8 + c] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // ================================ MoE / L2 norm / losses / dropout ==================================
 __global__ void moe_combine_bwd_kernel(const float* gate, const float* eo, const float* dout, float* dgate, float* deo, int B, int E, int C) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -847,13 +1039,38 @@ __device__ __forceinline__ unsigned hash32(unsigned long long v) {
   return (unsigned)v;
 }
 // y = keep ? x / (1-p) : 0, keep decided by a counter-based hash of (seed, index); the same call with dy gives dx
+// (one 64-bit hash decides the element pair (2j, 2j+1): low word / high word -- the scalar and the vector kernel draw the SAME mask,
+// so a forward through one and a backward through the other stay consistent)
+__device__ __forceinline__ unsigned long long hash64(unsigned long long v) {
+  v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
+  return v;
+}
 __global__ void dropout_kernel(const void* x, int x_dt, void* y, int y_dt, float p, AcbSeed seed_s, long long n) {
-  const unsigned long long seed = seed_s.get();
+  const unsigned long long seed = seed_s.get() * 0x9E3779B97F4A7C15ULL;
   const float inv = 1.0f / (1.0f - p);
   const unsigned thr = (unsigned)(p * 4294967296.0);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const bool keep = hash32(seed * 0x9E3779B97F4A7C15ULL + (unsigned long long)i) >= thr;
+    const unsigned long long h = hash64(seed + (unsigned long long)(i >> 1));
+    const bool keep = (unsigned)((i & 1) ? (h >> 32) : h) >= thr;
     st_any(y, i, y_dt, keep ? ld_any(x, i, x_dt) * inv : 0.0f);
+  }
+}
+// bf16 in and out, n % 8 == 0: 16 bytes per thread and step
+__global__ void __launch_bounds__(256) dropout_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, float p, AcbSeed seed_s, long long n8) {
+  const unsigned long long seed = seed_s.get() * 0x9E3779B97F4A7C15ULL;
+  const float inv = 1.0f / (1.0f - p);
+  const unsigned thr = (unsigned)(p * 4294967296.0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    uint4 v = __ldcs(x + i);
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned long long h = hash64(seed + (unsigned long long)(i * 4 + j));
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+      const __nv_bfloat162 o = __floats2bfloat162_rn((unsigned)h >= thr ? f.x * inv : 0.0f, (unsigned)(h >> 32) >= thr ? f.y * inv : 0.0f);
+      w[j] = *reinterpret_cast<const uint32_t*>(&o);
+    }
+    y[i] = v;
   }
 }
 
@@ -924,6 +1141,11 @@ int acb_ew(const void* a, int a_dtype, const void* b, int b_dtype, const float* 
            long long n, void* stream) {
   ACB_CHECK(a && y && n >= 0 && C > 0, "acb_ew: bad arguments");
   if (n == 0) return ACB_OK;
+  if (b && (op == 0 || op == 1 || op == 4) && a_dtype == ACB_BF16 && b_dtype == ACB_BF16 && y_dtype == ACB_BF16 && n % 8 == 0 &&
+      (((uintptr_t)a | (uintptr_t)b | (uintptr_t)y) & 15) == 0) {
+    ew_bf16x8_kernel<<<grid_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)y, op, s0, s1, n / 8);
+    LAUNCHED(1);
+  }
   ew_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(a, a_dtype, b, b_dtype, g, y, y_dtype, op, C, s0, s1, n);
   LAUNCHED(1);
 }
@@ -964,6 +1186,7 @@ int acb_layernorm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, 
     const bool done = x_dtype == ACB_F32 ? launch_ln_bwd_reg<float>(x, dy, w, b, gelu, dx, dw, db, rows, C, eps, (cudaStream_t)stream)
                                          : launch_ln_bwd_reg<bf16>(x, dy, w, b, gelu, dx, dw, db, rows, C, eps, (cudaStream_t)stream);
     if (done) { LAUNCHED(1); }
+    if (x_dtype == ACB_BF16 && rows >= 1024 && launch_ln_bwd_wide(x, dy, w, b, gelu, dx, dw, db, rows, C, eps, (cudaStream_t)stream)) { LAUNCHED(1); }
   }
   const int rpw = rows > (1 << 16) ? 16 : 1;
   const long long warps = (rows + rpw - 1) / rpw;
@@ -994,7 +1217,10 @@ int acb_attention_bwd_long(const void* qkv, const void* dout, const int* cu_seql
   ACB_CHECK(smem <= 200 * 1024, "acb_attention_packed_bwd: max_seqlen %d too long", max_seqlen);
   auto k = attention_bwd_kernel<16>;
   ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  k<<<dim3(grid_x, n_heads), 128, smem, st>>>(qkv, ACB_BF16, dout, ACB_BF16, cu_seqlens, n_heads, drop_p, acb_seed(seed), dqkv, ACB_BF16, long_list, n_long_dev);
+  // every sequence of the list has more than 128 tokens: one thread per token (the 128-thread default would run a second round
+  // with a handful of active threads)
+  const int threads = max_seqlen <= 512 ? ((max_seqlen + 31) / 32) * 32 : 512;
+  k<<<dim3(grid_x, n_heads), threads, smem, st>>>(qkv, ACB_BF16, dout, ACB_BF16, cu_seqlens, n_heads, drop_p, acb_seed(seed), dqkv, ACB_BF16, long_list, n_long_dev);
   LAUNCHED(1);
 }
 
@@ -1069,6 +1295,11 @@ int acb_maxpool_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, vo
                     void* stream) {
   ACB_CHECK(x && dy && dx && B > 0 && L > 0 && C > 0 && (window == 0 || window == 4), "acb_maxpool_bwd: bad arguments");
   const int Lo = window ? L / window : 1;
+  if (window == 4 && Lo > 0 && C % 8 == 0 && x_dtype == ACB_BF16 && dy_dtype == ACB_BF16 && dx_dtype == ACB_BF16 &&
+      (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0) {
+    maxpool4_bwd_bf16x8_kernel<<<grid_for((long long)B * Lo * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)dy, (uint4*)dx, B, L, C / 8);
+    LAUNCHED(1);
+  }
   maxpool_bwd_kernel<<<grid_for((long long)B * Lo * C), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, dy, dy_dtype, dx, dx_dtype, B, L, C, window);
   LAUNCHED(1);
 }
@@ -1099,6 +1330,10 @@ int acb_loss_fwd_bwd(const float* logits, const long long* labels, const float* 
 int acb_dropout(const void* x, int x_dtype, void* y, int y_dtype, float p, long long seed, long long n, void* stream) {
   ACB_CHECK(x && y && n >= 0 && p >= 0.0f && p < 1.0f, "acb_dropout: bad arguments");
   if (n == 0) return ACB_OK;
+  if (x_dtype == ACB_BF16 && y_dtype == ACB_BF16 && n % 8 == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+    dropout_bf16x8_kernel<<<grid_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, p, acb_seed(seed), n / 8);
+    LAUNCHED(1);
+  }
   dropout_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, y, y_dtype, p, acb_seed(seed), n);
   LAUNCHED(1);
 }

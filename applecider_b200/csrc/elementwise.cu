@@ -204,29 +204,38 @@ __global__ void __launch_bounds__(256) layernorm_cached_kernel(const TX* __restr
 // Streaming variant for the large bf16 activations (SpectraNet LayerNorm+GELU, >= 64 K rows): a warp owns RPW rows
 // and issues the loads of ALL of them before touching the first (RPW x C x 2 bytes in flight per warp -- one row per
 // warp leaves HBM latency-bound at ~2.6 TB/s), affine parameters live in registers across the rows.
-template <int NC, int RPW>
+// LPR = lanes per row: 32 (C = NC x 128), or 16 for C = NC x 64 rows such as the 192 channels of SpectraNet's first block -- a
+// warp then works on two rows side by side and the reductions stay inside a half-warp.
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NC, int RPW, int LPR = 32>
 __global__ void __launch_bounds__(256) layernorm_stream_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ b, bf16* __restrict__ y, long long rows, float eps,
                                                                int post_act, const int* __restrict__ rows_dev) {
-  constexpr int C = NC * 128;
-  const int lane = threadIdx.x & 31;
-  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  constexpr int CW = LPR * 4, C = NC * CW, RS = 32 / LPR;  // chunk width, row length, rows side by side in a warp
+  const int lane = threadIdx.x & (LPR - 1), sub = (threadIdx.x & 31) / LPR;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (RPW * RS) + sub;
   if (rows_dev) rows = min(rows, (long long)__ldg(rows_dev));
-  if (row0 >= rows) return;
+  if (row0 - sub >= rows) return;  // (warp-uniform: the shuffles below need every lane of a live warp)
   uint2 raw[RPW][NC];
 #pragma unroll
   for (int r = 0; r < RPW; ++r) {
-    const long long row = row0 + r < rows ? row0 + r : rows - 1;  // clamp: tail rows recompute the last row, stores are guarded
+    const long long row = row0 + r * RS < rows ? row0 + r * RS : rows - 1;  // clamp: tail rows recompute the last row, stores are guarded
 #pragma unroll
-    for (int k = 0; k < NC; ++k) raw[r][k] = __ldcs(reinterpret_cast<const uint2*>(x + row * C + lane * 4 + k * 128));
+    for (int k = 0; k < NC; ++k) raw[r][k] = __ldcs(reinterpret_cast<const uint2*>(x + row * C + lane * 4 + k * CW));
   }
   constexpr bool WREG = NC <= 6;  // wide rows re-read the affine parameters from L1 instead of pinning 8*NC registers
   float4 wv[WREG ? NC : 1], bv[WREG ? NC : 1];
   if constexpr (WREG) {
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-      wv[k] = *reinterpret_cast<const float4*>(w + lane * 4 + k * 128);
-      bv[k] = *reinterpret_cast<const float4*>(b + lane * 4 + k * 128);
+      wv[k] = *reinterpret_cast<const float4*>(w + lane * 4 + k * CW);
+      bv[k] = *reinterpret_cast<const float4*>(b + lane * 4 + k * CW);
     }
   }
 #pragma unroll
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(256) layernorm_stream_kernel(const bf16* __res
       v[k][0] = __low2float(a); v[k][1] = __high2float(a); v[k][2] = __low2float(c); v[k][3] = __high2float(c);
       s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
     }
-    const float mean = warp_sum(s) / (float)C;  // same arithmetic as layernorm_cached_kernel: results do not depend on the row count
+    const float mean = group_sum<LPR>(s) / (float)C;  // LPR = 32: same arithmetic as layernorm_cached_kernel, results do not depend on the row count
     float q = 0.0f;
 #pragma unroll
     for (int k = 0; k < NC; ++k)
@@ -248,14 +257,14 @@ __global__ void __launch_bounds__(256) layernorm_stream_kernel(const bf16* __res
       for (int i = 0; i < 4; ++i) {
         q += (v[k][i] - mean) * (v[k][i] - mean);
       }
-    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
-    if (row0 + r < rows) {
-      bf16* yr = y + (row0 + r) * C;
+    const float rstd = rsqrtf(group_sum<LPR>(q) / (float)C + eps);
+    if (row0 + r * RS < rows) {
+      bf16* yr = y + (row0 + r * RS) * C;
 #pragma unroll
       for (int k = 0; k < NC; ++k) {
         float o[4];
-        const float4 w4 = WREG ? wv[WREG ? k : 0] : *reinterpret_cast<const float4*>(w + lane * 4 + k * 128);
-        const float4 b4 = WREG ? bv[WREG ? k : 0] : *reinterpret_cast<const float4*>(b + lane * 4 + k * 128);
+        const float4 w4 = WREG ? wv[WREG ? k : 0] : *reinterpret_cast<const float4*>(w + lane * 4 + k * CW);
+        const float4 b4 = WREG ? bv[WREG ? k : 0] : *reinterpret_cast<const float4*>(b + lane * 4 + k * CW);
         o[0] = (v[k][0] - mean) * rstd * w4.x + b4.x;
         o[1] = (v[k][1] - mean) * rstd * w4.y + b4.y;
         o[2] = (v[k][2] - mean) * rstd * w4.z + b4.z;
@@ -271,7 +280,7 @@ __global__ void __launch_bounds__(256) layernorm_stream_kernel(const bf16* __res
         uint2 t;
         t.x = *reinterpret_cast<uint32_t*>(&h0);
         t.y = *reinterpret_cast<uint32_t*>(&h1);
-        *reinterpret_cast<uint2*>(yr + lane * 4 + k * 128) = t;
+        *reinterpret_cast<uint2*>(yr + lane * 4 + k * CW) = t;
       }
     }
   }
@@ -284,10 +293,11 @@ int launch_ln(const void* x, const void* res, const float* w, const float* b, vo
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
   const bool vec = (C % 4 == 0) && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)w | (uintptr_t)b) % 16 == 0);
   if constexpr (sizeof(TX) == 2 && sizeof(TY) == 2) {
-    if (vec && !res && !pre_gelu && rows >= 65536 && (C == 128 || C == 256 || C == 384 || C == 768 || C == 1536 || C == 3072)) {
+    if (vec && !res && !pre_gelu && rows >= 65536 && (C == 128 || C == 192 || C == 256 || C == 384 || C == 768 || C == 1536 || C == 3072)) {
       constexpr int RPW = 4;
       const unsigned g = (unsigned)((rows + (long long)wpb * RPW - 1) / ((long long)wpb * RPW));
-      if (C == 128) layernorm_stream_kernel<1, 8><<<(unsigned)((rows + wpb * 8LL - 1) / (wpb * 8LL)), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act, rows_dev);
+      if (C == 192) layernorm_stream_kernel<3, 4, 16><<<(unsigned)((rows + wpb * 8LL - 1) / (wpb * 8LL)), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act, rows_dev);
+      else if (C == 128) layernorm_stream_kernel<1, 8><<<(unsigned)((rows + wpb * 8LL - 1) / (wpb * 8LL)), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act, rows_dev);
       else if (C == 256) layernorm_stream_kernel<2, RPW><<<g, wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act, rows_dev);
       else if (C == 384) layernorm_stream_kernel<3, RPW><<<g, wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act, rows_dev);
       else if (C == 768) layernorm_stream_kernel<6, 2><<<(unsigned)((rows + wpb * 2LL - 1) / (wpb * 2LL)), wpb * 32, 0, st>>>((const bf16*)x, w, b, (bf16*)y, rows, eps, post_act, rows_dev);

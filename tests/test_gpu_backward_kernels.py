@@ -55,6 +55,29 @@ def test_layernorm(rows, C):
     _check(fn.layernorm(x, w, b, 1e-5), F.layer_norm(x2, (C,), w2, b2, 1e-5), (x, w, b), (x2, w2, b2), tol=5e-5)
 
 
+@pytest.mark.parametrize("rows,C", [(3000, 192), (2500, 1536), (1100, 3072), (1030, 1024), (70000, 192)])
+@pytest.mark.parametrize("gelu", [False, True])
+def test_layernorm_bf16(rows, C, gelu):
+    """bf16 LayerNorm (+GELU) forward / backward: the register kernels (C <= 768), the wide-row kernel (C >= 1024) and the streaming
+    forward (>= 65536 rows) against torch fp32 on the same bf16-rounded input."""
+    from applecider_b200 import fn, ops
+
+    x = _rand(rows, C, seed=5, scale=2.0).to(torch.bfloat16).requires_grad_(True)
+    w, b = (1 + 0.1 * _rand(C, seed=6)).requires_grad_(True), _rand(C, seed=7, grad=True)
+    x2 = x.detach().float().requires_grad_(True)
+    w2, b2 = [t.detach().clone().requires_grad_(True) for t in (w, b)]
+    y = fn.layernorm(x, w, b, 1e-5, post_act=ops.ACT_GELU if gelu else ops.ACT_NONE)
+    ref = F.layer_norm(x2, (C,), w2, b2, 1e-5)
+    ref = F.gelu(ref) if gelu else ref
+    assert_close(y.float(), ref, 1.2e-2, "forward")
+    go = _rand(rows, C, seed=99).to(torch.bfloat16)
+    y.backward(go)
+    ref.backward(go.float())
+    for name, a, r in (("dx", x.grad.float(), x2.grad), ("dw", w.grad, w2.grad), ("db", b.grad, b2.grad)):
+        s = r.abs().max().clamp_min(1e-12)
+        assert_close(a / s, r / s, 1.2e-2, name)
+
+
 @pytest.mark.parametrize("B,L,C", [(2, 1000, 64), (2, 250, 128), (3, 15, 16), (2, 1024, 64)])
 def test_maxpool(B, L, C):
     from applecider_b200 import fn
@@ -65,6 +88,22 @@ def test_maxpool(B, L, C):
     x.grad = None
     x2.grad = None
     _check(fn.MaxPool.apply(x, B, L, C, 0), x2.amax(1), (x,), (x2,), tol=1e-6)
+
+
+@pytest.mark.parametrize("B,L,C", [(3, 1003, 64), (2, 64, 1024), (5, 17, 8), (2, 40, 12)])
+def test_maxpool_bf16(B, L, C):
+    """bf16 MaxPool1d(4) backward (16-byte vector kernel when C % 8 == 0, scalar otherwise): exact, ties go to the first maximum."""
+    from applecider_b200 import fn
+
+    x = _rand(B, L, C, seed=8).to(torch.bfloat16).requires_grad_(True)
+    x2 = x.detach().float().requires_grad_(True)
+    y = fn.MaxPool.apply(x, B, L, C, 4)
+    ref = F.max_pool1d(x2.transpose(1, 2), 4).transpose(1, 2)
+    assert torch.equal(y.float().view(ref.shape), ref)
+    go = _rand(*ref.shape, seed=9).to(torch.bfloat16)
+    y.backward(go.view(y.shape))
+    ref.backward(go.float())
+    assert torch.equal(x.grad.float(), x2.grad)
 
 
 @pytest.mark.parametrize("B,L,Cin,Cout,ks", [(2, 250, 64, 128, [3, 31, 251]), (2, 1000, 1, 64, [3, 61, 1021]), (3, 62, 16, 32, [3, 7, 13]), (2, 256, 64, 128, [3, 31, 251])])

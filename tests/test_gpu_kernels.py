@@ -182,6 +182,21 @@ def test_layernorm(rows, C, dt_in, dt_out):
     assert_close(ops.layernorm(x, w, b, 1e-5, pre_gelu=True, out_dtype=dt_out), F.layer_norm(F.gelu(x.float()), (C,), w, b, 1e-5), tol, "gelu+ln")
 
 
+@pytest.mark.parametrize("C", [128, 192, 384])
+def test_layernorm_stream(C):
+    """>= 65536 bf16 rows take the streaming kernels (C = 192: two rows per warp); odd row count exercises the guarded tail."""
+    ops = _ops()
+    rows = 65536 + 77
+    x = _rand(rows, C, seed=5, scale=2.0).to(torch.bfloat16)
+    w, b = 1 + 0.1 * _rand(C, seed=3), _rand(C, seed=4)
+    ref = F.gelu(F.layer_norm(x.float(), (C,), w, b, 1e-5))
+    assert_close(ops.layernorm(x, w, b, 1e-5, post_act=ops.ACT_GELU), ref, 8e-3, f"stream ln+gelu C={C}")
+    assert_close(ops.layernorm(x, w, b, 1e-5), F.layer_norm(x.float(), (C,), w, b, 1e-5), 8e-3, f"stream ln C={C}")
+    # small-batch (cached kernel) and large-batch (streaming kernel) results agree to bf16 rounding
+    small = ops.layernorm(x[:1000].contiguous(), w, b, 1e-5).float()
+    assert_close(ops.layernorm(x, w, b, 1e-5)[:1000].float(), small, 8e-3, "stream vs cached")
+
+
 def test_cast_pool_softmax():
     ops = _ops()
     x = _rand(3, 43, 20, seed=1)

@@ -132,6 +132,23 @@ def test_dropout_kernel_statistics():
     assert torch.equal(x.grad > 0, y > 0), "backward must regenerate the same mask"
 
 
+def test_dropout_vector_and_scalar_kernels_draw_the_same_mask():
+    """bf16 tensors whose size is a multiple of 8 take the 16-byte kernel, everything else the scalar one: same seed -> same mask
+    (a forward through one and a backward through the other must agree), and the keep rate is right."""
+    from applecider_b200 import fn
+
+    n = (1 << 18) + 8
+    xb = torch.ones(n, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    yb = fn.Dropout.apply(xb, 0.25, 777)
+    yf = fn.Dropout.apply(torch.ones(n, device=DEV), 0.25, 777)
+    assert torch.equal(yb > 0, yf > 0)
+    assert abs((yb > 0).float().mean().item() - 0.75) < 5e-3
+    odd = fn.Dropout.apply(torch.ones(n - 3, device=DEV, dtype=torch.bfloat16), 0.25, 777)  # scalar kernel, bf16
+    assert torch.equal(odd > 0, (yf > 0)[: n - 3])
+    yb.float().sum().backward()
+    assert torch.equal(xb.grad > 0, yb > 0)
+
+
 def test_astrominn_gradients_vs_golden_and_oracle(golden_dir):
     g = load_golden(golden_dir, "astrominn")
     prod, oracle = _pair("AstroMiNN")
