@@ -118,6 +118,47 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* a, int a_dt, co
   }
 }
 
+// bf16 operands, N % 8 == 0, ld % 8 == 0, N <= 2048: thread = (row lane, group of 8 columns), whole rows move as consecutive 16-byte
+// loads; the row lanes meet in a shared-memory accumulator, one global atomic per column and CTA
+__global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, long long M, int N8,
+                                                            long long ld8, int rows_per_block, float* __restrict__ out) {
+  __shared__ float acc[2048];
+  for (int i = threadIdx.x; i < N8 * 8; i += 256) acc[i] = 0.0f;
+  __syncthreads();
+  const int lanes = 256 / N8;  // row lanes (>= 1); the last 256 % N8 threads idle
+  const int rl = threadIdx.x / N8, cg = threadIdx.x - rl * N8;
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  if (rl < lanes) {
+    float s[8] = {};
+    for (long long m = r0 + rl; m < r1; m += lanes) {
+      const uint4 v = __ldcs(a + m * ld8 + cg);
+      const uint32_t* vw = reinterpret_cast<const uint32_t*>(&v);
+      if (b) {
+        const uint4 u = __ldcs(b + m * ld8 + cg);
+        const uint32_t* uw = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[j]));
+          const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[j]));
+          s[2 * j] = fmaf(f.x, g.x, s[2 * j]);
+          s[2 * j + 1] = fmaf(f.y, g.y, s[2 * j + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[j]));
+          s[2 * j] += f.x;
+          s[2 * j + 1] += f.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&acc[cg * 8 + j], s[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N8 * 8; i += 256) atomicAdd(out + i, acc[i]);
+}
+
 __global__ void act_fwd_kernel(const void* x, int x_dt, void* y, int y_dt, int act, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     st_any(y, i, y_dt, apply_act(ld_any(x, i, x_dt), act));
@@ -1117,6 +1158,14 @@ int acb_colsum(const void* a, int a_dtype, const void* b, int b_dtype, long long
   ACB_CHECK(a && out && M > 0 && N > 0, "acb_colsum: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate) ACB_CUDA(cudaMemsetAsync(out, 0, (size_t)N * 4, st));
+  if (a_dtype == ACB_BF16 && (!b || b_dtype == ACB_BF16) && N % 8 == 0 && N <= 2048 && ld % 8 == 0 && M >= 512 &&
+      (((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
+    // ~4 CTAs per SM, at least 8 rows per row lane
+    const int lanes = 256 / (N / 8);
+    const int rpbv = (int)std::max<long long>(8LL * lanes, cdiv(M, 148 * 4));
+    colsum_bf16x8_kernel<<<(unsigned)cdiv(M, rpbv), 256, 0, st>>>((const uint4*)a, (const uint4*)b, M, N / 8, ld / 8, rpbv, out);
+    LAUNCHED(1);
+  }
   const int rpb = 1024;
   dim3 grid(cdiv(N, 32), cdiv(M, rpb));
   colsum_kernel<<<grid, 256, 0, st>>>(a, a_dtype, b, b_dtype, M, N, ld, rpb, out);

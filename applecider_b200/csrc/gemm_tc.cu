@@ -1183,7 +1183,7 @@ extern "C" int acb_wgrad_bias_bf16(const void* dY, int ldy, int a_col0, int M_ou
   // split-K choice: every split adds M_out * n_total fp32 atomics (the L2 retires ~150 G atomics/s, so one 128x256 tile
   // costs as much as ~60 K-chunks of tensor-core work), while too few splits leave SMs idle.  Minimise the modelled time
   //   waves(tiles * s) * chunks_per_split * t_chunk  +  s * M_out * n_total / atomic_rate      over s.
-  const long long tiles = (long long)mt * ntl;
+  const long long tiles = (long long)mt * (ntl + (db ? 1 : 0));  // (the bias-gradient tile of ones occupies a CTA slot like any other)
   const double t_chunk_us = 0.5 * bn / 256.0, atomics_per_us = 150e3;
   int splits = 1;
   double best = 1e30;

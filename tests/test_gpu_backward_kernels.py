@@ -90,6 +90,20 @@ def test_maxpool(B, L, C):
     _check(fn.MaxPool.apply(x, B, L, C, 0), x2.amax(1), (x,), (x2,), tol=1e-6)
 
 
+@pytest.mark.parametrize("M,N", [(5000, 96), (777, 384), (2049, 2048), (4000, 24), (600, 20)])
+def test_colsum_bf16(M, N):
+    """Column sums of bf16 matrices (bias gradients): 16-byte kernel when N % 8 == 0, scalar kernel otherwise; optional elementwise factor."""
+    from applecider_b200 import fn
+
+    a, b = _rand(M, N, seed=11).to(torch.bfloat16), _rand(M, N, seed=12).to(torch.bfloat16)
+    ref = a.float().sum(0)
+    s = ref.abs().max().clamp_min(1.0)
+    assert_close(fn.colsum(a) / s, ref / s, 2e-5, "colsum")
+    ref2 = (a.float() * b.float()).sum(0)
+    s2 = ref2.abs().max().clamp_min(1.0)
+    assert_close(fn.colsum(a, b) / s2, ref2 / s2, 2e-5, "colsum of products")
+
+
 @pytest.mark.parametrize("B,L,C", [(3, 1003, 64), (2, 64, 1024), (5, 17, 8), (2, 40, 12)])
 def test_maxpool_bf16(B, L, C):
     """bf16 MaxPool1d(4) backward (16-byte vector kernel when C % 8 == 0, scalar otherwise): exact, ties go to the first maximum."""
