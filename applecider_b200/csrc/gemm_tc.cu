@@ -809,6 +809,9 @@ struct TcWgradArgs {
   int chunks_per_split;
   float* C;
   int ldc;
+  // grouped rows (polyphase convolution, grp > 0): output tile row vm = 64 g + co reads dY columns a_col0 + g a_grp_stride + co and
+  // accumulates into C[co, n + g c_grp_step] -- the 8 phases of the stride-8 signal view are ONE launch with full 128-row tiles
+  int grp, a_grp_stride, c_grp_step;
   float* db;  // optional bias gradient db[m] = sum_rows dY[row, a_col0 + m]: computed by one extra N tile (blockIdx.y == gridDim.y - 1)
               // whose B operand is a constant tile of ones -- the column sums fall out of the tensor core instead of a second pass over dY
 };
@@ -881,8 +884,9 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
         const uint32_t sa = smem_base + s * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
         mbar_expect_tx(bar_full + 8 * s, bias_tile ? A_BYTES : STAGE_BYTES);
-        tma_load_3d(sa, &tmA, p.a_col0 + m0, l0, b, bar_full + 8 * s);
-        tma_load_3d(sa + 8192, &tmA, p.a_col0 + m0 + 64, l0, b, bar_full + 8 * s);
+        const int acol = p.grp ? p.a_col0 + (m0 >> 6) * p.a_grp_stride : p.a_col0 + m0;
+        tma_load_3d(sa, &tmA, acol, l0, b, bar_full + 8 * s);
+        tma_load_3d(sa + 8192, &tmA, acol + (p.grp ? p.a_grp_stride : 64), l0, b, bar_full + 8 * s);
         if (!bias_tile)
 #pragma unroll
         for (int qn = 0; qn < BN / 64; ++qn) {
@@ -927,7 +931,7 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
       uint32_t raw[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
       if (m < p.M_out) {
-        float* dst = p.C + (long long)m * p.ldc + n0 + c0;
+        float* dst = p.grp ? p.C + (long long)(m & 63) * p.ldc + n0 + c0 + (m >> 6) * p.c_grp_step : p.C + (long long)m * p.ldc + n0 + c0;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (n0 + c0 + i < p.n_total) atomicAdd(dst + i, __uint_as_float(raw[i]));
@@ -1142,8 +1146,29 @@ extern "C" int acb_wgrad_bf16(const void* dY, int ldy, int a_col0, int M_out, co
   return acb_wgrad_bias_bf16(dY, ldy, a_col0, M_out, X, nb, L, Cin, taps, pad, x_batch_stride, x_row_stride, dW, ldc, accumulate, nullptr, stream);
 }
 
+static int wgrad_impl(const void* dY, int ldy, int a_col0, int M_out, const void* X, int nb, int L, int Cin, int taps, int pad,
+                      long long x_batch_stride, long long x_row_stride, float* dW, int ldc, int accumulate, float* db, int grp, int a_grp_stride,
+                      int c_grp_step, void* stream);
+
 extern "C" int acb_wgrad_bias_bf16(const void* dY, int ldy, int a_col0, int M_out, const void* X, int nb, int L, int Cin, int taps, int pad,
                                    long long x_batch_stride, long long x_row_stride, float* dW, int ldc, int accumulate, float* db, void* stream) {
+  return wgrad_impl(dY, ldy, a_col0, M_out, X, nb, L, Cin, taps, pad, x_batch_stride, x_row_stride, dW, ldc, accumulate, db, 0, 0, 0, stream);
+}
+
+// G[co, n + g c_group_step] += sum_rows dY[row, a_col0 + g a_group_stride + co] X[row, n]   for g < n_groups, co < 64, n < width:
+// the weight gradient of a one-input-channel convolution on its polyphase (stride-n_groups) view, all phases in one launch.
+// G must be zeroed by the caller; the caller's pointer already includes the column offset of group 0.
+extern "C" int acb_wgrad_phases_bf16(const void* dY, int ldy, int a_col0, int n_groups, int a_group_stride, const void* X, int nb, int L,
+                                     int width, long long x_batch_stride, long long x_row_stride, float* G, int ldc, int c_group_step,
+                                     void* stream) {
+  ACB_CHECK(n_groups > 0 && a_group_stride % 8 == 0, "acb_wgrad_phases_bf16: bad arguments");
+  return wgrad_impl(dY, ldy, a_col0, 64 * n_groups, X, nb, L, width, 1, 0, x_batch_stride, x_row_stride, G, ldc, 1, nullptr, 1, a_group_stride,
+                    c_group_step, stream);
+}
+
+static int wgrad_impl(const void* dY, int ldy, int a_col0, int M_out, const void* X, int nb, int L, int Cin, int taps, int pad,
+                      long long x_batch_stride, long long x_row_stride, float* dW, int ldc, int accumulate, float* db, int grp, int a_grp_stride,
+                      int c_grp_step, void* stream) {
   ACB_CHECK(dY && X && dW && nb > 0 && L > 0 && Cin > 0 && taps > 0 && M_out > 0, "acb_wgrad_bf16: bad arguments");
   ACB_CHECK(taps == 1 || Cin % 64 == 0, "acb_wgrad_bf16: convolution weight gradients need Cin %% 64 == 0 (got %d)", Cin);
   ACB_CHECK(((uintptr_t)dY % 16 == 0) && ((uintptr_t)X % 16 == 0) && ldy % 8 == 0 && x_row_stride % 8 == 0 && x_batch_stride % 8 == 0,
@@ -1177,6 +1202,7 @@ extern "C" int acb_wgrad_bias_bf16(const void* dY, int ldy, int a_col0, int M_ou
   args.a_col0 = a_col0; args.M_out = M_out;
   args.C = dW; args.ldc = ldc;
   args.db = db;
+  args.grp = grp; args.a_grp_stride = a_grp_stride; args.c_grp_step = c_grp_step;
   const int bn = n_total >= 256 ? 256 : (n_total > 64 ? 128 : 64);
   const int mt = cdiv(M_out, TC_BM), ntl = cdiv(n_total, bn);
   const long long total_chunks = (long long)nb * args.cps;

@@ -183,9 +183,13 @@ class SpectraConvs(torch.autograd.Function):
                 width = ((_HALO + padj + _PHASES - n_start + 63) // 64) * 64
                 width = min(width, kp - n_start)
                 G = torch.zeros((cout, width + 8), dtype=F32, device=dev)
-                for r in range(_PHASES):
-                    fn.call("acb_wgrad_bf16", dy, _PHASES * ldy, r * ldy + j * cout, cout, ops._offset_ptr(xp, n_start), B, L // _PHASES, width, 1, 0,
-                            stride, _PHASES, ops._offset_ptr(G, _PHASES - r), width + 8, 1)
+                if cout == 64:  # all 8 phases in one launch (phase r accumulates (8 - r) columns to the right)
+                    fn.call("acb_wgrad_phases_bf16", dy, _PHASES * ldy, j * cout, _PHASES, ldy, ops._offset_ptr(xp, n_start), B, L // _PHASES, width,
+                            stride, _PHASES, ops._offset_ptr(G, _PHASES), width + 8, -1)
+                else:
+                    for r in range(_PHASES):
+                        fn.call("acb_wgrad_bf16", dy, _PHASES * ldy, r * ldy + j * cout, cout, ops._offset_ptr(xp, n_start), B, L // _PHASES, width, 1, 0,
+                                stride, _PHASES, ops._offset_ptr(G, _PHASES - r), width + 8, 1)
                 dW = torch.empty(conv.weight.shape, dtype=F32, device=dev)
                 fn.call("acb_copy2d", ops._offset_ptr(G, _HALO - padj - n_start + _PHASES), 0, width + 8, dW, 0, kj, cout, kj)
                 out[j] = dW

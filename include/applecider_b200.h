@@ -323,6 +323,14 @@ int acb_wgrad_bf16(const void* dY, int ldy, int a_col0, int M_out, const void* X
  * Conv1d backward: nn.Linear / nn.Conv1d bias gradients, e.g. spectranet.py:18-22, timm Mlp fc1/fc2). */
 int acb_wgrad_bias_bf16(const void* dY, int ldy, int a_col0, int M_out, const void* X, int nb, int L, int Cin, int taps, int pad,
                         long long x_batch_stride, long long x_row_stride, float* dW, int ldc, int accumulate, float* db, void* stream);
+/* weight gradient of a ONE-input-channel Conv1d on its polyphase view (SpectraNet's first block, spectranet.py:18-22 with
+ * in_channels = 1): dY is seen as [nb, L, n_groups * ...] rows of n_groups positions, X as overlapping `width`-sample windows of
+ * the zero-padded signal;  G[co, n + g*c_group_step] += sum_rows dY[row, a_col0 + g*a_group_stride + co] * X[row, n]  for
+ * g < n_groups, co < 64, n < width -- every phase g in one launch, two phases per 128-row tensor-core tile.  G (fp32, caller-zeroed)
+ * already points at the column of group 0. */
+int acb_wgrad_phases_bf16(const void* dY, int ldy, int a_col0, int n_groups, int a_group_stride, const void* X, int nb, int L,
+                          int width, long long x_batch_stride, long long x_row_stride, float* G, int ldc, int c_group_step,
+                          void* stream);
 /* out[n] (+)= sum_m a[m*ld+n] * (b ? b[m*ld+n] : 1)   (bias / layer-scale gradients; ld <= 0 means N) */
 int acb_colsum(const void* a, int a_dtype, const void* b, int b_dtype, long long M, int N, long long ld, float* out,
                int accumulate, void* stream);
