@@ -164,6 +164,27 @@ __global__ void act_fwd_kernel(const void* x, int x_dt, void* y, int y_dt, int a
     st_any(y, i, y_dt, apply_act(ld_any(x, i, x_dt), act));
 }
 
+// bf16 everywhere, n % 8 == 0, ReLU / GELU (the two activations of the big hidden layers): 16 bytes per thread and step
+__global__ void __launch_bounds__(256) act_bwd_bf16x8_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, uint4* __restrict__ dx, int act,
+                                                             long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    uint4 gv = __ldcs(dy + i);
+    const uint4 xv = __ldcs(x + i);
+    uint32_t* gw = reinterpret_cast<uint32_t*>(&gv);
+    const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[j]));
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[j]));
+      const float d0 = act == ACB_ACT_RELU ? (v.x > 0.0f ? 1.0f : 0.0f) : gelu_bf16_grad(v.x);
+      const float d1 = act == ACB_ACT_RELU ? (v.y > 0.0f ? 1.0f : 0.0f) : gelu_bf16_grad(v.y);
+      const __nv_bfloat162 o = __floats2bfloat162_rn(g.x * d0, g.y * d1);
+      gw[j] = *reinterpret_cast<const uint32_t*>(&o);
+    }
+    dx[i] = gv;
+  }
+}
+
 // dx = dy * act'(x)   (x = pre-activation)
 __global__ void act_bwd_kernel(const void* dy, int dy_dt, const void* x, int x_dt, void* dx, int dx_dt, int act, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -200,14 +221,20 @@ __global__ void ew_kernel(const void* a, int a_dt, const void* b, int b_dt, cons
   }
 }
 
-// a, b, y bf16, n % 8 == 0, ops 0 / 1 / 4: 16 bytes per thread and step
-__global__ void __launch_bounds__(256) ew_bf16x8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y, int op,
-                                                        float s0, float s1, long long n8) {
+// a, b, y bf16, n % 8 == 0 (ops 2 / 3: C % 8 == 0 as well): 16 bytes per thread and step
+__global__ void __launch_bounds__(256) ew_bf16x8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const float* __restrict__ g,
+                                                        uint4* __restrict__ y, int op, int C, float s0, float s1, long long n8) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     uint4 av = a[i];
-    const uint4 bv = b[i];
+    const uint4 bv = b ? b[i] : make_uint4(0u, 0u, 0u, 0u);
     uint32_t* aw = reinterpret_cast<uint32_t*>(&av);
     const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bv);
+    float gv[8];
+    if (op == 2 || op == 3) {
+      const float4* gp = reinterpret_cast<const float4*>(g + (int)((i * 8) % C));
+      const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+      gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w; gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[j]));
@@ -215,6 +242,8 @@ __global__ void __launch_bounds__(256) ew_bf16x8_kernel(const uint4* __restrict_
       float2 r;
       if (op == 0) r = make_float2(fa.x + fb.x, fa.y + fb.y);
       else if (op == 1) r = make_float2(fa.x * fb.x, fa.y * fb.y);
+      else if (op == 2) r = make_float2(fa.x + gv[2 * j] * fb.x, fa.y + gv[2 * j + 1] * fb.y);
+      else if (op == 3) r = make_float2(gv[2 * j] * fa.x, gv[2 * j + 1] * fa.y);
       else r = make_float2(fa.x * s0 + fb.x * s1, fa.y * s0 + fb.y * s1);
       const __nv_bfloat162 o = __floats2bfloat162_rn(r.x, r.y);
       aw[j] = *reinterpret_cast<const uint32_t*>(&o);
@@ -1182,6 +1211,11 @@ int acb_act_fwd(const void* x, int x_dtype, void* y, int y_dtype, int act, long 
 int acb_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx, int dx_dtype, int act, long long n, void* stream) {
   ACB_CHECK(dy && x && dx && n >= 0, "acb_act_bwd: bad arguments");
   if (n == 0) return ACB_OK;
+  if ((act == ACB_ACT_RELU || act == ACB_ACT_GELU) && dy_dtype == ACB_BF16 && x_dtype == ACB_BF16 && dx_dtype == ACB_BF16 && n % 8 == 0 &&
+      (((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx) & 15) == 0) {
+    act_bwd_bf16x8_kernel<<<grid_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)x, (uint4*)dx, act, n / 8);
+    LAUNCHED(1);
+  }
   act_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, x, x_dtype, dx, dx_dtype, act, n);
   LAUNCHED(1);
 }
@@ -1190,9 +1224,10 @@ int acb_ew(const void* a, int a_dtype, const void* b, int b_dtype, const float* 
            long long n, void* stream) {
   ACB_CHECK(a && y && n >= 0 && C > 0, "acb_ew: bad arguments");
   if (n == 0) return ACB_OK;
-  if (b && (op == 0 || op == 1 || op == 4) && a_dtype == ACB_BF16 && b_dtype == ACB_BF16 && y_dtype == ACB_BF16 && n % 8 == 0 &&
-      (((uintptr_t)a | (uintptr_t)b | (uintptr_t)y) & 15) == 0) {
-    ew_bf16x8_kernel<<<grid_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)y, op, s0, s1, n / 8);
+  const bool two = op == 0 || op == 1 || op == 2 || op == 4, col = op == 2 || op == 3;
+  if ((two || op == 3) && (b != nullptr) == two && (!two || b_dtype == ACB_BF16) && a_dtype == ACB_BF16 && y_dtype == ACB_BF16 && n % 8 == 0 &&
+      (!col || (g && C % 8 == 0 && ((uintptr_t)g & 15) == 0)) && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)y) & 15) == 0) {
+    ew_bf16x8_kernel<<<grid_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, g, (uint4*)y, op, C, s0, s1, n / 8);
     LAUNCHED(1);
   }
   ew_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(a, a_dtype, b, b_dtype, g, y, y_dtype, op, C, s0, s1, n);

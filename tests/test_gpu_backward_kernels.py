@@ -90,6 +90,27 @@ def test_maxpool(B, L, C):
     _check(fn.MaxPool.apply(x, B, L, C, 0), x2.amax(1), (x,), (x2,), tol=1e-6)
 
 
+@pytest.mark.parametrize("rows,C", [(1000, 96), (333, 20)])
+def test_elementwise_bf16(rows, C):
+    """bf16 elementwise ops and activation backward: 16-byte kernels when the size allows (C = 96), scalar kernels otherwise."""
+    from applecider_b200 import fn, ops
+
+    bf = torch.bfloat16
+    a, b = _rand(rows, C, seed=21).to(bf), _rand(rows, C, seed=22).to(bf)
+    g = _rand(C, seed=23)
+    af, bfl = a.float(), b.float()
+    for op, ref in ((0, af + bfl), (1, af * bfl), (2, af + g * bfl), (4, af * 0.25 + bfl * 0.5)):
+        got = fn.ew(a, b, op, g=g if op == 2 else None, C=C, s0=0.25, s1=0.5)
+        assert_close(got.float(), ref, 8e-3, f"ew op {op}")  # (fused multiply-adds: not bit-identical to torch's two roundings)
+    assert_close(fn.ew(a, None, 3, g=g, C=C).float(), g * af, 8e-3, "ew op 3")
+    for act, tf in ((ops.ACT_RELU, torch.relu), (ops.ACT_GELU, lambda t: F.gelu(t, approximate="tanh"))):
+        x2 = af.clone().requires_grad_(True)
+        tf(x2).backward(bfl)
+        dx = torch.empty_like(a)
+        fn.call("acb_act_bwd", b, 1, a, 1, dx, 1, act, a.numel())
+        assert_close(dx.float(), x2.grad, 1e-2, f"act_bwd {act}")
+
+
 @pytest.mark.parametrize("M,N", [(5000, 96), (777, 384), (2049, 2048), (4000, 24), (600, 20)])
 def test_colsum_bf16(M, N):
     """Column sums of bf16 matrices (bias gradients): 16-byte kernel when N % 8 == 0, scalar kernel otherwise; optional elementwise factor."""
