@@ -4,6 +4,8 @@
 // segmentation results are bit-exact, float32 results use the same operation order as the reference.
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -487,6 +489,264 @@ __global__ void __launch_bounds__(256) prep_spectrum_kernel(const double* __rest
   for (int g = tid; g < n_grid; g += nthr) ob[g] = (float)((yg[g] - mean) / scale);
 }
 
+// ---- register-resident variant (n_grid <= 14 x 256, i.e. the reference's 3481-point grid) ----------------------------------------
+// Same arithmetic as prep_spectrum_kernel, different data placement: a thread keeps the 14 resampled values of its contiguous run
+// of grid points in REGISTERS (the radix selects then read no shared memory and the 28 KB `yg` array disappears: 3 CTAs per SM
+// instead of 2), an all-finite spectrum is copied in with independent loads instead of the barrier-per-chunk compaction loop, a
+// radix pass costs two barriers (warp 0 scans the bins while the others zero the next pass's histogram), and the final
+// (y - mean) / scale is a Markstein-corrected multiplication by the reciprocal (correctly rounded like the division it replaces).
+constexpr int SP_PER = 14;
+
+__device__ __forceinline__ unsigned long long spectrum_select_reg(const unsigned long long (&key)[SP_PER], int k, unsigned* hist /* 2 x 256 */,
+                                                                  unsigned* sh_k /* 8 */, unsigned long long* cand /* 257 */) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  hist[tid] = 0;
+  if (tid == 0) sh_k[3] = 0;
+  __syncthreads();
+  unsigned long long prefix = 0, pmask = 0;
+  int set = 0;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    unsigned* h = hist + set * 256;
+    if (shift == 56) {  // sign + leading exponent bits: usually ONE bin for the whole spectrum
+      const unsigned d0 = __shfl_sync(0xffffffffu, (unsigned)(key[0] >> 56), 0);
+      bool same = true;
+#pragma unroll
+      for (int e = 0; e < SP_PER; ++e) same &= (unsigned)(key[e] >> 56) == d0;
+      if (__all_sync(0xffffffffu, same)) {
+        if (lane == 0) atomicAdd(&h[d0], 32u * SP_PER);
+      } else {
+#pragma unroll
+        for (int e = 0; e < SP_PER; ++e) atomicAdd(&h[(unsigned)(key[e] >> 56)], 1u);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < SP_PER; ++e)
+        if ((key[e] & pmask) == prefix) atomicAdd(&h[(unsigned)(key[e] >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    hist[(set ^ 1) * 256 + tid] = 0;  // the next pass's histogram
+    if (wid == 0) {
+      const uint4 lo = reinterpret_cast<const uint4*>(h)[2 * lane], hi = reinterpret_cast<const uint4*>(h)[2 * lane + 1];
+      const unsigned c[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      const unsigned tot = c[0] + c[1] + c[2] + c[3] + c[4] + c[5] + c[6] + c[7];
+      unsigned inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      unsigned kk = (unsigned)k - (inc - tot);
+      if (kk < tot) {  // exactly one lane
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (kk < c[j]) {
+            sh_k[0] = (unsigned)(8 * lane + j);
+            sh_k[1] = kk;
+            sh_k[2] = c[j];
+            kk = 0xffffffffu;
+          } else {
+            kk -= c[j];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= (unsigned long long)sh_k[0] << shift;
+    pmask |= 0xffull << shift;
+    k = (int)sh_k[1];
+    const unsigned members = sh_k[2];
+    set ^= 1;
+    if (shift > 0 && members <= (unsigned)SEL_CAND) {
+#pragma unroll
+      for (int e = 0; e < SP_PER; ++e)
+        if ((key[e] & pmask) == prefix) cand[atomicAdd(&sh_k[3], 1u)] = key[e];
+      __syncthreads();
+      if (tid < (int)members) {
+        const unsigned long long c = cand[tid];
+        int rank = 0;
+        for (int j = 0; j < (int)members; ++j) {
+          const unsigned long long o = cand[j];
+          rank += (o < c) || (o == c && j < tid);
+        }
+        if (rank == k) cand[SEL_THREADS] = c;
+      }
+      __syncthreads();
+      return cand[SEL_THREADS];
+    }
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(256, 3) prep_spectrum_reg_kernel(const double* __restrict__ wl, const double* __restrict__ fx,
+                                                                   const long long* __restrict__ offsets, int cap,
+                                                                   const float* __restrict__ grid, int n_grid, float* __restrict__ out,
+                                                                   int* __restrict__ idx_out) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  double* xs = reinterpret_cast<double*>(sm_raw);
+  double* ys = xs + cap;
+  __shared__ double red[34];
+  __shared__ __align__(16) unsigned hist[512];
+  __shared__ unsigned shk[8];
+  __shared__ int shi[16];
+  __shared__ unsigned long long cand[SEL_THREADS + 1];
+  const int b = blockIdx.x;
+  const long long r0 = offsets[b];
+  const int n_in = (int)(offsets[b + 1] - r0);
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+  float* ob = out + (long long)b * n_grid;
+
+  // ---- load: straight copy when every sample is finite (the usual case), else the stable compaction of the finite samples ----
+  bool bad = false;
+  for (int i = tid; i < n_in; i += nthr) {
+    const double xv = __ldcs(wl + r0 + i), yv = __ldcs(fx + r0 + i);
+    xs[i] = xv;
+    ys[i] = yv;
+    bad |= !(isfinite(xv) && isfinite(yv));
+  }
+  int n = n_in;
+  if (__syncthreads_or(bad)) {
+    if (tid == 0) shi[0] = 0;
+    __syncthreads();
+    for (int base = 0; base < n_in; base += nthr) {
+      const int i = base + tid;
+      double xv = 0.0, yv = 0.0;
+      bool ok = false;
+      if (i < n_in) {  // in place: position <= i, and this chunk is in registers before anything of it is overwritten
+        xv = xs[i];
+        yv = ys[i];
+        ok = isfinite(xv) && isfinite(yv);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      int* wcnt = shi + 1;
+      if (lane == 0) wcnt[wid] = __popc(m);
+      __syncthreads();
+      int off = shi[0];
+      for (int w = 0; w < wid; ++w) off += wcnt[w];
+      if (ok) {
+        const int pos = off + __popc(m & ((1u << lane) - 1u));
+        xs[pos] = xv;
+        ys[pos] = yv;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < nw; ++w) t += wcnt[w];
+        shi[0] += t;
+      }
+      __syncthreads();
+    }
+    n = shi[0];
+  }
+  if (n < 2) {
+    for (int g = tid; g < n_grid; g += nthr) {
+      ob[g] = CUDART_NAN_F;
+      if (idx_out) idx_out[(long long)b * n_grid + g] = -1;
+    }
+    return;
+  }
+  // ---- sort by wavelength if needed ----
+  int unsorted = 0;
+  for (int i = tid; i + 1 < n; i += nthr) unsorted |= (xs[i] > xs[i + 1]);
+  unsorted = __syncthreads_or(unsorted);
+  if (unsorted) {
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = n + tid; i < np2; i += nthr) { xs[i] = CUDART_INF; ys[i] = 0.0; }
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < np2; i += nthr) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const bool up = (i & k) == 0;
+            const double a = xs[i], c = xs[ixj];
+            if ((a > c) == up) {
+              xs[i] = c; xs[ixj] = a;
+              const double t = ys[i]; ys[i] = ys[ixj]; ys[ixj] = t;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  // ---- interpolation: thread t owns grid points [14 t, 14 t + 14); galloping + binary search from the previous position ----
+  double yv[SP_PER];
+  double s_loc = 0.0;
+  int nfin_loc = 0;
+  {
+    int prev_lo = 0;
+    double prev_x = -CUDART_INF;
+#pragma unroll
+    for (int e = 0; e < SP_PER; ++e) {
+      const int g = tid * SP_PER + e;
+      yv[e] = CUDART_NAN;
+      if (g < n_grid) {
+        const double xn = (double)grid[g];
+        int lo = xn >= prev_x ? prev_lo : 0;  // first index with xs[idx] >= xn  (numpy searchsorted side='left')
+        int hi = lo, step = 1;
+        while (hi < n && xs[hi] < xn) { lo = hi + 1; hi += step; step <<= 1; }
+        hi = min(hi, n);
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (xs[mid] < xn) lo = mid + 1; else hi = mid;
+        }
+        prev_lo = lo;
+        prev_x = xn;
+        if (idx_out) idx_out[(long long)b * n_grid + g] = lo;
+        const int ih = min(max(lo, 1), n - 1);
+        const int il = ih - 1;
+        const double slope = __ddiv_rn(__dsub_rn(ys[ih], ys[il]), __dsub_rn(xs[ih], xs[il]));
+        const double v = __dadd_rn(__dmul_rn(slope, __dsub_rn(xn, xs[il])), ys[il]);
+        yv[e] = v;
+        if (!isnan(v)) { s_loc += v; ++nfin_loc; }
+      }
+    }
+  }
+  const int nfin = (int)(block_sum_d((double)nfin_loc, red) + 0.5);
+  const double mean = block_sum_d(s_loc, red) / (double)nfin;
+  // ---- median and MAD (NaNs and the slots past the grid carry the largest key: select among the nfin smallest) ----
+  double scale = 1.0;
+  if (nfin > 0) {
+    unsigned long long key[SP_PER];
+#pragma unroll
+    for (int e = 0; e < SP_PER; ++e) key[e] = isnan(yv[e]) ? ~0ull : dkey(yv[e]);
+    double med = dkey_inv(spectrum_select_reg(key, (nfin - 1) / 2, hist, shk, cand));
+    if ((nfin & 1) == 0) med = 0.5 * (med + dkey_inv(spectrum_select_reg(key, nfin / 2, hist, shk, cand)));
+#pragma unroll
+    for (int e = 0; e < SP_PER; ++e) key[e] = isnan(yv[e]) ? ~0ull : dkey(fabs(yv[e] - med));
+    double mad = dkey_inv(spectrum_select_reg(key, (nfin - 1) / 2, hist, shk, cand));
+    if ((nfin & 1) == 0) mad = 0.5 * (mad + dkey_inv(spectrum_select_reg(key, nfin / 2, hist, shk, cand)));
+    if (!isfinite(mad) || mad == 0.0) {
+      double q = 0.0;
+#pragma unroll
+      for (int e = 0; e < SP_PER; ++e)
+        if (!isnan(yv[e])) q += (yv[e] - mean) * (yv[e] - mean);
+      const double sd = sqrt(block_sum_d(q, red) / (double)nfin);
+      scale = (isfinite(sd) && sd > 0.0) ? sd : 1.0;
+    } else {
+      scale = mad;
+    }
+  }
+  // ---- (y - mean) / scale -> float32, staged through shared memory (xs is free now) so that the rows leave as full lines ----
+  __syncthreads();
+  float* stage = reinterpret_cast<float*>(xs);
+  const double rinv = 1.0 / scale;
+#pragma unroll
+  for (int e = 0; e < SP_PER; ++e) {
+    const int g = tid * SP_PER + e;
+    if (g < n_grid) {
+      const double num = yv[e] - mean;
+      const double q0 = num * rinv;
+      double q = fma(fma(-q0, scale, num), rinv, q0);  // correctly rounded num / scale (Markstein) ...
+      if (!isfinite(q0) || !isfinite(rinv)) q = num / scale;  // ... except at the edges of the range
+      stage[g] = (float)q;
+    }
+  }
+  __syncthreads();
+  for (int g = tid; g < n_grid; g += nthr) ob[g] = stage[g];
+}
+
 // ================================ P4: cutouts =========================================================
 // mode 0: per channel  x -= lower_median; x /= (unbiased std + 1e-8)      (ImageAndMetadataDataset.get_image)
 // mode 2: per channel  x -= median; x /= population std (<= 1e-8 -> 1)     (Fusion_Dataset._normalize_image)
@@ -847,6 +1107,15 @@ int acb_prep_spectrum_resample_idx(const double* wl, const double* fx, const lon
   while (cap < max_n) cap <<= 1;
   const size_t smem = (size_t)(2 * cap + n_grid + 34) * 8 + (256 + 8 + 16) * 4 + 258 * 8;
   ACB_CHECK(smem <= 220 * 1024, "acb_prep_spectrum_resample: spectrum too long for shared memory (max_n=%d, n_grid=%d)", max_n, n_grid);
+  if (n_grid <= SP_PER * 256) {
+    const size_t smem_r = std::max((size_t)2 * cap * 8, (size_t)n_grid * 4);  // xs | ys, reused as the float staging row
+    auto kr = prep_spectrum_reg_kernel;
+    ACB_CUDA(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+    kr<<<B, 256, smem_r, (cudaStream_t)stream>>>(wl, fx, offsets, cap, grid, n_grid, out, idx_out);
+    ACB_LAUNCH_CHECK();
+    acb_count_launch();
+    return ACB_OK;
+  }
   auto k = prep_spectrum_kernel;
   ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<B, 256, smem, (cudaStream_t)stream>>>(wl, fx, offsets, cap, grid, n_grid, out, idx_out);
