@@ -577,7 +577,7 @@ __device__ __forceinline__ unsigned long long spectrum_select_reg(const unsigned
   return prefix;
 }
 
-__global__ void __launch_bounds__(256, 3) prep_spectrum_reg_kernel(const double* __restrict__ wl, const double* __restrict__ fx,
+__global__ void __launch_bounds__(256, 4) prep_spectrum_reg_kernel(const double* __restrict__ wl, const double* __restrict__ fx,
                                                                    const long long* __restrict__ offsets, int cap,
                                                                    const float* __restrict__ grid, int n_grid, float* __restrict__ out,
                                                                    int* __restrict__ idx_out) {
@@ -649,18 +649,15 @@ __global__ void __launch_bounds__(256, 3) prep_spectrum_reg_kernel(const double*
   for (int i = tid; i + 1 < n; i += nthr) unsorted |= (xs[i] > xs[i + 1]);
   unsorted = __syncthreads_or(unsorted);
   if (unsorted) {
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    for (int i = n + tid; i < np2; i += nthr) { xs[i] = CUDART_INF; ys[i] = 0.0; }
-    __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1) {
+    // bitonic network in its all-ascending form (first step of every merge pairs i with i ^ (2k - 1), the rest with i ^ j): virtual
+    // +inf padding above n never has to move, so pairs with a partner >= n are skipped and n need not be a power of two
+    for (int k = 2; (k >> 1) < n; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < np2; i += nthr) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const bool up = (i & k) == 0;
+        for (int i = tid; i < n; i += nthr) {
+          const int ixj = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
+          if (ixj > i && ixj < n) {
             const double a = xs[i], c = xs[ixj];
-            if ((a > c) == up) {
+            if (a > c) {
               xs[i] = c; xs[ixj] = a;
               const double t = ys[i]; ys[i] = ys[ixj]; ys[ixj] = t;
             }
@@ -670,7 +667,7 @@ __global__ void __launch_bounds__(256, 3) prep_spectrum_reg_kernel(const double*
       }
     }
   }
-  // ---- interpolation: thread t owns grid points [14 t, 14 t + 14); galloping + binary search from the previous position ----
+// ---- interpolation: thread t owns grid points [14 t, 14 t + 14); galloping + binary search from the previous position ----
   double yv[SP_PER];
   double s_loc = 0.0;
   int nfin_loc = 0;
@@ -1108,10 +1105,11 @@ int acb_prep_spectrum_resample_idx(const double* wl, const double* fx, const lon
   const size_t smem = (size_t)(2 * cap + n_grid + 34) * 8 + (256 + 8 + 16) * 4 + 258 * 8;
   ACB_CHECK(smem <= 220 * 1024, "acb_prep_spectrum_resample: spectrum too long for shared memory (max_n=%d, n_grid=%d)", max_n, n_grid);
   if (n_grid <= SP_PER * 256) {
-    const size_t smem_r = std::max((size_t)2 * cap * 8, (size_t)n_grid * 4);  // xs | ys, reused as the float staging row
+    const int cap_r = (max_n + 1) & ~1;  // (its sorting network takes any length: no power-of-two padding)
+    const size_t smem_r = std::max((size_t)2 * cap_r * 8, (size_t)n_grid * 4);  // xs | ys, reused as the float staging row
     auto kr = prep_spectrum_reg_kernel;
     ACB_CUDA(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-    kr<<<B, 256, smem_r, (cudaStream_t)stream>>>(wl, fx, offsets, cap, grid, n_grid, out, idx_out);
+    kr<<<B, 256, smem_r, (cudaStream_t)stream>>>(wl, fx, offsets, cap_r, grid, n_grid, out, idx_out);
     ACB_LAUNCH_CHECK();
     acb_count_launch();
     return ACB_OK;
