@@ -100,30 +100,53 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const T* __restrict__ x
 // at compile time.  LayerNorm: conv row -> smem -> warp per pixel, channel pairs per lane.
 // LayerNorm of the W pixels of one conv row held in shared memory (cv[W][C] fp32): warp per pixel, NPL = C/32 values
 // per lane in registers (read once), affine parameters from shared memory, two-pass statistics.
-template <typename T, int NPL>
+// A warp works on PB pixels AT ONCE: the two butterfly reductions of a pixel are 10 dependent shuffles, and with one pixel in
+// flight per warp (3 warps per CTA at C = 96) the LayerNorm phase was 45 % of the kernel's stall samples (ncu, short scoreboard).
+template <typename T, int NPL, int PB>
 __device__ __forceinline__ void dw_ln_row(const float* __restrict__ cv, const float* __restrict__ s_lnw, const float* __restrict__ s_lnb,
                                           float eps, T* __restrict__ yrow, int Wpix, int wid, int nw, int lane) {
   constexpr int C = NPL * 32;
-  for (int ox = wid; ox < Wpix; ox += nw) {
-    const float* v = cv + ox * C;
-    float t[NPL];
-    float s = 0.0f;
+  for (int ox0 = wid; ox0 < Wpix; ox0 += nw * PB) {
+    float t[PB][NPL], s[PB], q[PB];
 #pragma unroll
-    for (int k = 0; k < NPL; ++k) {
-      t[k] = v[lane + 32 * k];
-      s += t[k];
+    for (int p = 0; p < PB; ++p) {
+      const int ox = min(ox0 + p * nw, Wpix - 1);  // (clamped pixels are recomputed, their stores are skipped)
+      const float* v = cv + ox * C;
+      s[p] = 0.0f;
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) {
+        t[p][k] = v[lane + 32 * k];
+        s[p] += t[p][k];
+      }
     }
-    const float mean = warp_sum(s) * (1.0f / (float)C);
-    float q = 0.0f;
 #pragma unroll
-    for (int k = 0; k < NPL; ++k) {
-      t[k] -= mean;
-      q = fmaf(t[k], t[k], q);
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int p = 0; p < PB; ++p) s[p] += __shfl_xor_sync(0xffffffffu, s[p], o);
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+      const float mean = s[p] * (1.0f / (float)C);
+      q[p] = 0.0f;
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) {
+        t[p][k] -= mean;
+        q[p] = fmaf(t[p][k], t[p][k], q[p]);
+      }
     }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / (float)C) + eps);
-    T* o = yrow + (long long)ox * C;
 #pragma unroll
-    for (int k = 0; k < NPL; ++k) o[lane + 32 * k] = from_f<T>(fmaf(t[k] * rstd, s_lnw[lane + 32 * k], s_lnb[lane + 32 * k]));
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int p = 0; p < PB; ++p) q[p] += __shfl_xor_sync(0xffffffffu, q[p], o);
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+      const int ox = ox0 + p * nw;
+      if (ox < Wpix) {
+        const float rstd = rsqrtf(q[p] * (1.0f / (float)C) + eps);
+        T* o = yrow + (long long)ox * C;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) o[lane + 32 * k] = from_f<T>(fmaf(t[p][k] * rstd, s_lnw[lane + 32 * k], s_lnb[lane + 32 * k]));
+      }
+    }
   }
 }
 
@@ -142,8 +165,9 @@ __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const
   const int WC = W * C;
   T* in = reinterpret_cast<T*>(smraw);
   const size_t in_bytes = (((size_t)(R + 6) * WC * sizeof(T)) + 15) & ~(size_t)15;
+  constexpr bool STRIP_LN = W <= 3;  // small maps: LayerNorm once per strip over all its R x W pixels (one pixel per warp and row leaves most warps idle)
   float* cv = reinterpret_cast<float*>(smraw + in_bytes);
-  float* wsm = cv + WC;
+  float* wsm = cv + (STRIP_LN ? R * WC : WC);
   float* s_lnw = wsm + (use_wsm ? 49 * (C + 1) : 0);
   float* s_lnb = s_lnw + C;
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -206,19 +230,28 @@ __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const
         for (int ox = 0; ox < W; ++ox) o[ox * C] = from_f<T>(acc[ox]);
       } else {
 #pragma unroll
-        for (int ox = 0; ox < W; ++ox) cv[ox * C + c] = acc[ox];
+        for (int ox = 0; ox < W; ++ox) cv[(STRIP_LN ? r * WC : 0) + ox * C + c] = acc[ox];
       }
     }
     if (!do_ln) continue;  // uniform for the whole CTA
+    if (STRIP_LN && (C == 384 || C == 768)) {
+      if (r + 1 < rows) continue;
+      __syncthreads();
+      T* ybase = y + (((long long)b * H + oy0) * W) * C;  // the strip's rows are contiguous in y
+      if (C == 384) dw_ln_row<T, 12, 1>(cv, s_lnw, s_lnb, eps, ybase, rows * W, wid, nw, lane);
+      else dw_ln_row<T, 24, 1>(cv, s_lnw, s_lnb, eps, ybase, rows * W, wid, nw, lane);
+      __syncthreads();
+      continue;
+    }
     __syncthreads();
     {
       T* yrow = y + (((long long)b * H + oy0 + r) * W) * C;
       bool done = true;
       switch (C) {
-        case 96: dw_ln_row<T, 3>(cv, s_lnw, s_lnb, eps, yrow, W, wid, nw, lane); break;
-        case 192: dw_ln_row<T, 6>(cv, s_lnw, s_lnb, eps, yrow, W, wid, nw, lane); break;
-        case 384: dw_ln_row<T, 12>(cv, s_lnw, s_lnb, eps, yrow, W, wid, nw, lane); break;
-        case 768: dw_ln_row<T, 24>(cv, s_lnw, s_lnb, eps, yrow, W, wid, nw, lane); break;
+        case 96: dw_ln_row<T, 3, 5>(cv + (STRIP_LN ? r * WC : 0), s_lnw, s_lnb, eps, yrow, W, wid, nw, lane); break;
+        case 192: dw_ln_row<T, 6, 2>(cv + (STRIP_LN ? r * WC : 0), s_lnw, s_lnb, eps, yrow, W, wid, nw, lane); break;
+        case 384: dw_ln_row<T, 12, 1>(cv + (STRIP_LN ? r * WC : 0), s_lnw, s_lnb, eps, yrow, W, wid, nw, lane); break;
+        case 768: dw_ln_row<T, 24, 1>(cv + (STRIP_LN ? r * WC : 0), s_lnw, s_lnb, eps, yrow, W, wid, nw, lane); break;
         default: done = false;
       }
       if (done) {
@@ -227,7 +260,7 @@ __global__ void __launch_bounds__(dw_max_threads<W>()) dwconv7_ln_w_kernel(const
       }
     }
     for (int ox = wid; ox < W; ox += nw) {
-      const float* v = cv + ox * C;
+      const float* v = cv + (STRIP_LN ? r * WC : 0) + ox * C;
       float s = 0.0f;
       for (int cc = lane * 2; cc < C; cc += 64) {
         const float2 t = *reinterpret_cast<const float2*>(v + cc);
@@ -265,7 +298,7 @@ int launch_dwconv_w(const void* x, const float* w, const float* b, const float* 
   const int R = W >= 15 ? 5 : (W >= 7 ? 7 : (W >= 3 ? 3 : 1));
   const int use_wsm = 0;  // measured: reading the 49 taps straight from L2 beats staging them in smem (19 KB less smem -> 5 CTAs/SM: 0.54 -> 0.46 ms)
   const size_t in_bytes = (((size_t)(R + 6) * W * C * sizeof(T)) + 15) & ~(size_t)15;
-  const size_t smem = in_bytes + (size_t)W * C * 4 + (use_wsm ? (size_t)49 * (C + 1) * 4 : 0) + (size_t)2 * C * 4;
+  const size_t smem = in_bytes + (size_t)(W <= 3 ? R : 1) * W * C * 4 + (use_wsm ? (size_t)49 * (C + 1) * 4 : 0) + (size_t)2 * C * 4;
   auto k = dwconv7_ln_w_kernel<T, W>;
   ACB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int threads = ((C + 31) / 32) * 32;
