@@ -133,11 +133,15 @@ __device__ __forceinline__ void cl_epilogue_tile(const ConvLnArgs& p, int mt, in
 #pragma unroll
             for (int i4 = 0; i4 < 8; ++i4) {
               const float4 bb = b4[i4], gg = g4[i4], ee = e4[i4];
-              const float y0 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 0]) + bb.x - mean) * rstd * gg.x + ee.x);
-              const float y1 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 1]) + bb.y - mean) * rstd * gg.y + ee.y);
-              const float y2 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 2]) + bb.z - mean) * rstd * gg.z + ee.z);
-              const float y3 = gelu_bf16((__uint_as_float(raw[i4 * 4 + 3]) + bb.w - mean) * rstd * gg.w + ee.w);
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
+              // packed fp32 (two channels per instruction): ((raw + bias) - mean) * rstd * gamma + beta, then GELU
+              const float2 nm2 = make_float2(-mean, -mean), rs2 = make_float2(rstd, rstd);
+              const float2 a01 = __fmul2_rn(__fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(raw[i4 * 4 + 0]), __uint_as_float(raw[i4 * 4 + 1])),
+                                                                  make_float2(bb.x, bb.y)), nm2), rs2);
+              const float2 a23 = __fmul2_rn(__fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(raw[i4 * 4 + 2]), __uint_as_float(raw[i4 * 4 + 3])),
+                                                                  make_float2(bb.z, bb.w)), nm2), rs2);
+              const float2 y01 = gelu_bf16x2(__ffma2_rn(a01, make_float2(gg.x, gg.y), make_float2(ee.x, ee.y)));
+              const float2 y23 = gelu_bf16x2(__ffma2_rn(a23, make_float2(gg.z, gg.w), make_float2(ee.z, ee.w)));
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(y01.x, y01.y), h1 = __floats2bfloat162_rn(y23.x, y23.y);
               pk[i4 * 2 + 0] = *reinterpret_cast<uint32_t*>(&h0);
               pk[i4 * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
             }

@@ -580,10 +580,10 @@ __global__ void __launch_bounds__(TC_LN_THREADS, 2) gemm_ln_tc_kernel(const __gr
         for (int e = 0; e < 4; ++e) {
           const int k = c * 8 + 2 * e;
           const float2 g2 = *reinterpret_cast<const float2*>(gw + k), b2 = *reinterpret_cast<const float2*>(gb + k);
-          const float x0 = fmaf(__uint_as_float(w4[e] << 16), rstd, nmr), x1 = fmaf(__uint_as_float(w4[e] & 0xffff0000u), rstd, nmr);
-          const float y0 = gelu_bf16(fmaf(x0, g2.x, b2.x));
-          const float y1 = gelu_bf16(fmaf(x1, g2.y, b2.y));
-          __nv_bfloat162 hh = __floats2bfloat162_rn(y0, y1);
+          const float2 xn = __ffma2_rn(make_float2(__uint_as_float(w4[e] << 16), __uint_as_float(w4[e] & 0xffff0000u)), make_float2(rstd, rstd),
+                                       make_float2(nmr, nmr));
+          const float2 yy = gelu_bf16x2(__ffma2_rn(xn, g2, b2));
+          __nv_bfloat162 hh = __floats2bfloat162_rn(yy.x, yy.y);
           o4[e] = *reinterpret_cast<uint32_t*>(&hh);
         }
         *reinterpret_cast<uint4*>(row + (((half * 4 + c) ^ (r & 7)) << 4)) = make_uint4(o4[0], o4[1], o4[2], o4[3]);

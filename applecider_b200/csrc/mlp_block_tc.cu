@@ -186,8 +186,9 @@ __global__ void __launch_bounds__(MlpCfg<C, HC>::THREADS, 1) mlp_block_kernel(co
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const float2 b2v = *reinterpret_cast<const float2*>(bb + i);
-        const float u0 = __uint_as_float(raw[i]) + b2v.x, u1 = __uint_as_float(raw[i + 1]) + b2v.y;
-        __nv_bfloat162 hh = ACT == ACB_ACT_RELU ? __floats2bfloat162_rn(fmaxf(u0, 0.0f), fmaxf(u1, 0.0f)) : __floats2bfloat162_rn(gelu_bf16(u0), gelu_bf16(u1));
+        const float2 uu = __fadd2_rn(make_float2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])), b2v);
+        const float2 aa = ACT == ACB_ACT_RELU ? make_float2(fmaxf(uu.x, 0.0f), fmaxf(uu.y, 0.0f)) : gelu_bf16x2(uu);
+        __nv_bfloat162 hh = __floats2bfloat162_rn(aa.x, aa.y);
         pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
       }
       // H tile: K block (cg*32)/64, 16-byte chunks c0..c0+3 of row r, SWIZZLE_128B
