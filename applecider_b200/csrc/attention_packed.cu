@@ -303,16 +303,18 @@ __global__ void __launch_bounds__(AP_THREADS, 2) attention_packed_kernel(const _
         tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, raw);
         const unsigned off = (unsigned)(c0 - lo);
         const bool interior = c0 >= ilo && c0 + 32 <= ihi;  // warp-uniform
+        float2 ls2 = make_float2(0.0f, 0.0f);  // packed fp32: one FFMA2 / FADD2 per pair of scores
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
+          const float2 e2 = __ffma2_rn(make_float2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])), make_float2(SC, SC), make_float2(-mxs, -mxs));
           float p0, p1;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(raw[i]), SC, -mxs)));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(raw[i + 1]), SC, -mxs)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e2.x));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e2.y));
           if (!interior) {
             p0 = off + (unsigned)i < len ? p0 : 0.0f;
             p1 = off + (unsigned)(i + 1) < len ? p1 : 0.0f;
           }
-          lsum += p0 + p1;
+          ls2 = __fadd2_rn(ls2, make_float2(p0, p1));
           if (drop_p > 0.0f) {
             p0 = ap_hash(seed, bh, qi, (int)off + i) >= drop_thr ? p0 * drop_inv : 0.0f;
             p1 = ap_hash(seed, bh, qi, (int)off + i + 1) >= drop_thr ? p1 * drop_inv : 0.0f;
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(AP_THREADS, 2) attention_packed_kernel(const _
           __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
         }
+        lsum += ls2.x + ls2.y;
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) pk[i] = 0u;

@@ -195,12 +195,15 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const bf16* __
             const float mx2 = mx * LOG2E;
             if (interior) {  // no per-element range predicates (all chunks of a long sequence but its last one)
 #pragma unroll
+              float2 ls2 = make_float2(0.0f, 0.0f);  // packed fp32: one FFMA2 / FADD2 per pair of scores
               for (int i = 0; i < 32; i += 2) {
                 const int j0 = k0 + c0 + i;
+                const float2 e2 = __ffma2_rn(make_float2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])), make_float2(LOG2E, LOG2E),
+                                             make_float2(-mx2, -mx2));
                 float p0, p1;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(raw[i]), LOG2E, -mx2)));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(raw[i + 1]), LOG2E, -mx2)));
-                lsum += p0 + p1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e2.x));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e2.y));
+                ls2 = __fadd2_rn(ls2, make_float2(p0, p1));
                 if (drop_p > 0.0f) {
                   p0 = attn_hash_tc(seed, bh, qi, j0) >= drop_thr ? p0 * drop_inv : 0.0f;
                   p1 = attn_hash_tc(seed, bh, qi, j0 + 1) >= drop_thr ? p1 * drop_inv : 0.0f;
@@ -208,6 +211,7 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const bf16* __
                 __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
                 pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
               }
+              lsum += ls2.x + ls2.y;
             } else {
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {

@@ -87,7 +87,7 @@ __device__ __forceinline__ void cl_epilogue_tile(const ConvLnArgs& p, int mt, in
       const long long orow = m * p.row_mul + (long long)y * p.row_add_y + g;
       const bool valid = valid_row && orow < p.out_rows;
       // pass 1: statistics of (acc + bias) over the 3*gw channels of this position
-      float sum = 0.0f, sq = 0.0f;
+      float2 sum2 = make_float2(0.0f, 0.0f), sq2 = make_float2(0.0f, 0.0f);  // packed fp32: even / odd channels
       for (int j = 0; j < 3; ++j) {
         for (int c0 = 0; c0 < gw; c0 += 32) {
           if ((((g * 3 * gw + j * gw + c0) >> 6) % NPQ) != half) continue;  // 64-column blocks are dealt round-robin to the warps
@@ -97,13 +97,14 @@ __device__ __forceinline__ void cl_epilogue_tile(const ConvLnArgs& p, int mt, in
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4) {
             const float4 bb = b4[i4];
-            const float v0 = __uint_as_float(raw[i4 * 4 + 0]) + bb.x, v1 = __uint_as_float(raw[i4 * 4 + 1]) + bb.y;
-            const float v2 = __uint_as_float(raw[i4 * 4 + 2]) + bb.z, v3 = __uint_as_float(raw[i4 * 4 + 3]) + bb.w;
-            sum += (v0 + v1) + (v2 + v3);
-            sq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+            const float2 v01 = __fadd2_rn(make_float2(__uint_as_float(raw[i4 * 4 + 0]), __uint_as_float(raw[i4 * 4 + 1])), make_float2(bb.x, bb.y));
+            const float2 v23 = __fadd2_rn(make_float2(__uint_as_float(raw[i4 * 4 + 2]), __uint_as_float(raw[i4 * 4 + 3])), make_float2(bb.z, bb.w));
+            sum2 = __fadd2_rn(sum2, __fadd2_rn(v01, v23));
+            sq2 = __ffma2_rn(v23, v23, __ffma2_rn(v01, v01, sq2));
           }
         }
       }
+      float sum = sum2.x + sum2.y, sq = sq2.x + sq2.y;
       part[g][half][r][0] = sum;
       part[g][half][r][1] = sq;
       asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * NPQ) : "memory");  // the warps of this quarter
