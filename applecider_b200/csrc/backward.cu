@@ -423,15 +423,42 @@ __global__ void __launch_bounds__(256) layernorm_bwd_reg_kernel(const T* __restr
     for (int i = 0; i < NE; ++i) { xv[i] -= mean; q += xv[i] * xv[i]; }
     const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
     float sg = 0.0f, sgx = 0.0f;
+    if constexpr (VEC == 2 && sizeof(T) == 2) {
+      // bf16 rows: the per-element arithmetic on the packed fp32 pipe (two channels per instruction; the kernel is issue-bound: ncu 81 %)
+      float2 sg2 = make_float2(0.0f, 0.0f), sgx2 = make_float2(0.0f, 0.0f);
+      const float2 rs2 = make_float2(rstd, rstd);
 #pragma unroll
-    for (int i = 0; i < NE; ++i) {
-      xv[i] *= rstd;  // xhat
-      if (gelu) gv[i] *= (sizeof(T) == 2 ? gelu_bf16_grad(fmaf(xv[i], wv[i], bv[i])) : gelu_erf_grad(fmaf(xv[i], wv[i], bv[i])));
-      const float g = gv[i] * wv[i];
-      sg += g;
-      sgx += g * xv[i];
-      aw[i] = fmaf(gv[i], xv[i], aw[i]);
-      ab[i] += gv[i];
+      for (int k = 0; k < NCH; ++k) {
+        const float2 w2 = make_float2(wv[2 * k], wv[2 * k + 1]);
+        const float2 xh = __fmul2_rn(make_float2(xv[2 * k], xv[2 * k + 1]), rs2);  // xhat
+        float2 g2 = make_float2(gv[2 * k], gv[2 * k + 1]);
+        if (gelu) {
+          const float2 pre = __ffma2_rn(xh, w2, make_float2(bv[2 * k], bv[2 * k + 1]));
+          g2 = __fmul2_rn(g2, make_float2(gelu_bf16_grad(pre.x), gelu_bf16_grad(pre.y)));
+        }
+        const float2 gw = __fmul2_rn(g2, w2);
+        sg2 = __fadd2_rn(sg2, gw);
+        sgx2 = __ffma2_rn(gw, xh, sgx2);
+        const float2 a2 = __ffma2_rn(g2, xh, make_float2(aw[2 * k], aw[2 * k + 1]));
+        const float2 b2 = __fadd2_rn(make_float2(ab[2 * k], ab[2 * k + 1]), g2);
+        aw[2 * k] = a2.x; aw[2 * k + 1] = a2.y;
+        ab[2 * k] = b2.x; ab[2 * k + 1] = b2.y;
+        xv[2 * k] = xh.x; xv[2 * k + 1] = xh.y;
+        gv[2 * k] = gw.x; gv[2 * k + 1] = gw.y;  // from here on gv holds g * w
+      }
+      sg = sg2.x + sg2.y;
+      sgx = sgx2.x + sgx2.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        xv[i] *= rstd;  // xhat
+        if (gelu) gv[i] *= (sizeof(T) == 2 ? gelu_bf16_grad(fmaf(xv[i], wv[i], bv[i])) : gelu_erf_grad(fmaf(xv[i], wv[i], bv[i])));
+        const float g = gv[i] * wv[i];
+        sg += g;
+        sgx += g * xv[i];
+        aw[i] = fmaf(gv[i], xv[i], aw[i]);
+        ab[i] += gv[i];
+      }
     }
     sg = warp_sum(sg) / (float)C;
     sgx = warp_sum(sgx) / (float)C;
@@ -440,9 +467,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_reg_kernel(const T* __restr
     for (int k = 0; k < NCH; ++k) {
       const int c0 = (k * 32 + lane) * VEC;
       if constexpr (VEC == 2 && sizeof(T) == 2) {
-        const float o0 = rstd * (gv[k * 2] * wv[k * 2] - sg - xv[k * 2] * sgx);
-        const float o1 = rstd * (gv[k * 2 + 1] * wv[k * 2 + 1] - sg - xv[k * 2 + 1] * sgx);
-        *reinterpret_cast<__nv_bfloat162*>(dr + c0) = __floats2bfloat162_rn(o0, o1);
+        // rstd * (g w - sg - xhat sgx)
+        const float2 t2 = __ffma2_rn(make_float2(-xv[k * 2], -xv[k * 2 + 1]), make_float2(sgx, sgx),
+                                     __fadd2_rn(make_float2(gv[k * 2], gv[k * 2 + 1]), make_float2(-sg, -sg)));
+        const float2 o2 = __fmul2_rn(make_float2(rstd, rstd), t2);
+        *reinterpret_cast<__nv_bfloat162*>(dr + c0) = __floats2bfloat162_rn(o2.x, o2.y);
       } else {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
@@ -656,22 +685,48 @@ __global__ void __launch_bounds__(512) attention_bwd_kernel(const void* qkv, int
     Os[i] = ld_any(dout, (long long)(t0 + r) * D + h * DH + c, do_dt);
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < n; r += blockDim.x) {
-    float q[DH], go[DH];
+  // the dot products and rank-1 updates over the DH = 16 head channels run on the packed fp32 pipe (FFMA2: two channels per
+  // instruction); a row of K / V / Q / dO is four 16-byte shared-memory loads
+  auto dot16 = [](const float2 (&a)[DH / 2], const float* __restrict__ row) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
-    for (int c = 0; c < DH; ++c) { q[c] = Qs[r * DH + c]; go[c] = Os[r * DH + c]; }
-    float m = -INFINITY;
-    for (int j = 0; j < n; ++j) {
-      float s = 0.0f;
-#pragma unroll
-      for (int c = 0; c < DH; ++c) s = fmaf(q[c], Ks[j * DH + c], s);
-      m = fmaxf(m, s);
+    for (int c = 0; c < DH / 4; ++c) {
+      const float4 v = r4[c];
+      acc = __ffma2_rn(a[2 * c], make_float2(v.x, v.y), acc);
+      acc = __ffma2_rn(a[2 * c + 1], make_float2(v.z, v.w), acc);
     }
+    return acc.x + acc.y;
+  };
+  auto axpy16 = [](float2 (&y)[DH / 2], float a, const float* __restrict__ row) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    const float2 a2 = make_float2(a, a);
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c) {
+      const float4 v = r4[c];
+      y[2 * c] = __ffma2_rn(a2, make_float2(v.x, v.y), y[2 * c]);
+      y[2 * c + 1] = __ffma2_rn(a2, make_float2(v.z, v.w), y[2 * c + 1]);
+    }
+  };
+  auto load16 = [](float2 (&a)[DH / 2], const float* __restrict__ row) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c) {
+      const float4 v = r4[c];
+      a[2 * c] = make_float2(v.x, v.y);
+      a[2 * c + 1] = make_float2(v.z, v.w);
+    }
+  };
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    float2 q[DH / 2], go[DH / 2];
+    load16(q, Qs + r * DH);
+    load16(go, Os + r * DH);
+    float m = -INFINITY;
+    for (int j = 0; j < n; ++j) m = fmaxf(m, dot16(q, Ks + j * DH));
     float l = 0.0f, dsum = 0.0f;
     for (int j = 0; j < n; ++j) {
-      float s = 0.0f, dp = 0.0f;
-#pragma unroll
-      for (int c = 0; c < DH; ++c) { s = fmaf(q[c], Ks[j * DH + c], s); dp = fmaf(go[c], Vs[j * DH + c], dp); }
+      const float s = dot16(q, Ks + j * DH);
+      float dp = dot16(go, Vs + j * DH);
       const float e = expf(s - m);
       l += e;
       if (drop_p > 0.0f) dp = attn_hash(seed, bh, r, j) >= drop_thr ? dp * drop_inv : 0.0f;
@@ -681,31 +736,33 @@ __global__ void __launch_bounds__(512) attention_bwd_kernel(const void* qkv, int
     const float Dv = dsum / l;  // sum_j P_ij dP_ij
     lse[r] = L;
     Dr[r] = Dv;
-    float dq[DH];
+    float2 dq[DH / 2];
 #pragma unroll
-    for (int c = 0; c < DH; ++c) dq[c] = 0.0f;
+    for (int c = 0; c < DH / 2; ++c) dq[c] = make_float2(0.0f, 0.0f);
     for (int j = 0; j < n; ++j) {
-      float s = 0.0f, dp = 0.0f;
-#pragma unroll
-      for (int c = 0; c < DH; ++c) { s = fmaf(q[c], Ks[j * DH + c], s); dp = fmaf(go[c], Vs[j * DH + c], dp); }
+      const float s = dot16(q, Ks + j * DH);
+      float dp = dot16(go, Vs + j * DH);
       if (drop_p > 0.0f) dp = attn_hash(seed, bh, r, j) >= drop_thr ? dp * drop_inv : 0.0f;
       const float ds = expf(s - L) * (dp - Dv);
-#pragma unroll
-      for (int c = 0; c < DH; ++c) dq[c] = fmaf(ds, Ks[j * DH + c], dq[c]);
+      axpy16(dq, ds, Ks + j * DH);
     }
     const long long row = (long long)(t0 + r) * 3 * D + h * DH;
 #pragma unroll
-    for (int c = 0; c < DH; ++c) st_any(dqkv, row + c, dq_dt, dq[c] * scale);
+    for (int c = 0; c < DH / 2; ++c) {
+      st_any(dqkv, row + 2 * c, dq_dt, dq[c].x * scale);
+      st_any(dqkv, row + 2 * c + 1, dq_dt, dq[c].y * scale);
+    }
   }
   __syncthreads();
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    float k[DH], v[DH], dk[DH], dv[DH];
+    float2 k[DH / 2], v[DH / 2], dk[DH / 2], dv[DH / 2];
+    load16(k, Ks + j * DH);
+    load16(v, Vs + j * DH);
 #pragma unroll
-    for (int c = 0; c < DH; ++c) { k[c] = Ks[j * DH + c]; v[c] = Vs[j * DH + c]; dk[c] = 0.0f; dv[c] = 0.0f; }
+    for (int c = 0; c < DH / 2; ++c) { dk[c] = make_float2(0.0f, 0.0f); dv[c] = make_float2(0.0f, 0.0f); }
     for (int r = 0; r < n; ++r) {
-      float s = 0.0f, dp = 0.0f;
-#pragma unroll
-      for (int c = 0; c < DH; ++c) { s = fmaf(Qs[r * DH + c], k[c], s); dp = fmaf(Os[r * DH + c], v[c], dp); }
+      const float s = dot16(k, Qs + r * DH);
+      float dp = dot16(v, Os + r * DH);
       const float pr = expf(s - lse[r]);
       float pd = pr;
       if (drop_p > 0.0f) {
@@ -714,14 +771,16 @@ __global__ void __launch_bounds__(512) attention_bwd_kernel(const void* qkv, int
         pd = keep ? pr * drop_inv : 0.0f;
       }
       const float ds = pr * (dp - Dr[r]);
-#pragma unroll
-      for (int c = 0; c < DH; ++c) { dv[c] = fmaf(pd, Os[r * DH + c], dv[c]); dk[c] = fmaf(ds, Qs[r * DH + c], dk[c]); }
+      axpy16(dv, pd, Os + r * DH);
+      axpy16(dk, ds, Qs + r * DH);
     }
     const long long row = (long long)(t0 + j) * 3 * D + h * DH;
 #pragma unroll
-    for (int c = 0; c < DH; ++c) {
-      st_any(dqkv, row + D + c, dq_dt, dk[c]);  // Qs already carries the 1/sqrt(dh) factor
-      st_any(dqkv, row + 2 * D + c, dq_dt, dv[c]);
+    for (int c = 0; c < DH / 2; ++c) {
+      st_any(dqkv, row + D + 2 * c, dq_dt, dk[c].x);  // Qs already carries the 1/sqrt(dh) factor
+      st_any(dqkv, row + D + 2 * c + 1, dq_dt, dk[c].y);
+      st_any(dqkv, row + 2 * D + 2 * c, dq_dt, dv[c].x);
+      st_any(dqkv, row + 2 * D + 2 * c + 1, dq_dt, dv[c].y);
     }
   }
 }
