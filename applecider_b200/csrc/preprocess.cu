@@ -83,18 +83,36 @@ __device__ __forceinline__ P2Sum p2_window(const double* __restrict__ mjd, const
                                            const int* __restrict__ fid, long long i, long long j, int band) {
   const double eps = 1e-8;
   const double c_err = 2.5 / 2.302585092994046;  // 2.5 / ln(10)
+  // a 12 h window rarely holds more than a few detections of one band: the first four keep their flux / error (each an fp64 pow,
+  // ~150 instructions) in registers for the second pass, later ones are recomputed
+  constexpr int KEEP = 4;
+  double fl[KEEP], er[KEEP];
+  int cnt = 0;
   double totw = 0.0;
   for (long long k = i; k <= j; ++k) {
     if (fid[k] != band) continue;
     const double flux = pow(10.0, -0.4 * (mag[k] - 23.9));
     const double err = __dmul_rn(magerr[k] / c_err, flux);
     totw = __dadd_rn(totw, 1.0 / __dadd_rn(err, eps));
+#pragma unroll
+    for (int u = 0; u < KEEP; ++u)
+      if (cnt == u) { fl[u] = flux; er[u] = err; }
+    ++cnt;
   }
   P2Sum s{0.0, 0.0, 0.0};
+  cnt = 0;
   for (long long k = i; k <= j; ++k) {
     if (fid[k] != band) continue;
-    const double flux = pow(10.0, -0.4 * (mag[k] - 23.9));
-    const double err = __dmul_rn(magerr[k] / c_err, flux);
+    double flux = 0.0, err = 0.0;
+    if (cnt < KEEP) {
+#pragma unroll
+      for (int u = 0; u < KEEP; ++u)
+        if (cnt == u) { flux = fl[u]; err = er[u]; }
+    } else {
+      flux = pow(10.0, -0.4 * (mag[k] - 23.9));
+      err = __dmul_rn(magerr[k] / c_err, flux);
+    }
+    ++cnt;
     const double w = (1.0 / __dadd_rn(err, eps)) / totw;
     s.t = __dadd_rn(s.t, __dmul_rn(w, mjd[k]));
     s.f = __dadd_rn(s.f, __dmul_rn(w, flux));
@@ -672,8 +690,8 @@ __global__ void __launch_bounds__(256, 4) prep_spectrum_reg_kernel(const double*
   double s_loc = 0.0;
   int nfin_loc = 0;
   {
-    int prev_lo = 0;
-    double prev_x = -CUDART_INF;
+    int prev_lo = 0, prev_ih = -1;
+    double prev_x = -CUDART_INF, slope = 0.0, x_il = 0.0, y_il = 0.0;
 #pragma unroll
     for (int e = 0; e < SP_PER; ++e) {
       const int g = tid * SP_PER + e;
@@ -693,8 +711,13 @@ __global__ void __launch_bounds__(256, 4) prep_spectrum_reg_kernel(const double*
         if (idx_out) idx_out[(long long)b * n_grid + g] = lo;
         const int ih = min(max(lo, 1), n - 1);
         const int il = ih - 1;
-        const double slope = __ddiv_rn(__dsub_rn(ys[ih], ys[il]), __dsub_rn(xs[ih], xs[il]));
-        const double v = __dadd_rn(__dmul_rn(slope, __dsub_rn(xn, xs[il])), ys[il]);
+        if (ih != prev_ih) {  // consecutive grid points usually share the interval: one fp64 division per interval, not per point
+          x_il = xs[il];
+          y_il = ys[il];
+          slope = __ddiv_rn(__dsub_rn(ys[ih], y_il), __dsub_rn(xs[ih], x_il));
+          prev_ih = ih;
+        }
+        const double v = __dadd_rn(__dmul_rn(slope, __dsub_rn(xn, x_il)), y_il);
         yv[e] = v;
         if (!isnan(v)) { s_loc += v; ++nfin_loc; }
       }
