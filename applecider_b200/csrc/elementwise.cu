@@ -394,6 +394,35 @@ __global__ void __launch_bounds__(256) transpose_kernel(const void* in, int idt,
   }
 }
 
+// The same for MANY fp32 matrices in one launch (all the W^T bf16 copies the dgrad GEMMs of a training step need, refreshed
+// together after the optimizer step): job j = (src, dst, R, C) owns the global tiles [tile0[j], tile0[j+1]), a block finds its job
+// by binary search.  meta[j] = {R, C, tiles per row, first tile}.
+__global__ void __launch_bounds__(256) transpose_batch_kernel(const long long* __restrict__ src, const long long* __restrict__ dst,
+                                                              const int4* __restrict__ meta, int n_jobs) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.x;
+  int lo = 0, hi = n_jobs - 1;
+  while (lo < hi) {  // last job whose first tile is <= t
+    const int mid = (lo + hi + 1) >> 1;
+    if (meta[mid].w <= t) lo = mid; else hi = mid - 1;
+  }
+  const int4 m = meta[lo];
+  const int R = m.x, C = m.y, lt = t - m.w;
+  const int c0 = (lt % m.z) * 32, r0 = (lt / m.z) * 32;
+  const float* in = reinterpret_cast<const float*>(src[lo]);
+  bf16* out = reinterpret_cast<bf16*>(dst[lo]);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    if (r < R && c < C) tile[i][tx] = in[(long long)r * C + c];
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < R && c < C) out[(long long)c * R + r] = __float2bfloat16(tile[tx][i]);
+  }
+}
+
 // ---- pooling over L of channels-last [B, L, C] ---------------------------------------------------
 template <typename T>
 __global__ void maxpool4_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int L, int C) {
@@ -485,6 +514,14 @@ int acb_transpose(const void* in, int in_dtype, void* out, int out_dtype, int R,
   dim3 grid(cdiv(C, 32), cdiv(R, 32));
   ACB_CHECK(grid.y <= 65535, "acb_transpose: too many rows");
   transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, in_dtype, out, out_dtype, R, C);
+  ACB_LAUNCH_CHECK();
+  acb_count_launch();
+  return ACB_OK;
+}
+
+int acb_transpose_batch(const long long* src_ptrs, const long long* dst_ptrs, const int* meta, int n_jobs, int total_tiles, void* stream) {
+  ACB_CHECK(src_ptrs && dst_ptrs && meta && n_jobs > 0 && total_tiles > 0, "acb_transpose_batch: bad arguments");
+  transpose_batch_kernel<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(src_ptrs, dst_ptrs, reinterpret_cast<const int4*>(meta), n_jobs);
   ACB_LAUNCH_CHECK();
   acb_count_launch();
   return ACB_OK;

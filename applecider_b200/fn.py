@@ -83,6 +83,72 @@ def transpose(x, dtype):
     return y
 
 
+class _TransposedWeights:
+    """bf16 W^T copies of Linear weights for the input-gradient GEMMs (dX = dY @ W as a plain x @ B^T GEMM with B = W^T).
+
+    Every step needs all of them again (the optimizer has changed every weight), so they are refreshed TOGETHER: the first
+    request that finds its copy stale relaunches ONE `acb_transpose_batch` over every registered weight instead of one small
+    transpose kernel per layer (66 launches per fusion training step).  Staleness = the version counter of the parameter (a
+    view shares its base's counter; `optim.FusedAdam` bumps it, so does any in-place torch update).  An entry is keyed by
+    (data pointer, shape) and holds only a weak reference to the parameter; buffers and the device job table are stable across
+    steps, so a CUDA-graph capture records the one batched launch."""
+
+    def __init__(self):
+        self._by_dev = {}
+
+    def get(self, W):
+        import weakref
+
+        if W.dtype != F32 or not W.is_contiguous() or W.dim() != 2:
+            return transpose(W.detach(), BF16)
+        base = W._base if W._is_view() and W._base is not None else W
+        if not isinstance(base, torch.nn.Parameter):  # temporaries (concatenated / sliced copies of weights) die after the step
+            return transpose(W.detach(), BF16)
+        reg = self._by_dev.setdefault(W.device, {"entries": {}, "sig": None, "table": None})
+        key = (W.data_ptr(), W.shape[0], W.shape[1])
+        e = reg["entries"].get(key)
+        if e is not None and e[0]() is base:
+            if e[2] != base._version:
+                self._refresh(reg)
+            return e[1]
+        out = transpose(W.detach(), BF16)
+        reg["entries"][key] = [weakref.ref(base), out, base._version]
+        reg["sig"] = None
+        return out
+
+    @staticmethod
+    def _refresh(reg):
+        ents = reg["entries"]
+        for k in [k for k, e in ents.items() if e[0]() is None]:  # weights of models that are gone
+            del ents[k]
+            reg["sig"] = None
+        if reg["sig"] is None:
+            src, dst, meta, t0 = [], [], [], 0
+            for (ptr, R, C), e in ents.items():
+                src.append(ptr)
+                dst.append(e[1].data_ptr())
+                meta += [R, C, (C + 31) // 32, t0]
+                t0 += ((R + 31) // 32) * ((C + 31) // 32)
+            dev = next(iter(ents.values()))[1].device
+            reg["table"] = (torch.tensor(src, dtype=torch.int64).to(dev), torch.tensor(dst, dtype=torch.int64).to(dev),
+                            torch.tensor(meta, dtype=torch.int32).to(dev), len(src), t0)
+            reg["sig"] = True
+        src_t, dst_t, meta_t, n, tiles = reg["table"]
+        call("acb_transpose_batch", src_t, dst_t, meta_t, n, tiles)
+        for e in ents.values():
+            w = e[0]()
+            if w is not None:
+                e[2] = w._version
+
+
+_wT = _TransposedWeights()
+
+
+def transposed_weight(W):
+    """bf16 [K, N] copy of the fp32 parameter W [N, K], refreshed in one batched launch per optimizer step."""
+    return _wT.get(W)
+
+
 import os as _os
 
 FOLD_BIAS_GRAD = _os.environ.get("ACB_FOLD_BIAS_GRAD", "1") != "0"  # bias gradient from the wgrad launch (ones tile) vs a colsum pass
@@ -134,7 +200,7 @@ class Linear(Function):
         tc = x.dtype == BF16 and dy.dtype == BF16 and N % 8 == 0 and K % 8 == 0 and M >= 64
         if ctx.needs_input_grad[0]:
             if tc:  # tcgen05 dgrad: dX = dY @ W through a bf16 W^T copy
-                dx = ops.gemm(dy, transpose(W.detach(), BF16), None)
+                dx = ops.gemm(dy, transposed_weight(W), None)
             else:
                 dx = cast_to(gemm_ex(dy, dtype_tag(dy), W, 0, M, K, N, N, 1, 1, K, x.device), x.dtype)
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
@@ -290,9 +356,9 @@ class MlpBlock(Function):
         dgamma = colsum(dy.view(-1, C), v.view(-1, C))
         dv = ew(dy, None, 3, g=gamma, C=C, out_dtype=BF16)
         dW2, db2 = wgrad_tc(dv, C, 0, C, h, 1, M, H, 1, 0, M * H, H, y.device, want_db=True)
-        du = ops.gemm(dv, transpose(W2.detach(), BF16), None, res=u, res_mode=ops.RES_MUL_GELU_GRAD)  # [M,H] = (dv W2) * gelu'(u)
+        du = ops.gemm(dv, transposed_weight(W2), None, res=u, res_mode=ops.RES_MUL_GELU_GRAD)  # [M,H] = (dv W2) * gelu'(u)
         dW1, db1 = wgrad_tc(du, H, 0, H, y, 1, M, C, 1, 0, M * C, C, y.device, want_db=True)
-        dyin = ops.gemm(du, transpose(W1.detach(), BF16), None)
+        dyin = ops.gemm(du, transposed_weight(W1), None)
         return dy, dyin, dW1, db1, dW2, db2, dgamma, None, None
 
 

@@ -127,6 +127,10 @@ int acb_pack_polyphase_weight(const float* w, void* out, int out_dtype, int Cout
 int acb_cast(const void* in, int in_dtype, void* out, int out_dtype, long long n, void* stream);
 /* out[c*R + r] = in[r*C + c] */
 int acb_transpose(const void* in, int in_dtype, void* out, int out_dtype, int R, int C, void* stream);
+/* the fp32 -> bf16 transposes of MANY weight matrices in one launch (the W^T operands of every nn.Linear's input-gradient GEMM,
+ * refreshed together after an optimizer step): device arrays src_ptrs[n] (const float*), dst_ptrs[n] (bf16*), meta[n][4] =
+ * {R, C, ceil(C / 32), first global 32 x 32 tile of the job}; total_tiles = sum over jobs of ceil(R / 32) * ceil(C / 32). */
+int acb_transpose_batch(const long long* src_ptrs, const long long* dst_ptrs, const int* meta, int n_jobs, int total_tiles, void* stream);
 /* out[b*out_stride + lead + i] = in[b*L + i] (bf16/f32), buffer pre-zeroed by the caller */
 int acb_pad_signal(const float* in, void* out, int out_dtype, int nb, int L, long long out_stride, int lead,
                    void* stream);

@@ -90,6 +90,38 @@ def test_maxpool(B, L, C):
     _check(fn.MaxPool.apply(x, B, L, C, 0), x2.amax(1), (x,), (x2,), tol=1e-6)
 
 
+def test_linear_dgrad_weight_copies_follow_weight_updates():
+    """The bf16 W^T copies behind the tcgen05 input-gradient GEMMs are refreshed in ONE batched launch when a weight has changed
+    (fn.transposed_weight): the gradients must follow in-place updates of the weights, for plain parameters and for views."""
+    from applecider_b200 import _lib, fn
+
+    bf = torch.bfloat16
+    Ws = [torch.nn.Parameter(_rand(n, k, seed=60 + i, scale=k**-0.5)) for i, (n, k) in enumerate([(128, 96), (64, 128), (40, 72)])]
+    Wv = torch.nn.Parameter(_rand(2 * 64 * 48, seed=70, scale=0.1))  # used through a reshaping view, like the 1x1 downsample conv weights
+    xs = [_rand(256, W.shape[1], seed=80 + i).to(bf).requires_grad_(True) for i, W in enumerate(Ws)]
+    xv = _rand(256, 96, seed=90).to(bf).requires_grad_(True)
+
+    def run():
+        outs = [fn.linear(x, W) for x, W in zip(xs, Ws)] + [fn.linear(xv, Wv.view(64, 96))]
+        for x in xs + [xv]:
+            x.grad = None
+        sum(o.float().sum() for o in outs).backward()
+        return [x.grad.float().clone() for x in xs + [xv]]
+
+    def ref():
+        return [W.detach().to(bf).float().sum(0)[None, :].expand(256, -1) for W in Ws] + [Wv.detach().view(64, 96).to(bf).float().sum(0)[None, :].expand(256, -1)]
+
+    for step in range(3):
+        before = _lib.lib().acb_launch_count() if hasattr(_lib.lib(), "acb_launch_count") else None
+        got = run()
+        for g, r in zip(got, ref()):
+            assert_close(g, r, 1e-2, f"dX after {step} weight updates")
+        with torch.no_grad():  # in-place updates bump the version counters
+            for W in Ws + [Wv]:
+                W.mul_(-1.5).add_(0.01)
+        del before
+
+
 @pytest.mark.parametrize("rows,C", [(1000, 96), (333, 20)])
 def test_elementwise_bf16(rows, C):
     """bf16 elementwise ops and activation backward: 16-byte kernels when the size allows (C = 96), scalar kernels otherwise."""
