@@ -48,25 +48,75 @@ __global__ void __launch_bounds__(TOWER_WARPS * 32) tower_fwd_kernel(const Tower
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)p.hid + 1e-5f);
   __syncwarp();
-  // normalised hidden (shared statistics, two affine sets) folded into the two output GEMVs
-  for (int o = lane; o < p.out_dim; o += 32) {
+  // normalised hidden (shared statistics, two affine sets) folded into the two output GEMVs.  Lanes run along the HIDDEN axis, so a
+  // weight row is read as consecutive 128-byte lines (lanes along the outputs read it with a stride of `hid` floats: 32 sectors per
+  // load, which made this kernel L1-throughput bound), and every output is a warp reduction; lane (o mod 32) keeps output o.
+  constexpr int HPL = TOWER_MAX_HID / 32, OPL = 4;  // hidden values / outputs per lane
+  float z1[HPL], z2[HPL];
+#pragma unroll
+  for (int k = 0; k < HPL; ++k) {
+    const int h = lane + 32 * k;
+    z1[k] = 0.0f;
+    z2[k] = 0.0f;
+    if (h < p.hid) {
+      const float z = (s[h] - mean) * rstd;
+      z1[k] = fmaf(z, p.ln1w[h], p.ln1b[h]);
+      z2[k] = fmaf(z, p.ln2w[h], p.ln2b[h]);
+    }
+  }
+  float mm[OPL], gg[OPL], sk[OPL];
+#pragma unroll
+  for (int j = 0; j < OPL; ++j) mm[j] = gg[j] = sk[j] = 0.0f;
+  const bool wide_skip = p.Ws != nullptr && p.in_dim > 32;  // experts: 288 inputs -> lanes along the inputs as well
+#pragma unroll 4  // (independent outputs: lets the loads of the next ones issue under the shuffle chains)
+  for (int o = 0; o < p.out_dim; ++o) {
     const float* w1 = p.W1 + (long long)o * p.hid;
     const float* w2 = p.W2 + (long long)o * p.hid;
-    float m = p.b1[o], g = p.b2[o];
-    for (int h = 0; h < p.hid; ++h) {
-      const float z = (s[h] - mean) * rstd;
-      m = fmaf(__ldg(w1 + h), z * p.ln1w[h] + p.ln1b[h], m);
-      g = fmaf(__ldg(w2 + h), z * p.ln2w[h] + p.ln2b[h], g);
+    float m = 0.0f, g = 0.0f, k3 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < HPL; ++k) {
+      const int h = lane + 32 * k;
+      if (h < p.hid) {
+        m = fmaf(__ldg(w1 + h), z1[k], m);
+        g = fmaf(__ldg(w2 + h), z2[k], g);
+      }
     }
-    float sk;
-    if (p.Ws) {
+    if (wide_skip) {
       const float* ws = p.Ws + (long long)o * p.in_dim;
-      sk = p.bs[o];
-      for (int i = 0; i < p.in_dim; ++i) sk = fmaf(__ldg(ws + i), x[i], sk);
-    } else {
-      sk = x[o];
+      for (int i = lane; i < p.in_dim; i += 32) k3 = fmaf(__ldg(ws + i), x[i], k3);
     }
-    p.Y[(long long)row * p.ldy + p.y_off + o] = m * sigmoidf_(g) + sk;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      m += __shfl_xor_sync(0xffffffffu, m, off);
+      g += __shfl_xor_sync(0xffffffffu, g, off);
+      if (wide_skip) k3 += __shfl_xor_sync(0xffffffffu, k3, off);
+    }
+    if ((o & 31) == lane) {
+#pragma unroll
+      for (int j = 0; j < OPL; ++j)
+        if (j == (o >> 5)) {
+          mm[j] = m + p.b1[o];
+          gg[j] = g + p.b2[o];
+          sk[j] = k3 + (wide_skip ? p.bs[o] : 0.0f);
+        }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < OPL; ++j) {
+    const int o = lane + 32 * j;
+    if (o < p.out_dim) {
+      float skv = sk[j];
+      if (!wide_skip) {
+        if (p.Ws) {
+          const float* ws = p.Ws + (long long)o * p.in_dim;
+          skv = p.bs[o];
+          for (int i = 0; i < p.in_dim; ++i) skv = fmaf(__ldg(ws + i), x[i], skv);
+        } else {
+          skv = x[o];
+        }
+      }
+      p.Y[(long long)row * p.ldy + p.y_off + o] = mm[j] * sigmoidf_(gg[j]) + skv;
+    }
   }
 }
 
@@ -109,12 +159,37 @@ constexpr int FUSION_MAX_H = 256;
 
 __device__ __forceinline__ void proj_norm(const float* in, int dim, const float* W, const float* b, int H, float* e, int lane) {
   float ss = 0.0f;
-  for (int h = lane; h < H; h += 32) {
-    const float* wr = W + (long long)h * dim;
-    float a = b[h];
-    for (int i = 0; i < dim; ++i) a = fmaf(__ldg(wr + i), in[i], a);
-    e[h] = a;
-    ss += a * a;
+  if (dim >= 32) {
+    // wide input (the 128-d photometry embedding): lanes along the input so that weight rows are read as full lines, one warp
+    // reduction per output (lanes along the outputs read W with a stride of `dim` floats)
+    float xr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xr[k] = lane + 32 * k < dim ? in[lane + 32 * k] : 0.0f;
+#pragma unroll 4
+    for (int h = 0; h < H; ++h) {
+      const float* wr = W + (long long)h * dim;
+      float a = 0.0f;
+      if (dim <= 128) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (lane + 32 * k < dim) a = fmaf(__ldg(wr + lane + 32 * k), xr[k], a);
+      } else {
+        for (int i = lane; i < dim; i += 32) a = fmaf(__ldg(wr + i), in[i], a);
+      }
+      a = warp_sum(a) + b[h];  // (every lane holds the sum)
+      if (lane == (h & 31)) {
+        e[h] = a;
+        ss += a * a;
+      }
+    }
+  } else {
+    for (int h = lane; h < H; h += 32) {
+      const float* wr = W + (long long)h * dim;
+      float a = b[h];
+      for (int i = 0; i < dim; ++i) a = fmaf(__ldg(wr + i), in[i], a);
+      e[h] = a;
+      ss += a * a;
+    }
   }
   const float inv = 1.0f / sqrtf(warp_sum(ss));
   __syncwarp();
@@ -167,7 +242,7 @@ int acb_tower_fwd(const float* X, int ldx, const int* cols, int in_dim, int hid,
                   const float* ln2w, const float* ln2b, const float* W2, const float* b2, const float* Ws,
                   const float* bs, float* Y, int ldy, int y_off, int rows, const float* S_pre, int lds, int s_off, void* stream) {
   ACB_CHECK(X && Y && (S_pre || (W0 && b0)) && ln1w && ln1b && W1 && b1 && ln2w && ln2b && W2 && b2, "acb_tower_fwd: null argument");
-  ACB_CHECK(in_dim > 0 && in_dim <= TOWER_MAX_IN && hid > 0 && hid <= TOWER_MAX_HID && out_dim > 0,
+  ACB_CHECK(in_dim > 0 && in_dim <= TOWER_MAX_IN && hid > 0 && hid <= TOWER_MAX_HID && out_dim > 0 && out_dim <= 128,
             "acb_tower_fwd: dims out of range (in=%d hid=%d out=%d)", in_dim, hid, out_dim);
   ACB_CHECK(Ws != nullptr || in_dim == out_dim, "acb_tower_fwd: identity skip needs in_dim == out_dim");
   if (rows == 0) return ACB_OK;
