@@ -5,7 +5,6 @@ import ctypes
 
 import torch
 
-from . import _lib
 from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS, ACT_TANH, BF16, F32, RES_ADD, RES_MUL, RES_MUL_GELU_GRAD, RES_NONE, call, dtype_tag  # noqa: F401
 
 

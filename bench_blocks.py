@@ -12,7 +12,6 @@ max over ranks; every working set is far larger than the 126 MB L2.
 from __future__ import annotations
 
 import dataclasses
-import os
 import time
 
 import numpy as np
